@@ -1,0 +1,216 @@
+/*
+ * vitrs.h — C ABI of libvitrs.so: the B200 (sm_100a) replacement for the ViT.rs hot path.
+ *
+ * This is the drop-in boundary.  The reference has no plugin system; its
+ * boundary is the llm.c-style free-function set of /root/reference/train_vit.rs:376-670
+ * (raw f32 pointers, c_int dims, no return value) plus the model entry points
+ * ViT::build_from_checkpoint / forward / backward (rusty_vit.rs:79,269,354) and
+ * optimizer_step (rusty_vit.rs:949).  Every entry point below names the reference item it
+ * replaces.  Differences, all forced by the device:
+ *   - pointers are DEVICE pointers; calls are asynchronous on the context's stream;
+ *   - an int status is returned (0 = ok, <0 = error; vitrs_last_error() gives the text)
+ *     because a CUDA launch can fail where a CPU loop cannot;
+ *   - every op exists as _f32 (verify mode, fp32 multiply + fp32 accumulate) and _bf16
+ *     (production: bf16 activations/weights, fp32 statistics, accumulators and gradients
+ *     of parameters);
+ *   - attention takes an explicit `causal` flag (reference: causal, train_vit.rs:413; every
+ *     ViT config: 0) and its preatt/att buffers may be NULL (the fused kernel keeps only
+ *     lse[B,NH,T]).
+ * Semantics kept from the reference: forward ops overwrite their outputs; backward ops
+ * ACCUMULATE (+=) into dinp/dweight/dbias (train_vit.rs:538,549,552,626-633,650), so the
+ * caller zeroes gradients once per step; NULL bias / dbias are legal (train_vit.rs:388,548);
+ * ops never allocate, free or retain caller pointers.
+ *
+ * There is no CPU fallback: every entry point fails with VITRS_ERR_CUDA when no sm_100
+ * device is present.  Plain C types only — no torch / C++ types cross this boundary.
+ */
+#ifndef VITRS_H
+#define VITRS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITRS_OK 0
+#define VITRS_ERR_CUDA -1
+#define VITRS_ERR_ARG -2
+#define VITRS_ERR_UNSUPPORTED -3
+#define VITRS_ERR_NCCL -4
+
+typedef struct vitrs_ctx vitrs_ctx;
+typedef struct vitrs_model vitrs_model;
+typedef uint16_t vitrs_bf16; /* raw bfloat16 bits */
+
+/* ---- context ------------------------------------------------------------------------- */
+int vitrs_ctx_create(vitrs_ctx** out, int device);
+int vitrs_ctx_destroy(vitrs_ctx* ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the own stream */
+int vitrs_ctx_set_stream(vitrs_ctx* ctx, void* cuda_stream);
+void* vitrs_ctx_stream(vitrs_ctx* ctx);
+int vitrs_ctx_synchronize(vitrs_ctx* ctx);
+const char* vitrs_last_error(vitrs_ctx* ctx);
+/* kernels launched by this library on this context since creation (bench.py: gpu_launches) */
+uint64_t vitrs_launch_count(vitrs_ctx* ctx);
+const char* vitrs_version(void);
+
+/* device memory for hosts that have no allocator of their own (the Rust crate uses these) */
+int vitrs_malloc(vitrs_ctx* ctx, void** ptr, size_t bytes);
+int vitrs_free(vitrs_ctx* ctx, void* ptr);
+int vitrs_malloc_host(vitrs_ctx* ctx, void** ptr, size_t bytes); /* pinned */
+int vitrs_free_host(vitrs_ctx* ctx, void* ptr);
+int vitrs_memcpy_h2d(vitrs_ctx* ctx, void* dst, const void* src, size_t bytes);
+int vitrs_memcpy_d2h(vitrs_ctx* ctx, void* dst, const void* src, size_t bytes); /* synchronises */
+int vitrs_memset(vitrs_ctx* ctx, void* dst, int value, size_t bytes);
+/* conversions between the two modes' storage */
+int vitrs_cast_f32_to_bf16(vitrs_ctx* ctx, vitrs_bf16* dst, const float* src, size_t n);
+int vitrs_cast_bf16_to_f32(vitrs_ctx* ctx, float* dst, const vitrs_bf16* src, size_t n);
+
+/* ---- L1 operators, fp32 verify mode (train_vit.rs line of the op each one replaces) ---- */
+int vitrs_residual_forward_f32(vitrs_ctx*, float* out, const float* inp1, const float* inp2, int n);           /* :376 */
+int vitrs_matmul_forward_f32(vitrs_ctx*, float* out, const float* inp, const float* weight,
+                             const float* bias, int b, int t, int c, int oc);                                   /* :384 */
+int vitrs_attention_forward_f32(vitrs_ctx*, float* out, float* preatt, float* att, const float* inp,
+                                int b, int t, int c, int nh, int causal);                                       /* :400 */
+int vitrs_layernorm_forward_f32(vitrs_ctx*, float* out, float* mean, float* rstd, const float* inp,
+                                const float* weight, const float* bias, int b, int t, int c);                   /* :453 */
+int vitrs_gelu_forward_f32(vitrs_ctx*, float* out, const float* inp, int n);                                    /* :482 */
+int vitrs_softmax_forward_f32(vitrs_ctx*, float* probs, const float* logits, int b, int t, int v);              /* :493 */
+int vitrs_residual_backward_f32(vitrs_ctx*, float* dinp1, float* dinp2, const float* dout, int n);              /* :521 */
+int vitrs_matmul_backward_f32(vitrs_ctx*, float* dinp, float* dweight, float* dbias, const float* dout,
+                              const float* inp, const float* weight, int b, int t, int c, int oc);              /* :530 */
+int vitrs_attention_backward_f32(vitrs_ctx*, float* dinp, float* dpreatt, float* datt, const float* dout,
+                                 const float* inp, const float* att, int b, int t, int c, int nh, int causal);  /* :559 */
+int vitrs_layernorm_backward_f32(vitrs_ctx*, float* dinp, float* dweight, float* dbias, const float* dout,
+                                 const float* inp, const float* weight, const float* mean, const float* rstd,
+                                 int b, int t, int c);                                                          /* :603 */
+int vitrs_gelu_backward_f32(vitrs_ctx*, float* dinp, const float* inp, const float* dout, int n);               /* :639 */
+/* rusty_vit.rs:836 (loss = -ln p[target], DEVIATIONS D5) and the fused backward called at rusty_vit.rs:371 */
+int vitrs_crossentropy_forward_f32(vitrs_ctx*, float* losses, const float* probs, const int* targets, int b, int t, int v);
+int vitrs_crossentropy_softmax_backward_f32(vitrs_ctx*, float* dlogits, const float* dlosses, const float* probs,
+                                            const int* targets, int b, int t, int v);
+/* encoder_forward/backward as called at rusty_vit.rs:282,448 (token + position embedding) */
+int vitrs_encoder_forward_f32(vitrs_ctx*, float* encoded, const int* inputs, const float* wte, const float* wpe, int b, int t, int c);
+int vitrs_encoder_backward_f32(vitrs_ctx*, float* dwte, float* dwpe, const float* dencoded, const int* inputs, int b, int t, int c);
+/* ViT replacement of the encoder (DEVIATIONS D7): images [B,3,H,W] fp32 NCHW */
+int vitrs_patch_embed_forward_f32(vitrs_ctx*, float* encoded, const float* images, const float* patchw, const float* patchb,
+                                  const float* cls, const float* wpe, int b, int img, int patch, int c);
+int vitrs_patch_embed_backward_f32(vitrs_ctx*, float* dpatchw, float* dpatchb, float* dcls, float* dwpe,
+                                   const float* dencoded, const float* images, int b, int img, int patch, int c);
+
+/* ---- L1 operators, bf16 production mode ------------------------------------------------
+ * activations and matmul weights are bf16; biases, LayerNorm gains/biases, statistics and
+ * every parameter gradient are fp32.  attention_backward recomputes probabilities from
+ * lse (written by attention_forward_bf16), so att may be NULL. */
+int vitrs_residual_forward_bf16(vitrs_ctx*, vitrs_bf16* out, const vitrs_bf16* inp1, const vitrs_bf16* inp2, int n);
+int vitrs_matmul_forward_bf16(vitrs_ctx*, vitrs_bf16* out, const vitrs_bf16* inp, const vitrs_bf16* weight,
+                              const float* bias, int b, int t, int c, int oc);
+int vitrs_attention_forward_bf16(vitrs_ctx*, vitrs_bf16* out, float* lse, const vitrs_bf16* inp,
+                                 int b, int t, int c, int nh, int causal);
+int vitrs_layernorm_forward_bf16(vitrs_ctx*, vitrs_bf16* out, float* mean, float* rstd, const vitrs_bf16* inp,
+                                 const float* weight, const float* bias, int b, int t, int c);
+int vitrs_gelu_forward_bf16(vitrs_ctx*, vitrs_bf16* out, const vitrs_bf16* inp, int n);
+int vitrs_residual_backward_bf16(vitrs_ctx*, vitrs_bf16* dinp1, vitrs_bf16* dinp2, const vitrs_bf16* dout, int n);
+int vitrs_matmul_backward_bf16(vitrs_ctx*, vitrs_bf16* dinp, float* dweight, float* dbias, const vitrs_bf16* dout,
+                               const vitrs_bf16* inp, const vitrs_bf16* weight, int b, int t, int c, int oc);
+int vitrs_attention_backward_bf16(vitrs_ctx*, vitrs_bf16* dinp, const vitrs_bf16* dout, const vitrs_bf16* out,
+                                  const float* lse, const vitrs_bf16* inp, int b, int t, int c, int nh, int causal);
+int vitrs_layernorm_backward_bf16(vitrs_ctx*, vitrs_bf16* dinp, float* dweight, float* dbias, const vitrs_bf16* dout,
+                                  const vitrs_bf16* inp, const float* weight, const float* mean, const float* rstd,
+                                  int b, int t, int c);
+int vitrs_gelu_backward_bf16(vitrs_ctx*, vitrs_bf16* dinp, const vitrs_bf16* inp, const vitrs_bf16* dout, int n);
+
+/* raw GEMM entry (tests, tuning): D[M,N] = sum_k A(m,k) * B(n,k), bf16 in, fp32 accumulate on
+ * tcgen05.  a_mn_major / b_mn_major = 1 when the contraction index is the SLOW index of the
+ * operand in memory (A stored [K,M] / B stored [K,N]).  out_f32_accumulate: D is fp32 and is
+ * added into (split-K allowed); otherwise D is bf16 and overwritten. */
+int vitrs_gemm_bf16(vitrs_ctx*, void* D, const vitrs_bf16* A, const vitrs_bf16* B, int M, int N, int K,
+                    int lda, int ldb, int ldd, int a_mn_major, int b_mn_major, int out_f32_accumulate);
+
+/* ---- optimiser ---------------------------------------------------------------------------
+ * optimizer_step (train_vit.rs:737): SGD over the flat buffer.  adamw_step: DEVIATIONS D8.
+ * shadow (nullable): bf16 copy of the updated parameters written in the same pass. */
+int vitrs_sgd_step(vitrs_ctx*, float* params, const float* grads, size_t n, float lr, vitrs_bf16* shadow);
+int vitrs_adamw_step(vitrs_ctx*, float* params, const float* grads, float* m, float* v, size_t n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                     vitrs_bf16* shadow);
+/* init_parameters (train_vit.rs:674): U[lo,hi) from the counter generator shared with the oracle */
+int vitrs_fill_uniform(vitrs_ctx*, float* dst, size_t n, uint64_t seed, uint64_t stream, float lo, float hi);
+
+/* ---- L2 model (rusty_vit.rs:63-450) ------------------------------------------------------ */
+typedef struct {
+    int max_seq_len; /* (image/patch)^2 + 1 */
+    int vocab_size;  /* reference slot (rusty_vit.rs:12); carries num_classes */
+    int num_layers;
+    int num_heads;
+    int channels;
+    int image_size;
+    int patch_size;
+    int num_classes;
+    int causal;
+} vitrs_config;
+
+#define VITRS_MODE_F32 0  /* verify */
+#define VITRS_MODE_BF16 1 /* production */
+#define VITRS_NUM_PARAMETER_TENSORS 20
+#define VITRS_NUM_ACTIVATION_TENSORS 23
+
+/* ViT::build_from_checkpoint's allocation half (rusty_vit.rs:105-259): six flat device
+ * allocations carved into named views.  max_batch fixes the activation arena. */
+int vitrs_model_create(vitrs_ctx* ctx, const vitrs_config* cfg, int max_batch, int mode, vitrs_model** out);
+int vitrs_model_destroy(vitrs_model* m);
+/* init_parameters (rusty_vit.rs:864): init_mode 0 = U[0,1)*0.02 (reference), 1 = U[-1,1)*0.02 */
+int vitrs_model_init_parameters(vitrs_model* m, uint64_t seed, int init_mode);
+/* llm.c-style checkpoint (rusty_vit.rs:81-129): 256 x i32 header, fp32 params from byte 1024 */
+int vitrs_model_save_checkpoint(vitrs_model* m, const char* path);
+int vitrs_model_load_checkpoint(vitrs_model* m, const char* path);
+size_t vitrs_model_num_parameters(vitrs_model* m);
+/* named views: tensor index in the reference's order (see VITRS_PARAM_NAMES in the Python /
+ * Rust mirrors).  which: 0 params (fp32), 1 grads (fp32), 2 adam m, 3 adam v */
+int vitrs_model_param_view(vitrs_model* m, int which, int tensor, float** ptr, size_t* count);
+/* activations: which 0 = acts, 1 = grads_acts; elem_size 4 (f32 mode) or 2 (bf16 mode; the
+ * head tensors lnf..losses are fp32 in both modes).  ptr is NULL for tensors the fused path
+ * does not materialise (preatt, att, attproj, fcproj in bf16 mode). */
+int vitrs_model_act_view(vitrs_model* m, int which, int tensor, void** ptr, size_t* count, int* elem_size);
+/* 1/B_global for data parallel (generalises 1/(b*t), rusty_vit.rs:366); 0 => 1/b */
+int vitrs_model_set_dloss_scale(vitrs_model* m, float scale);
+/* ViT::forward (rusty_vit.rs:269): images [b,3,H,W] fp32 and labels [b] on the device;
+ * labels NULL => logits only, mean_loss = -1 (rusty_vit.rs:348-350) */
+int vitrs_model_forward(vitrs_model* m, const float* images, const int* labels, int b);
+int vitrs_model_zero_grad(vitrs_model* m);
+/* ViT::backward (rusty_vit.rs:354) */
+int vitrs_model_backward(vitrs_model* m);
+/* optimizer_step(model, lr) (rusty_vit.rs:949) and its AdamW form */
+int vitrs_model_optimizer_step(vitrs_model* m, float lr);
+int vitrs_model_update(vitrs_model* m, float lr, float beta1, float beta2, float eps, float weight_decay);
+/* mean_loss field (rusty_vit.rs:75): synchronises the stream and reads it back */
+int vitrs_model_mean_loss(vitrs_model* m, float* out);
+/* one whole training step from HOST buffers (pinned or pageable): H2D copy of images/labels,
+ * zero_grad, forward, backward, [all-reduce], AdamW, D2H of the loss.  prefetch stages the
+ * NEXT step's batch on the copy stream so it overlaps this step's compute. */
+int vitrs_model_prefetch_host(vitrs_model* m, const float* h_images, const int* h_labels, int b);
+int vitrs_model_train_step_host(vitrs_model* m, const float* h_images, const int* h_labels, int b,
+                                float lr, float beta1, float beta2, float eps, float weight_decay,
+                                float* loss_out);
+/* same step with the batch already resident on the device */
+int vitrs_model_train_step(vitrs_model* m, const float* images, const int* labels, int b,
+                           float lr, float beta1, float beta2, float eps, float weight_decay);
+
+/* ---- data parallel (not in the reference) ------------------------------------
+ * NCCL is resolved at run time from the already-loaded libnccl.so.2 (dlopen), so the library
+ * has no link-time dependency on it.  unique_id is the 128-byte ncclUniqueId made by rank 0. */
+int vitrs_comm_unique_id(vitrs_ctx* ctx, void* id128);
+int vitrs_comm_init(vitrs_ctx* ctx, const void* id128, int rank, int world);
+int vitrs_comm_destroy(vitrs_ctx* ctx);
+int vitrs_comm_world(vitrs_ctx* ctx, int* rank, int* world);
+/* sum all-reduce of the fp32 gradient buffer in reverse-layer buckets on the comm stream;
+ * called by train_step when a communicator exists, exported for tests */
+int vitrs_model_allreduce_grads(vitrs_model* m);
+int vitrs_allreduce_f32(vitrs_ctx* ctx, float* buf, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,695 @@
+// elementwise.cu — the bandwidth-bound operators: residual, GELU, LayerNorm forward/backward,
+// column sums, softmax / cross-entropy, AdamW / SGD, init and casts.
+// All are vectorised (16-byte accesses), coalesced, warp-shuffle kernels; statistics and
+// accumulators are fp32 in both modes.  Reference lines: train_vit.rs (tv), rusty_vit.rs (rv).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(long work_items, int per_block, int sm_count, int waves = 8) {
+    long g = (work_items + per_block - 1) / per_block;
+    long cap = (long)sm_count * waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---- residual (tv:376-382, tv:521-528) -------------------------------------------------------
+template <typename T>
+__global__ void residual_fwd_kernel(T* __restrict__ out, const T* __restrict__ a, const T* __restrict__ b, long n) {
+    constexpr int VN = Vec16<T>::N;
+    const long nv = n / VN;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        Vec16<T> x, y, o;
+        x.load(a + i * VN);
+        y.load(b + i * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o.set(j, x.get(j) + y.get(j));
+        o.store(out + i * VN);
+    }
+    for (long i = nv * VN + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = from_f32<T>(to_f32(a[i]) + to_f32(b[i]));
+}
+
+template <typename T>
+__global__ void residual_bwd_kernel(T* __restrict__ d1, T* __restrict__ d2, const T* __restrict__ dout, long n) {
+    constexpr int VN = Vec16<T>::N;
+    const long nv = n / VN;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        Vec16<T> g, x, y;
+        g.load(dout + i * VN);
+        x.load(d1 + i * VN);
+        y.load(d2 + i * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+            x.set(j, x.get(j) + g.get(j));
+            y.set(j, y.get(j) + g.get(j));
+        }
+        x.store(d1 + i * VN);
+        y.store(d2 + i * VN);
+    }
+    for (long i = nv * VN + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float g = to_f32(dout[i]);
+        d1[i] = from_f32<T>(to_f32(d1[i]) + g);
+        d2[i] = from_f32<T>(to_f32(d2[i]) + g);
+    }
+}
+
+// ---- GELU (tv:482-491, tv:639-653 with D4) ---------------------------------------------------
+template <typename T, bool FAST>
+__global__ void gelu_fwd_kernel(T* __restrict__ out, const T* __restrict__ inp, long n) {
+    constexpr int VN = Vec16<T>::N;
+    const long nv = n / VN;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        Vec16<T> x, o;
+        x.load(inp + i * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o.set(j, gelu_fwd<FAST>(x.get(j)));
+        o.store(out + i * VN);
+    }
+    for (long i = nv * VN + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = from_f32<T>(gelu_fwd<FAST>(to_f32(inp[i])));
+}
+
+template <typename T, bool FAST>
+__global__ void gelu_bwd_kernel(T* __restrict__ dinp, const T* __restrict__ inp, const T* __restrict__ dout, long n) {
+    constexpr int VN = Vec16<T>::N;
+    const long nv = n / VN;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        Vec16<T> x, g, d;
+        x.load(inp + i * VN);
+        g.load(dout + i * VN);
+        d.load(dinp + i * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) d.set(j, d.get(j) + gelu_grad<FAST>(x.get(j)) * g.get(j));
+        d.store(dinp + i * VN);
+    }
+    for (long i = nv * VN + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dinp[i] = from_f32<T>(to_f32(dinp[i]) + gelu_grad<FAST>(to_f32(inp[i])) * to_f32(dout[i]));
+}
+
+// ---- LayerNorm forward (tv:453-480): one warp per row, the row cached in registers ------------
+template <typename T, int MAXNV>
+__global__ void __launch_bounds__(kThreads)
+ln_fwd_kernel(T* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, const T* __restrict__ inp,
+              const float* __restrict__ w, const float* __restrict__ bias, long rows, int c) {
+    constexpr int VN = Vec16<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* x = inp + row * c;
+    Vec16<T> v[MAXNV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXNV; ++i) {
+        const int idx = (i * 32 + lane) * VN;
+        if (idx < c) {
+            v[i].load(x + idx);
+#pragma unroll
+            for (int j = 0; j < VN; ++j) s += v[i].get(j);
+        }
+    }
+    const float m = warp_sum(s) / (float)c;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXNV; ++i) {
+        const int idx = (i * 32 + lane) * VN;
+        if (idx < c) {
+#pragma unroll
+            for (int j = 0; j < VN; ++j) {
+                float d = v[i].get(j) - m;
+                q += d * d;
+            }
+        }
+    }
+    const float var = warp_sum(q) / (float)c;
+    const float rs = 1.0f / sqrtf(var + 1e-5f);
+    T* y = out + row * c;
+#pragma unroll
+    for (int i = 0; i < MAXNV; ++i) {
+        const int idx = (i * 32 + lane) * VN;
+        if (idx < c) {
+            Vec16<T> o;
+#pragma unroll
+            for (int j = 0; j < VN; ++j) o.set(j, (rs * (v[i].get(j) - m)) * __ldg(w + idx + j) + __ldg(bias + idx + j));
+            o.store(y + idx);
+        }
+    }
+    if (lane == 0) {
+        mean[row] = m;
+        rstd[row] = rs;
+    }
+}
+
+// any c (unaligned / very wide rows): scalar accesses, three passes through L1
+template <typename T>
+__global__ void ln_fwd_generic_kernel(T* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd,
+                                      const T* __restrict__ inp, const float* __restrict__ w,
+                                      const float* __restrict__ bias, long rows, int c) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* x = inp + row * c;
+    float s = 0.f;
+    for (int i = lane; i < c; i += 32) s += to_f32(x[i]);
+    const float m = warp_sum(s) / (float)c;
+    float q = 0.f;
+    for (int i = lane; i < c; i += 32) {
+        float d = to_f32(x[i]) - m;
+        q += d * d;
+    }
+    const float rs = 1.0f / sqrtf(warp_sum(q) / (float)c + 1e-5f);
+    for (int i = lane; i < c; i += 32) out[row * c + i] = from_f32<T>((rs * (to_f32(x[i]) - m)) * w[i] + bias[i]);
+    if (lane == 0) {
+        mean[row] = m;
+        rstd[row] = rs;
+    }
+}
+
+// ---- LayerNorm backward (tv:603-637) ---------------------------------------------------------
+// Warps stride over rows; each lane keeps fp32 partial column sums for the columns it owns
+// (dweight, dbias and, optionally, the column sum of the updated dinp), reduced across the
+// block's warps in shared memory and added to global with one atomic per column per block.
+template <typename T, int MAXNV, bool COLSUM>
+__global__ void __launch_bounds__(kThreads)
+ln_bwd_kernel(T* __restrict__ dinp, float* __restrict__ dweight, float* __restrict__ dbias, const T* __restrict__ dout,
+              const T* __restrict__ inp, const float* __restrict__ w, const float* __restrict__ mean,
+              const float* __restrict__ rstd, long rows, int c, float* __restrict__ colsum_out) {
+    constexpr int VN = Vec16<T>::N;
+    constexpr int NW = kThreads / 32;
+    extern __shared__ float red[];  // [NW][c]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float wreg[MAXNV * VN], dw_acc[MAXNV * VN], db_acc[MAXNV * VN], cs_acc[COLSUM ? MAXNV * VN : 1];
+#pragma unroll
+    for (int i = 0; i < MAXNV; ++i) {
+        const int idx = (i * 32 + lane) * VN;
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+            wreg[i * VN + j] = idx < c ? w[idx + j] : 0.f;
+            dw_acc[i * VN + j] = 0.f;
+            db_acc[i * VN + j] = 0.f;
+            if (COLSUM) cs_acc[i * VN + j] = 0.f;
+        }
+    }
+    for (long row = (long)blockIdx.x * NW + warp; row < rows; row += (long)gridDim.x * NW) {
+        const float m = mean[row], rs = rstd[row];
+        Vec16<T> gy[MAXNV], xv[MAXNV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXNV; ++i) {
+            const int idx = (i * 32 + lane) * VN;
+            if (idx < c) {
+                gy[i].load(dout + row * c + idx);
+                xv[i].load(inp + row * c + idx);
+#pragma unroll
+                for (int j = 0; j < VN; ++j) {
+                    float nrm = (xv[i].get(j) - m) * rs;
+                    float dn = wreg[i * VN + j] * gy[i].get(j);
+                    s1 += dn;
+                    s2 += dn * nrm;
+                }
+            }
+        }
+        const float dn_mean = warp_sum(s1) / (float)c;
+        const float dnn_mean = warp_sum(s2) / (float)c;
+#pragma unroll
+        for (int i = 0; i < MAXNV; ++i) {
+            const int idx = (i * 32 + lane) * VN;
+            if (idx < c) {
+                Vec16<T> d;
+                d.load(dinp + row * c + idx);
+#pragma unroll
+                for (int j = 0; j < VN; ++j) {
+                    float g = gy[i].get(j);
+                    float nrm = (xv[i].get(j) - m) * rs;
+                    float dn = wreg[i * VN + j] * g;
+                    db_acc[i * VN + j] += g;
+                    dw_acc[i * VN + j] += nrm * g;
+                    float dv = (dn - dn_mean - nrm * dnn_mean) * rs;
+                    float upd = d.get(j) + dv;
+                    d.set(j, upd);
+                    if (COLSUM) cs_acc[i * VN + j] += d.get(j);  // the value as stored (rounded)
+                }
+                d.store(dinp + row * c + idx);
+            }
+        }
+    }
+    // block reduction, one quantity at a time through the same [NW][c] buffer
+    for (int qn = 0; qn < (COLSUM ? 3 : 2); ++qn) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < MAXNV; ++i) {
+            const int idx = (i * 32 + lane) * VN;
+            if (idx < c) {
+#pragma unroll
+                for (int j = 0; j < VN; ++j)
+                    red[warp * c + idx + j] = qn == 0 ? dw_acc[i * VN + j] : (qn == 1 ? db_acc[i * VN + j] : cs_acc[COLSUM ? i * VN + j : 0]);
+            }
+        }
+        __syncthreads();
+        float* dst = qn == 0 ? dweight : (qn == 1 ? dbias : colsum_out);
+        for (int col = threadIdx.x; col < c; col += kThreads) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) s += red[k * c + col];
+            atomicAdd(dst + col, s);
+        }
+    }
+}
+
+template <typename T>
+__global__ void ln_bwd_generic_kernel(T* __restrict__ dinp, float* __restrict__ dweight, float* __restrict__ dbias,
+                                      const T* __restrict__ dout, const T* __restrict__ inp, const float* __restrict__ w,
+                                      const float* __restrict__ mean, const float* __restrict__ rstd, long rows, int c,
+                                      float* __restrict__ colsum_out) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float m = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < c; i += 32) {
+        float nrm = (to_f32(inp[row * c + i]) - m) * rs;
+        float dn = w[i] * to_f32(dout[row * c + i]);
+        s1 += dn;
+        s2 += dn * nrm;
+    }
+    const float dn_mean = warp_sum(s1) / (float)c, dnn_mean = warp_sum(s2) / (float)c;
+    for (int i = lane; i < c; i += 32) {
+        float g = to_f32(dout[row * c + i]);
+        float nrm = (to_f32(inp[row * c + i]) - m) * rs;
+        float dn = w[i] * g;
+        atomicAdd(dbias + i, g);
+        atomicAdd(dweight + i, nrm * g);
+        T upd = from_f32<T>(to_f32(dinp[row * c + i]) + (dn - dn_mean - nrm * dnn_mean) * rs);
+        dinp[row * c + i] = upd;
+        if (colsum_out) atomicAdd(colsum_out + i, to_f32(upd));
+    }
+}
+
+// ---- column sums: out[col] += sum_rows inp[row, col] (dbias of matmul_backward, tv:548-550) ----
+template <typename T>
+__global__ void colsum_kernel(float* __restrict__ out, const T* __restrict__ inp, long rows, int cols, long ld) {
+    constexpr int VN = Vec16<T>::N;
+    __shared__ float red[8][32 * VN + 1];
+    const int col0 = (blockIdx.x * 32 + threadIdx.x) * VN;
+    float acc[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) acc[j] = 0.f;
+    if (col0 < cols) {
+        for (long r = (long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long)gridDim.y * 8) {
+            Vec16<T> v;
+            v.load(inp + r * ld + col0);
+#pragma unroll
+            for (int j = 0; j < VN; ++j) acc[j] += v.get(j);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < VN; ++j) red[threadIdx.y][threadIdx.x * VN + j] = acc[j];
+    __syncthreads();
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int cidx = tid; cidx < 32 * VN; cidx += 256) {
+        const int col = blockIdx.x * 32 * VN + cidx;
+        if (col < cols) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += red[k][cidx];
+            atomicAdd(out + col, s);
+        }
+    }
+}
+
+template <typename T>
+__global__ void colsum_generic_kernel(float* __restrict__ out, const T* __restrict__ inp, long rows, int cols, long ld) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    float s = 0.f;
+    for (long r = blockIdx.y; r < rows; r += gridDim.y) s += to_f32(inp[r * ld + col]);
+    atomicAdd(out + col, s);
+}
+
+// ---- softmax / cross-entropy (tv:493-517, rv:836-843 with D5, rv:371) --------------------------
+__global__ void softmax_fwd_kernel(float* __restrict__ probs, const float* __restrict__ logits, long rows, int v) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* z = logits + row * v;
+    float mx = -INFINITY;
+    for (int i = lane; i < v; i += 32) mx = fmaxf(mx, z[i]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int i = lane; i < v; i += 32) s += expf(z[i] - mx);
+    s = warp_sum(s);
+    for (int i = lane; i < v; i += 32) probs[row * v + i] = expf(z[i] - mx) / s;
+}
+
+__global__ void ce_fwd_kernel(float* __restrict__ losses, const float* __restrict__ probs, const int* __restrict__ targets,
+                              long rows, int v) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) losses[r] = -logf(probs[r * v + targets[r]]);
+}
+
+__global__ void ce_softmax_bwd_kernel(float* __restrict__ dlogits, const float* __restrict__ dlosses,
+                                      const float* __restrict__ probs, const int* __restrict__ targets, long rows, int v) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * v) return;
+    const long r = i / v;
+    const int j = (int)(i - r * v);
+    const float ind = (j == targets[r]) ? 1.f : 0.f;
+    dlogits[i] += (probs[i] - ind) * dlosses[r];
+}
+
+// fused head: softmax_forward + crossentropy_forward + mean (rv:337-347) + the fused backward
+// (rv:366-371) in one pass, one warp per image.  mean_loss must be zeroed by the caller.
+__global__ void head_loss_kernel(float* __restrict__ probs, float* __restrict__ losses, float* __restrict__ mean_loss,
+                                 float* __restrict__ dlogits, const float* __restrict__ logits,
+                                 const int* __restrict__ targets, int rows, int v, float dloss) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* z = logits + (long)row * v;
+    float mx = -INFINITY;
+    for (int i = lane; i < v; i += 32) mx = fmaxf(mx, z[i]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int i = lane; i < v; i += 32) s += expf(z[i] - mx);
+    s = warp_sum(s);
+    const int tgt = targets ? targets[row] : -1;
+    for (int i = lane; i < v; i += 32) {
+        float p = expf(z[i] - mx) / s;
+        probs[(long)row * v + i] = p;
+        if (targets) {
+            if (dlogits) dlogits[(long)row * v + i] += (p - (i == tgt ? 1.f : 0.f)) * dloss;
+            if (i == tgt) {
+                float l = -logf(p);
+                losses[row] = l;
+                atomicAdd(mean_loss, l / (float)rows);
+            }
+        }
+    }
+}
+
+// ---- CLS row gather / scatter (D7) ------------------------------------------------------------
+template <typename T>
+__global__ void cls_gather_kernel(float* __restrict__ out, const T* __restrict__ inp, int b, int t, int c) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)b * c) return;
+    const long bi = i / c, ci = i - bi * c;
+    out[i] = to_f32(inp[bi * t * c + ci]);
+}
+template <typename T>
+__global__ void cls_scatter_kernel(T* __restrict__ dinp, const float* __restrict__ dout, int b, int t, int c) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)b * c) return;
+    const long bi = i / c, ci = i - bi * c;
+    const long o = bi * t * c + ci;
+    dinp[o] = from_f32<T>(to_f32(dinp[o]) + dout[i]);
+}
+
+// ---- optimiser (tv:737-743; AdamW per D8, torch.optim.AdamW operation order) -----------------
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                             float step_size, float bc2_sqrt, bf16* __restrict__ shadow) {
+    const size_t nv = n / 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float pj = pa[j] * (1.0f - lr * wd);
+            float mj = b1 * ma[j] + (1.0f - b1) * ga[j];
+            float vj = b2 * va[j] + (1.0f - b2) * ga[j] * ga[j];
+            ma[j] = mj;
+            va[j] = vj;
+            pa[j] = pj - step_size * (mj / (sqrtf(vj) / bc2_sqrt + eps));
+        }
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        if (shadow) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+            uint2 packed;
+            packed.x = *reinterpret_cast<uint32_t*>(&lo);
+            packed.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(shadow)[i] = packed;
+        }
+    }
+    for (size_t i = nv * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float pj = p[i] * (1.0f - lr * wd);
+        float mj = b1 * m[i] + (1.0f - b1) * g[i];
+        float vj = b2 * v[i] + (1.0f - b2) * g[i] * g[i];
+        m[i] = mj;
+        v[i] = vj;
+        pj = pj - step_size * (mj / (sqrtf(vj) / bc2_sqrt + eps));
+        p[i] = pj;
+        if (shadow) shadow[i] = __float2bfloat16_rn(pj);
+    }
+}
+
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, size_t n, float lr, bf16* __restrict__ shadow) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float pj = p[i] - lr * g[i];
+        p[i] = pj;
+        if (shadow) shadow[i] = __float2bfloat16_rn(pj);
+    }
+}
+
+// counter-based generator shared with oracle/vit_oracle.c::vit_rand_u01 (D9)
+__global__ void fill_uniform_kernel(float* __restrict__ dst, size_t n, uint64_t seed, uint64_t stream, float lo, float hi) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint64_t base = seed * 0x9E3779B97F4A7C15ull + stream * 0xD1B54A32D192ED03ull;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t x = base + i;
+        x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+        x ^= x >> 27; x *= 0x94D049BB133111EBull;
+        x ^= x >> 31;
+        float u = (float)(x >> 40) * (1.0f / 16777216.0f);
+        dst[i] = __fadd_rn(lo, __fmul_rn(hi - lo, u));  // no FMA contraction: bit-equal to the C oracle
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(bf16* __restrict__ dst, const float* __restrict__ src, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void cast_bf16_f32_kernel(float* __restrict__ dst, const bf16* __restrict__ src, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __bfloat162float(src[i]);
+}
+
+template <typename T> constexpr bool is_bf16() { return sizeof(T) == 2; }
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+// ================================ launchers ====================================================
+template <typename T> int op_residual_forward(vitrs_ctx* ctx, T* out, const T* a, const T* b, long n) {
+    if (n <= 0) return VITRS_OK;
+    VITRS_ARG(ctx, aligned16(out) && aligned16(a) && aligned16(b));
+    residual_fwd_kernel<T><<<grid_for(n / Vec16<T>::N + 1, kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(out, a, b, n);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+template <typename T> int op_residual_backward(vitrs_ctx* ctx, T* d1, T* d2, const T* dout, long n) {
+    if (n <= 0) return VITRS_OK;
+    VITRS_ARG(ctx, aligned16(d1) && aligned16(d2) && aligned16(dout));
+    residual_bwd_kernel<T><<<grid_for(n / Vec16<T>::N + 1, kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(d1, d2, dout, n);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+template <typename T> int op_gelu_forward(vitrs_ctx* ctx, T* out, const T* inp, long n) {
+    if (n <= 0) return VITRS_OK;
+    VITRS_ARG(ctx, aligned16(out) && aligned16(inp));
+    gelu_fwd_kernel<T, is_bf16<T>()><<<grid_for(n / Vec16<T>::N + 1, kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(out, inp, n);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+template <typename T> int op_gelu_backward(vitrs_ctx* ctx, T* dinp, const T* inp, const T* dout, long n) {
+    if (n <= 0) return VITRS_OK;
+    VITRS_ARG(ctx, aligned16(dinp) && aligned16(inp) && aligned16(dout));
+    gelu_bwd_kernel<T, is_bf16<T>()><<<grid_for(n / Vec16<T>::N + 1, kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(dinp, inp, dout, n);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+
+template <typename T>
+int op_layernorm_forward(vitrs_ctx* ctx, T* out, float* mean, float* rstd, const T* inp, const float* w, const float* b,
+                         long rows, int c) {
+    if (rows <= 0) return VITRS_OK;
+    constexpr int VN = Vec16<T>::N;
+    const int nv = (c + 32 * VN - 1) / (32 * VN);
+    const int grid = ceil_div(rows, kThreads / 32);
+    const bool vec_ok = (c % VN == 0) && aligned16(out) && aligned16(inp) && nv <= 8;
+    if (!vec_ok) {
+        ln_fwd_generic_kernel<T><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+    } else if (nv <= 1) {
+        ln_fwd_kernel<T, 1><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+    } else if (nv <= 2) {
+        ln_fwd_kernel<T, 2><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+    } else if (nv <= 3) {
+        ln_fwd_kernel<T, 3><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+    } else if (nv <= 4) {
+        ln_fwd_kernel<T, 4><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+    } else {
+        ln_fwd_kernel<T, 8><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+    }
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+
+template <typename T, int MAXNV>
+static int launch_ln_bwd(vitrs_ctx* ctx, T* dinp, float* dw, float* db, const T* dout, const T* inp, const float* w,
+                         const float* mean, const float* rstd, long rows, int c, float* colsum_out) {
+    int grid = ceil_div(rows, kThreads / 32);
+    if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
+    const size_t smem = (size_t)(kThreads / 32) * c * sizeof(float);
+    if (colsum_out) {
+        auto k = ln_bwd_kernel<T, MAXNV, true>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, kThreads, smem, ctx->stream>>>(dinp, dw, db, dout, inp, w, mean, rstd, rows, c, colsum_out);
+    } else {
+        auto k = ln_bwd_kernel<T, MAXNV, false>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, kThreads, smem, ctx->stream>>>(dinp, dw, db, dout, inp, w, mean, rstd, rows, c, colsum_out);
+    }
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+
+template <typename T>
+int op_layernorm_backward(vitrs_ctx* ctx, T* dinp, float* dw, float* db, const T* dout, const T* inp, const float* w,
+                          const float* mean, const float* rstd, long rows, int c, float* colsum_out) {
+    if (rows <= 0) return VITRS_OK;
+    constexpr int VN = Vec16<T>::N;
+    const int nv = (c + 32 * VN - 1) / (32 * VN);
+    const bool vec_ok = (c % VN == 0) && aligned16(dinp) && aligned16(dout) && aligned16(inp) && nv <= 8;
+    if (!vec_ok) {
+        ln_bwd_generic_kernel<T><<<ceil_div(rows, kThreads / 32), kThreads, 0, ctx->stream>>>(dinp, dw, db, dout, inp, w, mean,
+                                                                                            rstd, rows, c, colsum_out);
+        VITRS_LAUNCHED(ctx);
+        return VITRS_OK;
+    }
+    if (nv <= 1) return launch_ln_bwd<T, 1>(ctx, dinp, dw, db, dout, inp, w, mean, rstd, rows, c, colsum_out);
+    if (nv <= 2) return launch_ln_bwd<T, 2>(ctx, dinp, dw, db, dout, inp, w, mean, rstd, rows, c, colsum_out);
+    if (nv <= 3) return launch_ln_bwd<T, 3>(ctx, dinp, dw, db, dout, inp, w, mean, rstd, rows, c, colsum_out);
+    if (nv <= 4) return launch_ln_bwd<T, 4>(ctx, dinp, dw, db, dout, inp, w, mean, rstd, rows, c, colsum_out);
+    return launch_ln_bwd<T, 8>(ctx, dinp, dw, db, dout, inp, w, mean, rstd, rows, c, colsum_out);
+}
+
+template <typename T> int op_colsum(vitrs_ctx* ctx, float* out, const T* inp, long rows, int cols, long ld) {
+    if (rows <= 0 || cols <= 0) return VITRS_OK;
+    constexpr int VN = Vec16<T>::N;
+    if (cols % VN == 0 && ld % VN == 0 && aligned16(inp)) {
+        dim3 block(32, 8);
+        const int gx = ceil_div(cols, 32 * VN);
+        int gy = ceil_div(rows, 8 * 16);
+        const int cap = (4 * ctx->sm_count + gx - 1) / gx;
+        if (gy > cap) gy = cap;
+        if (gy < 1) gy = 1;
+        colsum_kernel<T><<<dim3(gx, gy), block, 0, ctx->stream>>>(out, inp, rows, cols, ld);
+    } else {
+        int gy = ceil_div(rows, 64);
+        if (gy > 256) gy = 256;
+        colsum_generic_kernel<T><<<dim3(ceil_div(cols, 128), gy), 128, 0, ctx->stream>>>(out, inp, rows, cols, ld);
+    }
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+
+int op_softmax_forward(vitrs_ctx* ctx, float* probs, const float* logits, long rows, int v) {
+    if (rows <= 0) return VITRS_OK;
+    softmax_fwd_kernel<<<ceil_div(rows, 4), 128, 0, ctx->stream>>>(probs, logits, rows, v);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+int op_crossentropy_forward(vitrs_ctx* ctx, float* losses, const float* probs, const int* targets, long rows, int v) {
+    if (rows <= 0) return VITRS_OK;
+    ce_fwd_kernel<<<ceil_div(rows, 128), 128, 0, ctx->stream>>>(losses, probs, targets, rows, v);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+int op_crossentropy_softmax_backward(vitrs_ctx* ctx, float* dlogits, const float* dlosses, const float* probs,
+                                     const int* targets, long rows, int v) {
+    if (rows <= 0) return VITRS_OK;
+    ce_softmax_bwd_kernel<<<ceil_div(rows * v, 256), 256, 0, ctx->stream>>>(dlogits, dlosses, probs, targets, rows, v);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+int op_head_loss(vitrs_ctx* ctx, float* probs, float* losses, float* mean_loss, float* dlogits, const float* logits,
+                 const int* targets, int rows, int v, float dloss) {
+    if (rows <= 0) return VITRS_OK;
+    head_loss_kernel<<<ceil_div(rows, 4), 128, 0, ctx->stream>>>(probs, losses, mean_loss, dlogits, logits, targets, rows, v, dloss);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+
+template <typename T> int op_cls_gather(vitrs_ctx* ctx, float* out, const T* inp, int b, int t, int c) {
+    cls_gather_kernel<T><<<ceil_div((long)b * c, 256), 256, 0, ctx->stream>>>(out, inp, b, t, c);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+template <typename T> int op_cls_scatter_add(vitrs_ctx* ctx, T* dinp, const float* dout, int b, int t, int c) {
+    cls_scatter_kernel<T><<<ceil_div((long)b * c, 256), 256, 0, ctx->stream>>>(dinp, dout, b, t, c);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+
+int op_adamw(vitrs_ctx* ctx, float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,
+             float eps, float wd, int step, bf16* shadow) {
+    if (n == 0) return VITRS_OK;
+    VITRS_ARG(ctx, aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!shadow || ((uintptr_t)shadow & 7) == 0));
+    const float bc1 = 1.0f - powf(b1, (float)step);
+    const float bc2 = 1.0f - powf(b2, (float)step);
+    adamw_kernel<<<grid_for((long)(n / 4 + 1), kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+        p, g, m, v, n, lr, b1, b2, eps, wd, lr / bc1, sqrtf(bc2), shadow);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+int op_sgd(vitrs_ctx* ctx, float* p, const float* g, size_t n, float lr, bf16* shadow) {
+    if (n == 0) return VITRS_OK;
+    sgd_kernel<<<grid_for((long)n, kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(p, g, n, lr, shadow);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+int op_fill_uniform(vitrs_ctx* ctx, float* dst, size_t n, uint64_t seed, uint64_t stream, float lo, float hi) {
+    if (n == 0) return VITRS_OK;
+    fill_uniform_kernel<<<grid_for((long)n, kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(dst, n, seed, stream, lo, hi);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+int op_cast_f32_bf16(vitrs_ctx* ctx, bf16* dst, const float* src, size_t n) {
+    if (n == 0) return VITRS_OK;
+    cast_f32_bf16_kernel<<<grid_for((long)n, kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(dst, src, n);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+int op_cast_bf16_f32(vitrs_ctx* ctx, float* dst, const bf16* src, size_t n) {
+    if (n == 0) return VITRS_OK;
+    cast_bf16_f32_kernel<<<grid_for((long)n, kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(dst, src, n);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+
+#define INSTANTIATE(T)                                                                                          \
+    template int op_residual_forward<T>(vitrs_ctx*, T*, const T*, const T*, long);                              \
+    template int op_residual_backward<T>(vitrs_ctx*, T*, T*, const T*, long);                                   \
+    template int op_gelu_forward<T>(vitrs_ctx*, T*, const T*, long);                                            \
+    template int op_gelu_backward<T>(vitrs_ctx*, T*, const T*, const T*, long);                                 \
+    template int op_layernorm_forward<T>(vitrs_ctx*, T*, float*, float*, const T*, const float*, const float*, long, int); \
+    template int op_layernorm_backward<T>(vitrs_ctx*, T*, float*, float*, const T*, const T*, const float*,     \
+                                          const float*, const float*, long, int, float*);                       \
+    template int op_colsum<T>(vitrs_ctx*, float*, const T*, long, int, long);                                   \
+    template int op_cls_gather<T>(vitrs_ctx*, float*, const T*, int, int, int);                                 \
+    template int op_cls_scatter_add<T>(vitrs_ctx*, T*, const float*, int, int, int);
+INSTANTIATE(float)
+INSTANTIATE(bf16)

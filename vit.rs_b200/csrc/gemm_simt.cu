@@ -1,0 +1,81 @@
+// gemm_simt.cu — plain SIMT FFMA GEMM with fp32 multiply and fp32 accumulate.
+// This is verify mode's matmul (TF32's 10-bit mantissa cannot meet the 1e-4 gate) and the
+// route for the few GEMMs too small or too ragged for the tcgen05 kernel (the class head).
+// D[m,n] = sum_k A(m,k) * B(n,k) with arbitrary element strides, then the shared epilogue.
+// Replaces the three-loop matmul_forward / matmul_backward of train_vit.rs:384-398, 530-557.
+#include "epilogue.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const T* __restrict__ A = reinterpret_cast<const T*>(g.A);
+    const T* __restrict__ B = reinterpret_cast<const T*>(g.B);
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long m0 = (long)blockIdx.y * BM;
+    const int n0 = blockIdx.x * BN;
+    const bool a_kfast = g.a_ks == 1, b_kfast = g.b_ks == 1;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256;
+            // consecutive threads follow the operand's unit-stride index
+            const int am = a_kfast ? e / BK : e % BM, ak = a_kfast ? e % BK : e / BM;
+            const long gm = m0 + am;
+            const int gk = k0 + ak;
+            As[ak][am] = (gm < g.M && gk < g.K) ? to_f32(A[gm * g.a_rs + gk * g.a_ks]) : 0.f;
+            const int bn = b_kfast ? e / BK : e % BN, bk = b_kfast ? e % BK : e / BN;
+            const int gn = n0 + bn;
+            const int gk2 = k0 + bk;
+            Bs[bk][bn] = (gn < g.N && gk2 < g.K) ? to_f32(B[(long)gn * g.b_rs + gk2 * g.b_ks]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < g.N) epi_store_scalar<T, FAST>(g.epi, m, n, acc[i][j]);
+        }
+    }
+}
+
+template <typename T, bool FAST> int launch(vitrs_ctx* ctx, const GemmDesc& g) {
+    if (g.M <= 0 || g.N <= 0) return VITRS_OK;
+    dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
+    gemm_simt_kernel<T, FAST><<<grid, 256, 0, ctx->stream>>>(g);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+
+}  // namespace
+
+int gemm_simt_f32(vitrs_ctx* ctx, const GemmDesc& g) { return launch<float, false>(ctx, g); }
+int gemm_simt_bf16(vitrs_ctx* ctx, const GemmDesc& g) { return launch<bf16, true>(ctx, g); }

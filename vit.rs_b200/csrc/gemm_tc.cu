@@ -1,0 +1,394 @@
+// gemm_tc.cu — the bf16 tensor-core GEMM: TMA -> shared-memory ring -> tcgen05.mma -> TMEM ->
+// tcgen05.ld epilogue, persistent over the 148 SMs, hand-written for sm_100a.
+//
+//   D[m,n] = sum_k A(m,k) * B(n,k)      bf16 operands, fp32 accumulation in tensor memory
+//
+// One kernel covers the three operand layouts the training step needs
+//   forward   Y  = X . W^T        A K-major,  B K-major    (matmul_forward, train_vit.rs:384)
+//   dinp      dX = dY . W         A K-major,  B MN-major   (matmul_backward pass 1, :532-541)
+//   dweight   dW = dY^T . X       A MN-major, B MN-major   (matmul_backward pass 2, :543-555)
+// "MN-major" = the contraction index is the slow index in memory; the 128B-swizzled
+// shared-memory tile is then [k rows][64 mn elements] per TMA box and the UMMA descriptor
+// carries the transpose, so no operand is ever transposed in HBM.
+//
+// CTA = 8 warps: warp 0 lane 0 issues TMA, warp 1 lane 0 issues tcgen05.mma and commits,
+// warp 2 owns the TMEM allocation, warps 4-7 are the epilogue (one TMEM lane quarter each).
+// Two accumulators live in TMEM (2 x BN columns) so tile i's epilogue overlaps tile i+1's
+// main loop.  dweight runs split-K with vectorised fp32 reductions (red.global.add.v4.f32),
+// which is exactly the += contract of the reference's backward ops.
+#include "epilogue.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kThreads = 256;
+constexpr int kEpilogueWarp0 = 4;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] . B[smem], one 128 x N x 16 bf16 MMA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// UMMA shared-memory descriptor (sm_100): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+
+struct TcParams {
+    int M, N, K;
+    int m_tiles, n_tiles, kb_total, kb_per_split, splits;
+    Epilogue epi;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+};
+
+// 8 consecutive output columns of one row: epilogue math, bf16 pack, 16-byte store
+template <bool FAST>
+__device__ __forceinline__ void epi_store8(const Epilogue& e, long m, int n, const uint32_t* acc_bits) {
+    const long orow = epi_out_row(e, m);
+    bf16* out = reinterpret_cast<bf16*>(e.out) + orow * e.ldo + n;
+    Vec16<bf16> aux, old, res, res2;
+    if (epi_needs_aux(e.kind)) aux.load(reinterpret_cast<const bf16*>(e.aux) + m * e.ldo + n);
+    if (e.accumulate) old.load(out);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float second = 0.f;
+        float a = epi_needs_aux(e.kind) ? aux.get(j) : 0.f;
+        float v = epi_value<bf16, FAST>(e, m, n + j, __uint_as_float(acc_bits[j]), a, &second);
+        if (e.accumulate) v += old.get(j);
+        res.set(j, v);
+        res2.set(j, second);
+    }
+    res.store(out);
+    if (e.kind == EPI_BIAS_GELU) res2.store(reinterpret_cast<bf16*>(e.out2) + orow * e.ldo + n);
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulators; power of two (256 or 512)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_units = p.m_tiles * p.n_tiles * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+            const int tile = unit / p.splits, split = unit - tile * p.splits;
+            const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+                const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+                const uint32_t sb = sa + L::A_BYTES;
+                const int k0 = kb * BK;
+                if (!A_MN) {
+                    tma_load_2d(sa, &tmA, full_bar(stage), k0, m0);  // box {64 k, 128 m}
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BM / 64; ++j)  // boxes {64 m, 64 k}
+                        tma_load_2d(sa + j * (BK * 128), &tmA, full_bar(stage), m0 + j * 64, k0);
+                }
+                if (!B_MN) {
+                    tma_load_2d(sb, &tmB, full_bar(stage), k0, n0);  // box {64 k, BN n}
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_2d(sb + j * (BK * 128), &tmB, full_bar(stage), n0 + j * 64, k0);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer (single thread) =====
+        // instruction descriptor: D fp32 [4,6)=1, A bf16 [7,10)=1, B bf16 [10,13)=1,
+        // A major bit 15, B major bit 16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+            const int split = unit % p.splits;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+                const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // K-major: 8-row groups 1024 B apart (SBO), +32 B per 16-element K step.
+                    // MN-major: 64-element MN atoms BK*128 B apart (LBO), 8-k groups 1024 B apart
+                    // (SBO), +2048 B per 16-element K step.
+                    const uint64_t adesc = A_MN ? make_desc(sa + k * 2048, BK * 128, 1024) : make_desc(sa + k * 32, 0, 1024);
+                    const uint64_t bdesc = B_MN ? make_desc(sb + k * 2048, BK * 128, 1024) : make_desc(sb + k * 32, 0, 1024);
+                    umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else if (warp >= kEpilogueWarp0) {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int quarter = warp - kEpilogueWarp0;  // == warp % 4: the TMEM lanes this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+            const int tile = unit / p.splits;
+            const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const long m = (long)m0 + quarter * 32 + lane;
+            const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(trow + ch * 32, v);  // warp-collective: no per-lane predicate around it
+                const int nb = n0 + ch * 32;
+                if (m < p.M && nb < p.N) {
+                    if (p.epi.kind == EPI_ACCUM_F32) {
+                        float* dst = reinterpret_cast<float*>(p.epi.out) + m * p.epi.ldo + nb;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            if (nb + g * 4 < p.N)
+                                red_add_v4(dst + g * 4, __uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
+                                           __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            if (nb + g * 8 < p.N) epi_store8<true>(p.epi, m, nb + g * 8, v + g * 8);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+int encode_map(vitrs_ctx* ctx, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_elems,
+               uint32_t box_inner, uint32_t box_outer) {
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {outer_stride_elems * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return vitrs_set_error(ctx, VITRS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu stride=%llu box=%ux%u",
+                               (int)r, (unsigned long long)inner, (unsigned long long)outer,
+                               (unsigned long long)outer_stride_elems, box_inner, box_outer);
+    return VITRS_OK;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+int launch_tc(vitrs_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
+    using L = SmemLayout<BN, STAGES>;
+    auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
+    static bool configured = false;
+    if (!configured) {
+        VITRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        configured = true;
+    }
+    const int units = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+    kern<<<grid, kThreads, L::TOTAL, ctx->stream>>>(tmA, tmB, p);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+
+template <int BN, int STAGES>
+int launch_tc_major(vitrs_ctx* ctx, bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
+    if (!a_mn && !b_mn) return launch_tc<BN, STAGES, false, false>(ctx, tmA, tmB, p);
+    if (!a_mn && b_mn) return launch_tc<BN, STAGES, false, true>(ctx, tmA, tmB, p);
+    if (a_mn && b_mn) return launch_tc<BN, STAGES, true, true>(ctx, tmA, tmB, p);
+    return launch_tc<BN, STAGES, true, false>(ctx, tmA, tmB, p);
+}
+
+inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+// true when the tcgen05 kernel can take this problem as described (alignment / layout rules of
+// TMA and of the vectorised epilogue); everything else is routed to the SIMT kernel by the caller
+static bool tc_eligible(const GemmDesc& g) {
+    const bool a_k = g.a_ks == 1, a_mn = g.a_rs == 1 && g.a_ks != 1;
+    const bool b_k = g.b_ks == 1, b_mn = g.b_rs == 1 && g.b_ks != 1;
+    if (!(a_k || a_mn) || !(b_k || b_mn)) return false;
+    if (!al16(g.A) || !al16(g.B) || !al16(g.epi.out)) return false;
+    if ((a_k ? g.a_rs : g.a_ks) % 8 || (b_k ? g.b_rs : g.b_ks) % 8) return false;
+    if (a_mn && g.M % 8) return false;  // TMA inner extent bytes must be a multiple of 16
+    if (b_mn && g.N % 8) return false;
+    if (a_k && g.K % 8) return false;
+    if (g.N % 8 || g.epi.ldo % 8) return false;
+    if (g.epi.aux && !al16(g.epi.aux)) return false;
+    if (g.epi.out2 && !al16(g.epi.out2)) return false;
+    if (g.M < 1 || g.N < 8 || g.K < 8) return false;
+    return true;
+}
+
+int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return VITRS_OK;
+    if (!tc_eligible(g)) return gemm_simt_bf16(ctx, g);
+    const bool a_mn = g.a_ks != 1, b_mn = g.b_ks != 1;
+    const int BN = g.N > 128 ? 256 : 128;
+    CUtensorMap tmA, tmB;
+    if (!a_mn) VITRS_TRY(encode_map(ctx, &tmA, g.A, g.K, g.M, g.a_rs, BK, BM));
+    else VITRS_TRY(encode_map(ctx, &tmA, g.A, g.M, g.K, g.a_ks, 64, BK));
+    if (!b_mn) VITRS_TRY(encode_map(ctx, &tmB, g.B, g.K, g.N, g.b_rs, BK, BN));
+    else VITRS_TRY(encode_map(ctx, &tmB, g.B, g.N, g.K, g.b_ks, 64, BK));
+
+    TcParams p;
+    p.M = g.M; p.N = g.N; p.K = g.K;
+    p.m_tiles = ceil_div(g.M, BM);
+    p.n_tiles = ceil_div(g.N, BN);
+    p.kb_total = ceil_div(g.K, BK);
+    p.epi = g.epi;
+    int splits = 1;
+    const int tiles = p.m_tiles * p.n_tiles;
+    if (g.epi.kind == EPI_ACCUM_F32 && tiles < 2 * ctx->sm_count) {
+        // pick the split count that best fills whole waves of the SMs (each split >= 8 k-blocks)
+        double best = 0.0;
+        const int max_s = p.kb_total / 8 > 1 ? (p.kb_total / 8 < 64 ? p.kb_total / 8 : 64) : 1;
+        for (int s = 1; s <= max_s; ++s) {
+            const long units = (long)tiles * s;
+            const long waves = (units + ctx->sm_count - 1) / ctx->sm_count;
+            const double eff = (double)units / (double)(waves * ctx->sm_count);
+            if (eff > best + 0.02) { best = eff; splits = s; }
+        }
+    }
+    p.kb_per_split = ceil_div(p.kb_total, splits);
+    p.splits = ceil_div(p.kb_total, p.kb_per_split);
+    if (BN == 256) return launch_tc_major<256, 4>(ctx, a_mn, b_mn, tmA, tmB, p);
+    return launch_tc_major<128, 6>(ctx, a_mn, b_mn, tmA, tmB, p);
+}
