@@ -47,14 +47,21 @@ typedef uint16_t vitrs_bf16; /* raw bfloat16 bits */
 /* ---- context ------------------------------------------------------------------------- */
 int vitrs_ctx_create(vitrs_ctx** out, int device);
 int vitrs_ctx_destroy(vitrs_ctx* ctx);
-/* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the own stream */
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL is CUDA's default stream,
+ * as everywhere in CUDA.  reset_stream returns to the context's own non-blocking stream. */
 int vitrs_ctx_set_stream(vitrs_ctx* ctx, void* cuda_stream);
+int vitrs_ctx_reset_stream(vitrs_ctx* ctx);
 void* vitrs_ctx_stream(vitrs_ctx* ctx);
 int vitrs_ctx_synchronize(vitrs_ctx* ctx);
 const char* vitrs_last_error(vitrs_ctx* ctx);
 /* kernels launched by this library on this context since creation (bench.py: gpu_launches) */
 uint64_t vitrs_launch_count(vitrs_ctx* ctx);
 const char* vitrs_version(void);
+/* measurement aid (bench.py roofline): between begin and end every tcgen05 GEMM launch is bracketed
+ * by CUDA events on the launching stream; end synchronises and returns their summed duration, the
+ * summed algorithmic flops (2*M*N*K) and the launch count. */
+int vitrs_profile_begin(vitrs_ctx* ctx);
+int vitrs_profile_end(vitrs_ctx* ctx, double* gemm_ms, double* gemm_flops, int* gemm_launches);
 
 /* device memory for hosts that have no allocator of their own (the Rust crate uses these) */
 int vitrs_malloc(vitrs_ctx* ctx, void** ptr, size_t bytes);
@@ -167,6 +174,8 @@ int vitrs_model_init_parameters(vitrs_model* m, uint64_t seed, int init_mode);
 int vitrs_model_save_checkpoint(vitrs_model* m, const char* path);
 int vitrs_model_load_checkpoint(vitrs_model* m, const char* path);
 size_t vitrs_model_num_parameters(vitrs_model* m);
+/* after writing parameters through param_view: rebuild the bf16 weight shadows (no-op in f32 mode) */
+int vitrs_model_sync_parameters(vitrs_model* m);
 /* named views: tensor index in the reference's order (see VITRS_PARAM_NAMES in the Python /
  * Rust mirrors).  which: 0 params (fp32), 1 grads (fp32), 2 adam m, 3 adam v */
 int vitrs_model_param_view(vitrs_model* m, int which, int tensor, float** ptr, size_t* count);

@@ -1,0 +1,67 @@
+"""CPU-side checks of the drop-in boundary: libvitrs.so loads, exports every symbol that
+include/vitrs.h declares (and nothing the header does not know), and refuses to run without a
+GPU instead of falling back to a CPU path.  No compute calls are made here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vitrs.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vitrs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_python_table_agree(vitrs):
+    assert declared_symbols() == vitrs.EXPORTED_SYMBOLS
+
+
+def test_library_exports_every_declared_symbol(vitrs):
+    assert os.path.exists(vitrs.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    handle = ctypes.CDLL(vitrs.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(handle, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", vitrs.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (vitrs_[a-z0-9_]+)$", out, flags=re.M)))
+    extra = [s for s in exported if s not in declared_symbols()]
+    assert extra == [], extra
+
+
+def test_library_has_no_oracle_or_torch_dependency(vitrs):
+    out = subprocess.run(["ldd", vitrs.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "torch" not in out and "libnccl" not in out  # NCCL is dlopen'ed at comm_init
+
+
+def test_sass_is_blackwell_native(vitrs):
+    """tcgen05.mma / tcgen05.ld / TMA must be in the shipped SASS (B200_PROFILING.md mnemonics)."""
+    out = subprocess.run(["cuobjdump", "-sass", vitrs.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    sass = out.stdout
+    assert "sm_100a" in sass
+    assert re.search(r"\bUTC\w*MMA\b", sass), "no tcgen05.mma in SASS"
+    assert "LDTM" in sass and "UTMALDG" in sass
+
+
+def test_no_cpu_fallback_without_gpu(vitrs):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(vitrs.VitrsError):
+        vitrs.Context(0)
+    # ops refuse a NULL context instead of computing anything
+    assert vitrs.lib().vitrs_residual_forward_f32(None, None, None, None, 4) == -2
+
+
+def test_config_table_and_flops(vitrs):
+    # train GFLOP / image
+    for name, want in (("ti16", 7.522), ("s16", 27.593), ("b16", 105.383), ("b8", 468.890)):
+        assert abs(vitrs.train_flops_per_image(name) / 1e9 - want) < 2e-3, name
+    cfg = vitrs.make_config("b16")
+    assert (cfg.max_seq_len, cfg.channels, cfg.num_heads, cfg.num_layers) == (197, 768, 12, 12)

@@ -1,0 +1,503 @@
+"""vitrs_b200 — Python host-side mirror of the ViT.rs model / operator surface over libvitrs.so.
+
+The product is the C-ABI library `libvitrs.so` (include/vitrs.h, sources in csrc/): hand-written
+sm_100a CUDA behind the reference's llm.c-style operator signatures (train_vit.rs:376-670) and
+its `ViT` model object (rusty_vit.rs:63-450).  This module only binds it with ctypes and uses
+PyTorch for device memory and streams — there is no Python or CPU compute path, and importing
+the ops without the built library raises.
+
+The directory is named after the reference (`vit.rs_b200`), which is not an importable module
+name; load it with `__graft_entry__.load_package()` (registers it as `vitrs_b200`).
+"""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvitrs.so")
+
+MODE_F32, MODE_BF16 = 0, 1
+
+PARAM_NAMES = ["patchw", "patchb", "cls", "wpe", "ln1w", "ln1b", "qkvw", "qkvb", "attprojw",
+               "attprojb", "ln2w", "ln2b", "fcw", "fcb", "fcprojw", "fcprojb", "lnfw", "lnfb",
+               "headw", "headb"]
+ACT_NAMES = ["encoded", "ln1", "ln1_mean", "ln1_rstd", "qkv", "atty", "preatt", "att", "attproj",
+             "residual2", "ln2", "ln2_mean", "ln2_rstd", "fch", "fch_gelu", "fcproj", "residual3",
+             "lnf", "lnf_mean", "lnf_rstd", "logits", "probs", "losses"]
+
+CONFIGS = {
+    # BASELINE.json configs[0]: build-defined tiny model
+    "tiny": dict(image_size=32, patch_size=4, channels=64, num_layers=2, num_heads=4, num_classes=10),
+    "ti16": dict(image_size=224, patch_size=16, channels=192, num_layers=12, num_heads=3, num_classes=1000),
+    "s16": dict(image_size=224, patch_size=16, channels=384, num_layers=12, num_heads=6, num_classes=1000),
+    "b16": dict(image_size=224, patch_size=16, channels=768, num_layers=12, num_heads=12, num_classes=1000),
+    "b8": dict(image_size=224, patch_size=8, channels=768, num_layers=12, num_heads=12, num_classes=1000),
+}
+
+
+class VitrsError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    """vitrs_config — ViTConfig (rusty_vit.rs:10-16) plus the ViT fields."""
+    _fields_ = [("max_seq_len", C.c_int), ("vocab_size", C.c_int), ("num_layers", C.c_int),
+                ("num_heads", C.c_int), ("channels", C.c_int), ("image_size", C.c_int),
+                ("patch_size", C.c_int), ("num_classes", C.c_int), ("causal", C.c_int)]
+
+
+def make_config(name_or_dict, causal=0):
+    d = dict(CONFIGS[name_or_dict]) if isinstance(name_or_dict, str) else dict(name_or_dict)
+    t = (d["image_size"] // d["patch_size"]) ** 2 + 1
+    return Config(t, d["num_classes"], d["num_layers"], d["num_heads"], d["channels"],
+                  d["image_size"], d["patch_size"], d["num_classes"], causal)
+
+
+def train_flops_per_image(cfg):
+    """Algorithmic training flops per image: 3 x forward matmul flops."""
+    d = CONFIGS[cfg] if isinstance(cfg, str) else cfg
+    p, c, l, v = d["patch_size"], d["channels"], d["num_layers"], d["num_classes"]
+    n = (d["image_size"] // p) ** 2
+    t = n + 1
+    fwd = 2 * n * (3 * p * p) * c + l * (24 * t * c * c + 4 * t * t * c) + 2 * c * v
+    return 3 * fwd
+
+
+_vp, _f32p, _i32p, _u16p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+_int, _sz, _f, _u64 = C.c_int, C.c_size_t, C.c_float, C.c_uint64
+
+# every symbol include/vitrs.h declares: name -> (restype, argtypes)
+_SIGNATURES = {
+    "vitrs_ctx_create": (_int, [C.POINTER(C.c_void_p), _int]),
+    "vitrs_ctx_destroy": (_int, [_vp]),
+    "vitrs_ctx_set_stream": (_int, [_vp, _vp]),
+    "vitrs_ctx_reset_stream": (_int, [_vp]),
+    "vitrs_ctx_stream": (_vp, [_vp]),
+    "vitrs_ctx_synchronize": (_int, [_vp]),
+    "vitrs_last_error": (C.c_char_p, [_vp]),
+    "vitrs_launch_count": (_u64, [_vp]),
+    "vitrs_version": (C.c_char_p, []),
+    "vitrs_profile_begin": (_int, [_vp]),
+    "vitrs_profile_end": (_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_int)]),
+    "vitrs_malloc": (_int, [_vp, C.POINTER(C.c_void_p), _sz]),
+    "vitrs_free": (_int, [_vp, _vp]),
+    "vitrs_malloc_host": (_int, [_vp, C.POINTER(C.c_void_p), _sz]),
+    "vitrs_free_host": (_int, [_vp, _vp]),
+    "vitrs_memcpy_h2d": (_int, [_vp, _vp, _vp, _sz]),
+    "vitrs_memcpy_d2h": (_int, [_vp, _vp, _vp, _sz]),
+    "vitrs_memset": (_int, [_vp, _vp, _int, _sz]),
+    "vitrs_cast_f32_to_bf16": (_int, [_vp, _vp, _vp, _sz]),
+    "vitrs_cast_bf16_to_f32": (_int, [_vp, _vp, _vp, _sz]),
+    "vitrs_gemm_bf16": (_int, [_vp, _vp, _vp, _vp] + [_int] * 9),
+    "vitrs_sgd_step": (_int, [_vp, _vp, _vp, _sz, _f, _vp]),
+    "vitrs_adamw_step": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _int, _vp]),
+    "vitrs_fill_uniform": (_int, [_vp, _vp, _sz, _u64, _u64, _f, _f]),
+    "vitrs_crossentropy_forward_f32": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int]),
+    "vitrs_crossentropy_softmax_backward_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int]),
+    "vitrs_softmax_forward_f32": (_int, [_vp, _vp, _vp, _int, _int, _int]),
+    "vitrs_encoder_forward_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int]),
+    "vitrs_encoder_backward_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int]),
+    "vitrs_patch_embed_forward_f32": (_int, [_vp] + [_vp] * 6 + [_int] * 4),
+    "vitrs_patch_embed_backward_f32": (_int, [_vp] + [_vp] * 6 + [_int] * 4),
+    "vitrs_attention_forward_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int]),
+    "vitrs_attention_backward_f32": (_int, [_vp] + [_vp] * 6 + [_int] * 5),
+    "vitrs_attention_forward_bf16": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int]),
+    "vitrs_attention_backward_bf16": (_int, [_vp] + [_vp] * 5 + [_int] * 5),
+    "vitrs_model_create": (_int, [_vp, C.POINTER(Config), _int, _int, C.POINTER(C.c_void_p)]),
+    "vitrs_model_destroy": (_int, [_vp]),
+    "vitrs_model_init_parameters": (_int, [_vp, _u64, _int]),
+    "vitrs_model_save_checkpoint": (_int, [_vp, C.c_char_p]),
+    "vitrs_model_load_checkpoint": (_int, [_vp, C.c_char_p]),
+    "vitrs_model_num_parameters": (_sz, [_vp]),
+    "vitrs_model_sync_parameters": (_int, [_vp]),
+    "vitrs_model_param_view": (_int, [_vp, _int, _int, C.POINTER(C.c_void_p), C.POINTER(_sz)]),
+    "vitrs_model_act_view": (_int, [_vp, _int, _int, C.POINTER(C.c_void_p), C.POINTER(_sz), C.POINTER(_int)]),
+    "vitrs_model_set_dloss_scale": (_int, [_vp, _f]),
+    "vitrs_model_forward": (_int, [_vp, _vp, _vp, _int]),
+    "vitrs_model_zero_grad": (_int, [_vp]),
+    "vitrs_model_backward": (_int, [_vp]),
+    "vitrs_model_optimizer_step": (_int, [_vp, _f]),
+    "vitrs_model_update": (_int, [_vp, _f, _f, _f, _f, _f]),
+    "vitrs_model_mean_loss": (_int, [_vp, C.POINTER(_f)]),
+    "vitrs_model_prefetch_host": (_int, [_vp, _vp, _vp, _int]),
+    "vitrs_model_train_step_host": (_int, [_vp, _vp, _vp, _int, _f, _f, _f, _f, _f, C.POINTER(_f)]),
+    "vitrs_model_train_step": (_int, [_vp, _vp, _vp, _int, _f, _f, _f, _f, _f]),
+    "vitrs_comm_unique_id": (_int, [_vp, _vp]),
+    "vitrs_comm_init": (_int, [_vp, _vp, _int, _int]),
+    "vitrs_comm_destroy": (_int, [_vp]),
+    "vitrs_comm_world": (_int, [_vp, C.POINTER(_int), C.POINTER(_int)]),
+    "vitrs_model_allreduce_grads": (_int, [_vp]),
+    "vitrs_allreduce_f32": (_int, [_vp, _vp, _sz]),
+}
+# the two-mode operator families share argument lists
+for _m in ("f32", "bf16"):
+    _SIGNATURES.update({
+        f"vitrs_residual_forward_{_m}": (_int, [_vp, _vp, _vp, _vp, _int]),
+        f"vitrs_matmul_forward_{_m}": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int]),
+        f"vitrs_layernorm_forward_{_m}": (_int, [_vp] + [_vp] * 6 + [_int] * 3),
+        f"vitrs_gelu_forward_{_m}": (_int, [_vp, _vp, _vp, _int]),
+        f"vitrs_residual_backward_{_m}": (_int, [_vp, _vp, _vp, _vp, _int]),
+        f"vitrs_matmul_backward_{_m}": (_int, [_vp] + [_vp] * 6 + [_int] * 4),
+        f"vitrs_layernorm_backward_{_m}": (_int, [_vp] + [_vp] * 8 + [_int] * 3),
+        f"vitrs_gelu_backward_{_m}": (_int, [_vp, _vp, _vp, _vp, _int]),
+    })
+
+EXPORTED_SYMBOLS = sorted(_SIGNATURES)
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VitrsError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(make -C vit.rs_b200/csrc). There is no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here = header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def _ptr(x):
+    """Device (torch) or host (numpy) buffer -> raw address; None -> NULL."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    assert x.is_contiguous(), "tensors crossing the C ABI must be contiguous"
+    return x.data_ptr()
+
+
+class Context:
+    """vitrs_ctx: device, streams, workspace, optional NCCL communicator."""
+
+    def __init__(self, device=0, use_torch_stream=True):
+        self._h = C.c_void_p()
+        rc = lib().vitrs_ctx_create(C.byref(self._h), device)
+        if rc != 0:
+            raise VitrsError(f"vitrs_ctx_create({device}) failed ({rc}): {lib().vitrs_last_error(None).decode()}")
+        self.device = device
+        if use_torch_stream:
+            import torch
+            self.set_stream(torch.cuda.current_stream(device).cuda_stream)
+
+    def check(self, rc):
+        if rc != 0:
+            raise VitrsError(f"libvitrs error {rc}: {lib().vitrs_last_error(self._h).decode()}")
+
+    def set_stream(self, cuda_stream):
+        self.check(lib().vitrs_ctx_set_stream(self._h, cuda_stream))
+
+    def synchronize(self):
+        self.check(lib().vitrs_ctx_synchronize(self._h))
+
+    @property
+    def launches(self):
+        return int(lib().vitrs_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().vitrs_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def profile_begin(self):
+        """Bracket every tcgen05 GEMM launch with CUDA events on the launching stream until profile_end()."""
+        self.check(lib().vitrs_profile_begin(self._h))
+
+    def profile_end(self):
+        """-> (total GEMM milliseconds, total GEMM flops, launches) since profile_begin(); synchronises."""
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int()
+        self.check(lib().vitrs_profile_end(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, n.value
+
+    # ---- data parallel ------------------------------------------------------------------
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        self.check(lib().vitrs_comm_unique_id(self._h, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def comm_init(self, uid, rank, world):
+        buf = C.create_string_buffer(uid, 128)
+        self.check(lib().vitrs_comm_init(self._h, C.cast(buf, C.c_void_p), rank, world))
+
+    def allreduce(self, t):
+        self.check(lib().vitrs_allreduce_f32(self._h, _ptr(t), t.numel()))
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+# ---- L1 operators: the reference's names and argument order (train_vit.rs:376-670) ----------
+def _sfx(t):
+    import torch
+    if t.dtype == torch.float32:
+        return "f32"
+    if t.dtype == torch.bfloat16:
+        return "bf16"
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _call(ctx, name, *args):
+    ctx = ctx or default_context()
+    conv = [_ptr(a) if not isinstance(a, (int, float)) or a is None else a for a in args]
+    ctx.check(getattr(lib(), name)(ctx._h, *conv))
+
+
+def residual_forward(out, inp1, inp2, n, ctx=None):
+    _call(ctx, f"vitrs_residual_forward_{_sfx(out)}", out, inp1, inp2, n)
+
+
+def residual_backward(dinp1, dinp2, dout, n, ctx=None):
+    _call(ctx, f"vitrs_residual_backward_{_sfx(dout)}", dinp1, dinp2, dout, n)
+
+
+def matmul_forward(out, inp, weight, bias, b, t, c, oc, ctx=None):
+    _call(ctx, f"vitrs_matmul_forward_{_sfx(out)}", out, inp, weight, bias, b, t, c, oc)
+
+
+def matmul_backward(dinp, dweight, dbias, dout, inp, weight, b, t, c, oc, ctx=None):
+    _call(ctx, f"vitrs_matmul_backward_{_sfx(dout)}", dinp, dweight, dbias, dout, inp, weight, b, t, c, oc)
+
+
+def attention_forward(out, preatt, att, inp, b, t, c, nh, causal=1, ctx=None):
+    """fp32: reference signature (preatt/att may be None).  bf16: pass lse as `preatt`, att=None."""
+    if _sfx(out) == "f32":
+        _call(ctx, "vitrs_attention_forward_f32", out, preatt, att, inp, b, t, c, nh, causal)
+    else:
+        _call(ctx, "vitrs_attention_forward_bf16", out, preatt, inp, b, t, c, nh, causal)
+
+
+def attention_backward(dinp, dpreatt, datt, dout, inp, att, b, t, c, nh, causal=1, ctx=None):
+    _call(ctx, "vitrs_attention_backward_f32", dinp, dpreatt, datt, dout, inp, att, b, t, c, nh, causal)
+
+
+def attention_backward_bf16(dinp, dout, out, lse, inp, b, t, c, nh, causal=0, ctx=None):
+    _call(ctx, "vitrs_attention_backward_bf16", dinp, dout, out, lse, inp, b, t, c, nh, causal)
+
+
+def layernorm_forward(out, mean, rstd, inp, weight, bias, b, t, c, ctx=None):
+    _call(ctx, f"vitrs_layernorm_forward_{_sfx(out)}", out, mean, rstd, inp, weight, bias, b, t, c)
+
+
+def layernorm_backward(dinp, dweight, dbias, dout, inp, weight, mean, rstd, b, t, c, ctx=None):
+    _call(ctx, f"vitrs_layernorm_backward_{_sfx(dout)}", dinp, dweight, dbias, dout, inp, weight, mean, rstd, b, t, c)
+
+
+def gelu_forward(out, inp, n, ctx=None):
+    _call(ctx, f"vitrs_gelu_forward_{_sfx(out)}", out, inp, n)
+
+
+def gelu_backward(dinp, inp, dout, n, ctx=None):
+    _call(ctx, f"vitrs_gelu_backward_{_sfx(dout)}", dinp, inp, dout, n)
+
+
+def softmax_forward(probs, logits, b, t, v, ctx=None):
+    _call(ctx, "vitrs_softmax_forward_f32", probs, logits, b, t, v)
+
+
+def crossentropy_forward(losses, probs, targets, b, t, v, ctx=None):
+    _call(ctx, "vitrs_crossentropy_forward_f32", losses, probs, targets, b, t, v)
+
+
+def crossentropy_softmax_backward(dlogits, dlosses, probs, targets, b, t, v, ctx=None):
+    _call(ctx, "vitrs_crossentropy_softmax_backward_f32", dlogits, dlosses, probs, targets, b, t, v)
+
+
+def encoder_forward(encoded, inputs, wte, wpe, b, t, c, ctx=None):
+    _call(ctx, "vitrs_encoder_forward_f32", encoded, inputs, wte, wpe, b, t, c)
+
+
+def encoder_backward(dwte, dwpe, dencoded, inputs, b, t, c, ctx=None):
+    _call(ctx, "vitrs_encoder_backward_f32", dwte, dwpe, dencoded, inputs, b, t, c)
+
+
+def patch_embed_forward(encoded, images, patchw, patchb, cls, wpe, b, img, patch, c, ctx=None):
+    _call(ctx, "vitrs_patch_embed_forward_f32", encoded, images, patchw, patchb, cls, wpe, b, img, patch, c)
+
+
+def patch_embed_backward(dpatchw, dpatchb, dcls, dwpe, dencoded, images, b, img, patch, c, ctx=None):
+    _call(ctx, "vitrs_patch_embed_backward_f32", dpatchw, dpatchb, dcls, dwpe, dencoded, images, b, img, patch, c)
+
+
+def gemm_bf16(D, A, B, M, N, K, lda, ldb, ldd, a_mn_major=0, b_mn_major=0, out_f32_accumulate=0, ctx=None):
+    _call(ctx, "vitrs_gemm_bf16", D, A, B, M, N, K, lda, ldb, ldd, a_mn_major, b_mn_major, out_f32_accumulate)
+
+
+def adamw_step(params, grads, m, v, lr, beta1, beta2, eps, weight_decay, step, shadow=None, ctx=None):
+    ctx = ctx or default_context()
+    ctx.check(lib().vitrs_adamw_step(ctx._h, _ptr(params), _ptr(grads), _ptr(m), _ptr(v), params.numel(), lr, beta1,
+                                     beta2, eps, weight_decay, step, _ptr(shadow)))
+
+
+def sgd_step(params, grads, lr, shadow=None, ctx=None):
+    ctx = ctx or default_context()
+    ctx.check(lib().vitrs_sgd_step(ctx._h, _ptr(params), _ptr(grads), params.numel(), lr, _ptr(shadow)))
+
+
+def fill_uniform(dst, seed, stream, lo, hi, ctx=None):
+    ctx = ctx or default_context()
+    ctx.check(lib().vitrs_fill_uniform(ctx._h, _ptr(dst), dst.numel(), seed, stream, lo, hi))
+
+
+class _DeviceView:
+    """__cuda_array_interface__ holder so torch can alias library-owned device memory."""
+
+    def __init__(self, ptr, count, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
+        self._owner = owner
+
+
+def _tensor_view(ptr, count, elem, device, owner):
+    import torch
+    if not ptr or count == 0:
+        return None
+    if elem == 4:
+        return torch.as_tensor(_DeviceView(ptr, count, "<f4", owner), device=f"cuda:{device}")
+    t = torch.as_tensor(_DeviceView(ptr, count, "<i2", owner), device=f"cuda:{device}")
+    return t.view(torch.bfloat16)
+
+
+class ViT:
+    """`struct ViT` + `impl ViT` of the reference (rusty_vit.rs:63-450) on the GPU.
+
+    forward(images, targets, b) / backward() / optimizer_step(lr) keep the reference's names
+    and meaning; update(lr, ...) is the AdamW form of the step (DEVIATIONS D8).  Parameters,
+    gradients and activations are exposed as the reference's named views (torch tensors that
+    alias the library's flat device buffers).
+    """
+
+    def __init__(self, cfg, max_batch, mode=MODE_BF16, seed=1337, init_mode=0, causal=0, ctx=None, init=True):
+        self.ctx = ctx or default_context()
+        self.cfg_dict = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
+        self.cfg = make_config(self.cfg_dict, causal)
+        self.mode = mode
+        self.max_batch = max_batch
+        self._h = C.c_void_p()
+        self.ctx.check(lib().vitrs_model_create(self.ctx._h, C.byref(self.cfg), max_batch, mode, C.byref(self._h)))
+        self.num_parameters = int(lib().vitrs_model_num_parameters(self._h))
+        self.batch_size = 0
+        if init:
+            self.init_parameters(seed, init_mode)
+
+    @classmethod
+    def build_from_checkpoint(cls, path, max_batch, mode=MODE_BF16, ctx=None):
+        """ViT::build_from_checkpoint (rusty_vit.rs:79-259): config from the 256-int header, then the parameters."""
+        with open(path, "rb") as f:
+            header = struct.unpack("<256i", f.read(1024))
+        cfg = dict(image_size=header[7], patch_size=header[8], channels=header[6], num_layers=header[4],
+                   num_heads=header[5], num_classes=header[9])
+        m = cls(cfg, max_batch, mode, causal=header[10], ctx=ctx, init=False)
+        m.load_checkpoint(path)
+        return m
+
+    def close(self):
+        if self._h:
+            lib().vitrs_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init_parameters(self, seed=1337, init_mode=0):
+        self.ctx.check(lib().vitrs_model_init_parameters(self._h, seed, init_mode))
+
+    def save_checkpoint(self, path):
+        self.ctx.check(lib().vitrs_model_save_checkpoint(self._h, path.encode()))
+
+    def load_checkpoint(self, path):
+        self.ctx.check(lib().vitrs_model_load_checkpoint(self._h, path.encode()))
+
+    def sync_parameters(self):
+        self.ctx.check(lib().vitrs_model_sync_parameters(self._h))
+
+    def _pview(self, which, name):
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        self.ctx.check(lib().vitrs_model_param_view(self._h, which, PARAM_NAMES.index(name), C.byref(ptr), C.byref(cnt)))
+        return _tensor_view(ptr.value, cnt.value, 4, self.ctx.device, self)
+
+    def param(self, name): return self._pview(0, name)
+    def grad(self, name): return self._pview(1, name)
+    def adam_m(self, name): return self._pview(2, name)
+    def adam_v(self, name): return self._pview(3, name)
+
+    def _flat(self, which):
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        self.ctx.check(lib().vitrs_model_param_view(self._h, which, 0, C.byref(ptr), C.byref(cnt)))
+        return _tensor_view(ptr.value, self.num_parameters, 4, self.ctx.device, self)
+
+    def params_flat(self): return self._flat(0)
+    def grads_flat(self): return self._flat(1)
+
+    def _aview(self, which, name):
+        ptr, cnt, elem = C.c_void_p(), C.c_size_t(), C.c_int()
+        self.ctx.check(lib().vitrs_model_act_view(self._h, which, ACT_NAMES.index(name), C.byref(ptr), C.byref(cnt), C.byref(elem)))
+        return _tensor_view(ptr.value, cnt.value, elem.value, self.ctx.device, self)
+
+    def act(self, name): return self._aview(0, name)
+    def grad_act(self, name): return self._aview(1, name)
+
+    def set_dloss_scale(self, s):
+        self.ctx.check(lib().vitrs_model_set_dloss_scale(self._h, s))
+
+    def forward(self, images, targets, b=None):
+        """images: cuda float32 [b,3,H,W]; targets: cuda int32 [b] or None (logits only, mean_loss = -1)."""
+        b = images.shape[0] if b is None else b
+        self._keep = (images, targets)
+        self.batch_size = b
+        self.ctx.check(lib().vitrs_model_forward(self._h, _ptr(images), _ptr(targets), b))
+
+    def zero_grad(self):
+        self.ctx.check(lib().vitrs_model_zero_grad(self._h))
+
+    def backward(self):
+        self.ctx.check(lib().vitrs_model_backward(self._h))
+
+    def optimizer_step(self, lr):
+        """optimizer_step(model, lr) — the reference's SGD (rusty_vit.rs:949-955)."""
+        self.ctx.check(lib().vitrs_model_optimizer_step(self._h, lr))
+
+    def update(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01):
+        self.ctx.check(lib().vitrs_model_update(self._h, lr, beta1, beta2, eps, weight_decay))
+
+    @property
+    def mean_loss(self):
+        out = C.c_float()
+        self.ctx.check(lib().vitrs_model_mean_loss(self._h, C.byref(out)))
+        return out.value
+
+    def train_step(self, images, targets, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01):
+        b = images.shape[0]
+        self._keep = (images, targets)
+        self.batch_size = b
+        self.ctx.check(lib().vitrs_model_train_step(self._h, _ptr(images), _ptr(targets), b, lr, beta1, beta2, eps, weight_decay))
+
+    def prefetch_host(self, h_images, h_labels):
+        self.ctx.check(lib().vitrs_model_prefetch_host(self._h, _ptr(h_images), _ptr(h_labels), h_images.shape[0]))
+
+    def train_step_host(self, h_images, h_labels, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01):
+        """One step from HOST buffers (pinned torch tensors or numpy): H2D, step, D2H of the loss."""
+        out = C.c_float()
+        b = h_images.shape[0]
+        self.batch_size = b
+        self.ctx.check(lib().vitrs_model_train_step_host(self._h, _ptr(h_images), _ptr(h_labels), b, lr, beta1, beta2, eps,
+                                                         weight_decay, C.byref(out)))
+        return out.value

@@ -29,6 +29,10 @@ struct vitrs_ctx {
     // scratch for two-stage reductions (LayerNorm backward partials, column sums)
     float* scratch;
     size_t scratch_floats;
+    // per-launch GEMM timing (vitrs_profile_begin / _end)
+    int prof_on, prof_count, prof_cap;
+    cudaEvent_t* prof_ev;  // 2 per launch
+    double* prof_flops;
     // NCCL (resolved with dlopen)
     void* nccl_lib;
     void* nccl_comm;
@@ -37,6 +41,9 @@ struct vitrs_ctx {
 
 int vitrs_set_error(vitrs_ctx* ctx, int code, const char* fmt, ...);
 int vitrs_ensure_scratch(vitrs_ctx* ctx, size_t floats);
+// event bracket for one GEMM launch while profiling is on (no-ops otherwise)
+void vitrs_prof_before(vitrs_ctx* ctx, double flops);
+void vitrs_prof_after(vitrs_ctx* ctx);
 
 #define VITRS_CUDA(ctx, expr)                                                                           \
     do {                                                                                                \
@@ -138,7 +145,7 @@ enum EpiKind {
     EPI_BIAS_RESIDUAL = 3, // out = acc + bias[n] + aux[m,n]              (proj + residual_forward)
     EPI_GELU_BWD = 4,      // out = acc * gelu'(aux[m,n])                 (fcproj dX + gelu_backward)
     EPI_ACCUM_F32 = 5,     // out(fp32) += acc, atomically (split-K)      (dweight)
-    EPI_PATCH = 6,         // out[(m/np)*(np+1) + 1 + m%np, n] = acc + bias[n] + pos[(1 + m%np), n]
+    EPI_PATCH = 6,         // tok = m % np: out = tok ? acc + bias[n] + pos[tok,n] : cls[n] + pos[0,n]   (patch embedding)
 };
 
 struct Epilogue {
@@ -149,8 +156,9 @@ struct Epilogue {
     void* out;
     void* out2;
     long ldo;           // leading dimension of out / out2 / aux
-    const float* pos;   // EPI_PATCH: wpe [np+1, N]
-    int np;             // EPI_PATCH: patches per image
+    const float* pos;   // EPI_PATCH: wpe [np, N]
+    const float* cls;   // EPI_PATCH: class token [N]
+    int np;             // EPI_PATCH: tokens per image (patches + 1)
 };
 
 // gemm operand description: element (row, k) of an operand is at base[row*rs + k*ks]
@@ -197,25 +205,27 @@ int op_adamw(vitrs_ctx*, float* p, const float* g, float* m, float* v, size_t n,
              float eps, float wd, int step, bf16* shadow);
 int op_sgd(vitrs_ctx*, float* p, const float* g, size_t n, float lr, bf16* shadow);
 int op_fill_uniform(vitrs_ctx*, float* dst, size_t n, uint64_t seed, uint64_t stream, float lo, float hi);
+int op_fill_const(vitrs_ctx*, float* dst, size_t n, float v);
+int op_scaled_sum(vitrs_ctx*, float* out_accum, const float* inp, long n, float scale);
 int op_cast_f32_bf16(vitrs_ctx*, bf16* dst, const float* src, size_t n);
 int op_cast_bf16_f32(vitrs_ctx*, float* dst, const bf16* src, size_t n);
 
 template <typename T> int op_attention_forward(vitrs_ctx*, T* out, float* preatt, float* att, float* lse, const T* qkv,
                                                int b, int t, int c, int nh, int causal);
-// dqkv += ...; probabilities are recomputed from lse.  dpreatt/datt (nullable, fp32) are the
-// reference's materialised buffers, filled (+=) only when given.
+// dqkv += ...; probabilities are read from att when given, else recomputed from lse.
+// dpreatt/datt (nullable, fp32) are the reference's materialised buffers, filled (+=) only when given.
 template <typename T> int op_attention_backward(vitrs_ctx*, T* dqkv, float* dpreatt, float* datt, const T* dout,
-                                                const T* qkv, const float* lse, int b, int t, int c, int nh, int causal);
+                                                const T* qkv, const float* att, const float* lse, int b, int t, int c,
+                                                int nh, int causal);
 // production attention (tensor cores); same contracts
 int op_attention_forward_tc(vitrs_ctx*, bf16* out, float* lse, const bf16* qkv, int b, int t, int c, int nh, int causal);
 int op_attention_backward_tc(vitrs_ctx*, bf16* dqkv, const bf16* dout, const bf16* out, const bf16* qkv, const float* lse,
                              int b, int t, int c, int nh, int causal);
 
-// patch embedding pieces
+// patch embedding pieces (patch_embed.cu): im2col rows are tokens, [B*T, 3*p*p], CLS rows zero
 template <typename T> int op_im2col(vitrs_ctx*, T* patches, const float* images, int b, int img, int patch);
-// dpatch_rows[b*np+n, :] = denc[b, 1+n, :]; dwpe += sum_b denc; dcls += sum_b denc[b,0]; dpatchb += colsum(patch rows)
-template <typename T> int op_patch_backward_gather(vitrs_ctx*, T* dpatch_rows, float* dwpe, float* dcls, float* dpatchb,
-                                                   const T* denc, int b, int np, int c);
-template <typename T> int op_cls_rows_forward(vitrs_ctx*, T* encoded, const float* cls, const float* wpe, int b, int t, int c);
+// dwpe += sum_b denc; dcls += sum_b denc[b,0]; dpatchb += sum over patch tokens
+template <typename T> int op_patch_backward_reduce(vitrs_ctx*, float* dwpe, float* dcls, float* dpatchb, const T* denc,
+                                                   int b, int t, int c);
 int op_encoder_forward(vitrs_ctx*, float* enc, const int* inputs, const float* wte, const float* wpe, int b, int t, int c);
 int op_encoder_backward(vitrs_ctx*, float* dwte, float* dwpe, const float* denc, const int* inputs, int b, int t, int c);

@@ -80,6 +80,11 @@ extern "C" int vitrs_ctx_destroy(vitrs_ctx* ctx) {
     cudaDeviceSynchronize();
     vitrs_comm_destroy(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->prof_ev) {
+        for (int i = 0; i < 2 * ctx->prof_cap; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+        free(ctx->prof_ev);
+        free(ctx->prof_flops);
+    }
     cudaStreamDestroy(ctx->own_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->comm_stream);
@@ -89,7 +94,13 @@ extern "C" int vitrs_ctx_destroy(vitrs_ctx* ctx) {
 
 extern "C" int vitrs_ctx_set_stream(vitrs_ctx* ctx, void* s) {
     if (!ctx) return VITRS_ERR_ARG;
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    ctx->stream = (cudaStream_t)s;
+    return VITRS_OK;
+}
+
+extern "C" int vitrs_ctx_reset_stream(vitrs_ctx* ctx) {
+    if (!ctx) return VITRS_ERR_ARG;
+    ctx->stream = ctx->own_stream;
     return VITRS_OK;
 }
 
@@ -102,6 +113,47 @@ extern "C" int vitrs_ctx_synchronize(vitrs_ctx* ctx) {
 }
 
 extern "C" uint64_t vitrs_launch_count(vitrs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void vitrs_prof_before(vitrs_ctx* ctx, double flops) {
+    if (!ctx->prof_on || ctx->prof_count >= ctx->prof_cap) return;
+    ctx->prof_flops[ctx->prof_count] = flops;
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_count], ctx->stream);
+}
+void vitrs_prof_after(vitrs_ctx* ctx) {
+    if (!ctx->prof_on || ctx->prof_count >= ctx->prof_cap) return;
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_count + 1], ctx->stream);
+    ctx->prof_count++;
+}
+
+extern "C" int vitrs_profile_begin(vitrs_ctx* ctx) {
+    if (!ctx) return VITRS_ERR_ARG;
+    if (!ctx->prof_ev) {
+        ctx->prof_cap = 4096;
+        ctx->prof_ev = (cudaEvent_t*)calloc(2 * ctx->prof_cap, sizeof(cudaEvent_t));
+        ctx->prof_flops = (double*)calloc(ctx->prof_cap, sizeof(double));
+        for (int i = 0; i < 2 * ctx->prof_cap; ++i) VITRS_CUDA(ctx, cudaEventCreate(&ctx->prof_ev[i]));
+    }
+    ctx->prof_count = 0;
+    ctx->prof_on = 1;
+    return VITRS_OK;
+}
+
+extern "C" int vitrs_profile_end(vitrs_ctx* ctx, double* gemm_ms, double* gemm_flops, int* gemm_launches) {
+    if (!ctx) return VITRS_ERR_ARG;
+    ctx->prof_on = 0;
+    VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double ms = 0.0, fl = 0.0;
+    for (int i = 0; i < ctx->prof_count; ++i) {
+        float t = 0.f;
+        VITRS_CUDA(ctx, cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        ms += t;
+        fl += ctx->prof_flops[i];
+    }
+    if (gemm_ms) *gemm_ms = ms;
+    if (gemm_flops) *gemm_flops = fl;
+    if (gemm_launches) *gemm_launches = ctx->prof_count;
+    return VITRS_OK;
+}
 
 int vitrs_ensure_scratch(vitrs_ctx* ctx, size_t floats) {
     if (ctx->scratch_floats >= floats) return VITRS_OK;

@@ -365,7 +365,8 @@ __global__ void ce_softmax_bwd_kernel(float* __restrict__ dlogits, const float* 
 }
 
 // fused head: softmax_forward + crossentropy_forward + mean (rv:337-347) + the fused backward
-// (rv:366-371) in one pass, one warp per image.  mean_loss must be zeroed by the caller.
+// (rv:366-371) in one pass, one warp per image.  mean_loss (+= loss * dloss, i.e. the mean when
+// dloss = 1/B) must be zeroed by the caller.
 __global__ void head_loss_kernel(float* __restrict__ probs, float* __restrict__ losses, float* __restrict__ mean_loss,
                                  float* __restrict__ dlogits, const float* __restrict__ logits,
                                  const int* __restrict__ targets, int rows, int v, float dloss) {
@@ -388,7 +389,7 @@ __global__ void head_loss_kernel(float* __restrict__ probs, float* __restrict__ 
             if (i == tgt) {
                 float l = -logf(p);
                 losses[row] = l;
-                atomicAdd(mean_loss, l / (float)rows);
+                atomicAdd(mean_loss, l * dloss);
             }
         }
     }
@@ -476,6 +477,19 @@ __global__ void fill_uniform_kernel(float* __restrict__ dst, size_t n, uint64_t 
         float u = (float)(x >> 40) * (1.0f / 16777216.0f);
         dst[i] = __fadd_rn(lo, __fmul_rn(hi - lo, u));  // no FMA contraction: bit-equal to the C oracle
     }
+}
+
+__global__ void fill_const_kernel(float* __restrict__ dst, size_t n, float v) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
+}
+
+// out += scale * sum(inp[0..n)), one warp, ascending strides (mean loss, rv:342-347)
+__global__ void scaled_sum_kernel(float* __restrict__ out, const float* __restrict__ inp, long n, float scale) {
+    float s = 0.f;
+    for (long i = threadIdx.x; i < n; i += 32) s += inp[i];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *out += s * scale;
 }
 
 __global__ void cast_f32_bf16_kernel(bf16* __restrict__ dst, const float* __restrict__ src, size_t n) {
@@ -664,6 +678,17 @@ int op_sgd(vitrs_ctx* ctx, float* p, const float* g, size_t n, float lr, bf16* s
 int op_fill_uniform(vitrs_ctx* ctx, float* dst, size_t n, uint64_t seed, uint64_t stream, float lo, float hi) {
     if (n == 0) return VITRS_OK;
     fill_uniform_kernel<<<grid_for((long)n, kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(dst, n, seed, stream, lo, hi);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+int op_fill_const(vitrs_ctx* ctx, float* dst, size_t n, float v) {
+    if (n == 0) return VITRS_OK;
+    fill_const_kernel<<<grid_for((long)n, kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(dst, n, v);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+int op_scaled_sum(vitrs_ctx* ctx, float* out, const float* inp, long n, float scale) {
+    scaled_sum_kernel<<<1, 32, 0, ctx->stream>>>(out, inp, n, scale);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
 }

@@ -27,8 +27,9 @@ __device__ __forceinline__ float epi_value(const Epilogue& e, long m, int n, flo
             v *= gelu_grad<FAST>(aux);
             break;
         case EPI_PATCH: {
-            const int tok = 1 + (int)(m % e.np);
-            if (e.bias) v += __ldg(e.bias + n);
+            const int tok = (int)(m % e.np);
+            if (tok == 0) v = __ldg(e.cls + n);
+            else if (e.bias) v += __ldg(e.bias + n);
             v += __ldg(e.pos + (long)tok * e.ldo + n);
             break;
         }
@@ -38,9 +39,7 @@ __device__ __forceinline__ float epi_value(const Epilogue& e, long m, int n, flo
     return v;
 }
 
-__device__ __forceinline__ long epi_out_row(const Epilogue& e, long m) {
-    return e.kind == EPI_PATCH ? (m / e.np) * (e.np + 1) + 1 + (m % e.np) : m;
-}
+__device__ __forceinline__ long epi_out_row(const Epilogue&, long m) { return m; }
 
 __device__ __forceinline__ bool epi_needs_aux(int kind) { return kind == EPI_BIAS_RESIDUAL || kind == EPI_GELU_BWD; }
 

@@ -1,0 +1,845 @@
+// model.cu — the L2 model object: storage, forward, backward, update, the training step, data
+// parallel gradient exchange and the llm.c-style checkpoint.  Mirrors `struct ViT` and
+// `impl ViT { build_from_checkpoint, forward, backward }` of rusty_vit.rs:63-450 (and the
+// #[repr(C)] flavour, train_vit.rs:65-374) with the ViT-specific pieces of DEVIATIONS.md D7/D8.
+//
+// Two modes share the storage conventions (flat fp32 params / grads / m / v in the reference's
+// tensor-major order, rusty_vit.rs:105-122; activations stacked [L, ...], :150-174):
+//   VITRS_MODE_F32   verify: the reference's op sequence, one launch per op, every activation
+//                    and activation gradient materialised (incl. preatt / att), fp32 throughout.
+//   VITRS_MODE_BF16  production: bf16 activations and weight shadows, fused GEMM epilogues
+//                    (bias, bias+GELU, bias+residual, GELU-backward), flash-style attention that
+//                    keeps only lse, LayerNorm-backward fused with the residual accumulation and
+//                    the next bias gradient; one layer's worth of gradient scratch.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+int vitrs_nccl_allreduce_group(vitrs_ctx* ctx, float* const* bufs, const size_t* counts, int count);
+
+enum ParamId {
+    P_PATCHW, P_PATCHB, P_CLS, P_WPE, P_LN1W, P_LN1B, P_QKVW, P_QKVB, P_ATTPROJW, P_ATTPROJB,
+    P_LN2W, P_LN2B, P_FCW, P_FCB, P_FCPROJW, P_FCPROJB, P_LNFW, P_LNFB, P_HEADW, P_HEADB, P_COUNT
+};
+enum ActId {
+    A_ENCODED, A_LN1, A_LN1_MEAN, A_LN1_RSTD, A_QKV, A_ATTY, A_PREATT, A_ATT, A_ATTPROJ, A_RESIDUAL2,
+    A_LN2, A_LN2_MEAN, A_LN2_RSTD, A_FCH, A_FCH_GELU, A_FCPROJ, A_RESIDUAL3, A_LNF, A_LNF_MEAN, A_LNF_RSTD,
+    A_LOGITS, A_PROBS, A_LOSSES, A_COUNT
+};
+static_assert(P_COUNT == VITRS_NUM_PARAMETER_TENSORS, "parameter table");
+static_assert(A_COUNT == VITRS_NUM_ACTIVATION_TENSORS, "activation table");
+
+struct Arena {
+    char* base;
+    size_t bytes;
+    char* view[A_COUNT];
+    size_t per_image[A_COUNT];  // elements per image (all L layers)
+    int elem[A_COUNT];          // bytes per element, 0 = not materialised
+};
+
+struct vitrs_model {
+    vitrs_ctx* ctx;
+    vitrs_config cfg;
+    int mode, max_batch;
+    size_t param_sizes[P_COUNT], param_off[P_COUNT], num_params;
+    float *params, *grads, *m, *v;
+    bf16* shadow;
+    Arena acts, gacts;
+    // extras outside the reference's 23 views
+    float* lse;          // [L, B, NH, T]
+    float* cls_rows;     // [B, C] gathered CLS rows (input of the final LayerNorm)
+    float* dcls_rows;    // [B, C]
+    void* patches;       // [B*T, 3*p*p] im2col rows
+    // bf16 mode: one layer of gradient scratch + fp32 head gradients
+    bf16 *dres, *dln, *dbig;
+    float *dlogits, *dlnf;
+    float* d_mean_loss;
+    float* h_mean_loss;  // pinned
+    // input staging (double-buffered) for the host-buffer step
+    float* stage_images[2];
+    int* stage_labels[2];
+    cudaEvent_t stage_ready[2], stage_free[2];
+    const void* stage_src[2];
+    int stage_batch[2];
+    int stage_next;
+    cudaEvent_t ev_bucket, ev_comm_done;
+    int batch, has_targets;
+    const float* images;  // borrowed device pointer of the current batch
+    const int* labels;
+    float dloss_scale;
+    int adam_step;
+};
+
+namespace {
+
+int tokens(const vitrs_config& c) { return (c.image_size / c.patch_size) * (c.image_size / c.patch_size) + 1; }
+
+void param_sizes_of(const vitrs_config& cfg, size_t* s) {
+    const size_t c = cfg.channels, l = cfg.num_layers, t = cfg.max_seq_len;
+    const size_t kdim = 3u * cfg.patch_size * cfg.patch_size;
+    s[P_PATCHW] = c * kdim; s[P_PATCHB] = c; s[P_CLS] = c; s[P_WPE] = t * c;
+    s[P_LN1W] = l * c; s[P_LN1B] = l * c; s[P_QKVW] = l * 3 * c * c; s[P_QKVB] = l * 3 * c;
+    s[P_ATTPROJW] = l * c * c; s[P_ATTPROJB] = l * c; s[P_LN2W] = l * c; s[P_LN2B] = l * c;
+    s[P_FCW] = l * 4 * c * c; s[P_FCB] = l * 4 * c; s[P_FCPROJW] = l * c * 4 * c; s[P_FCPROJB] = l * c;
+    s[P_LNFW] = c; s[P_LNFB] = c; s[P_HEADW] = (size_t)cfg.num_classes * c; s[P_HEADB] = cfg.num_classes;
+}
+
+// elements per image of each activation (rusty_vit.rs:150-174 with the batch factor restored)
+void act_sizes_of(const vitrs_config& cfg, size_t* s) {
+    const size_t T = cfg.max_seq_len, C = cfg.channels, L = cfg.num_layers, NH = cfg.num_heads, V = cfg.num_classes;
+    s[A_ENCODED] = T * C; s[A_LN1] = L * T * C; s[A_LN1_MEAN] = L * T; s[A_LN1_RSTD] = L * T;
+    s[A_QKV] = L * T * 3 * C; s[A_ATTY] = L * T * C; s[A_PREATT] = L * NH * T * T; s[A_ATT] = L * NH * T * T;
+    s[A_ATTPROJ] = L * T * C; s[A_RESIDUAL2] = L * T * C; s[A_LN2] = L * T * C; s[A_LN2_MEAN] = L * T;
+    s[A_LN2_RSTD] = L * T; s[A_FCH] = L * T * 4 * C; s[A_FCH_GELU] = L * T * 4 * C; s[A_FCPROJ] = L * T * C;
+    s[A_RESIDUAL3] = L * T * C; s[A_LNF] = C; s[A_LNF_MEAN] = 1; s[A_LNF_RSTD] = 1;
+    s[A_LOGITS] = V; s[A_PROBS] = V; s[A_LOSSES] = 1;
+}
+
+bool act_is_f32_always(int a) {
+    return a == A_LN1_MEAN || a == A_LN1_RSTD || a == A_LN2_MEAN || a == A_LN2_RSTD || a == A_PREATT || a == A_ATT || a >= A_LNF;
+}
+
+int arena_create(vitrs_ctx* ctx, Arena* ar, const vitrs_config& cfg, int max_batch, int mode, bool is_grad) {
+    act_sizes_of(cfg, ar->per_image);
+    size_t off = 0;
+    size_t offs[A_COUNT];
+    for (int a = 0; a < A_COUNT; ++a) {
+        int elem = (mode == VITRS_MODE_F32 || act_is_f32_always(a)) ? 4 : 2;
+        if (mode == VITRS_MODE_BF16) {
+            // the fused path never materialises these; its gradient arena keeps only the head tensors
+            if (a == A_PREATT || a == A_ATT || a == A_ATTPROJ || a == A_FCPROJ) elem = 0;
+            if (is_grad && a < A_LNF) elem = 0;
+        }
+        ar->elem[a] = elem;
+        offs[a] = off;
+        off += (ar->per_image[a] * max_batch * elem + 255) / 256 * 256;
+    }
+    ar->bytes = off;
+    ar->base = nullptr;
+    if (off) VITRS_CUDA(ctx, cudaMalloc(&ar->base, off));
+    for (int a = 0; a < A_COUNT; ++a) ar->view[a] = ar->elem[a] ? ar->base + offs[a] : nullptr;
+    return VITRS_OK;
+}
+
+// ---- GEMM call shapes ----------------------------------------------------------------------
+template <typename T>
+int gemm_fwd(vitrs_ctx* ctx, T* out, const T* inp, const T* w, const float* bias, long rows, int c, int oc, int kind,
+             const T* aux, T* out2) {
+    GemmDesc g = {};
+    g.A = inp; g.a_rs = c; g.a_ks = 1;
+    g.B = w; g.b_rs = c; g.b_ks = 1;
+    g.M = (int)rows; g.N = oc; g.K = c;
+    g.epi.kind = kind; g.epi.bias = bias; g.epi.aux = aux; g.epi.out = out; g.epi.out2 = out2; g.epi.ldo = oc;
+    return gemm_dispatch<T>(ctx, g);
+}
+template <typename T>
+int gemm_dx(vitrs_ctx* ctx, T* dinp, const T* dout, const T* w, long rows, int c, int oc, int kind, const T* aux, int accumulate) {
+    GemmDesc g = {};
+    g.A = dout; g.a_rs = oc; g.a_ks = 1;
+    g.B = w; g.b_rs = 1; g.b_ks = c;
+    g.M = (int)rows; g.N = c; g.K = oc;
+    g.epi.kind = kind; g.epi.aux = aux; g.epi.accumulate = accumulate; g.epi.out = dinp; g.epi.ldo = c;
+    return gemm_dispatch<T>(ctx, g);
+}
+template <typename T>
+int gemm_dw(vitrs_ctx* ctx, float* dw, const T* dout, const T* inp, long rows, int c, int oc) {
+    GemmDesc g = {};
+    g.A = dout; g.a_rs = 1; g.a_ks = oc;
+    g.B = inp; g.b_rs = 1; g.b_ks = c;
+    g.M = oc; g.N = c; g.K = (int)rows;
+    g.epi.kind = EPI_ACCUM_F32; g.epi.out = dw; g.epi.ldo = c;
+    return gemm_dispatch<T>(ctx, g);
+}
+
+struct Dims {
+    int B, T, C, L, NH, V, img, patch, kdim;
+    long btc;
+};
+Dims dims_of(const vitrs_model* m) {
+    Dims d;
+    d.B = m->batch; d.T = m->cfg.max_seq_len; d.C = m->cfg.channels; d.L = m->cfg.num_layers; d.NH = m->cfg.num_heads;
+    d.V = m->cfg.num_classes; d.img = m->cfg.image_size; d.patch = m->cfg.patch_size; d.kdim = 3 * d.patch * d.patch;
+    d.btc = (long)d.B * d.T * d.C;
+    return d;
+}
+
+template <typename T> T* act(const vitrs_model* m, int a) { return reinterpret_cast<T*>(m->acts.view[a]); }
+template <typename T> T* gact(const vitrs_model* m, int a) { return reinterpret_cast<T*>(m->gacts.view[a]); }
+inline float* P(const vitrs_model* m, int i) { return m->params + m->param_off[i]; }
+inline float* G(const vitrs_model* m, int i) { return m->grads + m->param_off[i]; }
+inline const bf16* S(const vitrs_model* m, int i) { return m->shadow + m->param_off[i]; }
+
+// ---- head: CLS rows -> final LayerNorm -> logits -> softmax / loss (rusty_vit.rs:335-347) --------
+template <typename T>
+int head_forward(vitrs_model* m, const T* last_residual, bool fused_loss) {
+    vitrs_ctx* ctx = m->ctx;
+    const Dims d = dims_of(m);
+    VITRS_TRY(op_cls_gather<T>(ctx, m->cls_rows, last_residual, d.B, d.T, d.C));
+    VITRS_TRY(op_layernorm_forward<float>(ctx, act<float>(m, A_LNF), act<float>(m, A_LNF_MEAN), act<float>(m, A_LNF_RSTD),
+                                          m->cls_rows, P(m, P_LNFW), P(m, P_LNFB), d.B, d.C));
+    VITRS_TRY((gemm_fwd<float>(ctx, act<float>(m, A_LOGITS), act<float>(m, A_LNF), P(m, P_HEADW), P(m, P_HEADB), d.B, d.C, d.V,
+                               EPI_BIAS, nullptr, nullptr)));
+    VITRS_CUDA(ctx, cudaMemsetAsync(m->d_mean_loss, 0, sizeof(float), ctx->stream));
+    const float scale = m->dloss_scale != 0.f ? m->dloss_scale : 1.0f / (float)d.B;
+    if (fused_loss) {
+        // probs, losses, mean loss and dlogits in one pass (production)
+        if (m->has_targets) VITRS_CUDA(ctx, cudaMemsetAsync(m->dlogits, 0, sizeof(float) * (size_t)d.B * d.V, ctx->stream));
+        VITRS_TRY(op_head_loss(ctx, act<float>(m, A_PROBS), act<float>(m, A_LOSSES), m->d_mean_loss,
+                               m->has_targets ? m->dlogits : nullptr, act<float>(m, A_LOGITS), m->has_targets ? m->labels : nullptr,
+                               d.B, d.V, scale));
+    } else {
+        VITRS_TRY(op_softmax_forward(ctx, act<float>(m, A_PROBS), act<float>(m, A_LOGITS), d.B, d.V));
+        if (m->has_targets) {
+            VITRS_TRY(op_crossentropy_forward(ctx, act<float>(m, A_LOSSES), act<float>(m, A_PROBS), m->labels, d.B, d.V));
+            VITRS_TRY(op_scaled_sum(ctx, m->d_mean_loss, act<float>(m, A_LOSSES), d.B, scale));
+        }
+    }
+    return VITRS_OK;
+}
+
+// ---- verify mode: the reference's op sequence (rusty_vit.rs:282-347) -------------------------------
+int forward_f32(vitrs_model* m) {
+    vitrs_ctx* ctx = m->ctx;
+    const Dims d = dims_of(m);
+    const long btc = d.btc;
+    float* patches = reinterpret_cast<float*>(m->patches);
+    VITRS_TRY(op_im2col<float>(ctx, patches, m->images, d.B, d.img, d.patch));
+    {
+        GemmDesc g = {};
+        g.A = patches; g.a_rs = d.kdim; g.a_ks = 1;
+        g.B = P(m, P_PATCHW); g.b_rs = d.kdim; g.b_ks = 1;
+        g.M = d.B * d.T; g.N = d.C; g.K = d.kdim;
+        g.epi.kind = EPI_PATCH; g.epi.bias = P(m, P_PATCHB); g.epi.cls = P(m, P_CLS); g.epi.pos = P(m, P_WPE); g.epi.np = d.T;
+        g.epi.out = act<float>(m, A_ENCODED); g.epi.ldo = d.C;
+        VITRS_TRY(gemm_simt_f32(ctx, g));
+    }
+    const int C = d.C, L = d.L;
+    for (int l = 0; l < L; ++l) {
+        const float* residual = l == 0 ? act<float>(m, A_ENCODED) : act<float>(m, A_RESIDUAL3) + (l - 1) * btc;
+        const long lbt = (long)l * d.B * d.T, latt = (long)l * d.B * d.NH * d.T * d.T;
+        float* ln1 = act<float>(m, A_LN1) + l * btc;
+        float* qkv = act<float>(m, A_QKV) + l * btc * 3;
+        float* atty = act<float>(m, A_ATTY) + l * btc;
+        float* attproj = act<float>(m, A_ATTPROJ) + l * btc;
+        float* residual2 = act<float>(m, A_RESIDUAL2) + l * btc;
+        float* ln2 = act<float>(m, A_LN2) + l * btc;
+        float* fch = act<float>(m, A_FCH) + l * btc * 4;
+        float* fch_gelu = act<float>(m, A_FCH_GELU) + l * btc * 4;
+        float* fcproj = act<float>(m, A_FCPROJ) + l * btc;
+        float* residual3 = act<float>(m, A_RESIDUAL3) + l * btc;
+        const long rows = (long)d.B * d.T;
+        VITRS_TRY(op_layernorm_forward<float>(ctx, ln1, act<float>(m, A_LN1_MEAN) + lbt, act<float>(m, A_LN1_RSTD) + lbt, residual,
+                                              P(m, P_LN1W) + l * C, P(m, P_LN1B) + l * C, rows, C));
+        VITRS_TRY((gemm_fwd<float>(ctx, qkv, ln1, P(m, P_QKVW) + (long)l * 3 * C * C, P(m, P_QKVB) + l * 3 * C, rows, C, 3 * C,
+                                   EPI_BIAS, nullptr, nullptr)));
+        VITRS_TRY(op_attention_forward<float>(ctx, atty, act<float>(m, A_PREATT) + latt, act<float>(m, A_ATT) + latt,
+                                              m->lse + (long)l * d.B * d.NH * d.T, qkv, d.B, d.T, C, d.NH, m->cfg.causal));
+        VITRS_TRY((gemm_fwd<float>(ctx, attproj, atty, P(m, P_ATTPROJW) + (long)l * C * C, P(m, P_ATTPROJB) + l * C, rows, C, C,
+                                   EPI_BIAS, nullptr, nullptr)));
+        VITRS_TRY(op_residual_forward<float>(ctx, residual2, residual, attproj, btc));
+        VITRS_TRY(op_layernorm_forward<float>(ctx, ln2, act<float>(m, A_LN2_MEAN) + lbt, act<float>(m, A_LN2_RSTD) + lbt, residual2,
+                                              P(m, P_LN2W) + l * C, P(m, P_LN2B) + l * C, rows, C));
+        VITRS_TRY((gemm_fwd<float>(ctx, fch, ln2, P(m, P_FCW) + (long)l * 4 * C * C, P(m, P_FCB) + l * 4 * C, rows, C, 4 * C,
+                                   EPI_BIAS, nullptr, nullptr)));
+        VITRS_TRY(op_gelu_forward<float>(ctx, fch_gelu, fch, btc * 4));
+        VITRS_TRY((gemm_fwd<float>(ctx, fcproj, fch_gelu, P(m, P_FCPROJW) + (long)l * C * 4 * C, P(m, P_FCPROJB) + l * C, rows,
+                                   4 * C, C, EPI_BIAS, nullptr, nullptr)));
+        VITRS_TRY(op_residual_forward<float>(ctx, residual3, residual2, fcproj, btc));
+    }
+    return head_forward<float>(m, act<float>(m, A_RESIDUAL3) + (L - 1) * btc, false);
+}
+
+// rusty_vit.rs:354-449
+int backward_f32(vitrs_model* m) {
+    vitrs_ctx* ctx = m->ctx;
+    const Dims d = dims_of(m);
+    const long btc = d.btc;
+    const int C = d.C, L = d.L, V = d.V;
+    const long rows = (long)d.B * d.T;
+    const float dloss = m->dloss_scale != 0.f ? m->dloss_scale : 1.0f / (float)d.B;
+    VITRS_TRY(op_fill_const(ctx, gact<float>(m, A_LOSSES), d.B, dloss));  // rusty_vit.rs:366-369
+    VITRS_TRY(op_crossentropy_softmax_backward(ctx, gact<float>(m, A_LOGITS), gact<float>(m, A_LOSSES), act<float>(m, A_PROBS),
+                                               m->labels, d.B, V));
+    VITRS_TRY((gemm_dx<float>(ctx, gact<float>(m, A_LNF), gact<float>(m, A_LOGITS), P(m, P_HEADW), d.B, C, V, EPI_NONE, nullptr, 1)));
+    VITRS_TRY((gemm_dw<float>(ctx, G(m, P_HEADW), gact<float>(m, A_LOGITS), act<float>(m, A_LNF), d.B, C, V)));
+    VITRS_TRY(op_colsum<float>(ctx, G(m, P_HEADB), gact<float>(m, A_LOGITS), d.B, V, V));
+    VITRS_TRY(op_layernorm_backward<float>(ctx, m->dcls_rows, G(m, P_LNFW), G(m, P_LNFB), gact<float>(m, A_LNF), m->cls_rows,
+                                           P(m, P_LNFW), act<float>(m, A_LNF_MEAN), act<float>(m, A_LNF_RSTD), d.B, C, nullptr));
+    VITRS_TRY(op_cls_scatter_add<float>(ctx, gact<float>(m, A_RESIDUAL3) + (L - 1) * btc, m->dcls_rows, d.B, d.T, C));
+
+    for (int l = L - 1; l >= 0; --l) {
+        const float* residual = l == 0 ? act<float>(m, A_ENCODED) : act<float>(m, A_RESIDUAL3) + (l - 1) * btc;
+        float* dresidual = l == 0 ? gact<float>(m, A_ENCODED) : gact<float>(m, A_RESIDUAL3) + (l - 1) * btc;
+        const long lbt = (long)l * d.B * d.T, latt = (long)l * d.B * d.NH * d.T * d.T;
+        // op order: rusty_vit.rs:436-445
+        VITRS_TRY(op_residual_backward<float>(ctx, gact<float>(m, A_RESIDUAL2) + l * btc, gact<float>(m, A_FCPROJ) + l * btc,
+                                              gact<float>(m, A_RESIDUAL3) + l * btc, btc));
+        {
+            const float* dout = gact<float>(m, A_FCPROJ) + l * btc;
+            VITRS_TRY((gemm_dx<float>(ctx, gact<float>(m, A_FCH_GELU) + l * btc * 4, dout, P(m, P_FCPROJW) + (long)l * C * 4 * C, rows,
+                                      4 * C, C, EPI_NONE, nullptr, 1)));
+            VITRS_TRY((gemm_dw<float>(ctx, G(m, P_FCPROJW) + (long)l * C * 4 * C, dout, act<float>(m, A_FCH_GELU) + l * btc * 4, rows,
+                                      4 * C, C)));
+            VITRS_TRY(op_colsum<float>(ctx, G(m, P_FCPROJB) + l * C, dout, rows, C, C));
+        }
+        VITRS_TRY(op_gelu_backward<float>(ctx, gact<float>(m, A_FCH) + l * btc * 4, act<float>(m, A_FCH) + l * btc * 4,
+                                          gact<float>(m, A_FCH_GELU) + l * btc * 4, btc * 4));
+        {
+            const float* dout = gact<float>(m, A_FCH) + l * btc * 4;
+            VITRS_TRY((gemm_dx<float>(ctx, gact<float>(m, A_LN2) + l * btc, dout, P(m, P_FCW) + (long)l * 4 * C * C, rows, C, 4 * C,
+                                      EPI_NONE, nullptr, 1)));
+            VITRS_TRY((gemm_dw<float>(ctx, G(m, P_FCW) + (long)l * 4 * C * C, dout, act<float>(m, A_LN2) + l * btc, rows, C, 4 * C)));
+            VITRS_TRY(op_colsum<float>(ctx, G(m, P_FCB) + l * 4 * C, dout, rows, 4 * C, 4 * C));
+        }
+        VITRS_TRY(op_layernorm_backward<float>(ctx, gact<float>(m, A_RESIDUAL2) + l * btc, G(m, P_LN2W) + l * C, G(m, P_LN2B) + l * C,
+                                               gact<float>(m, A_LN2) + l * btc, act<float>(m, A_RESIDUAL2) + l * btc,
+                                               P(m, P_LN2W) + l * C, act<float>(m, A_LN2_MEAN) + lbt, act<float>(m, A_LN2_RSTD) + lbt,
+                                               rows, C, nullptr));
+        VITRS_TRY(op_residual_backward<float>(ctx, dresidual, gact<float>(m, A_ATTPROJ) + l * btc, gact<float>(m, A_RESIDUAL2) + l * btc,
+                                              btc));
+        {
+            const float* dout = gact<float>(m, A_ATTPROJ) + l * btc;
+            VITRS_TRY((gemm_dx<float>(ctx, gact<float>(m, A_ATTY) + l * btc, dout, P(m, P_ATTPROJW) + (long)l * C * C, rows, C, C,
+                                      EPI_NONE, nullptr, 1)));
+            VITRS_TRY((gemm_dw<float>(ctx, G(m, P_ATTPROJW) + (long)l * C * C, dout, act<float>(m, A_ATTY) + l * btc, rows, C, C)));
+            VITRS_TRY(op_colsum<float>(ctx, G(m, P_ATTPROJB) + l * C, dout, rows, C, C));
+        }
+        VITRS_TRY(op_attention_backward<float>(ctx, gact<float>(m, A_QKV) + l * btc * 3, gact<float>(m, A_PREATT) + latt,
+                                               gact<float>(m, A_ATT) + latt, gact<float>(m, A_ATTY) + l * btc,
+                                               act<float>(m, A_QKV) + l * btc * 3, act<float>(m, A_ATT) + latt, nullptr, d.B, d.T, C,
+                                               d.NH, m->cfg.causal));
+        {
+            const float* dout = gact<float>(m, A_QKV) + l * btc * 3;
+            VITRS_TRY((gemm_dx<float>(ctx, gact<float>(m, A_LN1) + l * btc, dout, P(m, P_QKVW) + (long)l * 3 * C * C, rows, C, 3 * C,
+                                      EPI_NONE, nullptr, 1)));
+            VITRS_TRY((gemm_dw<float>(ctx, G(m, P_QKVW) + (long)l * 3 * C * C, dout, act<float>(m, A_LN1) + l * btc, rows, C, 3 * C)));
+            VITRS_TRY(op_colsum<float>(ctx, G(m, P_QKVB) + l * 3 * C, dout, rows, 3 * C, 3 * C));
+        }
+        VITRS_TRY(op_layernorm_backward<float>(ctx, dresidual, G(m, P_LN1W) + l * C, G(m, P_LN1B) + l * C,
+                                               gact<float>(m, A_LN1) + l * btc, residual, P(m, P_LN1W) + l * C,
+                                               act<float>(m, A_LN1_MEAN) + lbt, act<float>(m, A_LN1_RSTD) + lbt, rows, C, nullptr));
+    }
+    // patch embedding backward (D7)
+    const float* denc = gact<float>(m, A_ENCODED);
+    VITRS_TRY(op_patch_backward_reduce<float>(ctx, G(m, P_WPE), G(m, P_CLS), G(m, P_PATCHB), denc, d.B, d.T, C));
+    VITRS_TRY((gemm_dw<float>(ctx, G(m, P_PATCHW), denc, reinterpret_cast<const float*>(m->patches), rows, d.kdim, C)));
+    return VITRS_OK;
+}
+
+// ---- production mode -----------------------------------------------------------------------------
+int forward_bf16(vitrs_model* m) {
+    vitrs_ctx* ctx = m->ctx;
+    const Dims d = dims_of(m);
+    const long btc = d.btc;
+    const int C = d.C, L = d.L;
+    const long rows = (long)d.B * d.T;
+    bf16* patches = reinterpret_cast<bf16*>(m->patches);
+    VITRS_TRY(op_im2col<bf16>(ctx, patches, m->images, d.B, d.img, d.patch));
+    {
+        GemmDesc g = {};
+        g.A = patches; g.a_rs = d.kdim; g.a_ks = 1;
+        g.B = S(m, P_PATCHW); g.b_rs = d.kdim; g.b_ks = 1;
+        g.M = (int)rows; g.N = C; g.K = d.kdim;
+        g.epi.kind = EPI_PATCH; g.epi.bias = P(m, P_PATCHB); g.epi.cls = P(m, P_CLS); g.epi.pos = P(m, P_WPE); g.epi.np = d.T;
+        g.epi.out = act<bf16>(m, A_ENCODED); g.epi.ldo = C;
+        VITRS_TRY(gemm_tc_bf16(ctx, g));
+    }
+    for (int l = 0; l < L; ++l) {
+        const bf16* residual = l == 0 ? act<bf16>(m, A_ENCODED) : act<bf16>(m, A_RESIDUAL3) + (l - 1) * btc;
+        const long lbt = (long)l * rows;
+        bf16* ln1 = act<bf16>(m, A_LN1) + l * btc;
+        bf16* qkv = act<bf16>(m, A_QKV) + l * btc * 3;
+        bf16* atty = act<bf16>(m, A_ATTY) + l * btc;
+        bf16* residual2 = act<bf16>(m, A_RESIDUAL2) + l * btc;
+        bf16* ln2 = act<bf16>(m, A_LN2) + l * btc;
+        bf16* fch = act<bf16>(m, A_FCH) + l * btc * 4;
+        bf16* fch_gelu = act<bf16>(m, A_FCH_GELU) + l * btc * 4;
+        bf16* residual3 = act<bf16>(m, A_RESIDUAL3) + l * btc;
+        float* lse = m->lse + (long)l * d.B * d.NH * d.T;
+        VITRS_TRY(op_layernorm_forward<bf16>(ctx, ln1, act<float>(m, A_LN1_MEAN) + lbt, act<float>(m, A_LN1_RSTD) + lbt, residual,
+                                             P(m, P_LN1W) + l * C, P(m, P_LN1B) + l * C, rows, C));
+        VITRS_TRY((gemm_fwd<bf16>(ctx, qkv, ln1, S(m, P_QKVW) + (long)l * 3 * C * C, P(m, P_QKVB) + l * 3 * C, rows, C, 3 * C,
+                                  EPI_BIAS, nullptr, nullptr)));
+        int r = op_attention_forward_tc(ctx, atty, lse, qkv, d.B, d.T, C, d.NH, m->cfg.causal);
+        if (r == VITRS_ERR_UNSUPPORTED)
+            r = op_attention_forward<bf16>(ctx, atty, nullptr, nullptr, lse, qkv, d.B, d.T, C, d.NH, m->cfg.causal);
+        VITRS_TRY(r);
+        // out-projection + residual_forward in one epilogue (rusty_vit.rs:325-326)
+        VITRS_TRY((gemm_fwd<bf16>(ctx, residual2, atty, S(m, P_ATTPROJW) + (long)l * C * C, P(m, P_ATTPROJB) + l * C, rows, C, C,
+                                  EPI_BIAS_RESIDUAL, residual, nullptr)));
+        VITRS_TRY(op_layernorm_forward<bf16>(ctx, ln2, act<float>(m, A_LN2_MEAN) + lbt, act<float>(m, A_LN2_RSTD) + lbt, residual2,
+                                             P(m, P_LN2W) + l * C, P(m, P_LN2B) + l * C, rows, C));
+        // fc + gelu_forward (rusty_vit.rs:328-329): both fch and fch_gelu are kept for backward
+        VITRS_TRY((gemm_fwd<bf16>(ctx, fch, ln2, S(m, P_FCW) + (long)l * 4 * C * C, P(m, P_FCB) + l * 4 * C, rows, C, 4 * C,
+                                  EPI_BIAS_GELU, nullptr, fch_gelu)));
+        VITRS_TRY((gemm_fwd<bf16>(ctx, residual3, fch_gelu, S(m, P_FCPROJW) + (long)l * C * 4 * C, P(m, P_FCPROJB) + l * C, rows,
+                                  4 * C, C, EPI_BIAS_RESIDUAL, residual2, nullptr)));
+    }
+    return head_forward<bf16>(m, act<bf16>(m, A_RESIDUAL3) + (L - 1) * btc, true);
+}
+
+int allreduce_layer(vitrs_model* m, int l);
+int allreduce_tail(vitrs_model* m, bool head);
+
+int backward_bf16(vitrs_model* m) {
+    vitrs_ctx* ctx = m->ctx;
+    const Dims d = dims_of(m);
+    const long btc = d.btc;
+    const int C = d.C, L = d.L, V = d.V;
+    const long rows = (long)d.B * d.T;
+    // head (fp32): dlogits was produced with the loss
+    VITRS_TRY((gemm_dx<float>(ctx, m->dlnf, m->dlogits, P(m, P_HEADW), d.B, C, V, EPI_NONE, nullptr, 0)));
+    VITRS_TRY((gemm_dw<float>(ctx, G(m, P_HEADW), m->dlogits, act<float>(m, A_LNF), d.B, C, V)));
+    VITRS_TRY(op_colsum<float>(ctx, G(m, P_HEADB), m->dlogits, d.B, V, V));
+    VITRS_CUDA(ctx, cudaMemsetAsync(m->dcls_rows, 0, sizeof(float) * (size_t)d.B * C, ctx->stream));
+    VITRS_TRY(op_layernorm_backward<float>(ctx, m->dcls_rows, G(m, P_LNFW), G(m, P_LNFB), m->dlnf, m->cls_rows, P(m, P_LNFW),
+                                           act<float>(m, A_LNF_MEAN), act<float>(m, A_LNF_RSTD), d.B, C, nullptr));
+    bf16* dres = m->dres;
+    VITRS_CUDA(ctx, cudaMemsetAsync(dres, 0, sizeof(bf16) * (size_t)btc, ctx->stream));
+    VITRS_TRY(op_cls_scatter_add<bf16>(ctx, dres, m->dcls_rows, d.B, d.T, C));
+    VITRS_TRY(allreduce_tail(m, true));
+    // the fc-projection bias gradient of the last block; the others come fused from LN1-backward
+    VITRS_TRY(op_colsum<bf16>(ctx, G(m, P_FCPROJB) + (L - 1) * C, dres, rows, C, C));
+
+    for (int l = L - 1; l >= 0; --l) {
+        const bf16* residual = l == 0 ? act<bf16>(m, A_ENCODED) : act<bf16>(m, A_RESIDUAL3) + (l - 1) * btc;
+        const long lbt = (long)l * rows;
+        const bf16* fch = act<bf16>(m, A_FCH) + l * btc * 4;
+        const bf16* fch_gelu = act<bf16>(m, A_FCH_GELU) + l * btc * 4;
+        const bf16* ln2 = act<bf16>(m, A_LN2) + l * btc;
+        const bf16* residual2 = act<bf16>(m, A_RESIDUAL2) + l * btc;
+        const bf16* atty = act<bf16>(m, A_ATTY) + l * btc;
+        const bf16* qkv = act<bf16>(m, A_QKV) + l * btc * 3;
+        const bf16* ln1 = act<bf16>(m, A_LN1) + l * btc;
+        const float* lse = m->lse + (long)l * d.B * d.NH * d.T;
+        bf16* dfch = m->dbig;
+        bf16* dqkv = m->dbig;
+        bf16* dln = m->dln;
+        // dres == dresidual3[l] == dfcproj[l] (residual_backward, rusty_vit.rs:436)
+        // fcproj matmul_backward + gelu_backward in one epilogue: dfch = (dres . Wfcproj) * gelu'(fch)
+        VITRS_TRY((gemm_dx<bf16>(ctx, dfch, dres, S(m, P_FCPROJW) + (long)l * C * 4 * C, rows, 4 * C, C, EPI_GELU_BWD, fch, 0)));
+        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_FCPROJW) + (long)l * C * 4 * C, dres, fch_gelu, rows, 4 * C, C)));
+        VITRS_TRY((gemm_dx<bf16>(ctx, dln, dfch, S(m, P_FCW) + (long)l * 4 * C * C, rows, C, 4 * C, EPI_NONE, nullptr, 0)));
+        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_FCW) + (long)l * 4 * C * C, dfch, ln2, rows, C, 4 * C)));
+        VITRS_TRY(op_colsum<bf16>(ctx, G(m, P_FCB) + l * 4 * C, dfch, rows, 4 * C, 4 * C));
+        // dresidual2 = dres + LN2-backward(dln2); its column sum is the out-projection bias gradient
+        VITRS_TRY(op_layernorm_backward<bf16>(ctx, dres, G(m, P_LN2W) + l * C, G(m, P_LN2B) + l * C, dln, residual2,
+                                              P(m, P_LN2W) + l * C, act<float>(m, A_LN2_MEAN) + lbt, act<float>(m, A_LN2_RSTD) + lbt,
+                                              rows, C, G(m, P_ATTPROJB) + l * C));
+        VITRS_TRY((gemm_dx<bf16>(ctx, dln, dres, S(m, P_ATTPROJW) + (long)l * C * C, rows, C, C, EPI_NONE, nullptr, 0)));  // datty
+        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_ATTPROJW) + (long)l * C * C, dres, atty, rows, C, C)));
+        int r = op_attention_backward_tc(ctx, dqkv, dln, atty, qkv, lse, d.B, d.T, C, d.NH, m->cfg.causal);
+        if (r == VITRS_ERR_UNSUPPORTED) {
+            VITRS_CUDA(ctx, cudaMemsetAsync(dqkv, 0, sizeof(bf16) * (size_t)btc * 3, ctx->stream));
+            r = op_attention_backward<bf16>(ctx, dqkv, nullptr, nullptr, dln, qkv, nullptr, lse, d.B, d.T, C, d.NH, m->cfg.causal);
+        }
+        VITRS_TRY(r);
+        VITRS_TRY((gemm_dx<bf16>(ctx, dln, dqkv, S(m, P_QKVW) + (long)l * 3 * C * C, rows, C, 3 * C, EPI_NONE, nullptr, 0)));  // dln1
+        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_QKVW) + (long)l * 3 * C * C, dqkv, ln1, rows, C, 3 * C)));
+        VITRS_TRY(op_colsum<bf16>(ctx, G(m, P_QKVB) + l * 3 * C, dqkv, rows, 3 * C, 3 * C));
+        VITRS_TRY(op_layernorm_backward<bf16>(ctx, dres, G(m, P_LN1W) + l * C, G(m, P_LN1B) + l * C, dln, residual,
+                                              P(m, P_LN1W) + l * C, act<float>(m, A_LN1_MEAN) + lbt, act<float>(m, A_LN1_RSTD) + lbt,
+                                              rows, C, l > 0 ? G(m, P_FCPROJB) + (l - 1) * C : nullptr));
+        // every gradient of block l is final except fcprojb[l-1], which belongs to block l-1's bucket
+        VITRS_TRY(allreduce_layer(m, l));
+    }
+    VITRS_TRY(op_patch_backward_reduce<bf16>(ctx, G(m, P_WPE), G(m, P_CLS), G(m, P_PATCHB), dres, d.B, d.T, C));
+    VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_PATCHW), dres, reinterpret_cast<const bf16*>(m->patches), rows, d.kdim, C)));
+    VITRS_TRY(allreduce_tail(m, false));
+    return VITRS_OK;
+}
+
+// ---- data parallel: bucketed sum all-reduce on the comm stream, overlapped with backward ----------
+int bucket_begin(vitrs_model* m) {
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_CUDA(ctx, cudaEventRecord(m->ev_bucket, ctx->stream));
+    VITRS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, m->ev_bucket, 0));
+    return VITRS_OK;
+}
+
+// block l: its 12 slices of the tensor-major gradient buffer.  fcprojb[l] is completed by block
+// l+1's LN1-backward (or before the loop for the last block), so it is already final here.
+int allreduce_layer(vitrs_model* m, int l) {
+    if (!m->ctx->nccl_comm || m->mode != VITRS_MODE_BF16) return VITRS_OK;
+    VITRS_TRY(bucket_begin(m));
+    float* bufs[12];
+    size_t counts[12];
+    int n = 0;
+    for (int i = P_LN1W; i <= P_FCPROJB; ++i) {
+        const size_t per = m->param_sizes[i] / m->cfg.num_layers;
+        bufs[n] = G(m, i) + (size_t)l * per;
+        counts[n] = per;
+        ++n;
+    }
+    return vitrs_nccl_allreduce_group(m->ctx, bufs, counts, n);
+}
+
+int allreduce_tail(vitrs_model* m, bool head) {
+    if (!m->ctx->nccl_comm || m->mode != VITRS_MODE_BF16) return VITRS_OK;
+    VITRS_TRY(bucket_begin(m));
+    float* bufs[1];
+    size_t counts[1];
+    if (head) {  // lnfw, lnfb, headw, headb are contiguous
+        bufs[0] = G(m, P_LNFW);
+        counts[0] = m->num_params - m->param_off[P_LNFW];
+    } else {     // patchw, patchb, cls, wpe are contiguous
+        bufs[0] = G(m, P_PATCHW);
+        counts[0] = m->param_off[P_LN1W];
+    }
+    return vitrs_nccl_allreduce_group(m->ctx, bufs, counts, 1);
+}
+
+int comm_join(vitrs_model* m) {
+    vitrs_ctx* ctx = m->ctx;
+    if (!ctx->nccl_comm) return VITRS_OK;
+    VITRS_CUDA(ctx, cudaEventRecord(m->ev_comm_done, ctx->comm_stream));
+    VITRS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->ev_comm_done, 0));
+    return VITRS_OK;
+}
+
+int set_batch(vitrs_model* m, const float* images, const int* labels, int b) {
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_ARG(ctx, images != nullptr && b >= 1 && b <= m->max_batch);
+    m->batch = b;
+    m->images = images;
+    m->labels = labels;
+    m->has_targets = labels != nullptr;
+    return VITRS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vitrs_model_create(vitrs_ctx* ctx, const vitrs_config* cfg_in, int max_batch, int mode, vitrs_model** out) {
+    if (!ctx) return VITRS_ERR_ARG;
+    VITRS_ARG(ctx, cfg_in && out && max_batch >= 1 && (mode == VITRS_MODE_F32 || mode == VITRS_MODE_BF16));
+    vitrs_config cfg = *cfg_in;
+    VITRS_ARG(ctx, cfg.patch_size > 0 && cfg.image_size % cfg.patch_size == 0 && cfg.patch_size % 4 == 0);
+    VITRS_ARG(ctx, cfg.channels > 0 && cfg.num_heads > 0 && cfg.channels % cfg.num_heads == 0 && cfg.channels % 8 == 0);
+    VITRS_ARG(ctx, cfg.num_layers >= 1 && cfg.num_classes >= 1);
+    VITRS_ARG(ctx, cfg.max_seq_len == 0 || cfg.max_seq_len == tokens(cfg));
+    cfg.max_seq_len = tokens(cfg);
+    cfg.vocab_size = cfg.num_classes;
+    *out = nullptr;
+    VITRS_CUDA(ctx, cudaSetDevice(ctx->device));
+    vitrs_model* m = (vitrs_model*)calloc(1, sizeof(vitrs_model));
+    m->ctx = ctx; m->cfg = cfg; m->mode = mode; m->max_batch = max_batch;
+    param_sizes_of(cfg, m->param_sizes);
+    size_t off = 0;
+    for (int i = 0; i < P_COUNT; ++i) { m->param_off[i] = off; off += m->param_sizes[i]; }
+    m->num_params = off;
+    const size_t pbytes = off * sizeof(float);
+    const size_t B = max_batch, T = cfg.max_seq_len, C = cfg.channels, L = cfg.num_layers, NH = cfg.num_heads, V = cfg.num_classes;
+    const size_t kdim = 3u * cfg.patch_size * cfg.patch_size;
+    const size_t esz = mode == VITRS_MODE_F32 ? 4 : 2;
+#define MODEL_CUDA(expr)                                                                                           \
+    do {                                                                                                           \
+        cudaError_t e__ = (expr);                                                                                  \
+        if (e__ != cudaSuccess) {                                                                                  \
+            int rc__ = vitrs_set_error(ctx, VITRS_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,           \
+                                       cudaGetErrorString(e__));                                                   \
+            vitrs_model_destroy(m);                                                                                \
+            return rc__;                                                                                           \
+        }                                                                                                          \
+    } while (0)
+    MODEL_CUDA(cudaMalloc(&m->params, pbytes));
+    MODEL_CUDA(cudaMalloc(&m->grads, pbytes));
+    MODEL_CUDA(cudaMalloc(&m->m, pbytes));
+    MODEL_CUDA(cudaMalloc(&m->v, pbytes));
+    MODEL_CUDA(cudaMemsetAsync(m->params, 0, pbytes, ctx->stream));
+    MODEL_CUDA(cudaMemsetAsync(m->grads, 0, pbytes, ctx->stream));
+    MODEL_CUDA(cudaMemsetAsync(m->m, 0, pbytes, ctx->stream));
+    MODEL_CUDA(cudaMemsetAsync(m->v, 0, pbytes, ctx->stream));
+    if (mode == VITRS_MODE_BF16) {
+        MODEL_CUDA(cudaMalloc(&m->shadow, off * sizeof(bf16)));
+        MODEL_CUDA(cudaMemsetAsync(m->shadow, 0, off * sizeof(bf16), ctx->stream));
+    }
+    if (arena_create(ctx, &m->acts, cfg, max_batch, mode, false) != VITRS_OK ||
+        arena_create(ctx, &m->gacts, cfg, max_batch, mode, true) != VITRS_OK) {
+        vitrs_model_destroy(m);
+        return VITRS_ERR_CUDA;
+    }
+    MODEL_CUDA(cudaMalloc(&m->lse, sizeof(float) * L * B * NH * T));
+    MODEL_CUDA(cudaMalloc(&m->cls_rows, sizeof(float) * B * C));
+    MODEL_CUDA(cudaMalloc(&m->dcls_rows, sizeof(float) * B * C));
+    MODEL_CUDA(cudaMalloc(&m->patches, esz * B * T * kdim));
+    if (mode == VITRS_MODE_BF16) {
+        MODEL_CUDA(cudaMalloc(&m->dres, sizeof(bf16) * B * T * C));
+        MODEL_CUDA(cudaMalloc(&m->dln, sizeof(bf16) * B * T * C));
+        MODEL_CUDA(cudaMalloc(&m->dbig, sizeof(bf16) * B * T * 4 * C));
+        MODEL_CUDA(cudaMalloc(&m->dlogits, sizeof(float) * B * V));
+        MODEL_CUDA(cudaMalloc(&m->dlnf, sizeof(float) * B * C));
+    }
+    MODEL_CUDA(cudaMalloc(&m->d_mean_loss, sizeof(float)));
+    MODEL_CUDA(cudaMallocHost(&m->h_mean_loss, sizeof(float)));
+    *m->h_mean_loss = -1.0f;
+    for (int i = 0; i < 2; ++i) {
+        MODEL_CUDA(cudaEventCreateWithFlags(&m->stage_ready[i], cudaEventDisableTiming));
+        MODEL_CUDA(cudaEventCreateWithFlags(&m->stage_free[i], cudaEventDisableTiming));
+    }
+    MODEL_CUDA(cudaEventCreateWithFlags(&m->ev_bucket, cudaEventDisableTiming));
+    MODEL_CUDA(cudaEventCreateWithFlags(&m->ev_comm_done, cudaEventDisableTiming));
+    MODEL_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef MODEL_CUDA
+    *out = m;
+    return VITRS_OK;
+}
+
+int vitrs_model_destroy(vitrs_model* m) {
+    if (!m) return VITRS_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(m->params); cudaFree(m->grads); cudaFree(m->m); cudaFree(m->v); cudaFree(m->shadow);
+    cudaFree(m->acts.base); cudaFree(m->gacts.base);
+    cudaFree(m->lse); cudaFree(m->cls_rows); cudaFree(m->dcls_rows); cudaFree(m->patches);
+    cudaFree(m->dres); cudaFree(m->dln); cudaFree(m->dbig); cudaFree(m->dlogits); cudaFree(m->dlnf);
+    cudaFree(m->d_mean_loss);
+    if (m->h_mean_loss) cudaFreeHost(m->h_mean_loss);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(m->stage_images[i]); cudaFree(m->stage_labels[i]);
+        if (m->stage_ready[i]) cudaEventDestroy(m->stage_ready[i]);
+        if (m->stage_free[i]) cudaEventDestroy(m->stage_free[i]);
+    }
+    if (m->ev_bucket) cudaEventDestroy(m->ev_bucket);
+    if (m->ev_comm_done) cudaEventDestroy(m->ev_comm_done);
+    free(m);
+    return VITRS_OK;
+}
+
+static int refresh_shadow(vitrs_model* m) {
+    if (m->mode != VITRS_MODE_BF16) return VITRS_OK;
+    return op_cast_f32_bf16(m->ctx, m->shadow, m->params, m->num_params);
+}
+
+// init_parameters (rusty_vit.rs:864-903, DEVIATIONS D9): weights U[lo,hi) from the counter
+// generator (stream = tensor index), LayerNorm gains 1, every bias 0
+int vitrs_model_init_parameters(vitrs_model* m, uint64_t seed, int init_mode) {
+    if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_CUDA(ctx, cudaMemsetAsync(m->params, 0, m->num_params * sizeof(float), ctx->stream));
+    VITRS_CUDA(ctx, cudaMemsetAsync(m->m, 0, m->num_params * sizeof(float), ctx->stream));
+    VITRS_CUDA(ctx, cudaMemsetAsync(m->v, 0, m->num_params * sizeof(float), ctx->stream));
+    m->adam_step = 0;
+    const float lo = init_mode == 1 ? -0.02f : 0.0f, hi = 0.02f;
+    const int weight_ids[] = {P_PATCHW, P_CLS, P_WPE, P_QKVW, P_ATTPROJW, P_FCW, P_FCPROJW, P_HEADW};
+    for (int id : weight_ids) VITRS_TRY(op_fill_uniform(ctx, P(m, id), m->param_sizes[id], seed, (uint64_t)id, lo, hi));
+    const int gain_ids[] = {P_LN1W, P_LN2W, P_LNFW};
+    for (int id : gain_ids) VITRS_TRY(op_fill_const(ctx, P(m, id), m->param_sizes[id], 1.0f));
+    return refresh_shadow(m);
+}
+
+size_t vitrs_model_num_parameters(vitrs_model* m) { return m ? m->num_params : 0; }
+
+int vitrs_model_param_view(vitrs_model* m, int which, int tensor, float** ptr, size_t* count) {
+    if (!m) return VITRS_ERR_ARG;
+    VITRS_ARG(m->ctx, which >= 0 && which <= 3 && tensor >= 0 && tensor < P_COUNT && ptr);
+    float* base = which == 0 ? m->params : which == 1 ? m->grads : which == 2 ? m->m : m->v;
+    *ptr = base + m->param_off[tensor];
+    if (count) *count = m->param_sizes[tensor];
+    return VITRS_OK;
+}
+
+int vitrs_model_act_view(vitrs_model* m, int which, int tensor, void** ptr, size_t* count, int* elem_size) {
+    if (!m) return VITRS_ERR_ARG;
+    VITRS_ARG(m->ctx, (which == 0 || which == 1) && tensor >= 0 && tensor < A_COUNT && ptr);
+    const Arena& ar = which == 0 ? m->acts : m->gacts;
+    *ptr = ar.view[tensor];
+    if (count) *count = ar.view[tensor] ? ar.per_image[tensor] * (size_t)m->batch : 0;
+    if (elem_size) *elem_size = ar.elem[tensor];
+    return VITRS_OK;
+}
+
+int vitrs_model_set_dloss_scale(vitrs_model* m, float scale) {
+    if (!m) return VITRS_ERR_ARG;
+    m->dloss_scale = scale;
+    return VITRS_OK;
+}
+
+// weights changed behind the model's back (tests writing through param_view): rebuild the bf16 shadow
+int vitrs_model_sync_parameters(vitrs_model* m) {
+    if (!m) return VITRS_ERR_ARG;
+    return refresh_shadow(m);
+}
+
+int vitrs_model_forward(vitrs_model* m, const float* images, const int* labels, int b) {
+    if (!m) return VITRS_ERR_ARG;
+    VITRS_TRY(set_batch(m, images, labels, b));
+    VITRS_CUDA(m->ctx, cudaSetDevice(m->ctx->device));
+    VITRS_TRY(m->mode == VITRS_MODE_F32 ? forward_f32(m) : forward_bf16(m));
+    if (!m->has_targets) VITRS_TRY(op_fill_const(m->ctx, m->d_mean_loss, 1, -1.0f));  // rusty_vit.rs:348-350
+    return VITRS_OK;
+}
+
+int vitrs_model_zero_grad(vitrs_model* m) {
+    if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_CUDA(ctx, cudaMemsetAsync(m->grads, 0, m->num_params * sizeof(float), ctx->stream));
+    if (m->gacts.base) VITRS_CUDA(ctx, cudaMemsetAsync(m->gacts.base, 0, m->gacts.bytes, ctx->stream));
+    if (m->mode == VITRS_MODE_F32) VITRS_CUDA(ctx, cudaMemsetAsync(m->dcls_rows, 0, sizeof(float) * (size_t)m->max_batch * m->cfg.channels, ctx->stream));
+    return VITRS_OK;
+}
+
+int vitrs_model_backward(vitrs_model* m) {
+    if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_ARG(ctx, m->batch > 0 && m->has_targets);
+    VITRS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VITRS_TRY(m->mode == VITRS_MODE_F32 ? backward_f32(m) : backward_bf16(m));
+    if (ctx->nccl_comm && m->mode == VITRS_MODE_F32) VITRS_TRY(vitrs_allreduce_f32(ctx, m->grads, m->num_params));
+    return comm_join(m);
+}
+
+int vitrs_model_allreduce_grads(vitrs_model* m) {
+    if (!m) return VITRS_ERR_ARG;
+    return vitrs_allreduce_f32(m->ctx, m->grads, m->num_params);
+}
+
+int vitrs_model_optimizer_step(vitrs_model* m, float lr) {
+    if (!m) return VITRS_ERR_ARG;
+    return op_sgd(m->ctx, m->params, m->grads, m->num_params, lr, m->shadow);
+}
+
+int vitrs_model_update(vitrs_model* m, float lr, float beta1, float beta2, float eps, float weight_decay) {
+    if (!m) return VITRS_ERR_ARG;
+    m->adam_step += 1;
+    return op_adamw(m->ctx, m->params, m->grads, m->m, m->v, m->num_params, lr, beta1, beta2, eps, weight_decay, m->adam_step,
+                    m->shadow);
+}
+
+int vitrs_model_mean_loss(vitrs_model* m, float* out) {
+    if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_ARG(ctx, out != nullptr);
+    if (m->batch == 0) { *out = -1.0f; return VITRS_OK; }
+    if (ctx->nccl_comm && m->has_targets) {
+        // the local value is sum(losses) / B_global when a dloss scale is set: the global mean is the sum over ranks
+        VITRS_TRY(vitrs_allreduce_f32(ctx, m->d_mean_loss, 1));
+    }
+    VITRS_CUDA(ctx, cudaMemcpyAsync(m->h_mean_loss, m->d_mean_loss, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = *m->h_mean_loss;
+    return VITRS_OK;
+}
+
+int vitrs_model_train_step(vitrs_model* m, const float* images, const int* labels, int b, float lr, float beta1, float beta2,
+                           float eps, float weight_decay) {
+    if (!m) return VITRS_ERR_ARG;
+    VITRS_ARG(m->ctx, labels != nullptr);
+    VITRS_TRY(vitrs_model_zero_grad(m));
+    VITRS_TRY(vitrs_model_forward(m, images, labels, b));
+    VITRS_TRY(vitrs_model_backward(m));
+    return vitrs_model_update(m, lr, beta1, beta2, eps, weight_decay);
+}
+
+static int ensure_stage(vitrs_model* m) {
+    vitrs_ctx* ctx = m->ctx;
+    if (m->stage_images[0]) return VITRS_OK;
+    const size_t img_elems = (size_t)m->max_batch * 3 * m->cfg.image_size * m->cfg.image_size;
+    for (int i = 0; i < 2; ++i) {
+        VITRS_CUDA(ctx, cudaMalloc(&m->stage_images[i], img_elems * sizeof(float)));
+        VITRS_CUDA(ctx, cudaMalloc(&m->stage_labels[i], sizeof(int) * (size_t)m->max_batch));
+        m->stage_src[i] = nullptr;
+    }
+    return VITRS_OK;
+}
+
+// H2D of a batch on the copy stream into the staging slot the compute stream is not using
+int vitrs_model_prefetch_host(vitrs_model* m, const float* h_images, const int* h_labels, int b) {
+    if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_ARG(ctx, h_images && h_labels && b >= 1 && b <= m->max_batch);
+    VITRS_TRY(ensure_stage(m));
+    const int s = m->stage_next;
+    const size_t img_bytes = (size_t)b * 3 * m->cfg.image_size * m->cfg.image_size * sizeof(float);
+    VITRS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, m->stage_free[s], 0));
+    VITRS_CUDA(ctx, cudaMemcpyAsync(m->stage_images[s], h_images, img_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VITRS_CUDA(ctx, cudaMemcpyAsync(m->stage_labels[s], h_labels, sizeof(int) * (size_t)b, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VITRS_CUDA(ctx, cudaEventRecord(m->stage_ready[s], ctx->copy_stream));
+    m->stage_src[s] = h_images;
+    m->stage_batch[s] = b;
+    m->stage_next = s ^ 1;
+    return VITRS_OK;
+}
+
+int vitrs_model_train_step_host(vitrs_model* m, const float* h_images, const int* h_labels, int b, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, float* loss_out) {
+    if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_ARG(ctx, h_images && h_labels && b >= 1 && b <= m->max_batch);
+    VITRS_TRY(ensure_stage(m));
+    int s = -1;
+    for (int i = 0; i < 2; ++i)
+        if (m->stage_src[i] == h_images && m->stage_batch[i] == b) s = i;
+    if (s < 0) {  // not prefetched: copy now (still through the copy stream so slot reuse stays ordered)
+        VITRS_TRY(vitrs_model_prefetch_host(m, h_images, h_labels, b));
+        s = m->stage_next ^ 1;
+    }
+    VITRS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->stage_ready[s], 0));
+    m->stage_src[s] = nullptr;
+    VITRS_TRY(vitrs_model_train_step(m, m->stage_images[s], m->stage_labels[s], b, lr, beta1, beta2, eps, weight_decay));
+    VITRS_CUDA(ctx, cudaEventRecord(m->stage_free[s], ctx->stream));
+    if (loss_out) VITRS_TRY(vitrs_model_mean_loss(m, loss_out));
+    return VITRS_OK;
+}
+
+// ---- checkpoint: llm.c-style file (rusty_vit.rs:81-129): 256 x i32 header, fp32 params from byte 1024.
+// header[0] magic, [1] version, [2..6] max_seq_len, vocab(=classes), layers, heads, channels (the
+// reference's slots), [7..10] image, patch, classes, causal, [11] adam step, [12] has m/v.
+#define VITRS_CKPT_MAGIC 20261018
+int vitrs_model_save_checkpoint(vitrs_model* m, const char* path) {
+    if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_ARG(ctx, path != nullptr);
+    VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FILE* f = fopen(path, "wb");
+    if (!f) return vitrs_set_error(ctx, VITRS_ERR_ARG, "cannot open %s for writing", path);
+    int32_t header[256] = {0};
+    header[0] = VITRS_CKPT_MAGIC; header[1] = 1;
+    header[2] = m->cfg.max_seq_len; header[3] = m->cfg.num_classes; header[4] = m->cfg.num_layers;
+    header[5] = m->cfg.num_heads; header[6] = m->cfg.channels; header[7] = m->cfg.image_size;
+    header[8] = m->cfg.patch_size; header[9] = m->cfg.num_classes; header[10] = m->cfg.causal;
+    header[11] = m->adam_step; header[12] = 1;
+    bool ok = fwrite(header, sizeof(int32_t), 256, f) == 256;
+    float* host = (float*)malloc(m->num_params * sizeof(float));
+    float* srcs[3] = {m->params, m->m, m->v};
+    for (int k = 0; k < 3 && ok; ++k) {
+        if (cudaMemcpy(host, srcs[k], m->num_params * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+        else ok = fwrite(host, sizeof(float), m->num_params, f) == m->num_params;
+    }
+    free(host);
+    fclose(f);
+    return ok ? VITRS_OK : vitrs_set_error(ctx, VITRS_ERR_CUDA, "short write to %s", path);
+}
+
+int vitrs_model_load_checkpoint(vitrs_model* m, const char* path) {
+    if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_ARG(ctx, path != nullptr);
+    FILE* f = fopen(path, "rb");
+    if (!f) return vitrs_set_error(ctx, VITRS_ERR_ARG, "cannot open %s", path);
+    int32_t header[256];
+    if (fread(header, sizeof(int32_t), 256, f) != 256) { fclose(f); return vitrs_set_error(ctx, VITRS_ERR_ARG, "%s: short header", path); }
+    if (header[0] != VITRS_CKPT_MAGIC || header[2] != m->cfg.max_seq_len || header[4] != m->cfg.num_layers ||
+        header[5] != m->cfg.num_heads || header[6] != m->cfg.channels || header[8] != m->cfg.patch_size ||
+        header[9] != m->cfg.num_classes) {
+        fclose(f);
+        return vitrs_set_error(ctx, VITRS_ERR_ARG, "%s: header does not match the model configuration", path);
+    }
+    VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float* host = (float*)malloc(m->num_params * sizeof(float));
+    float* dsts[3] = {m->params, m->m, m->v};
+    const int sections = header[12] ? 3 : 1;
+    bool ok = true;
+    for (int k = 0; k < sections && ok; ++k) {
+        ok = fread(host, sizeof(float), m->num_params, f) == m->num_params &&
+             cudaMemcpy(dsts[k], host, m->num_params * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    free(host);
+    fclose(f);
+    if (!ok) return vitrs_set_error(ctx, VITRS_ERR_ARG, "%s: short read", path);
+    m->adam_step = header[11];
+    return refresh_shadow(m);
+}
+
+}  // extern "C"

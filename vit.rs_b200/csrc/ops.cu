@@ -1,0 +1,296 @@
+// ops.cu — the extern "C" operator entry points of include/vitrs.h: argument checks and the
+// mapping from the reference's llm.c-style signatures (train_vit.rs:376-670) onto the kernels.
+// Every op is asynchronous on the context stream; there is no CPU path.
+#include "common.cuh"
+
+namespace {
+
+#define CTX_OR_FAIL(ctx) \
+    if (!(ctx)) return VITRS_ERR_ARG
+
+// out[M, oc] = inp[M, c] . weight[oc, c]^T (+ bias)                       (train_vit.rs:384-398)
+template <typename T>
+int matmul_forward_impl(vitrs_ctx* ctx, T* out, const T* inp, const T* weight, const float* bias, long rows, int c, int oc) {
+    if (rows == 0) return VITRS_OK;
+    VITRS_ARG(ctx, out && inp && weight && rows >= 0 && c > 0 && oc > 0 && rows < (1l << 31));
+    GemmDesc g = {};
+    g.A = inp; g.a_rs = c; g.a_ks = 1;
+    g.B = weight; g.b_rs = c; g.b_ks = 1;
+    g.M = (int)rows; g.N = oc; g.K = c;
+    g.epi.kind = EPI_BIAS;
+    g.epi.bias = bias;
+    g.epi.out = out;
+    g.epi.ldo = oc;
+    return gemm_dispatch<T>(ctx, g);
+}
+
+// train_vit.rs:530-557: dinp += dout . W ; dweight += dout^T . inp ; dbias += colsum(dout)
+template <typename T>
+int matmul_backward_impl(vitrs_ctx* ctx, T* dinp, float* dweight, float* dbias, const T* dout, const T* inp, const T* weight,
+                         long rows, int c, int oc) {
+    if (rows == 0) return VITRS_OK;
+    VITRS_ARG(ctx, dout && rows >= 0 && c > 0 && oc > 0 && rows < (1l << 31));
+    if (dinp) {
+        VITRS_ARG(ctx, weight != nullptr);
+        GemmDesc g = {};
+        g.A = dout; g.a_rs = oc; g.a_ks = 1;
+        g.B = weight; g.b_rs = 1; g.b_ks = c;  // B(n = i, k = o) = W[o, i]
+        g.M = (int)rows; g.N = c; g.K = oc;
+        g.epi.kind = EPI_NONE;
+        g.epi.accumulate = 1;
+        g.epi.out = dinp;
+        g.epi.ldo = c;
+        VITRS_TRY(gemm_dispatch<T>(ctx, g));
+    }
+    if (dweight) {
+        VITRS_ARG(ctx, inp != nullptr);
+        GemmDesc g = {};
+        g.A = dout; g.a_rs = 1; g.a_ks = oc;  // A(m = o, k = r) = dout[r, o]
+        g.B = inp; g.b_rs = 1; g.b_ks = c;    // B(n = i, k = r) = inp[r, i]
+        g.M = oc; g.N = c; g.K = (int)rows;
+        g.epi.kind = EPI_ACCUM_F32;
+        g.epi.out = dweight;
+        g.epi.ldo = c;
+        VITRS_TRY(gemm_dispatch<T>(ctx, g));
+    }
+    if (dbias) VITRS_TRY(op_colsum<T>(ctx, dbias, dout, rows, oc, oc));
+    return VITRS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- fp32 verify mode ---------------------------------------------------------------------
+int vitrs_residual_forward_f32(vitrs_ctx* ctx, float* out, const float* a, const float* b, int n) {
+    CTX_OR_FAIL(ctx);
+    return op_residual_forward<float>(ctx, out, a, b, n);
+}
+int vitrs_matmul_forward_f32(vitrs_ctx* ctx, float* out, const float* inp, const float* weight, const float* bias, int b, int t,
+                             int c, int oc) {
+    CTX_OR_FAIL(ctx);
+    return matmul_forward_impl<float>(ctx, out, inp, weight, bias, (long)b * t, c, oc);
+}
+int vitrs_attention_forward_f32(vitrs_ctx* ctx, float* out, float* preatt, float* att, const float* inp, int b, int t, int c,
+                                int nh, int causal) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, out && inp);
+    return op_attention_forward<float>(ctx, out, preatt, att, nullptr, inp, b, t, c, nh, causal);
+}
+int vitrs_layernorm_forward_f32(vitrs_ctx* ctx, float* out, float* mean, float* rstd, const float* inp, const float* weight,
+                                const float* bias, int b, int t, int c) {
+    CTX_OR_FAIL(ctx);
+    if ((long)b * t == 0) return VITRS_OK;
+    VITRS_ARG(ctx, out && mean && rstd && inp && weight && bias && c > 0);
+    return op_layernorm_forward<float>(ctx, out, mean, rstd, inp, weight, bias, (long)b * t, c);
+}
+int vitrs_gelu_forward_f32(vitrs_ctx* ctx, float* out, const float* inp, int n) {
+    CTX_OR_FAIL(ctx);
+    return op_gelu_forward<float>(ctx, out, inp, n);
+}
+int vitrs_softmax_forward_f32(vitrs_ctx* ctx, float* probs, const float* logits, int b, int t, int v) {
+    CTX_OR_FAIL(ctx);
+    if ((long)b * t == 0) return VITRS_OK;
+    VITRS_ARG(ctx, probs && logits && v > 0);
+    return op_softmax_forward(ctx, probs, logits, (long)b * t, v);
+}
+int vitrs_residual_backward_f32(vitrs_ctx* ctx, float* d1, float* d2, const float* dout, int n) {
+    CTX_OR_FAIL(ctx);
+    return op_residual_backward<float>(ctx, d1, d2, dout, n);
+}
+int vitrs_matmul_backward_f32(vitrs_ctx* ctx, float* dinp, float* dweight, float* dbias, const float* dout, const float* inp,
+                              const float* weight, int b, int t, int c, int oc) {
+    CTX_OR_FAIL(ctx);
+    return matmul_backward_impl<float>(ctx, dinp, dweight, dbias, dout, inp, weight, (long)b * t, c, oc);
+}
+int vitrs_attention_backward_f32(vitrs_ctx* ctx, float* dinp, float* dpreatt, float* datt, const float* dout, const float* inp,
+                                 const float* att, int b, int t, int c, int nh, int causal) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, dinp && dout && inp && att);
+    return op_attention_backward<float>(ctx, dinp, dpreatt, datt, dout, inp, att, nullptr, b, t, c, nh, causal);
+}
+int vitrs_layernorm_backward_f32(vitrs_ctx* ctx, float* dinp, float* dweight, float* dbias, const float* dout, const float* inp,
+                                 const float* weight, const float* mean, const float* rstd, int b, int t, int c) {
+    CTX_OR_FAIL(ctx);
+    if ((long)b * t == 0) return VITRS_OK;
+    VITRS_ARG(ctx, dinp && dweight && dbias && dout && inp && weight && mean && rstd && c > 0);
+    return op_layernorm_backward<float>(ctx, dinp, dweight, dbias, dout, inp, weight, mean, rstd, (long)b * t, c, nullptr);
+}
+int vitrs_gelu_backward_f32(vitrs_ctx* ctx, float* dinp, const float* inp, const float* dout, int n) {
+    CTX_OR_FAIL(ctx);
+    return op_gelu_backward<float>(ctx, dinp, inp, dout, n);
+}
+int vitrs_crossentropy_forward_f32(vitrs_ctx* ctx, float* losses, const float* probs, const int* targets, int b, int t, int v) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, losses && probs && targets);
+    return op_crossentropy_forward(ctx, losses, probs, targets, (long)b * t, v);
+}
+int vitrs_crossentropy_softmax_backward_f32(vitrs_ctx* ctx, float* dlogits, const float* dlosses, const float* probs,
+                                            const int* targets, int b, int t, int v) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, dlogits && dlosses && probs && targets);
+    return op_crossentropy_softmax_backward(ctx, dlogits, dlosses, probs, targets, (long)b * t, v);
+}
+int vitrs_encoder_forward_f32(vitrs_ctx* ctx, float* enc, const int* inputs, const float* wte, const float* wpe, int b, int t,
+                              int c) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, enc && inputs && wte && wpe);
+    return op_encoder_forward(ctx, enc, inputs, wte, wpe, b, t, c);
+}
+int vitrs_encoder_backward_f32(vitrs_ctx* ctx, float* dwte, float* dwpe, const float* denc, const int* inputs, int b, int t,
+                               int c) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, dwte && dwpe && denc && inputs);
+    return op_encoder_backward(ctx, dwte, dwpe, denc, inputs, b, t, c);
+}
+
+// patch embedding through a temporary im2col matrix (freed after the stream has consumed it)
+int vitrs_patch_embed_forward_f32(vitrs_ctx* ctx, float* encoded, const float* images, const float* patchw, const float* patchb,
+                                  const float* cls, const float* wpe, int b, int img, int patch, int c) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, encoded && images && patchw && patchb && cls && wpe && b >= 0 && patch > 0 && img % patch == 0);
+    const int t = (img / patch) * (img / patch) + 1, kdim = 3 * patch * patch;
+    float* patches = nullptr;
+    VITRS_CUDA(ctx, cudaMallocAsync(&patches, sizeof(float) * (size_t)b * t * kdim, ctx->stream));
+    int r = op_im2col<float>(ctx, patches, images, b, img, patch);
+    if (r == VITRS_OK) {
+        GemmDesc g = {};
+        g.A = patches; g.a_rs = kdim; g.a_ks = 1;
+        g.B = patchw; g.b_rs = kdim; g.b_ks = 1;
+        g.M = b * t; g.N = c; g.K = kdim;
+        g.epi.kind = EPI_PATCH;
+        g.epi.bias = patchb; g.epi.cls = cls; g.epi.pos = wpe; g.epi.np = t;
+        g.epi.out = encoded; g.epi.ldo = c;
+        r = gemm_simt_f32(ctx, g);
+    }
+    cudaFreeAsync(patches, ctx->stream);
+    return r;
+}
+int vitrs_patch_embed_backward_f32(vitrs_ctx* ctx, float* dpatchw, float* dpatchb, float* dcls, float* dwpe,
+                                   const float* dencoded, const float* images, int b, int img, int patch, int c) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, dpatchw && dpatchb && dcls && dwpe && dencoded && images && patch > 0 && img % patch == 0);
+    const int t = (img / patch) * (img / patch) + 1, kdim = 3 * patch * patch;
+    float* patches = nullptr;
+    VITRS_CUDA(ctx, cudaMallocAsync(&patches, sizeof(float) * (size_t)b * t * kdim, ctx->stream));
+    int r = op_im2col<float>(ctx, patches, images, b, img, patch);
+    if (r == VITRS_OK) r = op_patch_backward_reduce<float>(ctx, dwpe, dcls, dpatchb, dencoded, b, t, c);
+    if (r == VITRS_OK) {
+        GemmDesc g = {};
+        g.A = dencoded; g.a_rs = 1; g.a_ks = c;
+        g.B = patches; g.b_rs = 1; g.b_ks = kdim;
+        g.M = c; g.N = kdim; g.K = b * t;
+        g.epi.kind = EPI_ACCUM_F32;
+        g.epi.out = dpatchw; g.epi.ldo = kdim;
+        r = gemm_simt_f32(ctx, g);
+    }
+    cudaFreeAsync(patches, ctx->stream);
+    return r;
+}
+
+// ---- bf16 production mode -----------------------------------------------------------------
+#define B16(p) reinterpret_cast<bf16*>(p)
+#define CB16(p) reinterpret_cast<const bf16*>(p)
+
+int vitrs_residual_forward_bf16(vitrs_ctx* ctx, vitrs_bf16* out, const vitrs_bf16* a, const vitrs_bf16* b, int n) {
+    CTX_OR_FAIL(ctx);
+    return op_residual_forward<bf16>(ctx, B16(out), CB16(a), CB16(b), n);
+}
+int vitrs_matmul_forward_bf16(vitrs_ctx* ctx, vitrs_bf16* out, const vitrs_bf16* inp, const vitrs_bf16* weight, const float* bias,
+                              int b, int t, int c, int oc) {
+    CTX_OR_FAIL(ctx);
+    return matmul_forward_impl<bf16>(ctx, B16(out), CB16(inp), CB16(weight), bias, (long)b * t, c, oc);
+}
+int vitrs_attention_forward_bf16(vitrs_ctx* ctx, vitrs_bf16* out, float* lse, const vitrs_bf16* inp, int b, int t, int c, int nh,
+                                 int causal) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, out && lse && inp);
+    int r = op_attention_forward_tc(ctx, B16(out), lse, CB16(inp), b, t, c, nh, causal);
+    if (r == VITRS_ERR_UNSUPPORTED) r = op_attention_forward<bf16>(ctx, B16(out), nullptr, nullptr, lse, CB16(inp), b, t, c, nh, causal);
+    return r;
+}
+int vitrs_layernorm_forward_bf16(vitrs_ctx* ctx, vitrs_bf16* out, float* mean, float* rstd, const vitrs_bf16* inp,
+                                 const float* weight, const float* bias, int b, int t, int c) {
+    CTX_OR_FAIL(ctx);
+    if ((long)b * t == 0) return VITRS_OK;
+    VITRS_ARG(ctx, out && mean && rstd && inp && weight && bias && c > 0);
+    return op_layernorm_forward<bf16>(ctx, B16(out), mean, rstd, CB16(inp), weight, bias, (long)b * t, c);
+}
+int vitrs_gelu_forward_bf16(vitrs_ctx* ctx, vitrs_bf16* out, const vitrs_bf16* inp, int n) {
+    CTX_OR_FAIL(ctx);
+    return op_gelu_forward<bf16>(ctx, B16(out), CB16(inp), n);
+}
+int vitrs_residual_backward_bf16(vitrs_ctx* ctx, vitrs_bf16* d1, vitrs_bf16* d2, const vitrs_bf16* dout, int n) {
+    CTX_OR_FAIL(ctx);
+    return op_residual_backward<bf16>(ctx, B16(d1), B16(d2), CB16(dout), n);
+}
+int vitrs_matmul_backward_bf16(vitrs_ctx* ctx, vitrs_bf16* dinp, float* dweight, float* dbias, const vitrs_bf16* dout,
+                               const vitrs_bf16* inp, const vitrs_bf16* weight, int b, int t, int c, int oc) {
+    CTX_OR_FAIL(ctx);
+    return matmul_backward_impl<bf16>(ctx, B16(dinp), dweight, dbias, CB16(dout), CB16(inp), CB16(weight), (long)b * t, c, oc);
+}
+int vitrs_attention_backward_bf16(vitrs_ctx* ctx, vitrs_bf16* dinp, const vitrs_bf16* dout, const vitrs_bf16* out, const float* lse,
+                                  const vitrs_bf16* inp, int b, int t, int c, int nh, int causal) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, dinp && dout && lse && inp);
+    int r = out ? op_attention_backward_tc(ctx, B16(dinp), CB16(dout), CB16(out), CB16(inp), lse, b, t, c, nh, causal)
+                : VITRS_ERR_UNSUPPORTED;
+    if (r == VITRS_ERR_UNSUPPORTED)
+        r = op_attention_backward<bf16>(ctx, B16(dinp), nullptr, nullptr, CB16(dout), CB16(inp), nullptr, lse, b, t, c, nh, causal);
+    return r;
+}
+int vitrs_layernorm_backward_bf16(vitrs_ctx* ctx, vitrs_bf16* dinp, float* dweight, float* dbias, const vitrs_bf16* dout,
+                                  const vitrs_bf16* inp, const float* weight, const float* mean, const float* rstd, int b, int t,
+                                  int c) {
+    CTX_OR_FAIL(ctx);
+    if ((long)b * t == 0) return VITRS_OK;
+    VITRS_ARG(ctx, dinp && dweight && dbias && dout && inp && weight && mean && rstd && c > 0);
+    return op_layernorm_backward<bf16>(ctx, B16(dinp), dweight, dbias, CB16(dout), CB16(inp), weight, mean, rstd, (long)b * t, c,
+                                       nullptr);
+}
+int vitrs_gelu_backward_bf16(vitrs_ctx* ctx, vitrs_bf16* dinp, const vitrs_bf16* inp, const vitrs_bf16* dout, int n) {
+    CTX_OR_FAIL(ctx);
+    return op_gelu_backward<bf16>(ctx, B16(dinp), CB16(inp), CB16(dout), n);
+}
+
+int vitrs_gemm_bf16(vitrs_ctx* ctx, void* D, const vitrs_bf16* A, const vitrs_bf16* B, int M, int N, int K, int lda, int ldb,
+                    int ldd, int a_mn_major, int b_mn_major, int out_f32_accumulate) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, D && A && B && M >= 0 && N >= 0 && K >= 0);
+    GemmDesc g = {};
+    g.A = A; g.B = B;
+    g.a_rs = a_mn_major ? 1 : lda; g.a_ks = a_mn_major ? lda : 1;
+    g.b_rs = b_mn_major ? 1 : ldb; g.b_ks = b_mn_major ? ldb : 1;
+    g.M = M; g.N = N; g.K = K;
+    g.epi.kind = out_f32_accumulate ? EPI_ACCUM_F32 : EPI_NONE;
+    g.epi.out = D; g.epi.ldo = ldd;
+    return gemm_tc_bf16(ctx, g);
+}
+
+// ---- optimiser, init, casts ----------------------------------------------------------------
+int vitrs_sgd_step(vitrs_ctx* ctx, float* params, const float* grads, size_t n, float lr, vitrs_bf16* shadow) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, params && grads);
+    return op_sgd(ctx, params, grads, n, lr, B16(shadow));
+}
+int vitrs_adamw_step(vitrs_ctx* ctx, float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, vitrs_bf16* shadow) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, params && grads && m && v && step >= 1);
+    return op_adamw(ctx, params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, step, B16(shadow));
+}
+int vitrs_fill_uniform(vitrs_ctx* ctx, float* dst, size_t n, uint64_t seed, uint64_t stream, float lo, float hi) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, dst != nullptr || n == 0);
+    return op_fill_uniform(ctx, dst, n, seed, stream, lo, hi);
+}
+int vitrs_cast_f32_to_bf16(vitrs_ctx* ctx, vitrs_bf16* dst, const float* src, size_t n) {
+    CTX_OR_FAIL(ctx);
+    return op_cast_f32_bf16(ctx, B16(dst), src, n);
+}
+int vitrs_cast_bf16_to_f32(vitrs_ctx* ctx, float* dst, const vitrs_bf16* src, size_t n) {
+    CTX_OR_FAIL(ctx);
+    return op_cast_bf16_f32(ctx, dst, CB16(src), n);
+}
+
+}  // extern "C"
