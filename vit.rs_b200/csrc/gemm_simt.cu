@@ -1,15 +1,22 @@
-// gemm_simt.cu — plain SIMT FFMA GEMM with fp32 multiply and fp32 accumulate.
+// gemm_simt.cu — plain SIMT GEMM with fp32 multiply and fp32 accumulate.
 // This is verify mode's matmul (TF32's 10-bit mantissa cannot meet the 1e-4 gate) and the
 // route for the few GEMMs too small or too ragged for the tcgen05 kernel (the class head).
 // D[m,n] = sum_k A(m,k) * B(n,k) with arbitrary element strides, then the shared epilogue.
 // Replaces the three-loop matmul_forward / matmul_backward of train_vit.rs:384-398, 530-557.
+//
+// In fp32 the reference's arithmetic is reproduced exactly, not just its result: the
+// accumulator starts at the bias (train_vit.rs:389) or at the value being accumulated into
+// (`+=`, :538,552), k runs ascending, and each step is a rounded multiply followed by a rounded
+// add (Rust never contracts to FMA).  With the reference's all-positive init the sums are long
+// same-sign chains whose rounding alone is ~1e-4 of the result, so matching the order is what
+// makes the 1e-4 verify gate meaningful.
 #include "epilogue.cuh"
 
 namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16;
 
-template <typename T, bool FAST>
+template <typename T, bool FAST, bool EXACT>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
@@ -20,11 +27,23 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
     const long m0 = (long)blockIdx.y * BM;
     const int n0 = blockIdx.x * BN;
     const bool a_kfast = g.a_ks == 1, b_kfast = g.b_ks == 1;
+    const Epilogue& e = g.epi;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) {
+            const long m = m0 + ty * 4 + i;
+            const int n = n0 + tx * 4 + j;
+            float init = 0.f;
+            if (m < g.M && n < g.N) {
+                if (e.kind == EPI_ACCUM_F32) init = reinterpret_cast<const float*>(e.out)[m * e.ldo + n];
+                else if (e.accumulate) init = to_f32(reinterpret_cast<const T*>(e.out)[m * e.ldo + n]);
+                else if (e.bias && (e.kind == EPI_BIAS || e.kind == EPI_BIAS_GELU || e.kind == EPI_BIAS_RESIDUAL || e.kind == EPI_PATCH))
+                    init = e.bias[n];
+            }
+            acc[i][j] = init;
+        }
 
     for (int k0 = 0; k0 < g.K; k0 += BK) {
 #pragma unroll
@@ -51,7 +70,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j)
+                    acc[i][j] = EXACT ? __fadd_rn(acc[i][j], __fmul_rn(a[i], b[j])) : fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
@@ -62,20 +82,28 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n < g.N) epi_store_scalar<T, FAST>(g.epi, m, n, acc[i][j]);
+            if (n >= g.N) continue;
+            if (e.kind == EPI_ACCUM_F32) {
+                reinterpret_cast<float*>(e.out)[m * e.ldo + n] = acc[i][j];  // the old value is already in acc
+            } else {
+                Epilogue e2 = e;  // bias / old value were the accumulator's starting point
+                e2.bias = nullptr;
+                e2.accumulate = 0;
+                epi_store_scalar<T, FAST>(e2, m, n, acc[i][j]);
+            }
         }
     }
 }
 
-template <typename T, bool FAST> int launch(vitrs_ctx* ctx, const GemmDesc& g) {
+template <typename T, bool FAST, bool EXACT> int launch(vitrs_ctx* ctx, const GemmDesc& g) {
     if (g.M <= 0 || g.N <= 0) return VITRS_OK;
     dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
-    gemm_simt_kernel<T, FAST><<<grid, 256, 0, ctx->stream>>>(g);
+    gemm_simt_kernel<T, FAST, EXACT><<<grid, 256, 0, ctx->stream>>>(g);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
 }
 
 }  // namespace
 
-int gemm_simt_f32(vitrs_ctx* ctx, const GemmDesc& g) { return launch<float, false>(ctx, g); }
-int gemm_simt_bf16(vitrs_ctx* ctx, const GemmDesc& g) { return launch<bf16, true>(ctx, g); }
+int gemm_simt_f32(vitrs_ctx* ctx, const GemmDesc& g) { return launch<float, false, true>(ctx, g); }
+int gemm_simt_bf16(vitrs_ctx* ctx, const GemmDesc& g) { return launch<bf16, true, false>(ctx, g); }
