@@ -30,15 +30,26 @@ def to_dev(images, labels):
 SMALL_HS64 = dict(image_size=64, patch_size=16, channels=128, num_layers=2, num_heads=2, num_classes=16)
 
 
-@pytest.mark.parametrize("cfg_name,b,causal", [("tiny", 4, 0), ("tiny", 3, 1), (SMALL_HS64, 2, 0)])
-def test_f32_step_matches_oracle(vitrs, cfg_name, b, causal):
+# init_mode 1 (symmetric weights) is well conditioned: the oracle itself is within ~1e-6 of exact arithmetic and
+# every tensor must agree to 1e-4.  init_mode 0 is the reference's all-positive init (rusty_vit.rs:864-903):
+# its matmuls are long cancelling sums and the oracle's OWN rounding error against float64 is 1e-4 of the
+# result (DESIGN.md "fp32 parity and conditioning"), so there loss and logits are held to 1e-4 and the
+# cancellation-prone tensors to 5e-4.
+@pytest.mark.parametrize("cfg_name,b,causal,init_mode", [("tiny", 4, 0, 1), ("tiny", 3, 1, 1), (SMALL_HS64, 2, 0, 1),
+                                                         ("tiny", 4, 0, 0), (SMALL_HS64, 2, 0, 0)])
+def test_f32_step_matches_oracle(vitrs, cfg_name, b, causal, init_mode):
     cfg = po.CONFIGS[cfg_name] if isinstance(cfg_name, str) else cfg_name
-    ref = po.ViT(cfg_name, seed=1337, causal=causal)
-    m = vitrs.ViT(cfg_name, max_batch=b, mode=vitrs.MODE_F32, seed=1337, causal=causal)
+    TOL_ALL = TOL_F32 if init_mode == 1 else 5e-4
+    ref = po.ViT(cfg_name, seed=1337, causal=causal, init_mode=init_mode)
+    m = vitrs.ViT(cfg_name, max_batch=b, mode=vitrs.MODE_F32, seed=1337, causal=causal, init_mode=init_mode)
     assert m.num_parameters == ref.num_parameters
     # init_parameters is bit-identical (shared counter generator, DEVIATIONS D9)
     assert np.array_equal(m.params_flat().cpu().numpy(), ref.params_flat())
     for step in range(3):
+        # every step is compared from identical weights: AdamW's g/sqrt(v) turns ~0 gradients into +-lr
+        # updates whose sign is rounding noise, which would otherwise leak into the next step's comparison
+        m.params_flat().copy_(torch.from_numpy(ref.params_flat()))
+        m.sync_parameters()
         images, labels = po.synthetic_batch(cfg, b, step=step)
         ref_loss = ref.forward(images, labels); ref.zero_grad(); ref.backward()
         m.zero_grad(); m.forward(*to_dev(images, labels)); m.backward()
@@ -46,14 +57,15 @@ def test_f32_step_matches_oracle(vitrs, cfg_name, b, causal):
         if step == 0:
             for name in po.ACT_NAMES:
                 got, want = m.act(name), ref.act(name)
-                assert got is not None and relerr(got.cpu().numpy(), want[:got.numel()]) <= TOL_F32, name
+                tol = TOL_F32 if name in ("logits", "probs", "losses") else TOL_ALL
+                assert got is not None and relerr(got.cpu().numpy(), want[:got.numel()]) <= tol, name
             for name in po.ACT_NAMES:
                 got, want = m.grad_act(name), ref.grad_act(name)
                 if name in ("probs", "lnf_mean", "lnf_rstd", "ln1_mean", "ln1_rstd", "ln2_mean", "ln2_rstd"):
                     continue  # no gradient flows into these buffers in either implementation
-                assert relerr(got.cpu().numpy(), want[:got.numel()]) <= TOL_F32, "d" + name
+                assert relerr(got.cpu().numpy(), want[:got.numel()]) <= TOL_ALL, "d" + name
         for name in po.PARAM_NAMES:
-            assert relerr(m.grad(name).cpu().numpy(), ref.grad(name)) <= TOL_F32, name
+            assert relerr(m.grad(name).cpu().numpy(), ref.grad(name)) <= TOL_ALL, name
         ref.update(1e-3); m.update(1e-3)
     d = np.abs(m.params_flat().cpu().numpy() - ref.params_flat())
     assert d.max() < 2e-4 and np.percentile(d, 99.9) < 1e-5  # AdamW amplifies rounding where g ~ 0
@@ -115,12 +127,12 @@ def test_bf16_step_within_tolerance(vitrs, cfg_name, b):
 
 def test_bf16_tracks_oracle_loss_curve_100_steps(vitrs):
     cfg = po.CONFIGS["tiny"]
-    b, steps, lr = 8, 100, 1e-3
+    b, steps, lr = 8, 100, 3e-4
     ref = po.ViT("tiny", seed=1337, init_mode=1)
     m = vitrs.ViT("tiny", max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)
     ref_curve, got_curve = [], []
     for step in range(steps):
-        images, labels = po.synthetic_batch(cfg, b, step=step % 4)  # 4 repeating batches: the loss must fall
+        images, labels = po.synthetic_batch(cfg, b, step=step % 16)  # 16 repeating batches: the loss must fall
         ref_curve.append(ref.forward(images, labels)); ref.zero_grad(); ref.backward(); ref.update(lr)
         d_images, d_labels = to_dev(images, labels)
         m.train_step(d_images, d_labels, lr)
@@ -128,13 +140,8 @@ def test_bf16_tracks_oracle_loss_curve_100_steps(vitrs):
     ref_curve, got_curve = np.array(ref_curve), np.array(got_curve)
     assert ref_curve[-4:].mean() < ref_curve[:4].mean() - 0.05  # it learns
     dev_ = np.abs(got_curve - ref_curve)
-    scale = ref_curve.max()
-    msg = f"max {dev_.max():.4f} mean {dev_.mean():.4f} first-half max {dev_[:50].max():.4f} last {got_curve[-4:]} vs {ref_curve[-4:]}"
-    # pointwise within 2e-2 while the two trajectories are still the same trajectory (first 50 steps);
-    # afterwards AdamW on 4 memorised batches is chaotic, so the curve is tracked on average
-    assert dev_[:50].max() <= TOL_BF16 * scale, msg
-    assert dev_.mean() <= 0.5 * TOL_BF16 * scale, msg
-    assert abs(got_curve[-8:].mean() - ref_curve[-8:].mean()) <= 0.1 * ref_curve[-8:].mean() + 0.01, msg
+    msg = f"max {dev_.max():.4f} mean {dev_.mean():.4f} last {got_curve[-4:]} vs {ref_curve[-4:]}"
+    assert dev_.max() <= TOL_BF16 * ref_curve.max(), msg  # every one of the 100 steps within 2e-2
     m.close()
 
 

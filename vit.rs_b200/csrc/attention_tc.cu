@@ -1,12 +1,442 @@
-// attention_tc.cu — tensor-core (tcgen05 / TMEM) fused attention for head size 64.
+// attention_tc.cu — fused multi-head attention on the sm_100a tensor path (tcgen05.mma, TMEM
+// accumulators, TMA loads) for head size 64 and sequences of up to 256 tokens (ViT-Ti/S/B at
+// patch 16: T = 197).  Replaces attention_forward / attention_backward of train_vit.rs:400-451,
+// 559-601: no T x T buffer ever reaches HBM; forward keeps lse[B,NH,T], backward recomputes the
+// probabilities from it and uses D = rowsum(dO * O) in place of the reference's O(T^3)
+// softmax-Jacobian loop (tv:583-589).
+//
+// One CTA owns one (batch, head).  Q, K, V (and dO) tiles of 128 tokens x 64 are read straight
+// out of the packed qkv[B,T,3C] activation by 3-D TMA boxes (row pitch 3C, column offset
+// {0,C,2C} + h*64, rows >= T zero-filled), so the reference layout needs no permute kernels.
+//
+// forward   S_i = Q_i K^T  (M=128 queries, N=T keys, fp32 in TMEM)  ->  one thread per query row:
+//           max / exp2 / sum from TMEM, P_i (bf16) into a 128B-swizzled shared tile  ->
+//           O_i = P_i V  ->  O_i / sum to out[B,T,C] at column h*64, lse.
+//           The two 128-row query tiles run on two 4-warp groups concurrently.
+// backward  transposed orientation, keys on TMEM lanes: for every (key tile j, query tile i)
+//           S^T = K_j Q_i^T and dP^T = V_j dO_i^T  ->  P^T = exp2(S^T*c - lse), dS^T = P^T o (dP^T - D) * scale
+//           written once to shared memory, where the same bytes serve as the K-major A operand of
+//           dV_j += P^T dO_i and dK_j += dS^T Q_i and as the MN-major A operand of dQ_i += dS K_j.
+//           dV_j, dK_j and both dQ_i accumulate in TMEM; nothing is reduced through global memory.
 #include "tc_ptx.cuh"
 
-int op_attention_forward_tc(vitrs_ctx* ctx, bf16* out, float* lse, const bf16* qkv, int b, int t, int c, int nh, int causal) {
-    (void)ctx; (void)out; (void)lse; (void)qkv; (void)b; (void)t; (void)c; (void)nh; (void)causal;
-    return VITRS_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int TILE = 128;             // tokens per tile
+constexpr int HS = 64;                // head size
+constexpr int TILE_BYTES = TILE * HS * 2;  // 16 KB: one TMA box, 128 rows of 128 bytes
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
 }
-int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const bf16* out, const bf16* qkv, const float* lse,
-                             int b, int t, int c, int nh, int causal) {
-    (void)ctx; (void)dqkv; (void)dout; (void)out; (void)qkv; (void)lse; (void)b; (void)t; (void)c; (void)nh; (void)causal;
-    return VITRS_ERR_UNSUPPORTED;
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// 16-byte chunk `c8` (8 bf16) of row `row` inside a [rows][64] bf16 tile with the 128-byte swizzle
+// that TMA and the UMMA descriptors use (chunk index xor row mod 8); tile base is 1024-aligned
+__device__ __forceinline__ uint32_t sw128(uint32_t tile_base, int row, int c8) {
+    return tile_base + row * 128 + ((c8 ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_addr, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_addr), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+// 32 fp32 values -> bf16 -> 64 contiguous bytes of global memory (optionally added to what is there)
+__device__ __forceinline__ void store_row32(bf16* dst, const uint32_t* v, float mul, bool accumulate) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]) * mul;
+        if (accumulate) {
+            Vec16<bf16> old;
+            old.load(dst + g * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += old.get(j);
+        }
+        uint4 o;
+        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+        *reinterpret_cast<uint4*>(dst + g * 8) = o;
+    }
+}
+
+// =============================================== forward ==========================================
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, float* __restrict__ lse, int T, int C, int NH,
+                   int causal, int NT, int NK, uint32_t tmem_cols) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const int NKB = (NK + 63) >> 6;  // 64-key blocks of the P tile
+    const uint32_t sQ = base, sK = sQ + NT * TILE_BYTES, sV = sK + NT * TILE_BYTES, sP = sV + NT * TILE_BYTES;
+    const uint32_t p_bytes = NKB * TILE_BYTES;
+    const uint32_t bar0 = sP + NT * p_bytes;
+    const uint32_t bar_load = bar0, bar_s = bar0 + 8, bar_o = bar0 + 24;  // bar_s[2], bar_o[2]
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 40);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int bh = blockIdx.x, b = bh / NH, h = bh - b * NH;
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        mbar_init(bar_load, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_s + 8 * i, 1); mbar_init(bar_o + 8 * i, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(smem_u32((const void*)slot), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+
+    if (tid == 0) {
+        mbar_expect_tx(bar_load, (uint32_t)(3 * NT * TILE_BYTES));
+        for (int i = 0; i < NT; ++i) {
+            tma_load_3d(sQ + i * TILE_BYTES, &tm_qkv, bar_load, h * HS, i * TILE, b);
+            tma_load_3d(sK + i * TILE_BYTES, &tm_qkv, bar_load, C + h * HS, i * TILE, b);
+            tma_load_3d(sV + i * TILE_BYTES, &tm_qkv, bar_load, 2 * C + h * HS, i * TILE, b);
+        }
+    }
+    const int grp = warp >> 2;  // query tile handled by this 4-warp group
+    if (grp < NT) {
+        const int r = tid & 127;
+        const bool leader = r == 0;
+        const uint32_t region = tmem_base + (uint32_t)(grp * 256);
+        const uint32_t lane_addr = region + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t sPi = sP + grp * p_bytes;
+        if (leader) {
+            mbar_wait(bar_load, 0);
+            tc_fence_after();
+            const uint32_t idesc = make_idesc(TILE, NK, 0, 0);
+#pragma unroll
+            for (int k = 0; k < HS / 16; ++k)
+                umma_bf16(region, make_desc(sQ + grp * TILE_BYTES + k * 32, 0, 1024), make_desc(sK + k * 32, 0, 1024), idesc, k > 0);
+            umma_commit(bar_s + 8 * grp);
+        }
+        mbar_wait(bar_s + 8 * grp, 0);
+        tc_fence_after();
+        const int q = grp * TILE + r;
+        const int kend = causal ? min(T, q + 1) : T;
+        const int nchunks = (NK + 31) >> 5;
+        const float sl2 = kLog2e / sqrtf((float)HS);
+        float mx = -INFINITY;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + ch * 32, v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (ch * 32 + c < kend) mx = fmaxf(mx, __uint_as_float(v[c]));
+        }
+        float sum = 0.f;
+        const float mxs = mx * sl2;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + ch * 32, v);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float p[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = ch * 32 + g * 8 + j;
+                    p[j] = k < kend ? ex2(__uint_as_float(v[g * 8 + j]) * sl2 - mxs) : 0.f;
+                    sum += p[j];
+                }
+                const int kcol = ch * 32 + g * 8;
+                st_shared_v4(sw128(sPi + (kcol >> 6) * TILE_BYTES, r, (kcol & 63) >> 3), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]),
+                             pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+            }
+        }
+        fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core's async proxy
+        tc_fence_before();
+        named_bar_sync(1 + grp, 128);
+        if (leader) {
+            tc_fence_after();
+            const uint32_t idesc = make_idesc(TILE, HS, 0, 1);  // B = V is MN-major: [key rows][64]
+            for (int k16 = 0; k16 < NK / 16; ++k16)
+                umma_bf16(region, make_desc(sPi + (k16 >> 2) * TILE_BYTES + (k16 & 3) * 32, 0, 1024),
+                          make_desc(sV + k16 * 2048, TILE_BYTES, 1024), idesc, k16 > 0);
+            umma_commit(bar_o + 8 * grp);
+        }
+        mbar_wait(bar_o + 8 * grp, 0);
+        tc_fence_after();
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + half * 32, v);
+            if (q < T) store_row32(out + ((long)b * T + q) * C + h * HS + half * 32, v, inv, false);
+        }
+        if (q < T) lse[(long)bh * T + q] = mx * (1.0f / sqrtf((float)HS)) + logf(sum);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// D[b,h,q] = sum_i dO[b,q,h*64+i] * O[b,q,h*64+i]: one warp per token, 8 lanes per head
+__global__ void attn_bwd_prep_kernel(float* __restrict__ dsum, const bf16* __restrict__ dout, const bf16* __restrict__ out, int B, int T,
+                                     int C, int NH) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (long)B * T) return;
+    const int b = (int)(row / T), q = (int)(row - (long)b * T);
+    for (int c8 = lane; c8 < C / 8; c8 += 32) {
+        Vec16<bf16> x, y;
+        x.load(dout + row * C + c8 * 8);
+        y.load(out + row * C + c8 * 8);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fmaf(x.get(j), y.get(j), s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if ((lane & 7) == 0) dsum[((long)b * NH + (c8 >> 3)) * T + q] = s;
+    }
+}
+
+// =============================================== backward =========================================
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, bf16* __restrict__ dqkv,
+                   const float* __restrict__ lse, const float* __restrict__ dsum, int T, int C, int NH, int causal, int NT,
+                   int accumulate) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sQ = base, sK = sQ + NT * TILE_BYTES, sV = sK + NT * TILE_BYTES, sdO = sV + NT * TILE_BYTES;
+    const uint32_t sPT = sdO + NT * TILE_BYTES;   // [2 blocks of 64 queries][128 keys][128 B]
+    const uint32_t sdST = sPT + 2 * TILE_BYTES;
+    const uint32_t sStat = sdST + 2 * TILE_BYTES;  // lse*log2e [256], D [256]
+    const uint32_t bar0 = sStat + 2 * 256 * 4;
+    const uint32_t bar_load = bar0, bar_s = bar0 + 8, bar_acc = bar0 + 16;
+    float* stat = reinterpret_cast<float*>(gen + (sStat - base));
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 24);
+    constexpr uint32_t TMEM_COLS = 512;
+    constexpr uint32_t cST = 0, cDPT = 128, cDV = 256, cDK = 320, cDQ = 384;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int bh = blockIdx.x, b = bh / NH, h = bh - b * NH;
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_do);
+        mbar_init(bar_load, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(smem_u32((const void*)slot), TMEM_COLS);
+    for (int i = tid; i < 256; i += kThreads) {
+        stat[i] = i < T ? lse[(long)bh * T + i] * kLog2e : 0.f;
+        stat[256 + i] = i < T ? dsum[(long)bh * T + i] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+    const bool leader = tid == 0;
+    if (leader) {
+        mbar_expect_tx(bar_load, (uint32_t)(4 * NT * TILE_BYTES));
+        for (int i = 0; i < NT; ++i) {
+            tma_load_3d(sQ + i * TILE_BYTES, &tm_qkv, bar_load, h * HS, i * TILE, b);
+            tma_load_3d(sK + i * TILE_BYTES, &tm_qkv, bar_load, C + h * HS, i * TILE, b);
+            tma_load_3d(sV + i * TILE_BYTES, &tm_qkv, bar_load, 2 * C + h * HS, i * TILE, b);
+            tma_load_3d(sdO + i * TILE_BYTES, &tm_do, bar_load, h * HS, i * TILE, b);
+        }
+        mbar_wait(bar_load, 0);
+    }
+    const int r = tid & 127;                 // TMEM lane = key (S^T phase) or output row (epilogues)
+    const int half = warp >> 2;              // which half of the columns this thread handles
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const float scale = 1.0f / sqrtf((float)HS);
+    const float sl2 = kLog2e * scale;
+    uint32_t s_phase = 0, acc_phase = 0;
+    uint32_t dq_started = 0;  // bit i: dQ_i already holds a partial sum
+
+    for (int j = 0; j < NT; ++j) {           // key tile
+        const int key = j * TILE + r;
+        const int nk16 = (min(TILE, T - j * TILE) + 15) & ~15;  // keys of this tile, padded to the MMA K step
+        bool first_i = true;
+        for (int i = causal ? j : 0; i < NT; ++i) {  // query tile (causal: tiles left of the diagonal are empty)
+            const int nq = min(TILE, T - i * TILE);  // valid queries in the tile
+            const int nq16 = (nq + 15) & ~15;
+            if (leader) {
+                tc_fence_after();
+                const uint32_t idesc = make_idesc(TILE, nq16, 0, 0);
+#pragma unroll
+                for (int k = 0; k < HS / 16; ++k)  // S^T = K_j Q_i^T
+                    umma_bf16(tmem_base + cST, make_desc(sK + j * TILE_BYTES + k * 32, 0, 1024),
+                              make_desc(sQ + i * TILE_BYTES + k * 32, 0, 1024), idesc, k > 0);
+#pragma unroll
+                for (int k = 0; k < HS / 16; ++k)  // dP^T = V_j dO_i^T
+                    umma_bf16(tmem_base + cDPT, make_desc(sV + j * TILE_BYTES + k * 32, 0, 1024),
+                              make_desc(sdO + i * TILE_BYTES + k * 32, 0, 1024), idesc, k > 0);
+                umma_commit(bar_s);  // also covers the dV/dK/dQ MMAs of the previous iteration (they read sPT / sdST)
+            }
+            mbar_wait(bar_s, s_phase);
+            s_phase ^= 1u;
+            tc_fence_after();
+            // columns (queries) are split between the two threads that share a TMEM lane
+            const int nchunks = (nq16 + 31) >> 5;
+            const int ch0 = half == 0 ? 0 : (nchunks + 1) >> 1, ch1 = half == 0 ? (nchunks + 1) >> 1 : nchunks;
+            for (int ch = ch0; ch < ch1; ++ch) {
+                uint32_t s[32], dp[32];
+                tmem_ld32(tmem_base + lane_off + cST + ch * 32, s);
+                tmem_ld32(tmem_base + lane_off + cDPT + ch * 32, dp);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float p[8], ds[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int qc = ch * 32 + g * 8 + c;  // query within the tile
+                        const int q = i * TILE + qc;
+                        const bool live = key < T && qc < nq && (!causal || key <= q);
+                        const float pv = live ? ex2(__uint_as_float(s[g * 8 + c]) * sl2 - stat[q & 255]) : 0.f;
+                        p[c] = pv;
+                        ds[c] = pv * (__uint_as_float(dp[g * 8 + c]) - stat[256 + (q & 255)]) * scale;
+                    }
+                    const int qcol = ch * 32 + g * 8;
+                    const uint32_t off = (qcol >> 6) * TILE_BYTES;
+                    const int c8 = (qcol & 63) >> 3;
+                    st_shared_v4(sw128(sPT + off, r, c8), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
+                                 pack_bf16(p[6], p[7]));
+                    st_shared_v4(sw128(sdST + off, r, c8), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
+                                 pack_bf16(ds[6], ds[7]));
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (leader) {
+                tc_fence_after();
+                const uint32_t idesc_kk = make_idesc(TILE, HS, 0, 1);  // A K-major (P^T / dS^T rows = keys), B MN-major
+                for (int k16 = 0; k16 < nq16 / 16; ++k16) {            // contraction over the queries of tile i
+                    const uint32_t aoff = (k16 >> 2) * TILE_BYTES + (k16 & 3) * 32;
+                    umma_bf16(tmem_base + cDV, make_desc(sPT + aoff, 0, 1024), make_desc(sdO + i * TILE_BYTES + k16 * 2048, TILE_BYTES, 1024),
+                              idesc_kk, (!first_i || k16 > 0) ? 1u : 0u);
+                    umma_bf16(tmem_base + cDK, make_desc(sdST + aoff, 0, 1024), make_desc(sQ + i * TILE_BYTES + k16 * 2048, TILE_BYTES, 1024),
+                              idesc_kk, (!first_i || k16 > 0) ? 1u : 0u);
+                }
+                // dQ_i += dS K_j: A = dS^T read MN-major (m = query contiguous, 64-query atoms TILE_BYTES apart), contraction over keys
+                const uint32_t idesc_mn = make_idesc(TILE, HS, 1, 1);
+                for (int k16 = 0; k16 < nk16 / 16; ++k16)
+                    umma_bf16(tmem_base + cDQ + i * HS, make_desc(sdST + k16 * 2048, TILE_BYTES, 1024),
+                              make_desc(sK + j * TILE_BYTES + k16 * 2048, TILE_BYTES, 1024), idesc_mn, (((dq_started >> i) & 1u) || k16 > 0) ? 1u : 0u);
+                dq_started |= 1u << i;
+            }
+            first_i = false;
+        }
+        // dV_j, dK_j are complete once every MMA issued so far has retired
+        if (leader) umma_commit(bar_acc);
+        mbar_wait(bar_acc, acc_phase);
+        acc_phase ^= 1u;
+        tc_fence_after();
+        {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + lane_off + cDV + half * 32, v);
+            if (key < T) store_row32(dqkv + ((long)b * T + key) * 3 * C + 2 * C + h * HS + half * 32, v, 1.0f, accumulate);
+            tmem_ld32(tmem_base + lane_off + cDK + half * 32, v);
+            if (key < T) store_row32(dqkv + ((long)b * T + key) * 3 * C + C + h * HS + half * 32, v, 1.0f, accumulate);
+        }
+        tc_fence_before();  // the next key tile's first dV/dK MMA overwrites these columns after the next __syncthreads
+    }
+    // dQ: all MMAs were covered by the last bar_acc commit
+    for (int i = 0; i < NT; ++i) {
+        const int q = i * TILE + r;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_off + cDQ + i * HS + half * 32, v);
+        if (q < T) store_row32(dqkv + ((long)b * T + q) * 3 * C + h * HS + half * 32, v, 1.0f, accumulate);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+int encode_map3d(vitrs_ctx* ctx, CUtensorMap* map, const void* basep, uint64_t cols, uint64_t rows, uint64_t batch) {
+    cuuint64_t dims[3] = {cols, rows, batch};
+    cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
+    cuuint32_t box[3] = {HS, TILE, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(basep), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return vitrs_set_error(ctx, VITRS_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d): cols=%llu rows=%llu batch=%llu", (int)r,
+                               (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)batch);
+    return VITRS_OK;
+}
+
+bool tc_shape_ok(const void* a, const void* b_, int t, int c, int nh) {
+    return nh > 0 && c % nh == 0 && c / nh == HS && t >= 1 && t <= 2 * TILE && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b_ & 15) == 0;
+}
+
+}  // namespace
+
+int op_attention_forward_tc(vitrs_ctx* ctx, bf16* out, float* lse, const bf16* qkv, int b, int t, int c, int nh, int causal) {
+    if (!tc_shape_ok(out, qkv, t, c, nh)) return VITRS_ERR_UNSUPPORTED;
+    if (b <= 0) return VITRS_OK;
+    CUtensorMap tm;
+    VITRS_TRY(encode_map3d(ctx, &tm, qkv, 3 * (uint64_t)c, t, b));
+    const int NT = (t + TILE - 1) / TILE;
+    const int NK = (t + 15) & ~15;
+    const int NKB = (NK + 63) >> 6;
+    const size_t smem = (size_t)NT * 3 * TILE_BYTES + (size_t)NT * NKB * TILE_BYTES + 64 + 1024;
+    const uint32_t tmem_cols = NT == 1 ? 128 : 512;
+    static size_t configured = 0;
+    if (smem > configured) {
+        VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    attn_fwd_tc_kernel<<<b * nh, kThreads, smem, ctx->stream>>>(tm, out, lse, t, c, nh, causal, NT, NK, tmem_cols);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+
+int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const bf16* out, const bf16* qkv, const float* lse, int b,
+                             int t, int c, int nh, int causal, int accumulate) {
+    if (!tc_shape_ok(dqkv, qkv, t, c, nh) || ((uintptr_t)dout & 15) || ((uintptr_t)out & 15)) return VITRS_ERR_UNSUPPORTED;
+    if (b <= 0) return VITRS_OK;
+    VITRS_TRY(vitrs_ensure_scratch(ctx, (size_t)b * nh * t));
+    float* dsum = ctx->scratch;
+    attn_bwd_prep_kernel<<<ceil_div((long)b * t, 8), 256, 0, ctx->stream>>>(dsum, dout, out, b, t, c, nh);
+    VITRS_LAUNCHED(ctx);
+    CUtensorMap tm_qkv, tm_do;
+    VITRS_TRY(encode_map3d(ctx, &tm_qkv, qkv, 3 * (uint64_t)c, t, b));
+    VITRS_TRY(encode_map3d(ctx, &tm_do, dout, (uint64_t)c, t, b));
+    const int NT = (t + TILE - 1) / TILE;
+    const size_t smem = (size_t)NT * 4 * TILE_BYTES + 4 * TILE_BYTES + 2 * 256 * 4 + 64 + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    attn_bwd_tc_kernel<<<b * nh, kThreads, smem, ctx->stream>>>(tm_qkv, tm_do, dqkv, lse, dsum, t, c, nh, causal, NT, accumulate);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
 }

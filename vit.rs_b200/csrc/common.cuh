@@ -220,7 +220,7 @@ template <typename T> int op_attention_backward(vitrs_ctx*, T* dqkv, float* dpre
 // production attention (tensor cores); same contracts
 int op_attention_forward_tc(vitrs_ctx*, bf16* out, float* lse, const bf16* qkv, int b, int t, int c, int nh, int causal);
 int op_attention_backward_tc(vitrs_ctx*, bf16* dqkv, const bf16* dout, const bf16* out, const bf16* qkv, const float* lse,
-                             int b, int t, int c, int nh, int causal);
+                             int b, int t, int c, int nh, int causal, int accumulate);
 
 // patch embedding pieces (patch_embed.cu): im2col rows are tokens, [B*T, 3*p*p], CLS rows zero
 template <typename T> int op_im2col(vitrs_ctx*, T* patches, const float* images, int b, int img, int patch);

@@ -428,7 +428,7 @@ int backward_bf16(vitrs_model* m) {
                                               rows, C, G(m, P_ATTPROJB) + l * C));
         VITRS_TRY((gemm_dx<bf16>(ctx, dln, dres, S(m, P_ATTPROJW) + (long)l * C * C, rows, C, C, EPI_NONE, nullptr, 0)));  // datty
         VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_ATTPROJW) + (long)l * C * C, dres, atty, rows, C, C)));
-        int r = op_attention_backward_tc(ctx, dqkv, dln, atty, qkv, lse, d.B, d.T, C, d.NH, m->cfg.causal);
+        int r = op_attention_backward_tc(ctx, dqkv, dln, atty, qkv, lse, d.B, d.T, C, d.NH, m->cfg.causal, 0);
         if (r == VITRS_ERR_UNSUPPORTED) {
             VITRS_CUDA(ctx, cudaMemsetAsync(dqkv, 0, sizeof(bf16) * (size_t)btc * 3, ctx->stream));
             r = op_attention_backward<bf16>(ctx, dqkv, nullptr, nullptr, dln, qkv, nullptr, lse, d.B, d.T, C, d.NH, m->cfg.causal);

@@ -233,7 +233,7 @@ int vitrs_attention_backward_bf16(vitrs_ctx* ctx, vitrs_bf16* dinp, const vitrs_
                                   const vitrs_bf16* inp, int b, int t, int c, int nh, int causal) {
     CTX_OR_FAIL(ctx);
     VITRS_ARG(ctx, dinp && dout && lse && inp);
-    int r = out ? op_attention_backward_tc(ctx, B16(dinp), CB16(dout), CB16(out), CB16(inp), lse, b, t, c, nh, causal)
+    int r = out ? op_attention_backward_tc(ctx, B16(dinp), CB16(dout), CB16(out), CB16(inp), lse, b, t, c, nh, causal, 1)
                 : VITRS_ERR_UNSUPPORTED;
     if (r == VITRS_ERR_UNSUPPORTED)
         r = op_attention_backward<bf16>(ctx, B16(dinp), nullptr, nullptr, CB16(dout), CB16(inp), nullptr, lse, b, t, c, nh, causal);
