@@ -37,29 +37,134 @@ struct SmemLayout {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;  // 4 epilogue warps x [32 rows][128 B]
+    static constexpr int STAGING_BYTES = 4 * 32 * 128;
+    static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
 };
 
-// 8 consecutive output columns of one row: epilogue math, bf16 pack, 16-byte store
-template <bool FAST>
-__device__ __forceinline__ void epi_store8(const Epilogue& e, long m, int n, const uint32_t* acc_bits) {
-    const long orow = epi_out_row(e, m);
-    bf16* out = reinterpret_cast<bf16*>(e.out) + orow * e.ldo + n;
-    Vec16<bf16> aux, old, res, res2;
-    if (epi_needs_aux(e.kind)) aux.load(reinterpret_cast<const bf16*>(e.aux) + m * e.ldo + n);
-    if (e.accumulate) old.load(out);
+// ---- epilogue: one warp, its 32 accumulator rows, one 64-column chunk ------------------------------
+// The accumulator row of a thread (TMEM lane) is contiguous along n, but a warp's 32 rows are ld
+// elements apart in global memory, so both directions go through a warp-private [32][128 B]
+// shared tile (16-byte chunks xor-swizzled by row): global traffic is whole 128-byte lines, 4 rows per
+// instruction, and the tile is read / written by row owners without bank conflicts.
+__device__ __forceinline__ uint32_t stage_addr(uint32_t stage, int row, int c8) { return stage + row * 128 + ((c8 ^ (row & 7)) << 4); }
+
+// rows [m_base, m_base+32) x columns [n_base, n_base+64) of a bf16 matrix -> the staging tile
+__device__ __forceinline__ void stage_load(uint32_t stage, const bf16* src, long ld, long m_base, int n_base, int M, int N, int lane) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float second = 0.f;
-        float a = epi_needs_aux(e.kind) ? aux.get(j) : 0.f;
-        float v = epi_value<bf16, FAST>(e, m, n + j, __uint_as_float(acc_bits[j]), a, &second);
-        if (e.accumulate) v += old.get(j);
-        res.set(j, v);
-        res2.set(j, second);
+    for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3), c8 = lane & 7;
+        const long gm = m_base + row;
+        const int gn = n_base + c8 * 8;
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (gm < M && gn < N) x = *reinterpret_cast<const uint4*>(src + gm * ld + gn);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(stage, row, c8)), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
     }
-    res.store(out);
-    if (e.kind == EPI_BIAS_GELU) res2.store(reinterpret_cast<bf16*>(e.out2) + orow * e.ldo + n);
+}
+__device__ __forceinline__ void stage_store(uint32_t stage, bf16* dst, long ld, long m_base, int n_base, int M, int N, int lane) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3), c8 = lane & 7;
+        const long gm = m_base + row;
+        const int gn = n_base + c8 * 8;
+        uint4 x;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(stage_addr(stage, row, c8)) : "memory");
+        if (gm < M && gn < N) *reinterpret_cast<uint4*>(dst + gm * ld + gn) = x;
+    }
+}
+// this thread's row (= lane) of the staging tile: 64 bf16 -> fp32
+__device__ __forceinline__ void stage_read_row(uint32_t stage, int lane, float (&f)[64]) {
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t x[4];
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(stage_addr(stage, lane, c8)) : "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f[c8 * 8 + 2 * j] = __uint_as_float(x[j] << 16);
+            f[c8 * 8 + 2 * j + 1] = __uint_as_float(x[j] & 0xFFFF0000u);
+        }
+    }
+}
+__device__ __forceinline__ void stage_write_row(uint32_t stage, int lane, const float (&f)[64]) {
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(f[c8 * 8 + 2 * j], f[c8 * 8 + 2 * j + 1]);
+            x[j] = *reinterpret_cast<uint32_t*>(&v);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(stage, lane, c8)), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]) : "memory");
+    }
+}
+
+// KIND is a compile-time constant here: the per-element code is straight-line (a runtime switch inside the
+// element loop is if-converted by the compiler and every output then pays for every epilogue kind)
+template <int KIND>
+__device__ __forceinline__ void epilogue_chunk(const Epilogue& e, uint32_t stage, uint32_t taddr, long m_base, int n_base, int M, int N, int lane) {
+    float acc[64];
+    {
+        uint32_t v[32];
+        tmem_ld32(taddr, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+        tmem_ld32(taddr + 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[32 + j] = __uint_as_float(v[j]);
+    }
+    if (n_base >= N) return;  // warp-uniform
+    const long m = m_base + lane;
+    bf16* out = reinterpret_cast<bf16*>(e.out);
+    if (KIND == EPI_BIAS || KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_RESIDUAL) {
+        if (e.bias) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+                if (n_base + j < N) acc[j] += __ldg(e.bias + n_base + j);
+        }
+    }
+    if (KIND == EPI_BIAS_RESIDUAL || KIND == EPI_GELU_BWD) {
+        float aux[64];
+        stage_load(stage, reinterpret_cast<const bf16*>(e.aux), e.ldo, m_base, n_base, M, N, lane);
+        __syncwarp();
+        stage_read_row(stage, lane, aux);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = KIND == EPI_BIAS_RESIDUAL ? acc[j] + aux[j] : acc[j] * gelu_grad<true>(aux[j]);
+    }
+    if (KIND == EPI_PATCH) {
+        const int tok = (int)(m % e.np);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            const int n = n_base + j;
+            if (m < M && n < N) {
+                float v = tok == 0 ? __ldg(e.cls + n) : acc[j] + (e.bias ? __ldg(e.bias + n) : 0.f);
+                acc[j] = v + __ldg(e.pos + (long)tok * e.ldo + n);
+            }
+        }
+    }
+    if (e.accumulate) {  // the reference's `+=` contract at the ABI; the fused model path never takes it
+        float old[64];
+        stage_load(stage, out, e.ldo, m_base, n_base, M, N, lane);
+        __syncwarp();
+        stage_read_row(stage, lane, old);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] += old[j];
+    }
+    stage_write_row(stage, lane, acc);
+    __syncwarp();
+    stage_store(stage, out, e.ldo, m_base, n_base, M, N, lane);
+    __syncwarp();
+    if (KIND == EPI_BIAS_GELU) {
+        // gelu_forward consumes the stored (bf16-rounded) pre-activation, as the unfused op would
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = gelu_fwd<true>(__bfloat162float(__float2bfloat16_rn(acc[j])));
+        stage_write_row(stage, lane, acc);
+        __syncwarp();
+        stage_store(stage, reinterpret_cast<bf16*>(e.out2), e.ldo, m_base, n_base, M, N, lane);
+        __syncwarp();
+    }
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
@@ -178,6 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp >= kEpilogueWarp0) {
         // ===== epilogue: TMEM -> registers -> global =====
         const int quarter = warp - kEpilogueWarp0;  // == warp % 4: the TMEM lanes this warp may read
+        const uint32_t stage_smem = smem_base + L::STAGING_OFFSET + quarter * (32 * 128);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -187,23 +293,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const long m = (long)m0 + quarter * 32 + lane;
             const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            const long m_base = (long)m0 + quarter * 32;
+            if (p.epi.kind == EPI_ACCUM_F32) {
+                // dweight: fp32 vector reductions straight from the accumulator rows (split-K partial sums)
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(trow + ch * 32, v);  // warp-collective: no per-lane predicate around it
-                const int nb = n0 + ch * 32;
-                if (m < p.M && nb < p.N) {
-                    if (p.epi.kind == EPI_ACCUM_F32) {
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + ch * 32, v);  // warp-collective: no per-lane predicate around it
+                    const int nb = n0 + ch * 32;
+                    if (m < p.M && nb < p.N) {
                         float* dst = reinterpret_cast<float*>(p.epi.out) + m * p.epi.ldo + nb;
 #pragma unroll
                         for (int g = 0; g < 8; ++g)
                             if (nb + g * 4 < p.N)
                                 red_add_v4(dst + g * 4, __uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
                                            __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            if (nb + g * 8 < p.N) epi_store8<true>(p.epi, m, nb + g * 8, v + g * 8);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 64; ++ch) {
+                    const uint32_t taddr = trow + ch * 64;
+                    const int nb = n0 + ch * 64;
+                    switch (p.epi.kind) {  // warp-uniform branch to straight-line per-kind code
+                        case EPI_BIAS: epilogue_chunk<EPI_BIAS>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
+                        case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
+                        case EPI_BIAS_RESIDUAL: epilogue_chunk<EPI_BIAS_RESIDUAL>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
+                        case EPI_GELU_BWD: epilogue_chunk<EPI_GELU_BWD>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
+                        case EPI_PATCH: epilogue_chunk<EPI_PATCH>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
+                        default: epilogue_chunk<EPI_NONE>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
                     }
                 }
             }
