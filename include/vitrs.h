@@ -217,6 +217,9 @@ int vitrs_comm_world(vitrs_ctx* ctx, int* rank, int* world);
 /* sum all-reduce of the fp32 gradient buffer in reverse-layer buckets on the comm stream;
  * called by train_step when a communicator exists, exported for tests */
 int vitrs_model_allreduce_grads(vitrs_model* m);
+/* the bucket schedule itself, computable on the host: bucket 0 = final LayerNorm + head, 1..L = blocks
+ * L-1..0 (12 slices each), L+1 = embeddings; offsets/counts (elements, capacity 12) index the flat buffer */
+int vitrs_grad_bucket(const vitrs_config* cfg, int bucket, size_t* offsets, size_t* counts, int* num_slices);
 int vitrs_allreduce_f32(vitrs_ctx* ctx, float* buf, size_t n);
 
 #ifdef __cplusplus

@@ -129,6 +129,7 @@ _SIGNATURES = {
     "vitrs_comm_destroy": (_int, [_vp]),
     "vitrs_comm_world": (_int, [_vp, C.POINTER(_int), C.POINTER(_int)]),
     "vitrs_model_allreduce_grads": (_int, [_vp]),
+    "vitrs_grad_bucket": (_int, [C.POINTER(Config), _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_int)]),
     "vitrs_allreduce_f32": (_int, [_vp, _vp, _sz]),
 }
 # the two-mode operator families share argument lists
@@ -232,6 +233,19 @@ class Context:
 
     def allreduce(self, t):
         self.check(lib().vitrs_allreduce_f32(self._h, _ptr(t), t.numel()))
+
+
+def grad_buckets(cfg):
+    """The gradient-exchange schedule (host arithmetic only): list of buckets, each a list of (offset, count)."""
+    c = make_config(cfg) if not isinstance(cfg, Config) else cfg
+    out = []
+    for b in range(c.num_layers + 2):
+        off, cnt, n = (C.c_size_t * 12)(), (C.c_size_t * 12)(), C.c_int()
+        rc = lib().vitrs_grad_bucket(C.byref(c), b, off, cnt, C.byref(n))
+        if rc != 0:
+            raise VitrsError(f"vitrs_grad_bucket failed ({rc})")
+        out.append([(off[i], cnt[i]) for i in range(n.value)])
+    return out
 
 
 _default_ctx = {}

@@ -11,10 +11,13 @@
 // shared-memory tile is then [k rows][64 mn elements] per TMA box and the UMMA descriptor
 // carries the transpose, so no operand is ever transposed in HBM.
 //
-// CTA = 8 warps: warp 0 lane 0 issues TMA, warp 1 lane 0 issues tcgen05.mma and commits,
-// warp 2 owns the TMEM allocation, warps 4-7 are the epilogue (one TMEM lane quarter each).
-// Two accumulators live in TMEM (2 x BN columns) so tile i's epilogue overlaps tile i+1's
-// main loop.  dweight runs split-K with vectorised fp32 reductions (red.global.add.v4.f32),
+// CTA = 12 warps: warp 0 lane 0 issues TMA, warp 1 lane 0 issues tcgen05.mma and commits,
+// warp 2 owns the TMEM allocation, warps 4-11 are the epilogue (two warps per TMEM lane quarter,
+// each taking half of the tile's 64-column chunks).  Two accumulators live in TMEM (2 x BN
+// columns) so tile i's epilogue overlaps tile i+1's main loop.  The epilogue moves whole
+// [32 rows][64 columns] bf16 boxes with TMA in both directions (residual / pre-GELU in, result
+// out) through a warp-private 128B-swizzled staging tile, so no thread computes a global address
+// and edge tiles are clipped by the tensor map.  dweight runs split-K with vectorised fp32 reductions (red.global.add.v4.f32),
 // which is exactly the += contract of the reference's backward ops.
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
@@ -23,8 +26,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
 constexpr int kEpilogueWarp0 = 4;
+constexpr int kEpilogueWarps = 8;
 
 struct TcParams {
     int M, N, K;
@@ -37,53 +41,35 @@ struct SmemLayout {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;  // 4 epilogue warps x [32 rows][128 B]
-    static constexpr int STAGING_BYTES = 4 * 32 * 128;
+    static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;  // 8 epilogue warps x [32 rows][128 B]
+    static constexpr int STAGING_BYTES = kEpilogueWarps * 32 * 128;
     static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
 };
 
 // ---- epilogue: one warp, its 32 accumulator rows, one 64-column chunk ------------------------------
 // The accumulator row of a thread (TMEM lane) is contiguous along n, but a warp's 32 rows are ld
-// elements apart in global memory, so both directions go through a warp-private [32][128 B]
-// shared tile (16-byte chunks xor-swizzled by row): global traffic is whole 128-byte lines, 4 rows per
-// instruction, and the tile is read / written by row owners without bank conflicts.
+// elements apart in global memory.  Both directions therefore go through a warp-private
+// [32 rows][128 B] shared tile in the TMA 128B-swizzle layout: TMA moves the box, threads touch only
+// their own row (16-byte chunks xor-swizzled by row -> conflict-free).
 __device__ __forceinline__ uint32_t stage_addr(uint32_t stage, int row, int c8) { return stage + row * 128 + ((c8 ^ (row & 7)) << 4); }
 
-// rows [m_base, m_base+32) x columns [n_base, n_base+64) of a bf16 matrix -> the staging tile
-__device__ __forceinline__ void stage_load(uint32_t stage, const bf16* src, long ld, long m_base, int n_base, int M, int N, int lane) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int row = it * 4 + (lane >> 3), c8 = lane & 7;
-        const long gm = m_base + row;
-        const int gn = n_base + c8 * 8;
-        uint4 x = make_uint4(0u, 0u, 0u, 0u);
-        if (gm < M && gn < N) x = *reinterpret_cast<const uint4*>(src + gm * ld + gn);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(stage, row, c8)), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
-    }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void stage_store(uint32_t stage, bf16* dst, long ld, long m_base, int n_base, int M, int N, int lane) {
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// this thread's row (= lane) of the staging tile, 8 bf16 at a time
+__device__ __forceinline__ void stage_read8(uint32_t stage, int lane, int c8, float (&f)[8]) {
+    uint32_t x[4];
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(stage_addr(stage, lane, c8)) : "memory");
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int row = it * 4 + (lane >> 3), c8 = lane & 7;
-        const long gm = m_base + row;
-        const int gn = n_base + c8 * 8;
-        uint4 x;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(stage_addr(stage, row, c8)) : "memory");
-        if (gm < M && gn < N) *reinterpret_cast<uint4*>(dst + gm * ld + gn) = x;
-    }
-}
-// this thread's row (= lane) of the staging tile: 64 bf16 -> fp32
-__device__ __forceinline__ void stage_read_row(uint32_t stage, int lane, float (&f)[64]) {
-#pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
-        uint32_t x[4];
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(stage_addr(stage, lane, c8)) : "memory");
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            f[c8 * 8 + 2 * j] = __uint_as_float(x[j] << 16);
-            f[c8 * 8 + 2 * j + 1] = __uint_as_float(x[j] & 0xFFFF0000u);
-        }
+    for (int j = 0; j < 4; ++j) {
+        f[2 * j] = __uint_as_float(x[j] << 16);
+        f[2 * j + 1] = __uint_as_float(x[j] & 0xFFFF0000u);
     }
 }
 __device__ __forceinline__ void stage_write_row(uint32_t stage, int lane, const float (&f)[64]) {
@@ -99,10 +85,34 @@ __device__ __forceinline__ void stage_write_row(uint32_t stage, int lane, const 
     }
 }
 
+struct EpiMaps {
+    const CUtensorMap* out;
+    const CUtensorMap* out2;
+    const CUtensorMap* aux;
+};
+
+// box [m_base, +32) x [n_base, +64) of `map` -> staging tile; every lane returns once the bytes have landed
+__device__ __forceinline__ void stage_fetch(const CUtensorMap* map, uint32_t stage, uint32_t bar, uint32_t& phase, int n_base, int m_base,
+                                            int lane) {
+    if (lane == 0) {
+        mbar_expect_tx(bar, 32 * 128);
+        tma_load_2d(stage, map, bar, n_base, m_base);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+}
+// staging tile (fully written by the warp) -> box of `map`
+__device__ __forceinline__ void stage_flush(const CUtensorMap* map, uint32_t stage, int n_base, int m_base, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) tma_store_2d(map, stage, n_base, m_base);
+}
+
 // KIND is a compile-time constant here: the per-element code is straight-line (a runtime switch inside the
 // element loop is if-converted by the compiler and every output then pays for every epilogue kind)
 template <int KIND>
-__device__ __forceinline__ void epilogue_chunk(const Epilogue& e, uint32_t stage, uint32_t taddr, long m_base, int n_base, int M, int N, int lane) {
+__device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps& maps, uint32_t stage, uint32_t bar, uint32_t& bar_phase,
+                                               uint32_t taddr, int m_base, int n_base, int M, int N, int lane, bool bias_vec) {
     float acc[64];
     {
         uint32_t v[32];
@@ -113,26 +123,39 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, uint32_t stage
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[32 + j] = __uint_as_float(v[j]);
     }
-    if (n_base >= N) return;  // warp-uniform
-    const long m = m_base + lane;
-    bf16* out = reinterpret_cast<bf16*>(e.out);
+    // the staging tile is reusable once the previous TMA store has finished reading it
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
     if (KIND == EPI_BIAS || KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_RESIDUAL) {
         if (e.bias) {
+            if (bias_vec) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j)
-                if (n_base + j < N) acc[j] += __ldg(e.bias + n_base + j);
+                for (int j4 = 0; j4 < 16; ++j4)
+                    if (n_base + j4 * 4 < N) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n_base) + j4);
+                        acc[j4 * 4] += b.x; acc[j4 * 4 + 1] += b.y; acc[j4 * 4 + 2] += b.z; acc[j4 * 4 + 3] += b.w;
+                    }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 64; ++j)
+                    if (n_base + j < N) acc[j] += __ldg(e.bias + n_base + j);
+            }
         }
     }
     if (KIND == EPI_BIAS_RESIDUAL || KIND == EPI_GELU_BWD) {
-        float aux[64];
-        stage_load(stage, reinterpret_cast<const bf16*>(e.aux), e.ldo, m_base, n_base, M, N, lane);
-        __syncwarp();
-        stage_read_row(stage, lane, aux);
-        __syncwarp();
+        stage_fetch(maps.aux, stage, bar, bar_phase, n_base, m_base, lane);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) acc[j] = KIND == EPI_BIAS_RESIDUAL ? acc[j] + aux[j] : acc[j] * gelu_grad<true>(aux[j]);
+        for (int c8 = 0; c8 < 8; ++c8) {
+            float a[8];
+            stage_read8(stage, lane, c8, a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                acc[c8 * 8 + j] = KIND == EPI_BIAS_RESIDUAL ? acc[c8 * 8 + j] + a[j] : acc[c8 * 8 + j] * gelu_grad<true>(a[j]);
+        }
+        __syncwarp();  // every lane has read its aux row before the tile is overwritten
     }
     if (KIND == EPI_PATCH) {
+        const long m = (long)m_base + lane;
         const int tok = (int)(m % e.np);
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
@@ -144,32 +167,33 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, uint32_t stage
         }
     }
     if (e.accumulate) {  // the reference's `+=` contract at the ABI; the fused model path never takes it
-        float old[64];
-        stage_load(stage, out, e.ldo, m_base, n_base, M, N, lane);
-        __syncwarp();
-        stage_read_row(stage, lane, old);
-        __syncwarp();
+        stage_fetch(maps.out, stage, bar, bar_phase, n_base, m_base, lane);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) acc[j] += old[j];
+        for (int c8 = 0; c8 < 8; ++c8) {
+            float a[8];
+            stage_read8(stage, lane, c8, a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c8 * 8 + j] += a[j];
+        }
+        __syncwarp();
     }
     stage_write_row(stage, lane, acc);
-    __syncwarp();
-    stage_store(stage, out, e.ldo, m_base, n_base, M, N, lane);
-    __syncwarp();
+    stage_flush(maps.out, stage, n_base, m_base, lane);
     if (KIND == EPI_BIAS_GELU) {
         // gelu_forward consumes the stored (bf16-rounded) pre-activation, as the unfused op would
 #pragma unroll
         for (int j = 0; j < 64; ++j) acc[j] = gelu_fwd<true>(__bfloat162float(__float2bfloat16_rn(acc[j])));
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
         stage_write_row(stage, lane, acc);
-        __syncwarp();
-        stage_store(stage, reinterpret_cast<bf16*>(e.out2), e.ldo, m_base, n_base, M, N, lane);
-        __syncwarp();
+        stage_flush(maps.out2, stage, n_base, m_base, lane);
     }
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmAux, const TcParams p) {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
@@ -180,7 +204,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 4));
+    auto aux_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4 + w); };  // one per epilogue warp
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 4 + kEpilogueWarps));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulators; power of two (256 or 512)
@@ -188,6 +213,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmOut);
+        tma_prefetch_desc(&tmOut2);
+        tma_prefetch_desc(&tmAux);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -196,8 +224,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(a), kEpilogueWarps);  // one arrive per epilogue warp
         }
+        for (int w = 0; w < kEpilogueWarps; ++w) mbar_init(aux_bar(w), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -282,8 +311,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= kEpilogueWarp0) {
         // ===== epilogue: TMEM -> registers -> global =====
-        const int quarter = warp - kEpilogueWarp0;  // == warp % 4: the TMEM lanes this warp may read
-        const uint32_t stage_smem = smem_base + L::STAGING_OFFSET + quarter * (32 * 128);
+        const int ew = warp - kEpilogueWarp0;       // 0..7
+        const int quarter = ew & 3;                 // == warp % 4: the TMEM lanes this warp may read
+        const int chalf = ew >> 2;                  // which half of the tile's 64-column chunks
+        constexpr int kChunksPerWarp = BN / 64 / 2;
+        const uint32_t stage_smem = smem_base + L::STAGING_OFFSET + ew * (32 * 128);
+        const uint32_t my_bar = aux_bar(ew);
+        uint32_t bar_phase = 0;
+        const EpiMaps maps = {&tmOut, &tmOut2, &tmAux};
+        const bool bias_vec = p.epi.bias != nullptr && ((uintptr_t)p.epi.bias & 15) == 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -291,13 +327,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const long m = (long)m0 + quarter * 32 + lane;
+            const int m_base = m0 + quarter * 32;
+            const long m = (long)m_base + lane;
             const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-            const long m_base = (long)m0 + quarter * 32;
             if (p.epi.kind == EPI_ACCUM_F32) {
                 // dweight: fp32 vector reductions straight from the accumulator rows (split-K partial sums)
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ++ch) {
+                for (int ch = chalf * (BN / 64); ch < (chalf + 1) * (BN / 64); ++ch) {
                     uint32_t v[32];
                     tmem_ld32(trow + ch * 32, v);  // warp-collective: no per-lane predicate around it
                     const int nb = n0 + ch * 32;
@@ -312,16 +348,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             } else {
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 64; ++ch) {
+                for (int ch = chalf * kChunksPerWarp; ch < (chalf + 1) * kChunksPerWarp; ++ch) {
                     const uint32_t taddr = trow + ch * 64;
                     const int nb = n0 + ch * 64;
+                    if (nb >= p.N || m_base >= p.M) continue;  // warp-uniform: nothing of this chunk is inside the matrix
                     switch (p.epi.kind) {  // warp-uniform branch to straight-line per-kind code
-                        case EPI_BIAS: epilogue_chunk<EPI_BIAS>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
-                        case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
-                        case EPI_BIAS_RESIDUAL: epilogue_chunk<EPI_BIAS_RESIDUAL>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
-                        case EPI_GELU_BWD: epilogue_chunk<EPI_GELU_BWD>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
-                        case EPI_PATCH: epilogue_chunk<EPI_PATCH>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
-                        default: epilogue_chunk<EPI_NONE>(p.epi, stage_smem, taddr, m_base, nb, p.M, p.N, lane); break;
+                        case EPI_BIAS: epilogue_chunk<EPI_BIAS>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
+                        case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
+                        case EPI_BIAS_RESIDUAL: epilogue_chunk<EPI_BIAS_RESIDUAL>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
+                        case EPI_GELU_BWD: epilogue_chunk<EPI_GELU_BWD>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
+                        case EPI_PATCH: epilogue_chunk<EPI_PATCH>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
+                        default: epilogue_chunk<EPI_NONE>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
                     }
                 }
             }
@@ -330,6 +367,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (lane == 0) bulk_wait_all();  // the last TMA stores must be complete before the CTA retires its shared memory
     }
 
     tc_fence_before();
@@ -358,7 +396,7 @@ int encode_map(vitrs_ctx* ctx, CUtensorMap* map, const void* base, uint64_t inne
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-int launch_tc(vitrs_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
+int launch_tc(vitrs_ctx* ctx, const CUtensorMap* maps, const TcParams& p) {
     using L = SmemLayout<BN, STAGES>;
     auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
     static bool configured = false;
@@ -369,18 +407,18 @@ int launch_tc(vitrs_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, co
     const int units = p.m_tiles * p.n_tiles * p.splits;
     const int grid = units < ctx->sm_count ? units : ctx->sm_count;
     vitrs_prof_before(ctx, 2.0 * p.M * p.N * p.K);
-    kern<<<grid, kThreads, L::TOTAL, ctx->stream>>>(tmA, tmB, p);
+    kern<<<grid, kThreads, L::TOTAL, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
     vitrs_prof_after(ctx);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
 }
 
 template <int BN, int STAGES>
-int launch_tc_major(vitrs_ctx* ctx, bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
-    if (!a_mn && !b_mn) return launch_tc<BN, STAGES, false, false>(ctx, tmA, tmB, p);
-    if (!a_mn && b_mn) return launch_tc<BN, STAGES, false, true>(ctx, tmA, tmB, p);
-    if (a_mn && b_mn) return launch_tc<BN, STAGES, true, true>(ctx, tmA, tmB, p);
-    return launch_tc<BN, STAGES, true, false>(ctx, tmA, tmB, p);
+int launch_tc_major(vitrs_ctx* ctx, bool a_mn, bool b_mn, const CUtensorMap* maps, const TcParams& p) {
+    if (!a_mn && !b_mn) return launch_tc<BN, STAGES, false, false>(ctx, maps, p);
+    if (!a_mn && b_mn) return launch_tc<BN, STAGES, false, true>(ctx, maps, p);
+    if (a_mn && b_mn) return launch_tc<BN, STAGES, true, true>(ctx, maps, p);
+    return launch_tc<BN, STAGES, true, false>(ctx, maps, p);
 }
 
 inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -410,11 +448,22 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     if (!tc_eligible(g)) return gemm_simt_bf16(ctx, g);
     const bool a_mn = g.a_ks != 1, b_mn = g.b_ks != 1;
     const int BN = g.N > 128 ? 256 : 128;
-    CUtensorMap tmA, tmB;
+    CUtensorMap maps[5];  // A, B, out, out2, aux
+    CUtensorMap &tmA = maps[0], &tmB = maps[1];
     if (!a_mn) VITRS_TRY(encode_map(ctx, &tmA, g.A, g.K, g.M, g.a_rs, BK, BM));
     else VITRS_TRY(encode_map(ctx, &tmA, g.A, g.M, g.K, g.a_ks, 64, BK));
     if (!b_mn) VITRS_TRY(encode_map(ctx, &tmB, g.B, g.K, g.N, g.b_rs, BK, BN));
     else VITRS_TRY(encode_map(ctx, &tmB, g.B, g.N, g.K, g.b_ks, 64, BK));
+    if (g.epi.kind == EPI_ACCUM_F32) {
+        maps[2] = maps[3] = maps[4] = tmA;  // unused by the reduction epilogue
+    } else {
+        // [M, N] bf16 matrices with leading dimension ldo, moved as boxes of 32 rows x 64 columns
+        VITRS_TRY(encode_map(ctx, &maps[2], g.epi.out, g.N, g.M, g.epi.ldo, 64, 32));
+        if (g.epi.out2) VITRS_TRY(encode_map(ctx, &maps[3], g.epi.out2, g.N, g.M, g.epi.ldo, 64, 32));
+        else maps[3] = maps[2];
+        if (g.epi.aux) VITRS_TRY(encode_map(ctx, &maps[4], g.epi.aux, g.N, g.M, g.epi.ldo, 64, 32));
+        else maps[4] = maps[2];
+    }
 
     TcParams p;
     p.M = g.M; p.N = g.N; p.K = g.K;
@@ -437,6 +486,6 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     }
     p.kb_per_split = ceil_div(p.kb_total, splits);
     p.splits = ceil_div(p.kb_total, p.kb_per_split);
-    if (BN == 256) return launch_tc_major<256, 4>(ctx, a_mn, b_mn, tmA, tmB, p);
-    return launch_tc_major<128, 6>(ctx, a_mn, b_mn, tmA, tmB, p);
+    if (BN == 256) return launch_tc_major<256, 4>(ctx, a_mn, b_mn, maps, p);
+    return launch_tc_major<128, 6>(ctx, a_mn, b_mn, maps, p);
 }

@@ -457,37 +457,46 @@ int bucket_begin(vitrs_model* m) {
     return VITRS_OK;
 }
 
-// block l: its 12 slices of the tensor-major gradient buffer.  fcprojb[l] is completed by block
-// l+1's LN1-backward (or before the loop for the last block), so it is already final here.
-int allreduce_layer(vitrs_model* m, int l) {
-    if (!m->ctx->nccl_comm || m->mode != VITRS_MODE_BF16) return VITRS_OK;
-    VITRS_TRY(bucket_begin(m));
-    float* bufs[12];
-    size_t counts[12];
+// Bucket b of the gradient exchange, in the order backward completes them: 0 = final LayerNorm + head,
+// 1..L = blocks L-1..0 (the block's 12 slices of the tensor-major buffer), L+1 = patch / cls / position
+// embeddings.  Returns the slice count; offsets / counts are in elements of the flat gradient buffer.
+int bucket_slices(const vitrs_config& cfg, const size_t* sizes, const size_t* offs, int bucket, size_t* out_off, size_t* out_cnt) {
+    const int L = cfg.num_layers;
+    if (bucket == 0) {  // lnfw, lnfb, headw, headb are contiguous
+        out_off[0] = offs[P_LNFW];
+        out_cnt[0] = sizes[P_LNFW] + sizes[P_LNFB] + sizes[P_HEADW] + sizes[P_HEADB];
+        return 1;
+    }
+    if (bucket == L + 1) {  // patchw, patchb, cls, wpe are contiguous
+        out_off[0] = offs[P_PATCHW];
+        out_cnt[0] = offs[P_LN1W];
+        return 1;
+    }
+    const int l = L - bucket;
     int n = 0;
     for (int i = P_LN1W; i <= P_FCPROJB; ++i) {
-        const size_t per = m->param_sizes[i] / m->cfg.num_layers;
-        bufs[n] = G(m, i) + (size_t)l * per;
-        counts[n] = per;
+        const size_t per = sizes[i] / L;
+        out_off[n] = offs[i] + (size_t)l * per;
+        out_cnt[n] = per;
         ++n;
     }
-    return vitrs_nccl_allreduce_group(m->ctx, bufs, counts, n);
+    return n;
 }
 
-int allreduce_tail(vitrs_model* m, bool head) {
+int allreduce_bucket(vitrs_model* m, int bucket) {
     if (!m->ctx->nccl_comm || m->mode != VITRS_MODE_BF16) return VITRS_OK;
     VITRS_TRY(bucket_begin(m));
-    float* bufs[1];
-    size_t counts[1];
-    if (head) {  // lnfw, lnfb, headw, headb are contiguous
-        bufs[0] = G(m, P_LNFW);
-        counts[0] = m->num_params - m->param_off[P_LNFW];
-    } else {     // patchw, patchb, cls, wpe are contiguous
-        bufs[0] = G(m, P_PATCHW);
-        counts[0] = m->param_off[P_LN1W];
-    }
-    return vitrs_nccl_allreduce_group(m->ctx, bufs, counts, 1);
+    size_t off[12], cnt[12];
+    float* bufs[12];
+    const int n = bucket_slices(m->cfg, m->param_sizes, m->param_off, bucket, off, cnt);
+    for (int i = 0; i < n; ++i) bufs[i] = m->grads + off[i];
+    return vitrs_nccl_allreduce_group(m->ctx, bufs, cnt, n);
 }
+
+// block l: fcprojb[l] is completed by block l+1's LN1-backward (or before the loop for the last block),
+// so every slice of the bucket is final when block l's backward has been issued
+int allreduce_layer(vitrs_model* m, int l) { return allreduce_bucket(m, m->cfg.num_layers - l); }
+int allreduce_tail(vitrs_model* m, bool head) { return allreduce_bucket(m, head ? 0 : m->cfg.num_layers + 1); }
 
 int comm_join(vitrs_model* m) {
     vitrs_ctx* ctx = m->ctx;
@@ -688,6 +697,19 @@ int vitrs_model_backward(vitrs_model* m) {
     VITRS_TRY(m->mode == VITRS_MODE_F32 ? backward_f32(m) : backward_bf16(m));
     if (ctx->nccl_comm && m->mode == VITRS_MODE_F32) VITRS_TRY(vitrs_allreduce_f32(ctx, m->grads, m->num_params));
     return comm_join(m);
+}
+
+// host-only description of the bucketed exchange (no device needed): slices of bucket `bucket` for `cfg`
+int vitrs_grad_bucket(const vitrs_config* cfg_in, int bucket, size_t* offsets, size_t* counts, int* num_slices) {
+    if (!cfg_in || !offsets || !counts || !num_slices) return VITRS_ERR_ARG;
+    vitrs_config cfg = *cfg_in;
+    cfg.max_seq_len = tokens(cfg);
+    if (bucket < 0 || bucket > cfg.num_layers + 1) return VITRS_ERR_ARG;
+    size_t sizes[P_COUNT], offs[P_COUNT], off = 0;
+    param_sizes_of(cfg, sizes);
+    for (int i = 0; i < P_COUNT; ++i) { offs[i] = off; off += sizes[i]; }
+    *num_slices = bucket_slices(cfg, sizes, offs, bucket, offsets, counts);
+    return VITRS_OK;
 }
 
 int vitrs_model_allreduce_grads(vitrs_model* m) {
