@@ -94,56 +94,79 @@ __global__ void gelu_bwd_kernel(T* __restrict__ dinp, const T* __restrict__ inp,
         dinp[i] = from_f32<T>(to_f32(dinp[i]) + gelu_grad<FAST>(to_f32(inp[i])) * to_f32(dout[i]));
 }
 
-// ---- LayerNorm forward (tv:453-480): one warp per row, the row cached in registers ------------
+// ---- LayerNorm forward (tv:453-480): warps stride over rows, the row cached in registers -------
+// Gains and biases for the lane's columns are loaded once (16-byte loads) and stay in registers, so a
+// row costs its own bytes only: MAXNV 16-byte loads in flight per lane, two shuffle reductions, MAXNV
+// 16-byte stores.
 template <typename T, int MAXNV>
 __global__ void __launch_bounds__(kThreads)
 ln_fwd_kernel(T* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, const T* __restrict__ inp,
               const float* __restrict__ w, const float* __restrict__ bias, long rows, int c) {
     constexpr int VN = Vec16<T>::N;
     const int lane = threadIdx.x & 31;
-    const long row = (long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const T* x = inp + row * c;
-    Vec16<T> v[MAXNV];
-    float s = 0.f;
+    float wr[MAXNV * VN], br[MAXNV * VN];
 #pragma unroll
     for (int i = 0; i < MAXNV; ++i) {
         const int idx = (i * 32 + lane) * VN;
-        if (idx < c) {
-            v[i].load(x + idx);
 #pragma unroll
-            for (int j = 0; j < VN; ++j) s += v[i].get(j);
+        for (int j4 = 0; j4 < VN / 4; ++j4) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
+            if (idx < c) {
+                a = __ldg(reinterpret_cast<const float4*>(w + idx) + j4);
+                b4 = __ldg(reinterpret_cast<const float4*>(bias + idx) + j4);
+            }
+            wr[i * VN + j4 * 4] = a.x; wr[i * VN + j4 * 4 + 1] = a.y; wr[i * VN + j4 * 4 + 2] = a.z; wr[i * VN + j4 * 4 + 3] = a.w;
+            br[i * VN + j4 * 4] = b4.x; br[i * VN + j4 * 4 + 1] = b4.y; br[i * VN + j4 * 4 + 2] = b4.z; br[i * VN + j4 * 4 + 3] = b4.w;
         }
     }
-    const float m = warp_sum(s) / (float)c;
-    float q = 0.f;
+    const long nwarps = (long)gridDim.x * (kThreads / 32);
+    for (long row = (long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); row < rows; row += nwarps) {
+        const T* x = inp + row * c;
+        Vec16<T> v[MAXNV];
+        float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXNV; ++i) {
-        const int idx = (i * 32 + lane) * VN;
-        if (idx < c) {
+        for (int i = 0; i < MAXNV; ++i) {
+            const int idx = (i * 32 + lane) * VN;
+            if (idx < c) v[i].load(x + idx);
+        }
 #pragma unroll
-            for (int j = 0; j < VN; ++j) {
-                float d = v[i].get(j) - m;
-                q += d * d;
+        for (int i = 0; i < MAXNV; ++i) {
+            const int idx = (i * 32 + lane) * VN;
+            if (idx < c) {
+#pragma unroll
+                for (int j = 0; j < VN; ++j) s += v[i].get(j);
             }
         }
-    }
-    const float var = warp_sum(q) / (float)c;
-    const float rs = 1.0f / sqrtf(var + 1e-5f);
-    T* y = out + row * c;
+        const float m = warp_sum(s) / (float)c;
+        float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXNV; ++i) {
-        const int idx = (i * 32 + lane) * VN;
-        if (idx < c) {
-            Vec16<T> o;
+        for (int i = 0; i < MAXNV; ++i) {
+            const int idx = (i * 32 + lane) * VN;
+            if (idx < c) {
 #pragma unroll
-            for (int j = 0; j < VN; ++j) o.set(j, (rs * (v[i].get(j) - m)) * __ldg(w + idx + j) + __ldg(bias + idx + j));
-            o.store(y + idx);
+                for (int j = 0; j < VN; ++j) {
+                    float d = v[i].get(j) - m;
+                    q += d * d;
+                }
+            }
         }
-    }
-    if (lane == 0) {
-        mean[row] = m;
-        rstd[row] = rs;
+        const float var = warp_sum(q) / (float)c;
+        const float rs = 1.0f / sqrtf(var + 1e-5f);
+        T* y = out + row * c;
+#pragma unroll
+        for (int i = 0; i < MAXNV; ++i) {
+            const int idx = (i * 32 + lane) * VN;
+            if (idx < c) {
+                Vec16<T> o;
+#pragma unroll
+                for (int j = 0; j < VN; ++j) o.set(j, (rs * (v[i].get(j) - m)) * wr[i * VN + j] + br[i * VN + j]);
+                o.store(y + idx);
+            }
+        }
+        if (lane == 0) {
+            mean[row] = m;
+            rstd[row] = rs;
+        }
     }
 }
 
@@ -176,41 +199,48 @@ __global__ void ln_fwd_generic_kernel(T* __restrict__ out, float* __restrict__ m
 // Warps stride over rows; each lane keeps fp32 partial column sums for the columns it owns
 // (dweight, dbias and, optionally, the column sum of the updated dinp), reduced across the
 // block's warps in shared memory and added to global with one atomic per column per block.
+// Gains live in shared memory (broadcast-free 16-byte reads) to keep the kernel at two blocks per SM;
+// all three row operands (dout, inp, dinp) are requested before the first reduction.
 template <typename T, int MAXNV, bool COLSUM>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MAXNV <= 4 ? 2 : 1)
 ln_bwd_kernel(T* __restrict__ dinp, float* __restrict__ dweight, float* __restrict__ dbias, const T* __restrict__ dout,
               const T* __restrict__ inp, const float* __restrict__ w, const float* __restrict__ mean,
               const float* __restrict__ rstd, long rows, int c, float* __restrict__ colsum_out) {
     constexpr int VN = Vec16<T>::N;
     constexpr int NW = kThreads / 32;
-    extern __shared__ float red[];  // [NW][c]
+    extern __shared__ float red[];  // [NW][c] reduction scratch, then [c] gains
+    float* wsm = red + NW * c;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float wreg[MAXNV * VN], dw_acc[MAXNV * VN], db_acc[MAXNV * VN], cs_acc[COLSUM ? MAXNV * VN : 1];
+    for (int i = threadIdx.x; i < c; i += kThreads) wsm[i] = w[i];
+    __syncthreads();
+    float dw_acc[MAXNV * VN], db_acc[MAXNV * VN], cs_acc[COLSUM ? MAXNV * VN : 1];
 #pragma unroll
-    for (int i = 0; i < MAXNV; ++i) {
-        const int idx = (i * 32 + lane) * VN;
-#pragma unroll
-        for (int j = 0; j < VN; ++j) {
-            wreg[i * VN + j] = idx < c ? w[idx + j] : 0.f;
-            dw_acc[i * VN + j] = 0.f;
-            db_acc[i * VN + j] = 0.f;
-            if (COLSUM) cs_acc[i * VN + j] = 0.f;
-        }
+    for (int i = 0; i < MAXNV * VN; ++i) {
+        dw_acc[i] = 0.f;
+        db_acc[i] = 0.f;
+        if (COLSUM) cs_acc[i] = 0.f;
     }
     for (long row = (long)blockIdx.x * NW + warp; row < rows; row += (long)gridDim.x * NW) {
-        const float m = mean[row], rs = rstd[row];
-        Vec16<T> gy[MAXNV], xv[MAXNV];
-        float s1 = 0.f, s2 = 0.f;
+        Vec16<T> gy[MAXNV], xv[MAXNV], dv[MAXNV];
 #pragma unroll
         for (int i = 0; i < MAXNV; ++i) {
             const int idx = (i * 32 + lane) * VN;
             if (idx < c) {
                 gy[i].load(dout + row * c + idx);
                 xv[i].load(inp + row * c + idx);
+                dv[i].load(dinp + row * c + idx);
+            }
+        }
+        const float m = mean[row], rs = rstd[row];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXNV; ++i) {
+            const int idx = (i * 32 + lane) * VN;
+            if (idx < c) {
 #pragma unroll
                 for (int j = 0; j < VN; ++j) {
                     float nrm = (xv[i].get(j) - m) * rs;
-                    float dn = wreg[i * VN + j] * gy[i].get(j);
+                    float dn = wsm[idx + j] * gy[i].get(j);
                     s1 += dn;
                     s2 += dn * nrm;
                 }
@@ -222,21 +252,18 @@ ln_bwd_kernel(T* __restrict__ dinp, float* __restrict__ dweight, float* __restri
         for (int i = 0; i < MAXNV; ++i) {
             const int idx = (i * 32 + lane) * VN;
             if (idx < c) {
-                Vec16<T> d;
-                d.load(dinp + row * c + idx);
 #pragma unroll
                 for (int j = 0; j < VN; ++j) {
                     float g = gy[i].get(j);
                     float nrm = (xv[i].get(j) - m) * rs;
-                    float dn = wreg[i * VN + j] * g;
+                    float dn = wsm[idx + j] * g;
                     db_acc[i * VN + j] += g;
                     dw_acc[i * VN + j] += nrm * g;
-                    float dv = (dn - dn_mean - nrm * dnn_mean) * rs;
-                    float upd = d.get(j) + dv;
-                    d.set(j, upd);
-                    if (COLSUM) cs_acc[i * VN + j] += d.get(j);  // the value as stored (rounded)
+                    float upd = dv[i].get(j) + (dn - dn_mean - nrm * dnn_mean) * rs;
+                    dv[i].set(j, upd);
+                    if (COLSUM) cs_acc[i * VN + j] += dv[i].get(j);  // the value as stored (rounded)
                 }
-                d.store(dinp + row * c + idx);
+                dv[i].store(dinp + row * c + idx);
             }
         }
     }
@@ -542,10 +569,15 @@ int op_layernorm_forward(vitrs_ctx* ctx, T* out, float* mean, float* rstd, const
     if (rows <= 0) return VITRS_OK;
     constexpr int VN = Vec16<T>::N;
     const int nv = (c + 32 * VN - 1) / (32 * VN);
-    const int grid = ceil_div(rows, kThreads / 32);
-    const bool vec_ok = (c % VN == 0) && aligned16(out) && aligned16(inp) && nv <= 8;
+    int grid = ceil_div(rows, kThreads / 32);
+    const bool vec_ok = (c % VN == 0) && aligned16(out) && aligned16(inp) && aligned16(w) && aligned16(b) && nv <= 8;
     if (!vec_ok) {
         ln_fwd_generic_kernel<T><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+        VITRS_LAUNCHED(ctx);
+        return VITRS_OK;
+    }
+    if (grid > 4 * ctx->sm_count) grid = 4 * ctx->sm_count;  // persistent: warps stride over rows
+    if (false) {
     } else if (nv <= 1) {
         ln_fwd_kernel<T, 1><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
     } else if (nv <= 2) {
@@ -566,7 +598,7 @@ static int launch_ln_bwd(vitrs_ctx* ctx, T* dinp, float* dw, float* db, const T*
                          const float* mean, const float* rstd, long rows, int c, float* colsum_out) {
     int grid = ceil_div(rows, kThreads / 32);
     if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
-    const size_t smem = (size_t)(kThreads / 32) * c * sizeof(float);
+    const size_t smem = (size_t)(kThreads / 32 + 1) * c * sizeof(float);
     if (colsum_out) {
         auto k = ln_bwd_kernel<T, MAXNV, true>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
