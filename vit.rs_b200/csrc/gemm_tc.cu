@@ -19,6 +19,8 @@
 // out) through a warp-private 128B-swizzled staging tile, so no thread computes a global address
 // and edge tiles are clipped by the tensor map.  dweight runs split-K with vectorised fp32 reductions (red.global.add.v4.f32),
 // which is exactly the += contract of the reference's backward ops.
+#include <stdlib.h>
+
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
 
@@ -240,14 +242,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_units = p.m_tiles * p.n_tiles * p.splits;
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int total_units = tiles * p.splits;
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         int stage = 0;
         uint32_t phase = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-            const int tile = unit / p.splits, split = unit - tile * p.splits;
+            // split-major: consecutive units (= concurrently running CTAs) walk the same K range, so every
+            // operand slab is fetched from HBM once and shared through L2
+            const int split = unit / tiles, tile = unit - split * tiles;
             const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -283,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-            const int split = unit % p.splits;
+            const int split = unit / tiles;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -323,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-            const int tile = unit / p.splits;
+            const int tile = unit % tiles;
             const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
@@ -473,16 +478,22 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     p.epi = g.epi;
     int splits = 1;
     const int tiles = p.m_tiles * p.n_tiles;
-    if (g.epi.kind == EPI_ACCUM_F32 && tiles < 2 * ctx->sm_count) {
-        // pick the split count that best fills whole waves of the SMs (each split >= 8 k-blocks)
+    if (g.epi.kind == EPI_ACCUM_F32 && tiles < ctx->sm_count) {
+        // Split K so that one wave of CTAs covers the SMs: the smallest split count that fills >= 92 % of
+        // whole waves, else the best fill.  More splits than needed cost fp32 reductions and, worse, break
+        // the sharing of operand slabs between concurrently running CTAs (measured: 37 splits -> 6x DRAM traffic).
+        const int max_s = p.kb_total / 16 > 1 ? (p.kb_total / 16 < 32 ? p.kb_total / 16 : 32) : 1;
         double best = 0.0;
-        const int max_s = p.kb_total / 8 > 1 ? (p.kb_total / 8 < 64 ? p.kb_total / 8 : 64) : 1;
         for (int s = 1; s <= max_s; ++s) {
             const long units = (long)tiles * s;
             const long waves = (units + ctx->sm_count - 1) / ctx->sm_count;
             const double eff = (double)units / (double)(waves * ctx->sm_count);
-            if (eff > best + 0.02) { best = eff; splits = s; }
+            if (eff > best + 1e-9) { best = eff; splits = s; }
+            if (eff >= 0.92) break;
         }
+    }
+    if (const char* ov = getenv("VITRS_GEMM_SPLITS")) {  // tuning aid (scripts/exp_dw.py)
+        if (g.epi.kind == EPI_ACCUM_F32 && atoi(ov) > 0) splits = atoi(ov);
     }
     p.kb_per_split = ceil_div(p.kb_total, splits);
     p.splits = ceil_div(p.kb_total, p.kb_per_split);
