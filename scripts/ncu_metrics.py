@@ -1,6 +1,6 @@
 """Print the headline metrics of every kernel in an ncu report (ncu -i X --page raw --csv)."""
 import csv, subprocess, sys
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(sys.argv[1]).read() if sys.argv[1].endswith(".csv") else subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 idx = {h: i for i, h in enumerate(hdr)}

@@ -18,6 +18,8 @@
 //           written once to shared memory, where the same bytes serve as the K-major A operand of
 //           dV_j += P^T dO_i and dK_j += dS^T Q_i and as the MN-major A operand of dQ_i += dS K_j.
 //           dV_j, dK_j and both dQ_i accumulate in TMEM; nothing is reduced through global memory.
+#include <stdlib.h>
+
 #include "tc_ptx.cuh"
 
 namespace {
@@ -192,6 +194,129 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict_
     }
     tc_fence_before();
     __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ---- forward, one CTA per (batch, head, 128-query tile), two CTAs per SM ------------------------------
+// P never leaves tensor memory: the softmax threads overwrite their S row in place with packed bf16
+// (tcgen05.st) and the P.V MMA takes its A operand from TMEM, so a CTA needs only Q_i, K, V in shared
+// memory (80 KB at T = 197) and 256 TMEM columns; the second resident CTA's loads and MMAs overlap this
+// CTA's exponentials.  O is staged through the dead Q tile and leaves with one TMA store (rows >= T clipped).
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1),
+                 "r"(c2)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse, int T,
+                    int C, int NH, int causal, int NT, int NK, uint32_t tmem_cols) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sQ = base, sK = sQ + TILE_BYTES, sV = sK + NT * TILE_BYTES;
+    const uint32_t bar0 = sV + NT * TILE_BYTES;
+    const uint32_t bar_qk = bar0, bar_v = bar0 + 8, bar_s = bar0 + 16, bar_o = bar0 + 24;
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 32);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int qt = blockIdx.x % NT, bh = blockIdx.x / NT, b = bh / NH, h = bh - b * NH;
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_out);
+        mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(smem_u32((const void*)slot), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+    const uint32_t o_col = tmem_cols - HS;  // O accumulator: the last 64 columns (dead part of S once P is packed)
+
+    if (tid == 0) {
+        mbar_expect_tx(bar_qk, (uint32_t)((1 + NT) * TILE_BYTES));
+        tma_load_3d(sQ, &tm_qkv, bar_qk, h * HS, qt * TILE, b);
+        for (int i = 0; i < NT; ++i) tma_load_3d(sK + i * TILE_BYTES, &tm_qkv, bar_qk, C + h * HS, i * TILE, b);
+        mbar_expect_tx(bar_v, (uint32_t)(NT * TILE_BYTES));
+        for (int i = 0; i < NT; ++i) tma_load_3d(sV + i * TILE_BYTES, &tm_qkv, bar_v, 2 * C + h * HS, i * TILE, b);
+        mbar_wait(bar_qk, 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(TILE, NK, 0, 0);
+#pragma unroll
+        for (int k = 0; k < HS / 16; ++k)
+            umma_bf16(tmem_base, make_desc(sQ + k * 32, 0, 1024), make_desc(sK + k * 32, 0, 1024), idesc, k > 0);
+        umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    const int r = tid;
+    const int q = qt * TILE + r;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int kend = causal ? min(T, q + 1) : T;
+    const int nchunks = (NK + 31) >> 5;
+    const float scale = 1.0f / sqrtf((float)HS);
+    const float sl2 = kLog2e * scale;
+    float mx = -INFINITY;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + ch * 32, v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (ch * 32 + c < kend) mx = fmaxf(mx, __uint_as_float(v[c]));
+    }
+    float sum = 0.f;
+    const float mxs = mx * sl2;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t v[32], pk[16];
+        tmem_ld32(lane_addr + ch * 32, v);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int k = ch * 32 + 2 * c;
+            const float p0 = k < kend ? ex2(__uint_as_float(v[2 * c]) * sl2 - mxs) : 0.f;
+            const float p1 = k + 1 < kend ? ex2(__uint_as_float(v[2 * c + 1]) * sl2 - mxs) : 0.f;
+            sum += p0 + p1;
+            pk[c] = pack_bf16(p0, p1);
+        }
+        tmem_st16(lane_addr + ch * 16, pk);  // in place: columns [16ch, 16ch+16) were consumed by chunk ch/2 <= ch
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        mbar_wait(bar_v, 0);
+        const uint32_t idesc = make_idesc(TILE, HS, 0, 1);  // A = P from TMEM (K-major by construction), B = V MN-major
+        for (int k16 = 0; k16 < NK / 16; ++k16)
+            umma_bf16_ts(tmem_base + o_col, tmem_base + k16 * 8, make_desc(sV + k16 * 2048, TILE_BYTES, 1024), idesc, k16 > 0);
+        umma_commit(bar_o);
+    }
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + o_col + half * 32, v);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            st_shared_v4(sw128(sQ, r, half * 4 + g), pack_bf16(__uint_as_float(v[g * 8]) * inv, __uint_as_float(v[g * 8 + 1]) * inv),
+                         pack_bf16(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv),
+                         pack_bf16(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv),
+                         pack_bf16(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv));
+    }
+    if (q < T) lse[(long)bh * T + q] = mx * scale + logf(sum);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tma_store_3d(&tm_out, sQ, h * HS, qt * TILE, b);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
@@ -401,10 +526,24 @@ bool tc_shape_ok(const void* a, const void* b_, int t, int c, int nh) {
 int op_attention_forward_tc(vitrs_ctx* ctx, bf16* out, float* lse, const bf16* qkv, int b, int t, int c, int nh, int causal) {
     if (!tc_shape_ok(out, qkv, t, c, nh)) return VITRS_ERR_UNSUPPORTED;
     if (b <= 0) return VITRS_OK;
-    CUtensorMap tm;
+    CUtensorMap tm, tm_out;
     VITRS_TRY(encode_map3d(ctx, &tm, qkv, 3 * (uint64_t)c, t, b));
     const int NT = (t + TILE - 1) / TILE;
     const int NK = (t + 15) & ~15;
+    static const bool use_v1 = getenv("VITRS_ATTN_FWD_V1") != nullptr;  // A/B aid: the two-tiles-per-CTA kernel with P in shared memory
+    if (!use_v1) {
+        VITRS_TRY(encode_map3d(ctx, &tm_out, out, (uint64_t)c, t, b));
+        const size_t smem = (size_t)(1 + 2 * NT) * TILE_BYTES + 64 + 1024;
+        const uint32_t tmem_cols = NK <= 128 ? 128 : 256;
+        static size_t configured2 = 0;
+        if (smem > configured2) {
+            VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured2 = smem;
+        }
+        attn_fwd_tc2_kernel<<<b * nh * NT, 128, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, causal, NT, NK, tmem_cols);
+        VITRS_LAUNCHED(ctx);
+        return VITRS_OK;
+    }
     const int NKB = (NK + 63) >> 6;
     const size_t smem = (size_t)NT * 3 * TILE_BYTES + (size_t)NT * NKB * TILE_BYTES + 64 + 1024;
     const uint32_t tmem_cols = NT == 1 ? 128 : 512;
