@@ -123,31 +123,31 @@ ln_fwd_kernel(T* __restrict__ out, float* __restrict__ mean, float* __restrict__
     for (long row = (long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); row < rows; row += nwarps) {
         const T* x = inp + row * c;
         Vec16<T> v[MAXNV];
-        float s = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXNV; ++i) {
             const int idx = (i * 32 + lane) * VN;
             if (idx < c) v[i].load(x + idx);
         }
+        float xf[MAXNV * VN];  // the row in fp32, converted once
+        float s = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXNV; ++i) {
-            const int idx = (i * 32 + lane) * VN;
-            if (idx < c) {
+            const bool live = (i * 32 + lane) * VN < c;
 #pragma unroll
-                for (int j = 0; j < VN; ++j) s += v[i].get(j);
+            for (int j = 0; j < VN; ++j) {
+                xf[i * VN + j] = live ? v[i].get(j) : 0.f;
+                s += xf[i * VN + j];
             }
         }
         const float m = warp_sum(s) / (float)c;
         float q = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXNV; ++i) {
-            const int idx = (i * 32 + lane) * VN;
-            if (idx < c) {
+            const bool live = (i * 32 + lane) * VN < c;
 #pragma unroll
-                for (int j = 0; j < VN; ++j) {
-                    float d = v[i].get(j) - m;
-                    q += d * d;
-                }
+            for (int j = 0; j < VN; ++j) {
+                xf[i * VN + j] -= m;
+                q += live ? xf[i * VN + j] * xf[i * VN + j] : 0.f;
             }
         }
         const float var = warp_sum(q) / (float)c;
@@ -159,7 +159,7 @@ ln_fwd_kernel(T* __restrict__ out, float* __restrict__ mean, float* __restrict__
             if (idx < c) {
                 Vec16<T> o;
 #pragma unroll
-                for (int j = 0; j < VN; ++j) o.set(j, (rs * (v[i].get(j) - m)) * wr[i * VN + j] + br[i * VN + j]);
+                for (int j = 0; j < VN; ++j) o.set(j, (rs * xf[i * VN + j]) * wr[i * VN + j] + br[i * VN + j]);
                 o.store(y + idx);
             }
         }
@@ -238,11 +238,20 @@ ln_bwd_kernel(T* __restrict__ dinp, float* __restrict__ dweight, float* __restri
             const int idx = (i * 32 + lane) * VN;
             if (idx < c) {
 #pragma unroll
-                for (int j = 0; j < VN; ++j) {
-                    float nrm = (xv[i].get(j) - m) * rs;
-                    float dn = wsm[idx + j] * gy[i].get(j);
-                    s1 += dn;
-                    s2 += dn * nrm;
+                for (int j4 = 0; j4 < VN / 4; ++j4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wsm + idx + j4 * 4);
+                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = j4 * 4 + jj;
+                        const float g = gy[i].get(j);
+                        const float nrm = (xv[i].get(j) - m) * rs;
+                        const float dn = wv[jj] * g;
+                        s1 += dn;
+                        s2 += dn * nrm;
+                        db_acc[i * VN + j] += g;
+                        dw_acc[i * VN + j] += nrm * g;
+                    }
                 }
             }
         }
@@ -253,15 +262,18 @@ ln_bwd_kernel(T* __restrict__ dinp, float* __restrict__ dweight, float* __restri
             const int idx = (i * 32 + lane) * VN;
             if (idx < c) {
 #pragma unroll
-                for (int j = 0; j < VN; ++j) {
-                    float g = gy[i].get(j);
-                    float nrm = (xv[i].get(j) - m) * rs;
-                    float dn = wsm[idx + j] * g;
-                    db_acc[i * VN + j] += g;
-                    dw_acc[i * VN + j] += nrm * g;
-                    float upd = dv[i].get(j) + (dn - dn_mean - nrm * dnn_mean) * rs;
-                    dv[i].set(j, upd);
-                    if (COLSUM) cs_acc[i * VN + j] += dv[i].get(j);  // the value as stored (rounded)
+                for (int j4 = 0; j4 < VN / 4; ++j4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wsm + idx + j4 * 4);
+                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = j4 * 4 + jj;
+                        const float nrm = (xv[i].get(j) - m) * rs;
+                        const float dn = wv[jj] * gy[i].get(j);
+                        const float upd = dv[i].get(j) + (dn - dn_mean - nrm * dnn_mean) * rs;
+                        dv[i].set(j, upd);
+                        if (COLSUM) cs_acc[i * VN + j] += dv[i].get(j);  // the value as stored (rounded)
+                    }
                 }
                 dv[i].store(dinp + row * c + idx);
             }
