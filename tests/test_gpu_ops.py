@@ -207,7 +207,8 @@ def test_attention_f32(vitrs, causal, b, t, c, nh):
 
 
 @pytest.mark.parametrize("causal", [0, 1])
-@pytest.mark.parametrize("b,t,c,nh", [(2, 65, 64, 4), (2, 197, 192, 3), (1, 50, 128, 2), (1, 300, 64, 1), (2, 128, 128, 2)])
+@pytest.mark.parametrize("b,t,c,nh", [(2, 65, 64, 4), (2, 197, 192, 3), (1, 50, 128, 2), (1, 300, 64, 1), (2, 128, 128, 2), (1, 785, 128, 2),
+                                      (3, 17, 64, 1), (1, 256, 64, 1), (1, 257, 64, 1)])
 def test_attention_bf16(vitrs, causal, b, t, c, nh):
     """Fused (lse-only) attention: hs = 64 runs the tensor-core kernel, others the SIMT one."""
     rng = np.random.default_rng(t + c)

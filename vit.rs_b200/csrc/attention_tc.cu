@@ -503,10 +503,465 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
 }
 
-int encode_map3d(vitrs_ctx* ctx, CUtensorMap* map, const void* basep, uint64_t cols, uint64_t rows, uint64_t batch) {
+
+// =====================================================================================================
+// Streaming kernels: any sequence length (ViT-B/8: T = 785), two CTAs per SM, every probability operand in
+// tensor memory.  Forward streams 128-key K/V tiles with an online softmax.  Backward is split in two
+// kernels so that nothing is reduced through global memory and each CTA needs only 256 TMEM columns:
+//   dKV: one CTA per (batch, head, 128-key tile), keys on TMEM lanes, streams 64-query tiles of Q and dO;
+//   dQ : one CTA per (batch, head, 128-query tile), queries on TMEM lanes, streams 64-key tiles of K and V.
+// S and dP are recomputed in both (7 matmuls instead of 5); P / dS are packed to bf16 in place in TMEM and
+// consumed as the A operand of the next MMA, so no probability ever touches shared or global memory.
+// =====================================================================================================
+constexpr int SUB = 64;                       // streamed sub-tile (rows)
+constexpr int SUB_BYTES = SUB * HS * 2;       // 8 KB
+
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
+                       int T, int C, int NH, int causal) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sQ = base, sK = sQ + TILE_BYTES, sV = sK + 2 * TILE_BYTES;
+    const uint32_t bar0 = sV + 2 * TILE_BYTES;
+    const uint32_t bar_q = bar0, bar_k = bar0 + 8, bar_v = bar0 + 24, bar_s = bar0 + 40, bar_o = bar0 + 48;  // bar_k[2], bar_v[2]
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 56);
+    constexpr uint32_t TMEM_COLS = 256, cO = 192;  // S [0,128) -> P packed [0,64); O [192,256)
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int NT = (T + TILE - 1) / TILE;
+    const int qt = blockIdx.x % NT, bh = blockIdx.x / NT, b = bh / NH, h = bh - b * NH;
+    const int NJ = causal ? qt + 1 : NT;
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_out);
+        mbar_init(bar_q, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_k + 8 * i, 1); mbar_init(bar_v + 8 * i, 1); }
+        mbar_init(bar_s, 1);
+        mbar_init(bar_o, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(smem_u32((const void*)slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+    if (tid == 0) {
+        mbar_expect_tx(bar_q, TILE_BYTES);
+        tma_load_3d(sQ, &tm_qkv, bar_q, h * HS, qt * TILE, b);
+        for (int j = 0; j < 2 && j < NJ; ++j) {
+            mbar_expect_tx(bar_k + 8 * j, TILE_BYTES);
+            tma_load_3d(sK + j * TILE_BYTES, &tm_qkv, bar_k + 8 * j, C + h * HS, j * TILE, b);
+            mbar_expect_tx(bar_v + 8 * j, TILE_BYTES);
+            tma_load_3d(sV + j * TILE_BYTES, &tm_qkv, bar_v + 8 * j, 2 * C + h * HS, j * TILE, b);
+        }
+    }
+    const int r = tid;
+    const int q = qt * TILE + r;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int kend = causal ? min(T, q + 1) : T;
+    const float scale = 1.0f / sqrtf((float)HS);
+    const float sl2 = kLog2e * scale;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < NJ; ++j) {
+        const int buf = j & 1;
+        const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        const int k0 = j * TILE;
+        const int nk16 = (min(TILE, T - k0) + 15) & ~15;
+        if (tid == 0) {
+            if (j == 0) mbar_wait(bar_q, 0);
+            mbar_wait(bar_k + 8 * buf, ph);
+            tc_fence_after();
+            const uint32_t idesc = make_idesc(TILE, nk16, 0, 0);
+#pragma unroll
+            for (int k = 0; k < HS / 16; ++k)
+                umma_bf16(tmem_base, make_desc(sQ + k * 32, 0, 1024), make_desc(sK + buf * TILE_BYTES + k * 32, 0, 1024), idesc, k > 0);
+            umma_commit(bar_s);
+        }
+        mbar_wait(bar_s, (uint32_t)(j & 1));
+        tc_fence_after();
+        if (tid == 0 && j + 2 < NJ) {  // the K buffer is free again
+            mbar_expect_tx(bar_k + 8 * buf, TILE_BYTES);
+            tma_load_3d(sK + buf * TILE_BYTES, &tm_qkv, bar_k + 8 * buf, C + h * HS, (j + 2) * TILE, b);
+        }
+        const int nchunks = (nk16 + 31) >> 5;
+        float tmax = -INFINITY;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + ch * 32, v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (k0 + ch * 32 + c < kend) tmax = fmaxf(tmax, __uint_as_float(v[c]));
+        }
+        const float m_new = fmaxf(m_run, tmax);
+        const float mns = m_new * sl2;
+        float rsum = 0.f;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t v[32], pk[16];
+            tmem_ld32(lane_addr + ch * 32, v);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const int k = k0 + ch * 32 + 2 * c;
+                const float p0 = k < kend ? ex2(__uint_as_float(v[2 * c]) * sl2 - mns) : 0.f;
+                const float p1 = k + 1 < kend ? ex2(__uint_as_float(v[2 * c + 1]) * sl2 - mns) : 0.f;
+                rsum += p0 + p1;
+                pk[c] = pack_bf16(p0, p1);
+            }
+            tmem_st16(lane_addr + ch * 16, pk);
+        }
+        const float alpha = m_run == -INFINITY ? 0.f : ex2((m_run - m_new) * sl2);
+        l_run = l_run * alpha + rsum;
+        m_run = m_new;
+        if (j > 0) {
+            mbar_wait(bar_o, (uint32_t)((j - 1) & 1));  // P_{j-1} V_{j-1} has landed in O
+            tc_fence_after();
+            if (tid == 0 && j + 1 < NJ) {  // its V buffer is free again
+                mbar_expect_tx(bar_v + 8 * ((j + 1) & 1), TILE_BYTES);
+                tma_load_3d(sV + ((j + 1) & 1) * TILE_BYTES, &tm_qkv, bar_v + 8 * ((j + 1) & 1), 2 * C + h * HS, (j + 1) * TILE, b);
+            }
+            if (!__all_sync(0xffffffffu, alpha == 1.0f)) {  // rescale the accumulator to the new running max
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + cO + half * 32, v);
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        uint32_t o16[16];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) o16[c] = __float_as_uint(__uint_as_float(v[g * 16 + c]) * alpha);
+                        tmem_st16(lane_addr + cO + half * 32 + g * 16, o16);
+                    }
+                }
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait(bar_v + 8 * buf, j == 1 ? 0u : ph);
+            const uint32_t idesc = make_idesc(TILE, HS, 0, 1);
+            for (int k16 = 0; k16 < nk16 / 16; ++k16)
+                umma_bf16_ts(tmem_base + cO, tmem_base + k16 * 8, make_desc(sV + buf * TILE_BYTES + k16 * 2048, TILE_BYTES, 1024), idesc,
+                             (j > 0 || k16 > 0) ? 1u : 0u);
+            umma_commit(bar_o);
+        }
+    }
+    mbar_wait(bar_o, (uint32_t)((NJ - 1) & 1));
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + cO + half * 32, v);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            st_shared_v4(sw128(sQ, r, half * 4 + g), pack_bf16(__uint_as_float(v[g * 8]) * inv, __uint_as_float(v[g * 8 + 1]) * inv),
+                         pack_bf16(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv),
+                         pack_bf16(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv),
+                         pack_bf16(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv));
+    }
+    if (q < T) lse[(long)bh * T + q] = m_run * scale + logf(l_run);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tma_store_3d(&tm_out, sQ, h * HS, qt * TILE, b);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// this thread's 32 fp32 accumulator columns -> (+ old bf16 values) -> bf16 -> its half-row of a swizzled [128][64] staging tile
+__device__ __forceinline__ void stage_half_row(uint32_t tile, int r, int half, const uint32_t (&v)[32], const bf16* old) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+        if (old) {
+            Vec16<bf16> o;
+            o.load(old + g * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += o.get(j);
+        }
+        st_shared_v4(sw128(tile, r, half * 4 + g), pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_do64,
+                    const __grid_constant__ CUtensorMap tm_dqkv, bf16* __restrict__ dqkv, const float* __restrict__ lse,
+                    const float* __restrict__ dsum, int T, int C, int NH, int causal, int accumulate) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sK = base, sV = sK + TILE_BYTES, sQ = sV + TILE_BYTES, sdO = sQ + 2 * SUB_BYTES;
+    const uint32_t bar0 = sdO + 2 * SUB_BYTES;
+    const uint32_t bar_kv = bar0, bar_q = bar0 + 8, bar_s = bar0 + 24, bar_acc = bar0 + 32;  // bar_q[2]: Q_s and dO_s of one buffer
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 40);
+    float* stat = reinterpret_cast<float*>(gen + (bar0 - base) + 64);  // lse*log2e [T], D [T]
+    constexpr uint32_t TMEM_COLS = 256, cST = 0, cDPT = 64, cDV = 128, cDK = 192;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int NT = (T + TILE - 1) / TILE, NS = (T + SUB - 1) / SUB;
+    const int jt = blockIdx.x % NT, bh = blockIdx.x / NT, b = bh / NH, h = bh - b * NH;
+    const int s0 = causal ? (jt * TILE) / SUB : 0;
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_q64); tma_prefetch_desc(&tm_do64); tma_prefetch_desc(&tm_dqkv);
+        mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_q + 8, 1); mbar_init(bar_s, 1); mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(smem_u32((const void*)slot), TMEM_COLS);
+    for (int i = tid; i < T; i += 256) {
+        stat[i] = lse[(long)bh * T + i] * kLog2e;
+        stat[T + i] = dsum[(long)bh * T + i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+    const bool leader = tid == 0;
+    auto load_sub = [&](int s, int buf) {
+        mbar_expect_tx(bar_q + 8 * buf, 2 * SUB_BYTES);
+        tma_load_3d(sQ + buf * SUB_BYTES, &tm_q64, bar_q + 8 * buf, h * HS, s * SUB, b);
+        tma_load_3d(sdO + buf * SUB_BYTES, &tm_do64, bar_q + 8 * buf, h * HS, s * SUB, b);
+    };
+    if (leader) {
+        mbar_expect_tx(bar_kv, 2 * TILE_BYTES);
+        tma_load_3d(sK, &tm_kv, bar_kv, C + h * HS, jt * TILE, b);
+        tma_load_3d(sV, &tm_kv, bar_kv, 2 * C + h * HS, jt * TILE, b);
+        load_sub(s0, 0);
+        if (s0 + 1 < NS) load_sub(s0 + 1, 1);
+    }
+    const int r = tid & 127, half = warp >> 2;
+    const int key = jt * TILE + r;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const float scale = 1.0f / sqrtf((float)HS);
+    const float sl2 = kLog2e * scale;
+
+    for (int s = s0; s < NS; ++s) {
+        const int it = s - s0, buf = it & 1;
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        const int nq = min(SUB, T - s * SUB), nq16 = (nq + 15) & ~15;
+        if (leader) {
+            if (it == 0) mbar_wait(bar_kv, 0);
+            mbar_wait(bar_q + 8 * buf, ph);
+            tc_fence_after();
+            const uint32_t idesc = make_idesc(TILE, nq16, 0, 0);
+#pragma unroll
+            for (int k = 0; k < HS / 16; ++k)  // S^T = K_j Q_s^T
+                umma_bf16(tmem_base + cST, make_desc(sK + k * 32, 0, 1024), make_desc(sQ + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
+#pragma unroll
+            for (int k = 0; k < HS / 16; ++k)  // dP^T = V_j dO_s^T
+                umma_bf16(tmem_base + cDPT, make_desc(sV + k * 32, 0, 1024), make_desc(sdO + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
+            umma_commit(bar_s);  // also covers the dV / dK MMAs of the previous sub-tile
+        }
+        mbar_wait(bar_s, (uint32_t)(it & 1));
+        tc_fence_after();
+        if (leader && it >= 1 && s + 1 < NS) load_sub(s + 1, buf ^ 1);  // the previous sub-tile's buffer is free
+        const bool mine = half * 32 < nq16;  // warp-uniform
+        uint32_t sv[32], dpv[32];
+        if (mine) {
+            tmem_ld32(tmem_base + lane_off + cST + half * 32, sv);
+            tmem_ld32(tmem_base + lane_off + cDPT + half * 32, dpv);
+        }
+        tc_fence_before();
+        __syncthreads();  // every S / dP column has been read: packing in place is safe
+        if (mine) {
+            uint32_t pp[16], dd[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                float pv[2], dv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int qc = half * 32 + 2 * c + e;
+                    const int q = s * SUB + qc;
+                    const bool live = key < T && qc < nq && (!causal || key <= q);
+                    const float p = live ? ex2(__uint_as_float(sv[2 * c + e]) * sl2 - stat[min(q, T - 1)]) : 0.f;
+                    pv[e] = p;
+                    dv[e] = p * (__uint_as_float(dpv[2 * c + e]) - stat[T + min(q, T - 1)]) * scale;
+                }
+                pp[c] = pack_bf16(pv[0], pv[1]);
+                dd[c] = pack_bf16(dv[0], dv[1]);
+            }
+            tmem_st16(tmem_base + lane_off + cST + half * 16, pp);
+            tmem_st16(tmem_base + lane_off + cDPT + half * 16, dd);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        if (leader) {
+            tc_fence_after();
+            const uint32_t idesc = make_idesc(TILE, HS, 0, 1);  // A from TMEM, B MN-major
+            for (int k16 = 0; k16 < nq16 / 16; ++k16) {
+                const uint32_t acc = (it > 0 || k16 > 0) ? 1u : 0u;
+                umma_bf16_ts(tmem_base + cDV, tmem_base + cST + k16 * 8, make_desc(sdO + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc, acc);
+                umma_bf16_ts(tmem_base + cDK, tmem_base + cDPT + k16 * 8, make_desc(sQ + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc, acc);
+            }
+        }
+    }
+    if (leader) umma_commit(bar_acc);
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    {
+        uint32_t v[32];
+        const bf16* oldv = (accumulate && key < T) ? dqkv + ((long)b * T + key) * 3 * C + 2 * C + h * HS + half * 32 : nullptr;
+        const bf16* oldk = (accumulate && key < T) ? dqkv + ((long)b * T + key) * 3 * C + C + h * HS + half * 32 : nullptr;
+        tmem_ld32(tmem_base + lane_off + cDV + half * 32, v);
+        stage_half_row(sV, r, half, v, oldv);
+        tmem_ld32(tmem_base + lane_off + cDK + half * 32, v);
+        stage_half_row(sK, r, half, v, oldk);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (leader) {
+        tma_store_3d(&tm_dqkv, sV, 2 * C + h * HS, jt * TILE, b);
+        tma_store_3d(&tm_dqkv, sK, C + h * HS, jt * TILE, b);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_kv64,
+                   const __grid_constant__ CUtensorMap tm_dqkv, bf16* __restrict__ dqkv, const float* __restrict__ lse,
+                   const float* __restrict__ dsum, int T, int C, int NH, int causal, int accumulate) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sQ = base, sdO = sQ + TILE_BYTES, sK = sdO + TILE_BYTES, sV = sK + 2 * SUB_BYTES;
+    const uint32_t bar0 = sV + 2 * SUB_BYTES;
+    const uint32_t bar_qdo = bar0, bar_kv = bar0 + 8, bar_s = bar0 + 24, bar_acc = bar0 + 32;  // bar_kv[2]
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 40);
+    constexpr uint32_t TMEM_COLS = 256, cS = 0, cDP = 64, cDQ = 128;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int NT = (T + TILE - 1) / TILE;
+    const int qt = blockIdx.x % NT, bh = blockIdx.x / NT, b = bh / NH, h = bh - b * NH;
+    const int kmax = causal ? min(T, (qt + 1) * TILE) : T;  // keys this query tile can see
+    const int NS = (kmax + SUB - 1) / SUB;
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_kv64); tma_prefetch_desc(&tm_dqkv);
+        mbar_init(bar_qdo, 1); mbar_init(bar_kv, 1); mbar_init(bar_kv + 8, 1); mbar_init(bar_s, 1); mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(smem_u32((const void*)slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+    const bool leader = tid == 0;
+    auto load_sub = [&](int s, int buf) {
+        mbar_expect_tx(bar_kv + 8 * buf, 2 * SUB_BYTES);
+        tma_load_3d(sK + buf * SUB_BYTES, &tm_kv64, bar_kv + 8 * buf, C + h * HS, s * SUB, b);
+        tma_load_3d(sV + buf * SUB_BYTES, &tm_kv64, bar_kv + 8 * buf, 2 * C + h * HS, s * SUB, b);
+    };
+    if (leader) {
+        mbar_expect_tx(bar_qdo, 2 * TILE_BYTES);
+        tma_load_3d(sQ, &tm_q, bar_qdo, h * HS, qt * TILE, b);
+        tma_load_3d(sdO, &tm_do, bar_qdo, h * HS, qt * TILE, b);
+        load_sub(0, 0);
+        if (1 < NS) load_sub(1, 1);
+    }
+    const int r = tid & 127, half = warp >> 2;
+    const int q = qt * TILE + r;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const float scale = 1.0f / sqrtf((float)HS);
+    const float sl2 = kLog2e * scale;
+    const float lse2 = q < T ? lse[(long)bh * T + q] * kLog2e : 0.f;
+    const float dq_ = q < T ? dsum[(long)bh * T + q] : 0.f;
+
+    for (int s = 0; s < NS; ++s) {
+        const int buf = s & 1;
+        const uint32_t ph = (uint32_t)((s >> 1) & 1);
+        const int nk = min(SUB, T - s * SUB), nk16 = (nk + 15) & ~15;
+        if (leader) {
+            if (s == 0) mbar_wait(bar_qdo, 0);
+            mbar_wait(bar_kv + 8 * buf, ph);
+            tc_fence_after();
+            const uint32_t idesc = make_idesc(TILE, nk16, 0, 0);
+#pragma unroll
+            for (int k = 0; k < HS / 16; ++k)  // S = Q_i K_s^T
+                umma_bf16(tmem_base + cS, make_desc(sQ + k * 32, 0, 1024), make_desc(sK + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
+#pragma unroll
+            for (int k = 0; k < HS / 16; ++k)  // dP = dO_i V_s^T
+                umma_bf16(tmem_base + cDP, make_desc(sdO + k * 32, 0, 1024), make_desc(sV + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
+            umma_commit(bar_s);  // also covers the dQ MMAs of the previous sub-tile
+        }
+        mbar_wait(bar_s, (uint32_t)(s & 1));
+        tc_fence_after();
+        if (leader && s >= 1 && s + 1 < NS) load_sub(s + 1, buf ^ 1);
+        const bool mine = half * 32 < nk16;
+        uint32_t sv[32], dpv[32];
+        if (mine) {
+            tmem_ld32(tmem_base + lane_off + cS + half * 32, sv);
+            tmem_ld32(tmem_base + lane_off + cDP + half * 32, dpv);
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (mine) {
+            uint32_t dd[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                float dv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int kc = half * 32 + 2 * c + e;
+                    const int key = s * SUB + kc;
+                    const bool live = q < T && kc < nk && (!causal || key <= q);
+                    const float p = live ? ex2(__uint_as_float(sv[2 * c + e]) * sl2 - lse2) : 0.f;
+                    dv[e] = p * (__uint_as_float(dpv[2 * c + e]) - dq_) * scale;
+                }
+                dd[c] = pack_bf16(dv[0], dv[1]);
+            }
+            tmem_st16(tmem_base + lane_off + cS + half * 16, dd);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        if (leader) {
+            tc_fence_after();
+            const uint32_t idesc = make_idesc(TILE, HS, 0, 1);
+            for (int k16 = 0; k16 < nk16 / 16; ++k16)  // dQ_i += dS K_s
+                umma_bf16_ts(tmem_base + cDQ, tmem_base + cS + k16 * 8, make_desc(sK + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc,
+                             (s > 0 || k16 > 0) ? 1u : 0u);
+        }
+    }
+    if (leader) umma_commit(bar_acc);
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    {
+        uint32_t v[32];
+        const bf16* old = (accumulate && q < T) ? dqkv + ((long)b * T + q) * 3 * C + h * HS + half * 32 : nullptr;
+        tmem_ld32(tmem_base + lane_off + cDQ + half * 32, v);
+        stage_half_row(sQ, r, half, v, old);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (leader) {
+        tma_store_3d(&tm_dqkv, sQ, h * HS, qt * TILE, b);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+int encode_map3d(vitrs_ctx* ctx, CUtensorMap* map, const void* basep, uint64_t cols, uint64_t rows, uint64_t batch, uint32_t box_rows = TILE) {
     cuuint64_t dims[3] = {cols, rows, batch};
     cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
-    cuuint32_t box[3] = {HS, TILE, 1};
+    cuuint32_t box[3] = {HS, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(basep), dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -518,7 +973,7 @@ int encode_map3d(vitrs_ctx* ctx, CUtensorMap* map, const void* basep, uint64_t c
 }
 
 bool tc_shape_ok(const void* a, const void* b_, int t, int c, int nh) {
-    return nh > 0 && c % nh == 0 && c / nh == HS && t >= 1 && t <= 2 * TILE && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b_ & 15) == 0;
+    return nh > 0 && c % nh == 0 && c / nh == HS && t >= 1 && t <= 4096 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b_ & 15) == 0;
 }
 
 }  // namespace
@@ -531,6 +986,19 @@ int op_attention_forward_tc(vitrs_ctx* ctx, bf16* out, float* lse, const bf16* q
     const int NT = (t + TILE - 1) / TILE;
     const int NK = (t + 15) & ~15;
     static const bool use_v1 = getenv("VITRS_ATTN_FWD_V1") != nullptr;  // A/B aid: the two-tiles-per-CTA kernel with P in shared memory
+    static const bool force_stream = getenv("VITRS_ATTN_FWD_STREAM") != nullptr;  // test aid: streaming kernel at any T
+    if (t > 2 * TILE || force_stream) {
+        VITRS_TRY(encode_map3d(ctx, &tm_out, out, (uint64_t)c, t, b));
+        const size_t smem = (size_t)5 * TILE_BYTES + 64 + 1024;
+        static bool configured_s = false;
+        if (!configured_s) {
+            VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured_s = true;
+        }
+        attn_fwd_stream_kernel<<<b * nh * NT, 128, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, causal);
+        VITRS_LAUNCHED(ctx);
+        return VITRS_OK;
+    }
     if (!use_v1) {
         VITRS_TRY(encode_map3d(ctx, &tm_out, out, (uint64_t)c, t, b));
         const size_t smem = (size_t)(1 + 2 * NT) * TILE_BYTES + 64 + 1024;
@@ -565,10 +1033,40 @@ int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const
     float* dsum = ctx->scratch;
     attn_bwd_prep_kernel<<<ceil_div((long)b * t, 8), 256, 0, ctx->stream>>>(dsum, dout, out, b, t, c, nh);
     VITRS_LAUNCHED(ctx);
+    const int NT = (t + TILE - 1) / TILE;
+    // T <= 256: the one-CTA-per-head kernel (5 matmuls, dQ kept in TMEM) is faster (measured 139.6 vs 143.8 ms per
+    // ViT-B/16 step); longer sequences take the two streaming kernels.  VITRS_ATTN_BWD_STREAM forces them (test / A-B aid).
+    static const bool force_stream = getenv("VITRS_ATTN_BWD_STREAM") != nullptr;
+    if (t > 2 * TILE || force_stream) {
+        CUtensorMap tm_q128, tm_q64, tm_do128, tm_do64, tm_dqkv;
+        VITRS_TRY(encode_map3d(ctx, &tm_q128, qkv, 3 * (uint64_t)c, t, b, TILE));
+        VITRS_TRY(encode_map3d(ctx, &tm_q64, qkv, 3 * (uint64_t)c, t, b, SUB));
+        VITRS_TRY(encode_map3d(ctx, &tm_do128, dout, (uint64_t)c, t, b, TILE));
+        VITRS_TRY(encode_map3d(ctx, &tm_do64, dout, (uint64_t)c, t, b, SUB));
+        VITRS_TRY(encode_map3d(ctx, &tm_dqkv, dqkv, 3 * (uint64_t)c, t, b, TILE));
+        const size_t smem_kv = (size_t)2 * TILE_BYTES + 4 * SUB_BYTES + 64 + 2 * (size_t)t * 4 + 1024;
+        const size_t smem_q = (size_t)2 * TILE_BYTES + 4 * SUB_BYTES + 64 + 1024;
+        static size_t conf_kv = 0;
+        static bool conf_q = false;
+        if (smem_kv > conf_kv) {
+            VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+            conf_kv = smem_kv;
+        }
+        if (!conf_q) {
+            VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+            conf_q = true;
+        }
+        attn_bwd_dkv_kernel<<<b * nh * NT, kThreads, smem_kv, ctx->stream>>>(tm_q128, tm_q64, tm_do64, tm_dqkv, dqkv, lse, dsum, t, c, nh, causal,
+                                                                           accumulate);
+        VITRS_LAUNCHED(ctx);
+        attn_bwd_dq_kernel<<<b * nh * NT, kThreads, smem_q, ctx->stream>>>(tm_q128, tm_do128, tm_q64, tm_dqkv, dqkv, lse, dsum, t, c, nh, causal,
+                                                                         accumulate);
+        VITRS_LAUNCHED(ctx);
+        return VITRS_OK;
+    }
     CUtensorMap tm_qkv, tm_do;
     VITRS_TRY(encode_map3d(ctx, &tm_qkv, qkv, 3 * (uint64_t)c, t, b));
     VITRS_TRY(encode_map3d(ctx, &tm_do, dout, (uint64_t)c, t, b));
-    const int NT = (t + TILE - 1) / TILE;
     const size_t smem = (size_t)NT * 4 * TILE_BYTES + 4 * TILE_BYTES + 2 * 256 * 4 + 64 + 1024;
     static size_t configured = 0;
     if (smem > configured) {
