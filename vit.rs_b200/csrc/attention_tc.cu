@@ -29,6 +29,8 @@ constexpr int TILE = 128;             // tokens per tile
 constexpr int HS = 64;                // head size
 constexpr int TILE_BYTES = TILE * HS * 2;  // 16 KB: one TMA box, 128 rows of 128 bytes
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr int SUB = 64;                       // 64-row sub-tile (streamed tiles, pipelined backward)
+constexpr int SUB_BYTES = SUB * HS * 2;       // 8 KB
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
@@ -504,6 +506,206 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 }
 
 
+// ---- backward, one CTA per (batch, head), software-pipelined (non-causal, T <= 256) ---------------------
+// Same five matmuls as attn_bwd_tc_kernel, but the work is cut into (128-key tile j) x (64-query sub-tile s)
+// iterations and three agents run concurrently:
+//   issuer (one thread)  : S^T / dP^T MMAs of iteration n+1 are in flight while iteration n is in its SIMT phase,
+//                          then the dV / dK (and, per query tile, dQ) MMAs of iteration n
+//   SIMT group A / B     : 128 threads each (one per key = TMEM lane), alternate iterations; P^T is packed to bf16
+//                          in place in tensor memory (A operand of dV), dS^T goes to one of four shared tiles that
+//                          serve as the K-major A operand of dK and, pairwise, as the MN-major A operand of dQ
+// TMEM: 2 x {S^T 64, dP^T 64} + dV 64 + dK 64 + dQ_0 64 + dQ_1 64 = 512 columns.
+constexpr int kPipeThreads = 384;  // warps 0-3: control (issuer = warp 0 lane 0, TMEM owner = warp 1), 4-7: group A, 8-11: group B
+
+__device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+__global__ void __launch_bounds__(kPipeThreads, 1)
+attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, bf16* __restrict__ dqkv,
+                     const float* __restrict__ lse, const float* __restrict__ dsum, int T, int C, int NH, int NT, int accumulate) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sQ = base, sK = sQ + NT * TILE_BYTES, sV = sK + NT * TILE_BYTES, sdO = sV + NT * TILE_BYTES;
+    const uint32_t sdS = sdO + NT * TILE_BYTES;            // 4 x [128 keys][64 queries] bf16, 128B-swizzled
+    const uint32_t sStat = sdS + 4 * TILE_BYTES;           // lse*log2e [256], D [256]
+    const uint32_t bar0 = sStat + 2 * 256 * 4;
+    const uint32_t bar_load = bar0, s_full = bar0 + 8, x_free = bar0 + 24, p_full = bar0 + 40, ds_free = bar0 + 56,  // [2],[2],[2],[4]
+                   acc_full = bar0 + 88, acc_free = bar0 + 96, dq_full = bar0 + 104;
+    float* stat = reinterpret_cast<float*>(gen + (sStat - base));
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 112);
+    constexpr uint32_t TMEM_COLS = 512, cDV = 256, cDK = 320, cDQ = 384;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bh = blockIdx.x, b = bh / NH, h = bh - b * NH;
+    const int NSUB = (T + SUB - 1) / SUB;   // 64-query sub-tiles
+    const int N = NT * NSUB;                // iterations: n = j * NSUB + s
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_do);
+        mbar_init(bar_load, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(x_free + 8 * i, 1); mbar_init(p_full + 8 * i, 128); }
+        for (int i = 0; i < 4; ++i) mbar_init(ds_free + 8 * i, 1);
+        mbar_init(acc_full, 1);
+        mbar_init(acc_free, 256);
+        mbar_init(dq_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_load, (uint32_t)(4 * NT * TILE_BYTES));
+        for (int i = 0; i < NT; ++i) {
+            tma_load_3d(sK + i * TILE_BYTES, &tm_qkv, bar_load, C + h * HS, i * TILE, b);
+            tma_load_3d(sQ + i * TILE_BYTES, &tm_qkv, bar_load, h * HS, i * TILE, b);
+            tma_load_3d(sV + i * TILE_BYTES, &tm_qkv, bar_load, 2 * C + h * HS, i * TILE, b);
+            tma_load_3d(sdO + i * TILE_BYTES, &tm_do, bar_load, h * HS, i * TILE, b);
+        }
+    }
+    if (warp == 1) tmem_alloc(smem_u32((const void*)slot), TMEM_COLS);
+    for (int i = tid; i < 256; i += kPipeThreads) {
+        stat[i] = i < T ? lse[(long)bh * T + i] * kLog2e : 0.f;
+        stat[256 + i] = i < T ? dsum[(long)bh * T + i] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+    const float scale = 1.0f / sqrtf((float)HS);
+    const float sl2 = kLog2e * scale;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================================ issuer ================================
+            mbar_wait(bar_load, 0);
+            tc_fence_after();
+            const uint32_t idesc_kk = make_idesc(TILE, HS, 0, 1);
+            const uint32_t idesc_mn = make_idesc(TILE, HS, 1, 1);
+            for (int n = 0; n <= N; ++n) {
+                if (n < N) {  // S^T and dP^T of iteration n
+                    const int j = n / NSUB, s_ = n - j * NSUB, bx = n & 1;
+                    const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
+                    if (n >= 2) mbar_wait(x_free + 8 * bx, (uint32_t)(((n >> 1) - 1) & 1));
+                    tc_fence_after();
+                    const uint32_t idesc = make_idesc(TILE, nq16, 0, 0);
+                    const uint32_t qoff = (s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES;
+#pragma unroll
+                    for (int k = 0; k < HS / 16; ++k)
+                        umma_bf16(tmem_base + bx * 128, make_desc(sK + j * TILE_BYTES + k * 32, 0, 1024), make_desc(sQ + qoff + k * 32, 0, 1024),
+                                  idesc, k > 0);
+#pragma unroll
+                    for (int k = 0; k < HS / 16; ++k)
+                        umma_bf16(tmem_base + bx * 128 + 64, make_desc(sV + j * TILE_BYTES + k * 32, 0, 1024),
+                                  make_desc(sdO + qoff + k * 32, 0, 1024), idesc, k > 0);
+                    umma_commit(s_full + 8 * bx);
+                }
+                if (n >= 1) {  // dV, dK (and dQ) of iteration n-1
+                    const int m = n - 1, j = m / NSUB, s_ = m - j * NSUB, bx = m & 1;
+                    const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
+                    const int nk16 = (min(TILE, T - j * TILE) + 15) & ~15;
+                    const uint32_t qoff = (s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES;
+                    mbar_wait(p_full + 8 * bx, (uint32_t)((m >> 1) & 1));
+                    tc_fence_after();
+                    if (s_ == 0 && j > 0) {  // the previous key tile's dV / dK have been read out
+                        mbar_wait(acc_free, (uint32_t)((j - 1) & 1));
+                        tc_fence_after();
+                    }
+                    const uint32_t sbuf = sdS + (s_ & 3) * TILE_BYTES;
+                    for (int k16 = 0; k16 < nq16 / 16; ++k16) {
+                        const uint32_t acc = (s_ > 0 || k16 > 0) ? 1u : 0u;
+                        umma_bf16_ts(tmem_base + cDV, tmem_base + bx * 128 + k16 * 8, make_desc(sdO + qoff + k16 * 2048, TILE_BYTES, 1024), idesc_kk, acc);
+                        umma_bf16(tmem_base + cDK, make_desc(sbuf + k16 * 32, 0, 1024), make_desc(sQ + qoff + k16 * 2048, TILE_BYTES, 1024), idesc_kk, acc);
+                    }
+                    umma_commit(x_free + 8 * bx);
+                    if ((s_ & 1) || s_ == NSUB - 1) {  // query tile i = s/2 is complete for this key tile: dQ_i += dS K_j
+                        const int i = s_ >> 1;
+                        for (int k16 = 0; k16 < nk16 / 16; ++k16)
+                            umma_bf16(tmem_base + cDQ + i * HS, make_desc(sdS + (2 * i) * TILE_BYTES + k16 * 2048, TILE_BYTES, 1024),
+                                      make_desc(sK + j * TILE_BYTES + k16 * 2048, TILE_BYTES, 1024), idesc_mn, (j > 0 || k16 > 0) ? 1u : 0u);
+                        umma_commit(ds_free + 8 * ((2 * i) & 3));
+                        if (s_ & 1) umma_commit(ds_free + 8 * ((2 * i + 1) & 3));
+                    }
+                    if (s_ == NSUB - 1) umma_commit(acc_full);
+                }
+            }
+            umma_commit(dq_full);
+        }
+    } else if (warp >= 4) {
+        // ================================ SIMT groups ================================
+        const int g = (warp - 4) >> 2;          // group 0 / 1
+        const int r = (warp & 3) * 32 + lane;   // TMEM lane = key within the tile / output row
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t ds_uses = 0;                   // per buffer: how many times this group has written it (2 bits each... counts mod 2 suffice)
+        for (int j = 0; j < NT; ++j) {
+            const int key = j * TILE + r;
+            for (int s_ = 0; s_ < NSUB; ++s_) {
+                const int n = j * NSUB + s_;
+                if ((n & 1) != g) continue;
+                const int nq = min(SUB, T - s_ * SUB), nq16 = (nq + 15) & ~15;
+                const uint32_t xb = tmem_base + lane_off + (uint32_t)(g * 128);
+                mbar_wait(s_full + 8 * g, (uint32_t)((n >> 1) & 1));
+                tc_fence_after();
+                const int bs = s_ & 3;
+                const uint32_t sbuf = sdS + bs * TILE_BYTES;
+                if (j > 0) mbar_wait(ds_free + 8 * bs, (uint32_t)((j - 1) & 1));  // the MMAs that read this tile last time have retired
+                (void)ds_uses;
+                const int nch = (nq16 + 31) >> 5;
+                for (int ch = 0; ch < nch; ++ch) {
+                    uint32_t sv[32], dp[32], pk[16];
+                    tmem_ld32(xb + ch * 32, sv);
+                    tmem_ld32(xb + 64 + ch * 32, dp);
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        float ds[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int qc = ch * 32 + g8 * 8 + c;
+                            const int q = s_ * SUB + qc;
+                            const bool live = key < T && qc < nq;
+                            const float pv = live ? ex2(__uint_as_float(sv[g8 * 8 + c]) * sl2 - stat[q & 255]) : 0.f;
+                            ds[c] = pv * (__uint_as_float(dp[g8 * 8 + c]) - stat[256 + (q & 255)]) * scale;
+                            sv[g8 * 8 + c] = __float_as_uint(pv);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) pk[g8 * 4 + c] = pack_bf16(__uint_as_float(sv[g8 * 8 + 2 * c]), __uint_as_float(sv[g8 * 8 + 2 * c + 1]));
+                        st_shared_v4(sw128(sbuf, r, ch * 4 + g8), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
+                                     pack_bf16(ds[6], ds[7]));
+                    }
+                    tmem_st16(xb + ch * 16, pk);  // P^T in place: columns [16ch, 16ch+16) were consumed by chunk <= ch
+                }
+                tmem_st_wait();
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive_cnt(p_full + 8 * g);
+            }
+            // ---- dV_j (group 0) / dK_j (group 1) ----
+            mbar_wait(acc_full, (uint32_t)(j & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_off + (g == 0 ? cDV : cDK) + half * 32, v);
+                if (key < T) store_row32(dqkv + ((long)b * T + key) * 3 * C + (g == 0 ? 2 * C : C) + h * HS + half * 32, v, 1.0f, accumulate);
+            }
+            tc_fence_before();
+            mbar_arrive_cnt(acc_free);
+        }
+        // ---- dQ_0 (group 0) / dQ_1 (group 1) ----
+        mbar_wait(dq_full, 0);
+        tc_fence_after();
+        if (g < NT) {
+            const int q = g * TILE + r;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_off + cDQ + g * HS + half * 32, v);
+                if (q < T) store_row32(dqkv + ((long)b * T + q) * 3 * C + h * HS + half * 32, v, 1.0f, accumulate);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // =====================================================================================================
 // Streaming kernels: any sequence length (ViT-B/8: T = 785), two CTAs per SM, every probability operand in
 // tensor memory.  Forward streams 128-key K/V tiles with an online softmax.  Backward is split in two
@@ -513,8 +715,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 // S and dP are recomputed in both (7 matmuls instead of 5); P / dS are packed to bf16 in place in TMEM and
 // consumed as the A operand of the next MMA, so no probability ever touches shared or global memory.
 // =====================================================================================================
-constexpr int SUB = 64;                       // streamed sub-tile (rows)
-constexpr int SUB_BYTES = SUB * HS * 2;       // 8 KB
 
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
@@ -1067,6 +1267,18 @@ int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const
     CUtensorMap tm_qkv, tm_do;
     VITRS_TRY(encode_map3d(ctx, &tm_qkv, qkv, 3 * (uint64_t)c, t, b));
     VITRS_TRY(encode_map3d(ctx, &tm_do, dout, (uint64_t)c, t, b));
+    static const bool use_v1 = getenv("VITRS_ATTN_BWD_V1") != nullptr;  // A/B aid: the unpipelined kernel
+    if (!causal && !use_v1) {
+        const size_t smem_p = (size_t)NT * 4 * TILE_BYTES + 4 * TILE_BYTES + 2 * 256 * 4 + 128 + 1024;
+        static size_t conf_p = 0;
+        if (smem_p > conf_p) {
+            VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            conf_p = smem_p;
+        }
+        attn_bwd_pipe_kernel<<<b * nh, kPipeThreads, smem_p, ctx->stream>>>(tm_qkv, tm_do, dqkv, lse, dsum, t, c, nh, NT, accumulate);
+        VITRS_LAUNCHED(ctx);
+        return VITRS_OK;
+    }
     const size_t smem = (size_t)NT * 4 * TILE_BYTES + 4 * TILE_BYTES + 2 * 256 * 4 + 64 + 1024;
     static size_t configured = 0;
     if (smem > configured) {

@@ -1,6 +1,8 @@
 // ops.cu — the extern "C" operator entry points of include/vitrs.h: argument checks and the
 // mapping from the reference's llm.c-style signatures (train_vit.rs:376-670) onto the kernels.
 // Every op is asynchronous on the context stream; there is no CPU path.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -233,7 +235,9 @@ int vitrs_attention_backward_bf16(vitrs_ctx* ctx, vitrs_bf16* dinp, const vitrs_
                                   const vitrs_bf16* inp, int b, int t, int c, int nh, int causal) {
     CTX_OR_FAIL(ctx);
     VITRS_ARG(ctx, dinp && dout && lse && inp);
-    int r = out ? op_attention_backward_tc(ctx, B16(dinp), CB16(dout), CB16(out), CB16(inp), lse, b, t, c, nh, causal, 1)
+    // the reference's `+=` contract; VITRS_ATTN_BWD_OVERWRITE (benchmark aid) times the overwrite path the fused model step uses
+    static const int accumulate = getenv("VITRS_ATTN_BWD_OVERWRITE") ? 0 : 1;
+    int r = out ? op_attention_backward_tc(ctx, B16(dinp), CB16(dout), CB16(out), CB16(inp), lse, b, t, c, nh, causal, accumulate)
                 : VITRS_ERR_UNSUPPORTED;
     if (r == VITRS_ERR_UNSUPPORTED)
         r = op_attention_backward<bf16>(ctx, B16(dinp), nullptr, nullptr, CB16(dout), CB16(inp), nullptr, lse, b, t, c, nh, causal);
