@@ -137,6 +137,39 @@ template <bool FAST> __device__ __forceinline__ float gelu_grad(float x) {
     return 0.5f * (1.0f + th) + x * 0.5f * sech2 * VITRS_GELU_S * (1.0f + 3.0f * VITRS_GELU_K * x * x);
 }
 
+// Two-wide fp32 versions on sm_100's packed f32x2 FMA / MUL (one issue slot for two lanes of a thread): the GEMM
+// epilogues that apply GELU / GELU' are instruction-issue-bound, and this halves their fp32 ALU instructions.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 gelu_fwd2(float2 x) {
+    const float2 x2 = mul2(x, x);
+    const float2 u = mul2(x, fma2(x2, splat2(VITRS_GELU_S * VITRS_GELU_K), splat2(VITRS_GELU_S)));
+    const float2 th = make_float2(tanh_sel<true>(u.x), tanh_sel<true>(u.y));
+    const float2 hx = mul2(x, splat2(0.5f));
+    return fma2(hx, th, hx);
+}
+__device__ __forceinline__ float2 gelu_grad2(float2 x) {
+    const float2 x2 = mul2(x, x);
+    const float2 u = mul2(x, fma2(x2, splat2(VITRS_GELU_S * VITRS_GELU_K), splat2(VITRS_GELU_S)));
+    const float2 th = make_float2(tanh_sel<true>(u.x), tanh_sel<true>(u.y));
+    const float2 nth = make_float2(-th.x, -th.y);
+    const float2 sech2 = fma2(nth, th, splat2(1.0f));
+    const float2 a = fma2(th, splat2(0.5f), splat2(0.5f));
+    const float2 p = fma2(x2, splat2(3.0f * VITRS_GELU_K * VITRS_GELU_S), splat2(VITRS_GELU_S));
+    const float2 q = mul2(mul2(x, splat2(0.5f)), sech2);
+    return fma2(q, p, a);
+}
+
 // ---- GEMM epilogues shared by the SIMT (fp32) and tcgen05 (bf16) kernels -------------------
 enum EpiKind {
     EPI_NONE = 0,          // out = acc

@@ -49,111 +49,126 @@ struct SmemLayout {
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
 };
 
-// ---- epilogue: one warp, its 32 accumulator rows, one 32-column piece -------------------------------
+// ---- epilogue: one warp, its 32 accumulator rows, one 64-column chunk ------------------------------
 // The accumulator row of a thread (TMEM lane) is contiguous along n, but a warp's 32 rows are ld
-// elements apart in global memory.  Results therefore leave through a warp-private [32 rows][64 B]
-// shared tile in the TMA 64B-swizzle layout and one TMA store per piece (edge tiles are clipped by the
-// tensor map); two tiles alternate so a store's shared-memory read overlaps the next piece's math.
-// Residual / pre-GELU inputs come straight into registers (64 contiguous bytes per row, whole sectors),
-// requested one piece ahead.
-__device__ __forceinline__ uint32_t stage_addr(uint32_t tile, int row, int c4) { return tile + row * 64 + ((c4 ^ ((row >> 1) & 3)) << 4); }
+// elements apart in global memory.  Both directions therefore go through a warp-private
+// [32 rows][128 B] shared tile in the TMA 128B-swizzle layout: TMA moves the box, threads touch only
+// their own row (16-byte chunks xor-swizzled by row -> conflict-free).
+__device__ __forceinline__ uint32_t stage_addr(uint32_t stage, int row, int c8) { return stage + row * 128 + ((c8 ^ (row & 7)) << 4); }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// this thread's row (= lane) of the staging tile, 8 bf16 at a time
+__device__ __forceinline__ void stage_read8(uint32_t stage, int lane, int c8, float (&f)[8]) {
+    uint32_t x[4];
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(stage_addr(stage, lane, c8)) : "memory");
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f[2 * j] = __uint_as_float(x[j] << 16);
+        f[2 * j + 1] = __uint_as_float(x[j] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ void stage_write_row(uint32_t stage, int lane, const float (&f)[64]) {
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(f[c8 * 8 + 2 * j], f[c8 * 8 + 2 * j + 1]);
+            x[j] = *reinterpret_cast<uint32_t*>(&v);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(stage, lane, c8)), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]) : "memory");
+    }
+}
 
 struct EpiMaps {
     const CUtensorMap* out;
     const CUtensorMap* out2;
-};
-struct AuxRow {
-    uint4 v[4];  // 32 bf16 of this thread's row
+    const CUtensorMap* aux;
 };
 
-// 32 bf16 of row m, columns [n_base, n_base+32) of a row-major matrix (zero outside the matrix)
-__device__ __forceinline__ void load_row32(AuxRow& a, const bf16* src, long ld, long m, int n_base, int M, int N) {
-#pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) {
-        a.v[c4] = make_uint4(0u, 0u, 0u, 0u);
-        if (m < M && n_base + c4 * 8 < N) a.v[c4] = __ldg(reinterpret_cast<const uint4*>(src + m * ld + n_base) + c4);
+// box [m_base, +32) x [n_base, +64) of `map` -> staging tile; every lane returns once the bytes have landed
+__device__ __forceinline__ void stage_fetch(const CUtensorMap* map, uint32_t stage, uint32_t bar, uint32_t& phase, int n_base, int m_base,
+                                            int lane) {
+    if (lane == 0) {
+        mbar_expect_tx(bar, 32 * 128);
+        tma_load_2d(stage, map, bar, n_base, m_base);
     }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
 }
-__device__ __forceinline__ void unpack_row32(const AuxRow& a, float (&f)[32]) {
-#pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) {
-        const uint32_t x[4] = {a.v[c4].x, a.v[c4].y, a.v[c4].z, a.v[c4].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            f[c4 * 8 + 2 * j] = __uint_as_float(x[j] << 16);
-            f[c4 * 8 + 2 * j + 1] = __uint_as_float(x[j] & 0xFFFF0000u);
-        }
-    }
-}
-// this thread's row -> staging tile -> TMA store of the [32 x 32] box; nstore counts this warp's stores
-__device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint32_t stage, uint32_t& nstore, const float (&f)[32], int n_base,
-                                                int m_base, int lane) {
-    const uint32_t tile = stage + (nstore & 1u) * 2048u;
-    if (lane == 0) bulk_wait_read1();  // the store issued two stores ago (same tile) has finished reading it
-    __syncwarp();
-#pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t x[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 v = __floats2bfloat162_rn(f[c4 * 8 + 2 * j], f[c4 * 8 + 2 * j + 1]);
-            x[j] = *reinterpret_cast<uint32_t*>(&v);
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(tile, lane, c4)), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]) : "memory");
-    }
+// staging tile (fully written by the warp) -> box of `map`
+__device__ __forceinline__ void stage_flush(const CUtensorMap* map, uint32_t stage, int n_base, int m_base, int lane) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    if (lane == 0) tma_store_2d(map, tile, n_base, m_base);
-    ++nstore;
+    if (lane == 0) tma_store_2d(map, stage, n_base, m_base);
 }
 
 // KIND is a compile-time constant here: the per-element code is straight-line (a runtime switch inside the
 // element loop is if-converted by the compiler and every output then pays for every epilogue kind)
 template <int KIND>
-__device__ __forceinline__ void epilogue_piece(const Epilogue& e, const EpiMaps& maps, uint32_t stage, uint32_t& nstore, uint32_t taddr,
-                                               int m_base, int n_base, int M, int N, int lane, bool bias_vec, const AuxRow& aux) {
-    float acc[32];
+__device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps& maps, uint32_t stage, uint32_t bar, uint32_t& bar_phase,
+                                               uint32_t taddr, int m_base, int n_base, int M, int N, int lane, bool bias_vec) {
+    float acc[64];
     {
         uint32_t v[32];
         tmem_ld32(taddr, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+        tmem_ld32(taddr + 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[32 + j] = __uint_as_float(v[j]);
     }
-    const long m = (long)m_base + lane;
+    // the staging tile is reusable once the previous TMA store has finished reading it
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
     if (KIND == EPI_BIAS || KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_RESIDUAL) {
         if (e.bias) {
             if (bias_vec) {
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4)
+                for (int j4 = 0; j4 < 16; ++j4)
                     if (n_base + j4 * 4 < N) {
                         const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n_base) + j4);
                         acc[j4 * 4] += b.x; acc[j4 * 4 + 1] += b.y; acc[j4 * 4 + 2] += b.z; acc[j4 * 4 + 3] += b.w;
                     }
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
+                for (int j = 0; j < 64; ++j)
                     if (n_base + j < N) acc[j] += __ldg(e.bias + n_base + j);
             }
         }
     }
     if (KIND == EPI_BIAS_RESIDUAL || KIND == EPI_GELU_BWD) {
-        float a[32];
-        unpack_row32(aux, a);
+        stage_fetch(maps.aux, stage, bar, bar_phase, n_base, m_base, lane);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = KIND == EPI_BIAS_RESIDUAL ? acc[j] + a[j] : acc[j] * gelu_grad<true>(a[j]);
+        for (int c8 = 0; c8 < 8; ++c8) {
+            float a[8];
+            stage_read8(stage, lane, c8, a);
+            if (KIND == EPI_BIAS_RESIDUAL) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[c8 * 8 + j] += a[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {  // packed f32x2 math: this epilogue is instruction-issue-bound
+                    const float2 g = mul2(make_float2(acc[c8 * 8 + j], acc[c8 * 8 + j + 1]), gelu_grad2(make_float2(a[j], a[j + 1])));
+                    acc[c8 * 8 + j] = g.x;
+                    acc[c8 * 8 + j + 1] = g.y;
+                }
+            }
+        }
+        __syncwarp();  // every lane has read its aux row before the tile is overwritten
     }
     if (KIND == EPI_PATCH) {
+        const long m = (long)m_base + lane;
         const int tok = (int)(m % e.np);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 64; ++j) {
             const int n = n_base + j;
             if (m < M && n < N) {
                 float v = tok == 0 ? __ldg(e.cls + n) : acc[j] + (e.bias ? __ldg(e.bias + n) : 0.f);
@@ -162,26 +177,37 @@ __device__ __forceinline__ void epilogue_piece(const Epilogue& e, const EpiMaps&
         }
     }
     if (e.accumulate) {  // the reference's `+=` contract at the ABI; the fused model path never takes it
-        AuxRow old;
-        float a[32];
-        load_row32(old, reinterpret_cast<const bf16*>(e.out), e.ldo, m, n_base, M, N);
-        unpack_row32(old, a);
+        stage_fetch(maps.out, stage, bar, bar_phase, n_base, m_base, lane);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] += a[j];
+        for (int c8 = 0; c8 < 8; ++c8) {
+            float a[8];
+            stage_read8(stage, lane, c8, a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c8 * 8 + j] += a[j];
+        }
+        __syncwarp();
     }
-    stage_and_store(maps.out, stage, nstore, acc, n_base, m_base, lane);
+    stage_write_row(stage, lane, acc);
+    stage_flush(maps.out, stage, n_base, m_base, lane);
     if (KIND == EPI_BIAS_GELU) {
         // gelu_forward consumes the stored (bf16-rounded) pre-activation, as the unfused op would
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = gelu_fwd<true>(__bfloat162float(__float2bfloat16_rn(acc[j])));
-        stage_and_store(maps.out2, stage, nstore, acc, n_base, m_base, lane);
+        for (int j = 0; j < 64; j += 2) {
+            const float2 g = gelu_fwd2(make_float2(__bfloat162float(__float2bfloat16_rn(acc[j])), __bfloat162float(__float2bfloat16_rn(acc[j + 1]))));
+            acc[j] = g.x;
+            acc[j + 1] = g.y;
+        }
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        stage_write_row(stage, lane, acc);
+        stage_flush(maps.out2, stage, n_base, m_base, lane);
     }
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
-               const __grid_constant__ CUtensorMap tmOut2, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmAux, const TcParams p) {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
@@ -192,7 +218,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 4));
+    auto aux_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4 + w); };  // one per epilogue warp
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 4 + kEpilogueWarps));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulators; power of two (256 or 512)
@@ -202,6 +229,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmOut);
         tma_prefetch_desc(&tmOut2);
+        tma_prefetch_desc(&tmAux);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -212,6 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), kEpilogueWarps);  // one arrive per epilogue warp
         }
+        for (int w = 0; w < kEpilogueWarps; ++w) mbar_init(aux_bar(w), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -302,25 +331,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ew = warp - kEpilogueWarp0;       // 0..7
         const int quarter = ew & 3;                 // == warp % 4: the TMEM lanes this warp may read
         const int chalf = ew >> 2;                  // which half of the tile's 64-column chunks
-        constexpr int kPieces = BN / 2 / 32;        // 32-column pieces per warp per tile
-        const uint32_t stage_smem = smem_base + L::STAGING_OFFSET + ew * (32 * 128);  // two [32][64 B] tiles
-        uint32_t nstore = 0;
-        const EpiMaps maps = {&tmOut, &tmOut2};
+        constexpr int kChunksPerWarp = BN / 64 / 2;
+        const uint32_t stage_smem = smem_base + L::STAGING_OFFSET + ew * (32 * 128);
+        const uint32_t my_bar = aux_bar(ew);
+        uint32_t bar_phase = 0;
+        const EpiMaps maps = {&tmOut, &tmOut2, &tmAux};
         const bool bias_vec = p.epi.bias != nullptr && ((uintptr_t)p.epi.bias & 15) == 0;
-        const bool has_aux = p.epi.kind == EPI_BIAS_RESIDUAL || p.epi.kind == EPI_GELU_BWD;
-        const bf16* auxp = reinterpret_cast<const bf16*>(p.epi.aux);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
             const int tile = unit % tiles;
             const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
-            const int m_base = m0 + quarter * 32;
-            const long m = (long)m_base + lane;
-            const int nw0 = n0 + chalf * (BN / 2);  // first column of this warp's half of the tile
-            AuxRow aux_next;
-            if (has_aux) load_row32(aux_next, auxp, p.epi.ldo, m, nw0, p.M, p.N);  // does not depend on the accumulator
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
+            const int m_base = m0 + quarter * 32;
+            const long m = (long)m_base + lane;
             const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
             if (p.epi.kind == EPI_ACCUM_F32) {
                 // dweight: fp32 vector reductions straight from the accumulator rows (split-K partial sums)
@@ -340,19 +365,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             } else {
 #pragma unroll 1
-                for (int pc = 0; pc < kPieces; ++pc) {
-                    const int nb = nw0 + pc * 32;
-                    const uint32_t taddr = trow + chalf * (BN / 2) + pc * 32;
-                    const AuxRow aux = aux_next;
-                    if (has_aux && pc + 1 < kPieces) load_row32(aux_next, auxp, p.epi.ldo, m, nb + 32, p.M, p.N);
-                    if (nb >= p.N || m_base >= p.M) continue;  // warp-uniform: nothing of this piece is inside the matrix
+                for (int ch = chalf * kChunksPerWarp; ch < (chalf + 1) * kChunksPerWarp; ++ch) {
+                    const uint32_t taddr = trow + ch * 64;
+                    const int nb = n0 + ch * 64;
+                    if (nb >= p.N || m_base >= p.M) continue;  // warp-uniform: nothing of this chunk is inside the matrix
                     switch (p.epi.kind) {  // warp-uniform branch to straight-line per-kind code
-                        case EPI_BIAS: epilogue_piece<EPI_BIAS>(p.epi, maps, stage_smem, nstore, taddr, m_base, nb, p.M, p.N, lane, bias_vec, aux); break;
-                        case EPI_BIAS_GELU: epilogue_piece<EPI_BIAS_GELU>(p.epi, maps, stage_smem, nstore, taddr, m_base, nb, p.M, p.N, lane, bias_vec, aux); break;
-                        case EPI_BIAS_RESIDUAL: epilogue_piece<EPI_BIAS_RESIDUAL>(p.epi, maps, stage_smem, nstore, taddr, m_base, nb, p.M, p.N, lane, bias_vec, aux); break;
-                        case EPI_GELU_BWD: epilogue_piece<EPI_GELU_BWD>(p.epi, maps, stage_smem, nstore, taddr, m_base, nb, p.M, p.N, lane, bias_vec, aux); break;
-                        case EPI_PATCH: epilogue_piece<EPI_PATCH>(p.epi, maps, stage_smem, nstore, taddr, m_base, nb, p.M, p.N, lane, bias_vec, aux); break;
-                        default: epilogue_piece<EPI_NONE>(p.epi, maps, stage_smem, nstore, taddr, m_base, nb, p.M, p.N, lane, bias_vec, aux); break;
+                        case EPI_BIAS: epilogue_chunk<EPI_BIAS>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
+                        case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
+                        case EPI_BIAS_RESIDUAL: epilogue_chunk<EPI_BIAS_RESIDUAL>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
+                        case EPI_GELU_BWD: epilogue_chunk<EPI_GELU_BWD>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
+                        case EPI_PATCH: epilogue_chunk<EPI_PATCH>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
+                        default: epilogue_chunk<EPI_NONE>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
                     }
                 }
             }
@@ -374,13 +397,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ---- host side --------------------------------------------------------------------------------
 int encode_map(vitrs_ctx* ctx, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_elems,
-               uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+               uint32_t box_inner, uint32_t box_outer) {
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {outer_stride_elems * 2};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return vitrs_set_error(ctx, VITRS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu stride=%llu box=%ux%u",
@@ -401,7 +424,7 @@ int launch_tc(vitrs_ctx* ctx, const CUtensorMap* maps, const TcParams& p) {
     const int units = p.m_tiles * p.n_tiles * p.splits;
     const int grid = units < ctx->sm_count ? units : ctx->sm_count;
     vitrs_prof_before(ctx, 2.0 * p.M * p.N * p.K);
-    kern<<<grid, kThreads, L::TOTAL, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    kern<<<grid, kThreads, L::TOTAL, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
     vitrs_prof_after(ctx);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
@@ -442,19 +465,21 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     if (!tc_eligible(g)) return gemm_simt_bf16(ctx, g);
     const bool a_mn = g.a_ks != 1, b_mn = g.b_ks != 1;
     const int BN = g.N > 128 ? 256 : 128;
-    CUtensorMap maps[4];  // A, B, out, out2
+    CUtensorMap maps[5];  // A, B, out, out2, aux
     CUtensorMap &tmA = maps[0], &tmB = maps[1];
     if (!a_mn) VITRS_TRY(encode_map(ctx, &tmA, g.A, g.K, g.M, g.a_rs, BK, BM));
     else VITRS_TRY(encode_map(ctx, &tmA, g.A, g.M, g.K, g.a_ks, 64, BK));
     if (!b_mn) VITRS_TRY(encode_map(ctx, &tmB, g.B, g.K, g.N, g.b_rs, BK, BN));
     else VITRS_TRY(encode_map(ctx, &tmB, g.B, g.N, g.K, g.b_ks, 64, BK));
     if (g.epi.kind == EPI_ACCUM_F32) {
-        maps[2] = maps[3] = tmA;  // unused by the reduction epilogue
+        maps[2] = maps[3] = maps[4] = tmA;  // unused by the reduction epilogue
     } else {
-        // [M, N] bf16 matrices with leading dimension ldo, stored as boxes of 32 rows x 32 columns (64-byte swizzle)
-        VITRS_TRY(encode_map(ctx, &maps[2], g.epi.out, g.N, g.M, g.epi.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-        if (g.epi.out2) VITRS_TRY(encode_map(ctx, &maps[3], g.epi.out2, g.N, g.M, g.epi.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+        // [M, N] bf16 matrices with leading dimension ldo, moved as boxes of 32 rows x 64 columns
+        VITRS_TRY(encode_map(ctx, &maps[2], g.epi.out, g.N, g.M, g.epi.ldo, 64, 32));
+        if (g.epi.out2) VITRS_TRY(encode_map(ctx, &maps[3], g.epi.out2, g.N, g.M, g.epi.ldo, 64, 32));
         else maps[3] = maps[2];
+        if (g.epi.aux) VITRS_TRY(encode_map(ctx, &maps[4], g.epi.aux, g.N, g.M, g.epi.ldo, 64, 32));
+        else maps[4] = maps[2];
     }
 
     TcParams p;
