@@ -201,6 +201,7 @@ struct GemmDesc {
     long a_rs, a_ks, b_rs, b_ks;
     int M, N, K;
     Epilogue epi;
+    float* a_colsum;  // optional, MN-major A only (a_rs == 1): a_colsum[m] += sum_k A(m, k), fused into the tensor-core GEMM
 };
 
 int gemm_simt_f32(vitrs_ctx* ctx, const GemmDesc& g);

@@ -35,6 +35,7 @@ constexpr int kEpilogueWarps = 8;
 struct TcParams {
     int M, N, K;
     int m_tiles, n_tiles, kb_total, kb_per_split, splits;
+    float* a_colsum;  // MN-major A only: a_colsum[m] += sum_k A(m, k)  (the bias gradient of matmul_backward, tv:548-550)
     Epilogue epi;
 };
 
@@ -234,7 +235,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            // freed by the MMA commit and, when the column sums of A ride along, by the eight epilogue warps that read the tile
+            mbar_init(empty_bar(s), (A_MN && p.a_colsum) ? 1 + kEpilogueWarps : 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -339,9 +341,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool bias_vec = p.epi.bias != nullptr && ((uintptr_t)p.epi.bias & 15) == 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int cs_stage = 0;        // column-sum consumer: walks the stage ring in step with the MMA warp
+        uint32_t cs_phase = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
             const int tile = unit % tiles;
             const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+            if (A_MN && p.a_colsum) {
+                // dbias fused into the weight-gradient GEMM: the A tiles ([64 k][64 m] boxes of dout) pass through shared
+                // memory anyway; the otherwise idle epilogue warps sum them over k.  Only the n_tile == 0 units do the sums
+                // (every n-tile sees the same A), but every unit takes part in the stage hand-shake.
+                const int split = unit / tiles;
+                const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const bool sum_here = (tile % p.n_tiles) == 0;
+                const int et = ew * 32 + lane;                      // 0..255
+                const int box = et >> 7, c8 = et & 7, rg = (et & 127) >> 3;  // 64-column box, 16-byte chunk, group of 4 k-rows
+                float part[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) part[i] = 0.f;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar(cs_stage), cs_phase);
+                    if (sum_here) {
+                        const uint32_t abox = smem_base + cs_stage * L::STAGE_BYTES + box * (BK * 128);
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const int row = rg * 4 + rr;
+                            uint32_t x[4];
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
+                                         : "r"(abox + row * 128 + ((c8 ^ (row & 7)) << 4)) : "memory");
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                part[2 * j] += __uint_as_float(x[j] << 16);
+                                part[2 * j + 1] += __uint_as_float(x[j] & 0xFFFF0000u);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty_bar(cs_stage));
+                    if (++cs_stage == STAGES) { cs_stage = 0; cs_phase ^= 1u; }
+                }
+                if (sum_here) {  // CTA-uniform: 16 row groups -> one sum per column, through the (unused here) staging area
+                    float* scratch = reinterpret_cast<float*>(smem_gen + L::STAGING_OFFSET);  // [2 boxes][16 groups][64 columns]
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) scratch[(box * 16 + rg) * 64 + c8 * 8 + i] = part[i];
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (et < BM) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) sum += scratch[((et >> 6) * 16 + k) * 64 + (et & 63)];
+                        if (m0 + et < p.M) atomicAdd(p.a_colsum + m0 + et, sum);
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+            }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const int m_base = m0 + quarter * 32;
@@ -462,7 +513,10 @@ static bool tc_eligible(const GemmDesc& g) {
 
 int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return VITRS_OK;
-    if (!tc_eligible(g)) return gemm_simt_bf16(ctx, g);
+    if (!tc_eligible(g)) {
+        if (g.a_colsum) VITRS_TRY(op_colsum<bf16>(ctx, g.a_colsum, reinterpret_cast<const bf16*>(g.A), g.K, g.M, g.a_ks));
+        return gemm_simt_bf16(ctx, g);
+    }
     const bool a_mn = g.a_ks != 1, b_mn = g.b_ks != 1;
     const int BN = g.N > 128 ? 256 : 128;
     CUtensorMap maps[5];  // A, B, out, out2, aux
@@ -488,6 +542,7 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     p.n_tiles = ceil_div(g.N, BN);
     p.kb_total = ceil_div(g.K, BK);
     p.epi = g.epi;
+    p.a_colsum = g.a_colsum;
     int splits = 1;
     const int tiles = p.m_tiles * p.n_tiles;
     if (g.epi.kind == EPI_ACCUM_F32 && tiles < ctx->sm_count) {

@@ -142,8 +142,9 @@ int gemm_dx(vitrs_ctx* ctx, T* dinp, const T* dout, const T* w, long rows, int c
     return gemm_dispatch<T>(ctx, g);
 }
 template <typename T>
-int gemm_dw(vitrs_ctx* ctx, float* dw, const T* dout, const T* inp, long rows, int c, int oc) {
+int gemm_dw(vitrs_ctx* ctx, float* dw, const T* dout, const T* inp, long rows, int c, int oc, float* dbias = nullptr) {
     GemmDesc g = {};
+    g.a_colsum = dbias;  // bias gradient = column sums of dout, fused into the tensor-core weight-gradient GEMM
     g.A = dout; g.a_rs = 1; g.a_ks = oc;
     g.B = inp; g.b_rs = 1; g.b_ks = c;
     g.M = oc; g.N = c; g.K = (int)rows;
@@ -398,8 +399,6 @@ int backward_bf16(vitrs_model* m) {
     VITRS_CUDA(ctx, cudaMemsetAsync(dres, 0, sizeof(bf16) * (size_t)btc, ctx->stream));
     VITRS_TRY(op_cls_scatter_add<bf16>(ctx, dres, m->dcls_rows, d.B, d.T, C));
     VITRS_TRY(allreduce_tail(m, true));
-    // the fc-projection bias gradient of the last block; the others come fused from LN1-backward
-    VITRS_TRY(op_colsum<bf16>(ctx, G(m, P_FCPROJB) + (L - 1) * C, dres, rows, C, C));
 
     for (int l = L - 1; l >= 0; --l) {
         const bf16* residual = l == 0 ? act<bf16>(m, A_ENCODED) : act<bf16>(m, A_RESIDUAL3) + (l - 1) * btc;
@@ -418,16 +417,15 @@ int backward_bf16(vitrs_model* m) {
         // dres == dresidual3[l] == dfcproj[l] (residual_backward, rusty_vit.rs:436)
         // fcproj matmul_backward + gelu_backward in one epilogue: dfch = (dres . Wfcproj) * gelu'(fch)
         VITRS_TRY((gemm_dx<bf16>(ctx, dfch, dres, S(m, P_FCPROJW) + (long)l * C * 4 * C, rows, 4 * C, C, EPI_GELU_BWD, fch, 0)));
-        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_FCPROJW) + (long)l * C * 4 * C, dres, fch_gelu, rows, 4 * C, C)));
+        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_FCPROJW) + (long)l * C * 4 * C, dres, fch_gelu, rows, 4 * C, C, G(m, P_FCPROJB) + l * C)));
         VITRS_TRY((gemm_dx<bf16>(ctx, dln, dfch, S(m, P_FCW) + (long)l * 4 * C * C, rows, C, 4 * C, EPI_NONE, nullptr, 0)));
-        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_FCW) + (long)l * 4 * C * C, dfch, ln2, rows, C, 4 * C)));
-        VITRS_TRY(op_colsum<bf16>(ctx, G(m, P_FCB) + l * 4 * C, dfch, rows, 4 * C, 4 * C));
-        // dresidual2 = dres + LN2-backward(dln2); its column sum is the out-projection bias gradient
+        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_FCW) + (long)l * 4 * C * C, dfch, ln2, rows, C, 4 * C, G(m, P_FCB) + l * 4 * C)));
+        // dresidual2 = dres + LN2-backward(dln2)
         VITRS_TRY(op_layernorm_backward<bf16>(ctx, dres, G(m, P_LN2W) + l * C, G(m, P_LN2B) + l * C, dln, residual2,
                                               P(m, P_LN2W) + l * C, act<float>(m, A_LN2_MEAN) + lbt, act<float>(m, A_LN2_RSTD) + lbt,
-                                              rows, C, G(m, P_ATTPROJB) + l * C));
+                                              rows, C, nullptr));
         VITRS_TRY((gemm_dx<bf16>(ctx, dln, dres, S(m, P_ATTPROJW) + (long)l * C * C, rows, C, C, EPI_NONE, nullptr, 0)));  // datty
-        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_ATTPROJW) + (long)l * C * C, dres, atty, rows, C, C)));
+        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_ATTPROJW) + (long)l * C * C, dres, atty, rows, C, C, G(m, P_ATTPROJB) + l * C)));
         int r = op_attention_backward_tc(ctx, dqkv, dln, atty, qkv, lse, d.B, d.T, C, d.NH, m->cfg.causal, 0);
         if (r == VITRS_ERR_UNSUPPORTED) {
             VITRS_CUDA(ctx, cudaMemsetAsync(dqkv, 0, sizeof(bf16) * (size_t)btc * 3, ctx->stream));
@@ -435,12 +433,11 @@ int backward_bf16(vitrs_model* m) {
         }
         VITRS_TRY(r);
         VITRS_TRY((gemm_dx<bf16>(ctx, dln, dqkv, S(m, P_QKVW) + (long)l * 3 * C * C, rows, C, 3 * C, EPI_NONE, nullptr, 0)));  // dln1
-        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_QKVW) + (long)l * 3 * C * C, dqkv, ln1, rows, C, 3 * C)));
-        VITRS_TRY(op_colsum<bf16>(ctx, G(m, P_QKVB) + l * 3 * C, dqkv, rows, 3 * C, 3 * C));
+        VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_QKVW) + (long)l * 3 * C * C, dqkv, ln1, rows, C, 3 * C, G(m, P_QKVB) + l * 3 * C)));
         VITRS_TRY(op_layernorm_backward<bf16>(ctx, dres, G(m, P_LN1W) + l * C, G(m, P_LN1B) + l * C, dln, residual,
                                               P(m, P_LN1W) + l * C, act<float>(m, A_LN1_MEAN) + lbt, act<float>(m, A_LN1_RSTD) + lbt,
-                                              rows, C, l > 0 ? G(m, P_FCPROJB) + (l - 1) * C : nullptr));
-        // every gradient of block l is final except fcprojb[l-1], which belongs to block l-1's bucket
+                                              rows, C, nullptr));
+        // every gradient of block l is final
         VITRS_TRY(allreduce_layer(m, l));
     }
     VITRS_TRY(op_patch_backward_reduce<bf16>(ctx, G(m, P_WPE), G(m, P_CLS), G(m, P_PATCHB), dres, d.B, d.T, C));
@@ -493,8 +490,8 @@ int allreduce_bucket(vitrs_model* m, int bucket) {
     return vitrs_nccl_allreduce_group(m->ctx, bufs, cnt, n);
 }
 
-// block l: fcprojb[l] is completed by block l+1's LN1-backward (or before the loop for the last block),
-// so every slice of the bucket is final when block l's backward has been issued
+// block l: every slice of its bucket is final when the block's backward has been issued (the bias gradients come out of
+// the weight-gradient GEMMs of the same block)
 int allreduce_layer(vitrs_model* m, int l) { return allreduce_bucket(m, m->cfg.num_layers - l); }
 int allreduce_tail(vitrs_model* m, bool head) { return allreduce_bucket(m, head ? 0 : m->cfg.num_layers + 1); }
 
