@@ -87,6 +87,30 @@ __device__ __forceinline__ void store_row32(bf16* dst, const uint32_t* v, float 
     }
 }
 
+// this thread's 32 fp32 accumulator columns -> (+ old bf16 values) -> bf16 -> its half-row of a swizzled [128][64] staging tile
+__device__ __forceinline__ void stage_half_row(uint32_t tile, int r, int half, const uint32_t (&v)[32], const bf16* old) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+        if (old) {
+            Vec16<bf16> o;
+            o.load(old + g * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += o.get(j);
+        }
+        st_shared_v4(sw128(tile, r, half * 4 + g), pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    }
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1),
+                 "r"(c2)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 // =============================================== forward ==========================================
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, float* __restrict__ lse, int T, int C, int NH,
@@ -207,13 +231,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict_
 // (tcgen05.st) and the P.V MMA takes its A operand from TMEM, so a CTA needs only Q_i, K, V in shared
 // memory (80 KB at T = 197) and 256 TMEM columns; the second resident CTA's loads and MMAs overlap this
 // CTA's exponentials.  O is staged through the dead Q tile and leaves with one TMA store (rows >= T clipped).
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1),
-                 "r"(c2)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse, int T,
                     int C, int NH, int causal, int NT, int NK, uint32_t tmem_cols) {
@@ -520,8 +537,9 @@ constexpr int kPipeThreads = 384;  // warps 0-3: control (issuer = warp 0 lane 0
 __device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 __global__ void __launch_bounds__(kPipeThreads, 1)
-attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, bf16* __restrict__ dqkv,
-                     const float* __restrict__ lse, const float* __restrict__ dsum, int T, int C, int NH, int NT, int accumulate) {
+attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                     const __grid_constant__ CUtensorMap tm_dqkv, bf16* __restrict__ dqkv, const float* __restrict__ lse,
+                     const float* __restrict__ dsum, int T, int C, int NH, int NT, int accumulate) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -572,10 +590,18 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     if (warp == 0) {
         if (lane == 0) {
             // ================================ issuer ================================
+            // Every shared-memory descriptor is built once; per-MMA descriptors are the base plus a byte offset >> 4 in the
+            // start-address field (the issuing thread is on the critical path: ~40 MMAs per iteration).
             mbar_wait(bar_load, 0);
             tc_fence_after();
             const uint32_t idesc_kk = make_idesc(TILE, HS, 0, 1);
             const uint32_t idesc_mn = make_idesc(TILE, HS, 1, 1);
+            const uint64_t dK_k = make_desc(sK, 0, 1024), dV_k = make_desc(sV, 0, 1024);          // K-major A operands (rows = keys)
+            const uint64_t dQ_k = make_desc(sQ, 0, 1024), ddO_k = make_desc(sdO, 0, 1024);        // K-major B operands (rows = queries)
+            const uint64_t dQ_mn = make_desc(sQ, TILE_BYTES, 1024), ddO_mn = make_desc(sdO, TILE_BYTES, 1024);  // MN-major B operands
+            const uint64_t dK_mn = make_desc(sK, TILE_BYTES, 1024);
+            const uint64_t ddS_k = make_desc(sdS, 0, 1024), ddS_mn = make_desc(sdS, TILE_BYTES, 1024);
+            auto off = [](uint32_t bytes) { return (uint64_t)(bytes >> 4); };
             for (int n = 0; n <= N; ++n) {
                 if (n < N) {  // S^T and dP^T of iteration n
                     const int j = n / NSUB, s_ = n - j * NSUB, bx = n & 1;
@@ -583,40 +609,36 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
                     if (n >= 2) mbar_wait(x_free + 8 * bx, (uint32_t)(((n >> 1) - 1) & 1));
                     tc_fence_after();
                     const uint32_t idesc = make_idesc(TILE, nq16, 0, 0);
-                    const uint32_t qoff = (s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES;
+                    const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES), ko = off(j * TILE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < HS / 16; ++k)
-                        umma_bf16(tmem_base + bx * 128, make_desc(sK + j * TILE_BYTES + k * 32, 0, 1024), make_desc(sQ + qoff + k * 32, 0, 1024),
-                                  idesc, k > 0);
+                    for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + bx * 128, dK_k + ko + 2 * k, dQ_k + qo + 2 * k, idesc, k > 0);
 #pragma unroll
-                    for (int k = 0; k < HS / 16; ++k)
-                        umma_bf16(tmem_base + bx * 128 + 64, make_desc(sV + j * TILE_BYTES + k * 32, 0, 1024),
-                                  make_desc(sdO + qoff + k * 32, 0, 1024), idesc, k > 0);
+                    for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + bx * 128 + 64, dV_k + ko + 2 * k, ddO_k + qo + 2 * k, idesc, k > 0);
                     umma_commit(s_full + 8 * bx);
                 }
                 if (n >= 1) {  // dV, dK (and dQ) of iteration n-1
                     const int m = n - 1, j = m / NSUB, s_ = m - j * NSUB, bx = m & 1;
                     const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
                     const int nk16 = (min(TILE, T - j * TILE) + 15) & ~15;
-                    const uint32_t qoff = (s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES;
+                    const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES);
                     mbar_wait(p_full + 8 * bx, (uint32_t)((m >> 1) & 1));
                     tc_fence_after();
                     if (s_ == 0 && j > 0) {  // the previous key tile's dV / dK have been read out
                         mbar_wait(acc_free, (uint32_t)((j - 1) & 1));
                         tc_fence_after();
                     }
-                    const uint32_t sbuf = sdS + (s_ & 3) * TILE_BYTES;
+                    const uint64_t so = off((s_ & 3) * TILE_BYTES);
                     for (int k16 = 0; k16 < nq16 / 16; ++k16) {
                         const uint32_t acc = (s_ > 0 || k16 > 0) ? 1u : 0u;
-                        umma_bf16_ts(tmem_base + cDV, tmem_base + bx * 128 + k16 * 8, make_desc(sdO + qoff + k16 * 2048, TILE_BYTES, 1024), idesc_kk, acc);
-                        umma_bf16(tmem_base + cDK, make_desc(sbuf + k16 * 32, 0, 1024), make_desc(sQ + qoff + k16 * 2048, TILE_BYTES, 1024), idesc_kk, acc);
+                        umma_bf16_ts(tmem_base + cDV, tmem_base + bx * 128 + k16 * 8, ddO_mn + qo + 128 * k16, idesc_kk, acc);
+                        umma_bf16(tmem_base + cDK, ddS_k + so + 2 * k16, dQ_mn + qo + 128 * k16, idesc_kk, acc);
                     }
                     umma_commit(x_free + 8 * bx);
                     if ((s_ & 1) || s_ == NSUB - 1) {  // query tile i = s/2 is complete for this key tile: dQ_i += dS K_j
                         const int i = s_ >> 1;
+                        const uint64_t ao = off((2 * i) * TILE_BYTES), ko = off(j * TILE_BYTES);
                         for (int k16 = 0; k16 < nk16 / 16; ++k16)
-                            umma_bf16(tmem_base + cDQ + i * HS, make_desc(sdS + (2 * i) * TILE_BYTES + k16 * 2048, TILE_BYTES, 1024),
-                                      make_desc(sK + j * TILE_BYTES + k16 * 2048, TILE_BYTES, 1024), idesc_mn, (j > 0 || k16 > 0) ? 1u : 0u);
+                            umma_bf16(tmem_base + cDQ + i * HS, ddS_mn + ao + 128 * k16, dK_mn + ko + 128 * k16, idesc_mn, (j > 0 || k16 > 0) ? 1u : 0u);
                         umma_commit(ds_free + 8 * ((2 * i) & 3));
                         if (s_ & 1) umma_commit(ds_free + 8 * ((2 * i + 1) & 3));
                     }
@@ -649,20 +671,25 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
                     uint32_t sv[32], dp[32], pk[16];
                     tmem_ld32(xb + ch * 32, sv);
                     tmem_ld32(xb + 64 + ch * 32, dp);
+                    const int q0 = s_ * SUB + ch * 32;             // first query of the chunk (q0 + 31 < 256)
+                    const bool full = key < T && ch * 32 + 32 <= nq;  // warp-uniform except for the key tail: no per-element masks
 #pragma unroll
                     for (int g8 = 0; g8 < 4; ++g8) {
-                        float ds[8];
+                        // lse*log2e and D of the 8 queries: two 16-byte broadcast loads each instead of 16 scalar loads
+                        const float4 l0 = *reinterpret_cast<const float4*>(stat + q0 + g8 * 8), l1 = *reinterpret_cast<const float4*>(stat + q0 + g8 * 8 + 4);
+                        const float4 d0 = *reinterpret_cast<const float4*>(stat + 256 + q0 + g8 * 8), d1 = *reinterpret_cast<const float4*>(stat + 256 + q0 + g8 * 8 + 4);
+                        const float lq[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                        const float dq[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                        float ds[8], pv[8];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             const int qc = ch * 32 + g8 * 8 + c;
-                            const int q = s_ * SUB + qc;
-                            const bool live = key < T && qc < nq;
-                            const float pv = live ? ex2(__uint_as_float(sv[g8 * 8 + c]) * sl2 - stat[q & 255]) : 0.f;
-                            ds[c] = pv * (__uint_as_float(dp[g8 * 8 + c]) - stat[256 + (q & 255)]) * scale;
-                            sv[g8 * 8 + c] = __float_as_uint(pv);
+                            const float e = ex2(__uint_as_float(sv[g8 * 8 + c]) * sl2 - lq[c]);
+                            pv[c] = (full || (key < T && qc < nq)) ? e : 0.f;
+                            ds[c] = pv[c] * (__uint_as_float(dp[g8 * 8 + c]) - dq[c]) * scale;
                         }
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) pk[g8 * 4 + c] = pack_bf16(__uint_as_float(sv[g8 * 8 + 2 * c]), __uint_as_float(sv[g8 * 8 + 2 * c + 1]));
+                        for (int c = 0; c < 4; ++c) pk[g8 * 4 + c] = pack_bf16(pv[2 * c], pv[2 * c + 1]);
                         st_shared_v4(sw128(sbuf, r, ch * 4 + g8), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
                                      pack_bf16(ds[6], ds[7]));
                     }
@@ -673,30 +700,42 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
                 tc_fence_before();
                 mbar_arrive_cnt(p_full + 8 * g);
             }
-            // ---- dV_j (group 0) / dK_j (group 1) ----
+            // ---- dV_j (group 0) / dK_j (group 1): staged through the dead V_j / K_j tile, one TMA store each ----
             mbar_wait(acc_full, (uint32_t)(j & 1));
             tc_fence_after();
+            {
+                const uint32_t tile = (g == 0 ? sV : sK) + j * TILE_BYTES;  // every MMA that read it has retired (acc_full)
+                const long gcol = (g == 0 ? 2 * C : C) + h * HS;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_off + (g == 0 ? cDV : cDK) + half * 32, v);
-                if (key < T) store_row32(dqkv + ((long)b * T + key) * 3 * C + (g == 0 ? 2 * C : C) + h * HS + half * 32, v, 1.0f, accumulate);
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_off + (g == 0 ? cDV : cDK) + half * 32, v);
+                    stage_half_row(tile, r, half, v, (accumulate && key < T) ? dqkv + ((long)b * T + key) * 3 * C + gcol + half * 32 : nullptr);
+                }
+                tc_fence_before();
+                mbar_arrive_cnt(acc_free);  // the accumulators are free; the store below only reads shared memory
+                fence_proxy_async();
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+                if ((warp & 3) == 0 && lane == 0) tma_store_3d(&tm_dqkv, tile, (int)gcol, j * TILE, b);
             }
-            tc_fence_before();
-            mbar_arrive_cnt(acc_free);
         }
         // ---- dQ_0 (group 0) / dQ_1 (group 1) ----
         mbar_wait(dq_full, 0);
         tc_fence_after();
         if (g < NT) {
             const int q = g * TILE + r;
+            const uint32_t tile = sQ + g * TILE_BYTES;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + lane_off + cDQ + g * HS + half * 32, v);
-                if (q < T) store_row32(dqkv + ((long)b * T + q) * 3 * C + h * HS + half * 32, v, 1.0f, accumulate);
+                stage_half_row(tile, r, half, v, (accumulate && q < T) ? dqkv + ((long)b * T + q) * 3 * C + h * HS + half * 32 : nullptr);
             }
+            fence_proxy_async();
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+            if ((warp & 3) == 0 && lane == 0) tma_store_3d(&tm_dqkv, tile, h * HS, g * TILE, b);
         }
+        if ((warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -873,23 +912,6 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
-
-// this thread's 32 fp32 accumulator columns -> (+ old bf16 values) -> bf16 -> its half-row of a swizzled [128][64] staging tile
-__device__ __forceinline__ void stage_half_row(uint32_t tile, int r, int half, const uint32_t (&v)[32], const bf16* old) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-        if (old) {
-            Vec16<bf16> o;
-            o.load(old + g * 8);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += o.get(j);
-        }
-        st_shared_v4(sw128(tile, r, half * 4 + g), pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
     }
 }
 
@@ -1275,7 +1297,9 @@ int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const
             VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
             conf_p = smem_p;
         }
-        attn_bwd_pipe_kernel<<<b * nh, kPipeThreads, smem_p, ctx->stream>>>(tm_qkv, tm_do, dqkv, lse, dsum, t, c, nh, NT, accumulate);
+        CUtensorMap tm_dq;
+        VITRS_TRY(encode_map3d(ctx, &tm_dq, dqkv, 3 * (uint64_t)c, t, b));
+        attn_bwd_pipe_kernel<<<b * nh, kPipeThreads, smem_p, ctx->stream>>>(tm_qkv, tm_do, tm_dq, dqkv, lse, dsum, t, c, nh, NT, accumulate);
         VITRS_LAUNCHED(ctx);
         return VITRS_OK;
     }
