@@ -263,12 +263,12 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         for (int i = 0; i < NT; ++i) tma_load_3d(sK + i * TILE_BYTES, &tm_qkv, bar_qk, C + h * HS, i * TILE, b);
         mbar_expect_tx(bar_v, (uint32_t)(NT * TILE_BYTES));
         for (int i = 0; i < NT; ++i) tma_load_3d(sV + i * TILE_BYTES, &tm_qkv, bar_v, 2 * C + h * HS, i * TILE, b);
+        const uint32_t idesc = make_idesc(TILE, NK, 0, 0);
+        const uint64_t dq = make_desc(sQ, 0, 1024), dk = make_desc(sK, 0, 1024);
         mbar_wait(bar_qk, 0);
         tc_fence_after();
-        const uint32_t idesc = make_idesc(TILE, NK, 0, 0);
 #pragma unroll
-        for (int k = 0; k < HS / 16; ++k)
-            umma_bf16(tmem_base, make_desc(sQ + k * 32, 0, 1024), make_desc(sK + k * 32, 0, 1024), idesc, k > 0);
+        for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base, dq + 2 * k, dk + 2 * k, idesc, k > 0);
         umma_commit(bar_s);
     }
     mbar_wait(bar_s, 0);
@@ -308,10 +308,10 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     __syncthreads();
     if (tid == 0) {
         tc_fence_after();
-        mbar_wait(bar_v, 0);
         const uint32_t idesc = make_idesc(TILE, HS, 0, 1);  // A = P from TMEM (K-major by construction), B = V MN-major
-        for (int k16 = 0; k16 < NK / 16; ++k16)
-            umma_bf16_ts(tmem_base + o_col, tmem_base + k16 * 8, make_desc(sV + k16 * 2048, TILE_BYTES, 1024), idesc, k16 > 0);
+        const uint64_t dv = make_desc(sV, TILE_BYTES, 1024);
+        mbar_wait(bar_v, 0);
+        for (int k16 = 0; k16 < NK / 16; ++k16) umma_bf16_ts(tmem_base + o_col, tmem_base + k16 * 8, dv + 128 * k16, idesc, k16 > 0);
         umma_commit(bar_o);
     }
     mbar_wait(bar_o, 0);
@@ -334,7 +334,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     __syncthreads();
     if (tid == 0) {
         tma_store_3d(&tm_out, sQ, h * HS, qt * TILE, b);
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     if (warp == 0) {
         tc_fence_after();
@@ -735,7 +735,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
             if ((warp & 3) == 0 && lane == 0) tma_store_3d(&tm_dqkv, tile, h * HS, g * TILE, b);
         }
-        if ((warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if ((warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -907,7 +907,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     __syncthreads();
     if (tid == 0) {
         tma_store_3d(&tm_out, sQ, h * HS, qt * TILE, b);
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     if (warp == 0) {
         tc_fence_after();
@@ -1045,7 +1045,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     if (leader) {
         tma_store_3d(&tm_dqkv, sV, 2 * C + h * HS, jt * TILE, b);
         tma_store_3d(&tm_dqkv, sK, C + h * HS, jt * TILE, b);
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     if (warp == 0) {
         tc_fence_after();
@@ -1172,7 +1172,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     __syncthreads();
     if (leader) {
         tma_store_3d(&tm_dqkv, sQ, h * HS, qt * TILE, b);
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     if (warp == 0) {
         tc_fence_after();

@@ -31,6 +31,7 @@ constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kThreads = 384;
 constexpr int kEpilogueWarp0 = 4;
 constexpr int kEpilogueWarps = 8;
+constexpr int kColsumWarps = 4;  // epilogue warps that also sum the A tiles (fused bias gradient)
 
 struct TcParams {
     int M, N, K;
@@ -115,7 +116,22 @@ __device__ __forceinline__ void stage_flush(const CUtensorMap* map, uint32_t sta
 // element loop is if-converted by the compiler and every output then pays for every epilogue kind)
 template <int KIND>
 __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps& maps, uint32_t stage, uint32_t bar, uint32_t& bar_phase,
-                                               uint32_t taddr, int m_base, int n_base, int M, int N, int lane, bool bias_vec) {
+                                               uint32_t taddr, int m_base, int n_base, int M, int N, int lane, bool bias_vec,
+                                               bool aux_issued) {
+    constexpr bool kAux = KIND == EPI_BIAS_RESIDUAL || KIND == EPI_GELU_BWD;
+    // the staging tile is reusable once the previous TMA store has finished reading it; the residual / pre-GELU box is
+    // requested before the accumulator is read so that its latency overlaps the TMEM loads and the bias adds (the first
+    // chunk of a tile was requested before the tile's main loop finished: aux_issued)
+    if (!aux_issued) {
+        if (lane == 0) {
+            bulk_wait_read0();
+            if (kAux) {
+                mbar_expect_tx(bar, 32 * 128);
+                tma_load_2d(stage, maps.aux, bar, n_base, m_base);
+            }
+        }
+        __syncwarp();
+    }
     float acc[64];
     {
         uint32_t v[32];
@@ -126,9 +142,6 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[32 + j] = __uint_as_float(v[j]);
     }
-    // the staging tile is reusable once the previous TMA store has finished reading it
-    if (lane == 0) bulk_wait_read0();
-    __syncwarp();
     if (KIND == EPI_BIAS || KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_RESIDUAL) {
         if (e.bias) {
             if (bias_vec) {
@@ -145,8 +158,9 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
             }
         }
     }
-    if (KIND == EPI_BIAS_RESIDUAL || KIND == EPI_GELU_BWD) {
-        stage_fetch(maps.aux, stage, bar, bar_phase, n_base, m_base, lane);
+    if (kAux) {
+        mbar_wait(bar, bar_phase);
+        bar_phase ^= 1u;
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8) {
             float a[8];
@@ -235,8 +249,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            // freed by the MMA commit and, when the column sums of A ride along, by the eight epilogue warps that read the tile
-            mbar_init(empty_bar(s), (A_MN && p.a_colsum) ? 1 + kEpilogueWarps : 1);
+            // freed by the MMA commit and, when the column sums of A ride along, by the four epilogue warps that read the tile
+            mbar_init(empty_bar(s), (A_MN && p.a_colsum) ? 1 + kColsumWarps : 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -346,25 +360,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
             const int tile = unit % tiles;
             const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
-            if (A_MN && p.a_colsum) {
+            if (A_MN && p.a_colsum && (ew & 2)) {
                 // dbias fused into the weight-gradient GEMM: the A tiles ([64 k][64 m] boxes of dout) pass through shared
-                // memory anyway; the otherwise idle epilogue warps sum them over k.  Only the n_tile == 0 units do the sums
-                // (every n-tile sees the same A), but every unit takes part in the stage hand-shake.
+                // memory anyway; four of the otherwise idle epilogue warps (those on the schedulers that host neither the TMA
+                // nor the MMA warp) sum them over k.  The n_tiles units that see the same A tile share the work: the unit with
+                // n-tile t sums the 4-row groups rg with rg % n_tiles == t.
                 const int split = unit / tiles;
                 const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-                const bool sum_here = (tile % p.n_tiles) == 0;
-                const int et = ew * 32 + lane;                      // 0..255
-                const int box = et >> 7, c8 = et & 7, rg = (et & 127) >> 3;  // 64-column box, 16-byte chunk, group of 4 k-rows
+                const int box = ew & 1, c8 = lane & 7;           // 64-column box, 16-byte chunk
+                const int rg0 = (ew >> 2) * 8 + (lane >> 3) * 2;  // this thread's two 4-row groups of the 64 k-rows
+                const int nt_ = tile % p.n_tiles;
+                bool own[2];
+#pragma unroll
+                for (int g2 = 0; g2 < 2; ++g2) own[g2] = p.n_tiles <= 16 ? ((rg0 + g2) % p.n_tiles) == nt_ : (rg0 + g2) == nt_;
                 float part[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) part[i] = 0.f;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(cs_stage), cs_phase);
-                    if (sum_here) {
-                        const uint32_t abox = smem_base + cs_stage * L::STAGE_BYTES + box * (BK * 128);
+                    const uint32_t abox = smem_base + cs_stage * L::STAGE_BYTES + box * (BK * 128);
+#pragma unroll
+                    for (int g2 = 0; g2 < 2; ++g2) {
+                        if (!own[g2]) continue;
 #pragma unroll
                         for (int rr = 0; rr < 4; ++rr) {
-                            const int row = rg * 4 + rr;
+                            const int row = (rg0 + g2) * 4 + rr;
                             uint32_t x[4];
                             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
                                          : "r"(abox + row * 128 + ((c8 ^ (row & 7)) << 4)) : "memory");
@@ -379,24 +399,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (lane == 0) mbar_arrive(empty_bar(cs_stage));
                     if (++cs_stage == STAGES) { cs_stage = 0; cs_phase ^= 1u; }
                 }
-                if (sum_here) {  // CTA-uniform: 16 row groups -> one sum per column, through the (unused here) staging area
-                    float* scratch = reinterpret_cast<float*>(smem_gen + L::STAGING_OFFSET);  // [2 boxes][16 groups][64 columns]
+                // 4 row pairs -> one sum per column (lanes with equal c8 hold the same 8 columns)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) scratch[(box * 16 + rg) * 64 + c8 * 8 + i] = part[i];
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (et < BM) {
-                        float sum = 0.f;
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) sum += scratch[((et >> 6) * 16 + k) * 64 + (et & 63)];
-                        if (m0 + et < p.M) atomicAdd(p.a_colsum + m0 + et, sum);
-                    }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int i = 0; i < 8; ++i) {
+                    part[i] += __shfl_xor_sync(0xffffffffu, part[i], 8);
+                    part[i] += __shfl_xor_sync(0xffffffffu, part[i], 16);
                 }
+                if ((lane >> 3) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int col = m0 + box * 64 + c8 * 8 + i;
+                        if (col < p.M) atomicAdd(p.a_colsum + col, part[i]);
+                    }
+                }
+            }
+            const int m_base = m0 + quarter * 32;
+            const long m = (long)m_base + lane;
+            const bool has_aux = p.epi.kind == EPI_BIAS_RESIDUAL || p.epi.kind == EPI_GELU_BWD;
+            const int nb_first = n0 + chalf * kChunksPerWarp * 64;
+            const bool first_live = nb_first < p.N && m_base < p.M;
+            if (has_aux && first_live) {  // this tile's first residual / pre-GELU box, while the main loop is still running
+                if (lane == 0) {
+                    bulk_wait_read0();
+                    mbar_expect_tx(my_bar, 32 * 128);
+                    tma_load_2d(stage_smem, &tmAux, my_bar, nb_first, m_base);
+                }
+                __syncwarp();
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const int m_base = m0 + quarter * 32;
-            const long m = (long)m_base + lane;
             const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
             if (p.epi.kind == EPI_ACCUM_F32) {
                 // dweight: fp32 vector reductions straight from the accumulator rows (split-K partial sums)
@@ -420,13 +451,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t taddr = trow + ch * 64;
                     const int nb = n0 + ch * 64;
                     if (nb >= p.N || m_base >= p.M) continue;  // warp-uniform: nothing of this chunk is inside the matrix
+                    const bool pre = has_aux && nb == nb_first;
                     switch (p.epi.kind) {  // warp-uniform branch to straight-line per-kind code
-                        case EPI_BIAS: epilogue_chunk<EPI_BIAS>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
-                        case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
-                        case EPI_BIAS_RESIDUAL: epilogue_chunk<EPI_BIAS_RESIDUAL>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
-                        case EPI_GELU_BWD: epilogue_chunk<EPI_GELU_BWD>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
-                        case EPI_PATCH: epilogue_chunk<EPI_PATCH>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
-                        default: epilogue_chunk<EPI_NONE>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec); break;
+                        case EPI_BIAS: epilogue_chunk<EPI_BIAS>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
+                        case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
+                        case EPI_BIAS_RESIDUAL: epilogue_chunk<EPI_BIAS_RESIDUAL>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
+                        case EPI_GELU_BWD: epilogue_chunk<EPI_GELU_BWD>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
+                        case EPI_PATCH: epilogue_chunk<EPI_PATCH>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
+                        default: epilogue_chunk<EPI_NONE>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
                     }
                 }
             }
