@@ -249,8 +249,14 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         tma_prefetch_desc(&tm_out);
         mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the loads are in flight while the CTA allocates tensor memory and synchronises
+        mbar_expect_tx(bar_qk, (uint32_t)((1 + NT) * TILE_BYTES));
+        tma_load_3d(sQ, &tm_qkv, bar_qk, h * HS, qt * TILE, b);
+        for (int i = 0; i < NT; ++i) tma_load_3d(sK + i * TILE_BYTES, &tm_qkv, bar_qk, C + h * HS, i * TILE, b);
+        mbar_expect_tx(bar_v, (uint32_t)(NT * TILE_BYTES));
+        for (int i = 0; i < NT; ++i) tma_load_3d(sV + i * TILE_BYTES, &tm_qkv, bar_v, 2 * C + h * HS, i * TILE, b);
     }
-    if (warp == 0) tmem_alloc(smem_u32((const void*)slot), tmem_cols);
+    if (warp == 1) tmem_alloc(smem_u32((const void*)slot), tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -258,11 +264,6 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     const uint32_t o_col = tmem_cols - HS;  // O accumulator: the last 64 columns (dead part of S once P is packed)
 
     if (tid == 0) {
-        mbar_expect_tx(bar_qk, (uint32_t)((1 + NT) * TILE_BYTES));
-        tma_load_3d(sQ, &tm_qkv, bar_qk, h * HS, qt * TILE, b);
-        for (int i = 0; i < NT; ++i) tma_load_3d(sK + i * TILE_BYTES, &tm_qkv, bar_qk, C + h * HS, i * TILE, b);
-        mbar_expect_tx(bar_v, (uint32_t)(NT * TILE_BYTES));
-        for (int i = 0; i < NT; ++i) tma_load_3d(sV + i * TILE_BYTES, &tm_qkv, bar_v, 2 * C + h * HS, i * TILE, b);
         const uint32_t idesc = make_idesc(TILE, NK, 0, 0);
         const uint64_t dq = make_desc(sQ, 0, 1024), dk = make_desc(sK, 0, 1024);
         mbar_wait(bar_qk, 0);
@@ -358,7 +359,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         tma_store_3d(&tm_out, sQ, h * HS, qt * TILE, b);
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
