@@ -116,19 +116,17 @@ __device__ __forceinline__ void stage_flush(const CUtensorMap* map, uint32_t sta
 // element loop is if-converted by the compiler and every output then pays for every epilogue kind)
 template <int KIND>
 __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps& maps, uint32_t stage, uint32_t bar, uint32_t& bar_phase,
-                                               uint32_t taddr, int m_base, int n_base, int M, int N, int lane, bool bias_vec,
+                                               uint32_t taddr, int m_base, int n_base, int M, int N, int lane, float2 bias2,
                                                bool aux_issued) {
     constexpr bool kAux = KIND == EPI_BIAS_RESIDUAL || KIND == EPI_GELU_BWD;
     // the staging tile is reusable once the previous TMA store has finished reading it; the residual / pre-GELU box is
     // requested before the accumulator is read so that its latency overlaps the TMEM loads and the bias adds (the first
     // chunk of a tile was requested before the tile's main loop finished: aux_issued)
-    if (!aux_issued) {
+    if (kAux && !aux_issued) {
         if (lane == 0) {
             bulk_wait_read0();
-            if (kAux) {
-                mbar_expect_tx(bar, 32 * 128);
-                tma_load_2d(stage, maps.aux, bar, n_base, m_base);
-            }
+            mbar_expect_tx(bar, 32 * 128);
+            tma_load_2d(stage, maps.aux, bar, n_base, m_base);
         }
         __syncwarp();
     }
@@ -143,19 +141,12 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
         for (int j = 0; j < 32; ++j) acc[32 + j] = __uint_as_float(v[j]);
     }
     if (KIND == EPI_BIAS || KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_RESIDUAL) {
-        if (e.bias) {
-            if (bias_vec) {
+        // bias[n_base + 2*lane .. +1] was fetched by this lane before the tile's accumulator was ready (this kernel leaves the
+        // L1 no capacity, a global load here costs an L2 round trip per chunk); every lane needs all 64 values: shuffle broadcast
 #pragma unroll
-                for (int j4 = 0; j4 < 16; ++j4)
-                    if (n_base + j4 * 4 < N) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n_base) + j4);
-                        acc[j4 * 4] += b.x; acc[j4 * 4 + 1] += b.y; acc[j4 * 4 + 2] += b.z; acc[j4 * 4 + 3] += b.w;
-                    }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 64; ++j)
-                    if (n_base + j < N) acc[j] += __ldg(e.bias + n_base + j);
-            }
+        for (int j = 0; j < 64; j += 2) {
+            acc[j] += __shfl_sync(0xffffffffu, bias2.x, j >> 1);
+            acc[j + 1] += __shfl_sync(0xffffffffu, bias2.y, j >> 1);
         }
     }
     if (kAux) {
@@ -192,6 +183,10 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
         }
     }
     if (e.accumulate) {  // the reference's `+=` contract at the ABI; the fused model path never takes it
+        if (!kAux) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+        }
         stage_fetch(maps.out, stage, bar, bar_phase, n_base, m_base, lane);
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8) {
@@ -200,6 +195,10 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[c8 * 8 + j] += a[j];
         }
+        __syncwarp();
+    }
+    if (!kAux && !e.accumulate) {  // (the aux / accumulate paths already waited before fetching their box)
+        if (lane == 0) bulk_wait_read0();
         __syncwarp();
     }
     stage_write_row(stage, lane, acc);
@@ -352,7 +351,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t my_bar = aux_bar(ew);
         uint32_t bar_phase = 0;
         const EpiMaps maps = {&tmOut, &tmOut2, &tmAux};
-        const bool bias_vec = p.epi.bias != nullptr && ((uintptr_t)p.epi.bias & 15) == 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         int cs_stage = 0;        // column-sum consumer: walks the stage ring in step with the MMA warp
@@ -418,6 +416,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool has_aux = p.epi.kind == EPI_BIAS_RESIDUAL || p.epi.kind == EPI_GELU_BWD;
             const int nb_first = n0 + chalf * kChunksPerWarp * 64;
             const bool first_live = nb_first < p.N && m_base < p.M;
+            float2 bias2[kChunksPerWarp];  // this lane's two bias values of each of the warp's chunks, requested ahead of the accumulator
+#pragma unroll
+            for (int c = 0; c < kChunksPerWarp; ++c) {
+                const int n = nb_first + c * 64 + 2 * lane;
+                bias2[c] = make_float2(0.f, 0.f);
+                if (p.epi.bias && p.epi.kind != EPI_PATCH && p.epi.kind != EPI_ACCUM_F32) {
+                    if (n < p.N) bias2[c].x = __ldg(p.epi.bias + n);
+                    if (n + 1 < p.N) bias2[c].y = __ldg(p.epi.bias + n + 1);
+                }
+            }
             if (has_aux && first_live) {  // this tile's first residual / pre-GELU box, while the main loop is still running
                 if (lane == 0) {
                     bulk_wait_read0();
@@ -452,13 +460,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int nb = n0 + ch * 64;
                     if (nb >= p.N || m_base >= p.M) continue;  // warp-uniform: nothing of this chunk is inside the matrix
                     const bool pre = has_aux && nb == nb_first;
+                    float2 b2 = bias2[0];  // static indices only: a runtime index would put the array in local memory
+#pragma unroll
+                    for (int c = 1; c < kChunksPerWarp; ++c)
+                        if (ch - chalf * kChunksPerWarp == c) b2 = bias2[c];
                     switch (p.epi.kind) {  // warp-uniform branch to straight-line per-kind code
-                        case EPI_BIAS: epilogue_chunk<EPI_BIAS>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
-                        case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
-                        case EPI_BIAS_RESIDUAL: epilogue_chunk<EPI_BIAS_RESIDUAL>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
-                        case EPI_GELU_BWD: epilogue_chunk<EPI_GELU_BWD>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
-                        case EPI_PATCH: epilogue_chunk<EPI_PATCH>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
-                        default: epilogue_chunk<EPI_NONE>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, bias_vec, pre); break;
+                        case EPI_BIAS: epilogue_chunk<EPI_BIAS>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
+                        case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
+                        case EPI_BIAS_RESIDUAL: epilogue_chunk<EPI_BIAS_RESIDUAL>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
+                        case EPI_GELU_BWD: epilogue_chunk<EPI_GELU_BWD>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
+                        case EPI_PATCH: epilogue_chunk<EPI_PATCH>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
+                        default: epilogue_chunk<EPI_NONE>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                     }
                 }
             }
