@@ -40,10 +40,12 @@ struct TcParams {
     Epilogue epi;
 };
 
-template <int BN, int STAGES>
+// CG = CTAs per tile: 1, or 2 = a CTA pair (cta_group::2) that computes a [256 x BN] tile with each CTA staging its own 128
+// rows of A and BN/2 rows of B — per CTA the tensor core then reads a third less shared memory per flop
+template <int BN, int STAGES, int CG>
 struct SmemLayout {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = BN / CG * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;  // 8 epilogue warps x [32 rows][128 B]
     static constexpr int STAGING_BYTES = kEpilogueWarps * 32 * 128;
@@ -218,11 +220,11 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
     }
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmAux, const TcParams p) {
-    using L = SmemLayout<BN, STAGES>;
+    using L = SmemLayout<BN, STAGES, CG>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -230,10 +232,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bar_base = smem_base + L::BAR_OFFSET;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    auto aux_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4 + w); };  // one per epilogue warp
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 4 + kEpilogueWarps));
+    auto mdone_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };  // CTA pair + column sums only: MMAs of stage s retired
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
+    auto aux_bar = [&](int w) { return bar_base + 8u * (3 * STAGES + 4 + w); };  // one per epilogue warp
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (3 * STAGES + 4 + kEpilogueWarps));
+    static_assert(8 * (3 * STAGES + 4 + kEpilogueWarps) + 4 <= 256, "barrier block");
+    // CTA pair: rank 0 (the leader) issues the MMAs and owns the full / tempty barriers; both CTAs load, both run epilogues
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool colsum = A_MN && p.a_colsum != nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulators; power of two (256 or 512)
@@ -249,72 +256,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             // freed by the MMA commit and, when the column sums of A ride along, by the four epilogue warps that read the tile
-            mbar_init(empty_bar(s), (A_MN && p.a_colsum) ? 1 + kColsumWarps : 1);
+            // (in a CTA pair the column-sum warps of the peer cannot see the leader's full barrier: there they read the tile after
+            // its MMAs have retired — mdone — and the slot is freed by them alone)
+            mbar_init(empty_bar(s), colsum ? (CG == 2 ? kColsumWarps : 1 + kColsumWarps) : 1);
+            mbar_init(mdone_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), kEpilogueWarps);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(a), CG * kEpilogueWarps);  // one arrive per epilogue warp (of both CTAs of a pair)
         }
         for (int w = 0; w < kEpilogueWarps; ++w) mbar_init(aux_bar(w), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
-                     "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything is signalled across the pair
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int tiles = p.m_tiles * p.n_tiles;
+    const int tiles = p.m_tiles * p.n_tiles;  // tiles of CG*128 rows
     const int total_units = tiles * p.splits;
+    const int unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
+    constexpr int TM = BM * CG;
+    const int m_rank = (int)rank * BM, n_rank = (int)rank * (BN / CG);  // this CTA's share of the operand tiles
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         int stage = 0;
         uint32_t phase = 0;
-        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+            if (CG == 2) tma_load_2d_pair(dst, map, bar, c0, c1);
+            else tma_load_2d(dst, map, bar, c0, c1);
+        };
+        for (int unit = unit0; unit < total_units; unit += unit_step) {
             // split-major: consecutive units (= concurrently running CTAs) walk the same K range, so every
             // operand slab is fetched from HBM once and shared through L2
             const int split = unit / tiles, tile = unit - split * tiles;
-            const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+            const int m0 = (tile / p.n_tiles) * TM + m_rank, n0 = (tile % p.n_tiles) * BN + n_rank;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+                // pair: both CTAs' bytes are counted on the leader's barrier, which the leader arms for both
+                if (rank == 0) mbar_expect_tx(full_bar(stage), CG * L::STAGE_BYTES);
+                const uint32_t fb = CG == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
                 const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
                 const uint32_t sb = sa + L::A_BYTES;
                 const int k0 = kb * BK;
                 if (!A_MN) {
-                    tma_load_2d(sa, &tmA, full_bar(stage), k0, m0);  // box {64 k, 128 m}
+                    load(sa, &tmA, fb, k0, m0);  // box {64 k, 128 m}
                 } else {
 #pragma unroll
                     for (int j = 0; j < BM / 64; ++j)  // boxes {64 m, 64 k}
-                        tma_load_2d(sa + j * (BK * 128), &tmA, full_bar(stage), m0 + j * 64, k0);
+                        load(sa + j * (BK * 128), &tmA, fb, m0 + j * 64, k0);
                 }
                 if (!B_MN) {
-                    tma_load_2d(sb, &tmB, full_bar(stage), k0, n0);  // box {64 k, BN n}
+                    load(sb, &tmB, fb, k0, n0);  // box {64 k, BN/CG n}
                 } else {
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j)
-                        tma_load_2d(sb + j * (BK * 128), &tmB, full_bar(stage), n0 + j * 64, k0);
+                    for (int j = 0; j < BN / CG / 64; ++j)
+                        load(sb + j * (BK * 128), &tmB, fb, n0 + j * 64, k0);
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer (single thread) =====
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ===== MMA issuer (single thread; of the leader CTA in a pair) =====
         // instruction descriptor: D fp32 [4,6)=1, A bf16 [7,10)=1, B bf16 [10,13)=1,
         // A major bit 15, B major bit 16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
-        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        for (int unit = unit0; unit < total_units; unit += unit_step) {
             const int split = unit / tiles;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -333,12 +360,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // (SBO), +2048 B per 16-element K step.
                     const uint64_t adesc = A_MN ? make_desc(sa + k * 2048, BK * 128, 1024) : make_desc(sa + k * 32, 0, 1024);
                     const uint64_t bdesc = B_MN ? make_desc(sb + k * 2048, BK * 128, 1024) : make_desc(sb + k * 32, 0, 1024);
-                    umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    if (CG == 2) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                // frees the smem slot when these MMAs retire
+                if (CG == 2) umma_commit_pair(colsum ? mdone_bar(stage) : empty_bar(stage));
+                else umma_commit(empty_bar(stage));
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+            // accumulator complete -> epilogue (of both CTAs)
+            if (CG == 2) umma_commit_pair(tfull_bar(acc));
+            else umma_commit(tfull_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (warp >= kEpilogueWarp0) {
@@ -355,10 +387,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc_phase = 0;
         int cs_stage = 0;        // column-sum consumer: walks the stage ring in step with the MMA warp
         uint32_t cs_phase = 0;
-        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const uint32_t tempty_remote0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : 0u;
+        for (int unit = unit0; unit < total_units; unit += unit_step) {
             const int tile = unit % tiles;
-            const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
-            if (A_MN && p.a_colsum && (ew & 2)) {
+            const int m0 = (tile / p.n_tiles) * TM + m_rank, n0 = (tile % p.n_tiles) * BN;
+            if (colsum && (ew & 2)) {
                 // dbias fused into the weight-gradient GEMM: the A tiles ([64 k][64 m] boxes of dout) pass through shared
                 // memory anyway; four of the otherwise idle epilogue warps (those on the schedulers that host neither the TMA
                 // nor the MMA warp) sum them over k.  The n_tiles units that see the same A tile share the work: the unit with
@@ -375,7 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) part[i] = 0.f;
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(full_bar(cs_stage), cs_phase);
+                    mbar_wait(CG == 2 ? mdone_bar(cs_stage) : full_bar(cs_stage), cs_phase);
                     const uint32_t abox = smem_base + cs_stage * L::STAGE_BYTES + box * (BK * 128);
 #pragma unroll
                     for (int g2 = 0; g2 < 2; ++g2) {
@@ -476,17 +509,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(tempty_remote0 + 8u * acc);
+                else mbar_arrive(tempty_bar(acc));
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
         if (lane == 0) bulk_wait_all();  // the last TMA stores must be complete before the CTA retires its shared memory
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();  // neither CTA retires shared / tensor memory the other may still signal or write
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -507,30 +545,43 @@ int encode_map(vitrs_ctx* ctx, CUtensorMap* map, const void* base, uint64_t inne
     return VITRS_OK;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CG>
 int launch_tc(vitrs_ctx* ctx, const CUtensorMap* maps, const TcParams& p) {
-    using L = SmemLayout<BN, STAGES>;
-    auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
+    using L = SmemLayout<BN, STAGES, CG>;
+    auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, CG>;
     static bool configured = false;
     if (!configured) {
         VITRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
     const int units = p.m_tiles * p.n_tiles * p.splits;
-    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+    const int slots = ctx->sm_count / CG;
+    const int grid = CG * (units < slots ? units : slots);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;  // a pair = the two SMs of one TPC
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     vitrs_prof_before(ctx, 2.0 * p.M * p.N * p.K);
-    kern<<<grid, kThreads, L::TOTAL, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+    VITRS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], p));
     vitrs_prof_after(ctx);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG>
 int launch_tc_major(vitrs_ctx* ctx, bool a_mn, bool b_mn, const CUtensorMap* maps, const TcParams& p) {
-    if (!a_mn && !b_mn) return launch_tc<BN, STAGES, false, false>(ctx, maps, p);
-    if (!a_mn && b_mn) return launch_tc<BN, STAGES, false, true>(ctx, maps, p);
-    if (a_mn && b_mn) return launch_tc<BN, STAGES, true, true>(ctx, maps, p);
-    return launch_tc<BN, STAGES, true, false>(ctx, maps, p);
+    if (!a_mn && !b_mn) return launch_tc<BN, STAGES, false, false, CG>(ctx, maps, p);
+    if (!a_mn && b_mn) return launch_tc<BN, STAGES, false, true, CG>(ctx, maps, p);
+    if (a_mn && b_mn) return launch_tc<BN, STAGES, true, true, CG>(ctx, maps, p);
+    return launch_tc<BN, STAGES, true, false, CG>(ctx, maps, p);
 }
 
 inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -563,11 +614,16 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     }
     const bool a_mn = g.a_ks != 1, b_mn = g.b_ks != 1;
     const int BN = g.N > 128 ? 256 : 128;
+    // a CTA pair per [256 x 256] tile whenever the problem has that many rows
+    int CG = (BN == 256 && g.M > BM) ? 2 : 1;
+    if (const char* ov = getenv("VITRS_GEMM_CG")) {  // tuning aid (scripts/bench_gemm.py)
+        if (atoi(ov) == 1) CG = 1;
+    }
     CUtensorMap maps[5];  // A, B, out, out2, aux
     CUtensorMap &tmA = maps[0], &tmB = maps[1];
     if (!a_mn) VITRS_TRY(encode_map(ctx, &tmA, g.A, g.K, g.M, g.a_rs, BK, BM));
     else VITRS_TRY(encode_map(ctx, &tmA, g.A, g.M, g.K, g.a_ks, 64, BK));
-    if (!b_mn) VITRS_TRY(encode_map(ctx, &tmB, g.B, g.K, g.N, g.b_rs, BK, BN));
+    if (!b_mn) VITRS_TRY(encode_map(ctx, &tmB, g.B, g.K, g.N, g.b_rs, BK, BN / CG));
     else VITRS_TRY(encode_map(ctx, &tmB, g.B, g.N, g.K, g.b_ks, 64, BK));
     if (g.epi.kind == EPI_ACCUM_F32) {
         maps[2] = maps[3] = maps[4] = tmA;  // unused by the reduction epilogue
@@ -582,14 +638,15 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
 
     TcParams p;
     p.M = g.M; p.N = g.N; p.K = g.K;
-    p.m_tiles = ceil_div(g.M, BM);
+    p.m_tiles = ceil_div(g.M, BM * CG);
     p.n_tiles = ceil_div(g.N, BN);
     p.kb_total = ceil_div(g.K, BK);
     p.epi = g.epi;
     p.a_colsum = g.a_colsum;
     int splits = 1;
     const int tiles = p.m_tiles * p.n_tiles;
-    if (g.epi.kind == EPI_ACCUM_F32 && tiles < ctx->sm_count) {
+    const int slots = ctx->sm_count / CG;  // tiles in flight
+    if (g.epi.kind == EPI_ACCUM_F32 && tiles < slots) {
         // Split K so that one wave of CTAs covers the SMs: the smallest split count that fills >= 92 % of
         // whole waves, else the best fill.  More splits than needed cost fp32 reductions and, worse, break
         // the sharing of operand slabs between concurrently running CTAs (measured: 37 splits -> 6x DRAM traffic).
@@ -597,8 +654,8 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
         double best = 0.0;
         for (int s = 1; s <= max_s; ++s) {
             const long units = (long)tiles * s;
-            const long waves = (units + ctx->sm_count - 1) / ctx->sm_count;
-            const double eff = (double)units / (double)(waves * ctx->sm_count);
+            const long waves = (units + slots - 1) / slots;
+            const double eff = (double)units / (double)(waves * slots);
             if (eff > best + 1e-9) { best = eff; splits = s; }
             if (eff >= 0.92) break;
         }
@@ -608,6 +665,7 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     }
     p.kb_per_split = ceil_div(p.kb_total, splits);
     p.splits = ceil_div(p.kb_total, p.kb_per_split);
-    if (BN == 256) return launch_tc_major<256, 4>(ctx, a_mn, b_mn, maps, p);
-    return launch_tc_major<128, 6>(ctx, a_mn, b_mn, maps, p);
+    if (CG == 2) return launch_tc_major<256, 6, 2>(ctx, a_mn, b_mn, maps, p);
+    if (BN == 256) return launch_tc_major<256, 4, 1>(ctx, a_mn, b_mn, maps, p);
+    return launch_tc_major<128, 6, 1>(ctx, a_mn, b_mn, maps, p);
 }
