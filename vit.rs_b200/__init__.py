@@ -16,7 +16,8 @@ import struct
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvitrs.so")
+# VITRS_LIB: A/B aid for kernel experiments (scripts/ab_bench.sh); the product is the in-tree library
+LIB_PATH = os.environ.get("VITRS_LIB") or os.path.join(_HERE, "libvitrs.so")
 
 MODE_F32, MODE_BF16 = 0, 1
 
