@@ -136,6 +136,17 @@ int vitrs_gelu_backward_bf16(vitrs_ctx*, vitrs_bf16* dinp, const vitrs_bf16* inp
 int vitrs_gemm_bf16(vitrs_ctx*, void* D, const vitrs_bf16* A, const vitrs_bf16* B, int M, int N, int K,
                     int lda, int ldb, int ldd, int a_mn_major, int b_mn_major, int out_f32_accumulate);
 
+/* the same GEMM with one of the fused epilogues of the training step (tests, tuning; bf16 D, overwritten):
+ *   1 BIAS           D = acc + bias[n]                              matmul_forward (train_vit.rs:384)
+ *   2 BIAS_GELU      D = acc + bias[n]; D2 = gelu(D)                 matmul_forward + gelu_forward (:482)
+ *   3 BIAS_RESIDUAL  D = acc + bias[n] + aux[m,n]                    matmul_forward + residual_forward (:376)
+ *   4 GELU_BWD       D = acc * gelu'(aux[m,n])                       matmul_backward dinp + gelu_backward (:639)
+ * D, D2, aux are [M, ldd] bf16; bias may be NULL (kinds 1-3); a_colsum (nullable, MN-major A only) receives
+ * a_colsum[m] += sum_k A(m,k), the fused bias gradient of matmul_backward (:548-550). */
+int vitrs_gemm_bf16_fused(vitrs_ctx*, vitrs_bf16* D, vitrs_bf16* D2, const vitrs_bf16* aux, const float* bias,
+                          float* a_colsum, const vitrs_bf16* A, const vitrs_bf16* B, int M, int N, int K, int lda, int ldb,
+                          int ldd, int a_mn_major, int b_mn_major, int epilogue);
+
 /* ---- optimiser ---------------------------------------------------------------------------
  * optimizer_step (train_vit.rs:737): SGD over the flat buffer.  adamw_step: DEVIATIONS D8.
  * shadow (nullable): bf16 copy of the updated parameters written in the same pass. */

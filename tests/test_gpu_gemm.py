@@ -49,3 +49,67 @@ def test_gemm_f32_accumulate(vitrs, M, N, K, a_mn, b_mn):
     torch.cuda.synchronize()
     err = (D.double() - want).abs().max().item() / want.abs().max().item()
     assert err <= 2e-5, err
+
+
+def _gelu(x):
+    return 0.5 * x * (1.0 + torch.tanh(0.7978845608028654 * (x + 0.044715 * x ** 3)))
+
+
+def _gelu_grad(x):
+    u = 0.7978845608028654 * (x + 0.044715 * x ** 3)
+    th = torch.tanh(u)
+    return 0.5 * (1.0 + th) + x * 0.5 * (1.0 - th * th) * 0.7978845608028654 * (1.0 + 3.0 * 0.044715 * x * x)
+
+
+@pytest.mark.parametrize("epi", [1, 2, 3, 4])
+@pytest.mark.parametrize("M,N,K,b_mn", [(256, 512, 768, 0), (200, 192, 192, 0), (129, 264, 72, 1), (1576, 3072, 768, 0), (1000, 768, 3072, 1),
+                                        (64, 48, 48, 0), (130, 64, 256, 0)])
+def test_gemm_fused_epilogues(vitrs, M, N, K, b_mn, epi):
+    """Each fused epilogue of the training step (vitrs_gemm_bf16_fused) against the unfused fp32 op sequence
+    (matmul_forward train_vit.rs:384, gelu_forward :482, residual_forward :376, gelu_backward :639)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N * 3 + K * 5 + epi)
+    A = (torch.randn(M, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    B = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    aux = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    acc = A.float() @ B.float().t()
+    Bm = B.t().contiguous() if b_mn else B
+    D = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    D2 = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    vitrs.gemm_bf16_fused(D, D2 if epi == 2 else None, aux if epi in (3, 4) else None, bias if epi != 4 else None, None, A, Bm, M, N, K,
+                          K, N if b_mn else K, N, 0, b_mn, epi)
+    torch.cuda.synchronize()
+    if epi == 1:
+        want = acc + bias
+    elif epi == 2:
+        want = acc + bias
+    elif epi == 3:
+        want = acc + bias + aux.float()
+    else:
+        want = acc * _gelu_grad(aux.float())
+    scale = want.abs().max().item()
+    assert (D.float() - want).abs().max().item() <= 2.0 ** -7 * scale
+    if epi == 2:
+        # gelu_forward consumes the stored (bf16) pre-activation, as the unfused op would
+        want2 = _gelu(D.float())
+        assert (D2.float() - want2).abs().max().item() <= 2.0 ** -7 * max(want2.abs().max().item(), 1.0)
+    else:
+        assert (D2 == 7.0).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(768, 768, 1576), (2304, 768, 4000), (192, 256, 600)])
+def test_gemm_fused_colsum(vitrs, M, N, K):
+    """dweight-style GEMM (both operands MN-major) with the bias gradient riding along: a_colsum[m] += sum_k A(m,k) (tv:548-550)."""
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)   # dout^T
+    B = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    Am, Bm = A.t().contiguous(), B.t().contiguous()
+    cs0 = torch.randn(M, device="cuda", generator=g)
+    cs = cs0.clone()
+    D = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    vitrs.gemm_bf16_fused(D, None, None, None, cs, Am, Bm, M, N, K, M, N, N, 1, 1, 1)
+    torch.cuda.synchronize()
+    want = A.float() @ B.float().t()
+    assert (D.float() - want).abs().max().item() <= 2.0 ** -7 * want.abs().max().item()
+    want_cs = cs0.double() + A.double().sum(dim=1)
+    assert (cs.double() - want_cs).abs().max().item() <= 1e-4 * max(want_cs.abs().max().item(), 1.0)

@@ -92,6 +92,7 @@ _SIGNATURES = {
     "vitrs_cast_f32_to_bf16": (_int, [_vp, _vp, _vp, _sz]),
     "vitrs_cast_bf16_to_f32": (_int, [_vp, _vp, _vp, _sz]),
     "vitrs_gemm_bf16": (_int, [_vp, _vp, _vp, _vp] + [_int] * 9),
+    "vitrs_gemm_bf16_fused": (_int, [_vp] * 8 + [_int] * 9),
     "vitrs_sgd_step": (_int, [_vp, _vp, _vp, _sz, _f, _vp]),
     "vitrs_adamw_step": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _int, _vp]),
     "vitrs_fill_uniform": (_int, [_vp, _vp, _sz, _u64, _u64, _f, _f]),
@@ -348,6 +349,14 @@ def patch_embed_forward(encoded, images, patchw, patchb, cls, wpe, b, img, patch
 
 def patch_embed_backward(dpatchw, dpatchb, dcls, dwpe, dencoded, images, b, img, patch, c, ctx=None):
     _call(ctx, "vitrs_patch_embed_backward_f32", dpatchw, dpatchb, dcls, dwpe, dencoded, images, b, img, patch, c)
+
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_GELU_BWD = 1, 2, 3, 4
+
+
+def gemm_bf16_fused(D, D2, aux, bias, a_colsum, A, B, M, N, K, lda, ldb, ldd, a_mn_major=0, b_mn_major=0, epilogue=EPI_BIAS, ctx=None):
+    """The tcgen05 GEMM with one of the training step's fused epilogues (include/vitrs.h: vitrs_gemm_bf16_fused)."""
+    _call(ctx, "vitrs_gemm_bf16_fused", D, D2, aux, bias, a_colsum, A, B, M, N, K, lda, ldb, ldd, a_mn_major, b_mn_major, epilogue)
 
 
 def gemm_bf16(D, A, B, M, N, K, lda, ldb, ldd, a_mn_major=0, b_mn_major=0, out_f32_accumulate=0, ctx=None):

@@ -209,7 +209,10 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
         // gelu_forward consumes the stored (bf16-rounded) pre-activation, as the unfused op would
 #pragma unroll
         for (int j = 0; j < 64; j += 2) {
-            const float2 g = gelu_fwd2(make_float2(__bfloat162float(__float2bfloat16_rn(acc[j])), __bfloat162float(__float2bfloat16_rn(acc[j + 1]))));
+            // (rounded through the packed conversion: the scalar cvt shares the quarter-rate unit with tanh)
+            const __nv_bfloat162 r2 = __floats2bfloat162_rn(acc[j], acc[j + 1]);
+            const uint32_t rw = *reinterpret_cast<const uint32_t*>(&r2);
+            const float2 g = gelu_fwd2(make_float2(__uint_as_float(rw << 16), __uint_as_float(rw & 0xFFFF0000u)));
             acc[j] = g.x;
             acc[j + 1] = g.y;
         }

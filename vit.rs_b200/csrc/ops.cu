@@ -271,6 +271,27 @@ int vitrs_gemm_bf16(vitrs_ctx* ctx, void* D, const vitrs_bf16* A, const vitrs_bf
     return gemm_tc_bf16(ctx, g);
 }
 
+int vitrs_gemm_bf16_fused(vitrs_ctx* ctx, vitrs_bf16* D, vitrs_bf16* D2, const vitrs_bf16* aux, const float* bias, float* a_colsum,
+                          const vitrs_bf16* A, const vitrs_bf16* B, int M, int N, int K, int lda, int ldb, int ldd, int a_mn_major,
+                          int b_mn_major, int epilogue) {
+    CTX_OR_FAIL(ctx);
+    VITRS_ARG(ctx, D && A && B && M >= 0 && N >= 0 && K >= 0);
+    VITRS_ARG(ctx, epilogue >= EPI_BIAS && epilogue <= EPI_GELU_BWD);
+    VITRS_ARG(ctx, epilogue != EPI_BIAS_GELU || D2);
+    VITRS_ARG(ctx, (epilogue != EPI_BIAS_RESIDUAL && epilogue != EPI_GELU_BWD) || aux);
+    VITRS_ARG(ctx, !a_colsum || a_mn_major);
+    GemmDesc g = {};
+    g.A = A; g.B = B;
+    g.a_rs = a_mn_major ? 1 : lda; g.a_ks = a_mn_major ? lda : 1;
+    g.b_rs = b_mn_major ? 1 : ldb; g.b_ks = b_mn_major ? ldb : 1;
+    g.M = M; g.N = N; g.K = K;
+    g.epi.kind = epilogue;
+    g.epi.bias = epilogue == EPI_GELU_BWD ? nullptr : bias;
+    g.epi.aux = aux; g.epi.out = D; g.epi.out2 = D2; g.epi.ldo = ldd;
+    g.a_colsum = a_colsum;
+    return gemm_tc_bf16(ctx, g);
+}
+
 // ---- optimiser, init, casts ----------------------------------------------------------------
 int vitrs_sgd_step(vitrs_ctx* ctx, float* params, const float* grads, size_t n, float lr, vitrs_bf16* shadow) {
     CTX_OR_FAIL(ctx);
