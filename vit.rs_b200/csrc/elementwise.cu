@@ -95,38 +95,41 @@ __global__ void gelu_bwd_kernel(T* __restrict__ dinp, const T* __restrict__ inp,
 }
 
 // ---- LayerNorm forward (tv:453-480): warps stride over rows, the row cached in registers -------
-// Gains and biases for the lane's columns are loaded once (16-byte loads) and stay in registers, so a
-// row costs its own bytes only: MAXNV 16-byte loads in flight per lane, two shuffle reductions, MAXNV
-// 16-byte stores.
+// Gains and biases sit in shared memory (16-byte reads, conflict-free) so that the kernel fits three blocks per SM, and
+// each warp requests its next row before it reduces the current one: per SM ~24 warps x 2 rows x 48 B per lane are in
+// flight, which is what 6.5 TB/s x HBM latency asks for (one row per warp at two blocks per SM reached 68 % of it).
 template <typename T, int MAXNV>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MAXNV <= 4 ? 3 : 1)
 ln_fwd_kernel(T* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, const T* __restrict__ inp,
               const float* __restrict__ w, const float* __restrict__ bias, long rows, int c) {
     constexpr int VN = Vec16<T>::N;
-    const int lane = threadIdx.x & 31;
-    float wr[MAXNV * VN], br[MAXNV * VN];
-#pragma unroll
-    for (int i = 0; i < MAXNV; ++i) {
-        const int idx = (i * 32 + lane) * VN;
-#pragma unroll
-        for (int j4 = 0; j4 < VN / 4; ++j4) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
-            if (idx < c) {
-                a = __ldg(reinterpret_cast<const float4*>(w + idx) + j4);
-                b4 = __ldg(reinterpret_cast<const float4*>(bias + idx) + j4);
-            }
-            wr[i * VN + j4 * 4] = a.x; wr[i * VN + j4 * 4 + 1] = a.y; wr[i * VN + j4 * 4 + 2] = a.z; wr[i * VN + j4 * 4 + 3] = a.w;
-            br[i * VN + j4 * 4] = b4.x; br[i * VN + j4 * 4 + 1] = b4.y; br[i * VN + j4 * 4 + 2] = b4.z; br[i * VN + j4 * 4 + 3] = b4.w;
-        }
+    extern __shared__ float ln_wb[];  // [c] gains, [c] biases
+    float* wsm = ln_wb;
+    float* bsm = ln_wb + c;
+    for (int i = threadIdx.x; i < c; i += kThreads) {
+        wsm[i] = w[i];
+        bsm[i] = bias[i];
     }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
     const long nwarps = (long)gridDim.x * (kThreads / 32);
-    for (long row = (long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); row < rows; row += nwarps) {
-        const T* x = inp + row * c;
-        Vec16<T> v[MAXNV];
+    long row = (long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    Vec16<T> v[MAXNV], nx[MAXNV];
+    if (row < rows) {
 #pragma unroll
         for (int i = 0; i < MAXNV; ++i) {
             const int idx = (i * 32 + lane) * VN;
-            if (idx < c) v[i].load(x + idx);
+            if (idx < c) v[i].load(inp + row * c + idx);
+        }
+    }
+    for (; row < rows; row += nwarps) {
+        const long next = row + nwarps;
+        if (next < rows) {
+#pragma unroll
+            for (int i = 0; i < MAXNV; ++i) {
+                const int idx = (i * 32 + lane) * VN;
+                if (idx < c) nx[i].load(inp + next * c + idx);
+            }
         }
         float xf[MAXNV * VN];  // the row in fp32, converted once
         float s = 0.f;
@@ -159,7 +162,14 @@ ln_fwd_kernel(T* __restrict__ out, float* __restrict__ mean, float* __restrict__
             if (idx < c) {
                 Vec16<T> o;
 #pragma unroll
-                for (int j = 0; j < VN; ++j) o.set(j, (rs * xf[i * VN + j]) * wr[i * VN + j] + br[i * VN + j]);
+                for (int j4 = 0; j4 < VN / 4; ++j4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wsm + idx + j4 * 4);
+                    const float4 b4 = *reinterpret_cast<const float4*>(bsm + idx + j4 * 4);
+                    o.set(j4 * 4 + 0, (rs * xf[i * VN + j4 * 4 + 0]) * w4.x + b4.x);
+                    o.set(j4 * 4 + 1, (rs * xf[i * VN + j4 * 4 + 1]) * w4.y + b4.y);
+                    o.set(j4 * 4 + 2, (rs * xf[i * VN + j4 * 4 + 2]) * w4.z + b4.z);
+                    o.set(j4 * 4 + 3, (rs * xf[i * VN + j4 * 4 + 3]) * w4.w + b4.w);
+                }
                 o.store(y + idx);
             }
         }
@@ -167,6 +177,8 @@ ln_fwd_kernel(T* __restrict__ out, float* __restrict__ mean, float* __restrict__
             mean[row] = m;
             rstd[row] = rs;
         }
+#pragma unroll
+        for (int i = 0; i < MAXNV; ++i) v[i] = nx[i];
     }
 }
 
@@ -212,13 +224,19 @@ ln_bwd_kernel(T* __restrict__ dinp, float* __restrict__ dweight, float* __restri
     float* wsm = red + NW * c;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < c; i += kThreads) wsm[i] = w[i];
+    if (threadIdx.x == 0) wsm[c] = 1.0f;
     __syncthreads();
-    float dw_acc[MAXNV * VN], db_acc[MAXNV * VN], cs_acc[COLSUM ? MAXNV * VN : 1];
+    // x + y as one FFMA2 (x * one + y): ptxas splits add.f32x2, and a literal 1.0 multiplier, into two FADDs; a value it cannot
+    // fold keeps the packed form
+    const float2 one2 = splat2(wsm[c]);
+    // packed f32x2 arithmetic throughout (the kernel is co-limited by instruction issue: ~27 -> ~17 instructions per element)
+    constexpr int NP = MAXNV * VN / 2;
+    float2 dw_acc[NP], db_acc[NP], cs_acc[COLSUM ? NP : 1];
 #pragma unroll
-    for (int i = 0; i < MAXNV * VN; ++i) {
-        dw_acc[i] = 0.f;
-        db_acc[i] = 0.f;
-        if (COLSUM) cs_acc[i] = 0.f;
+    for (int i = 0; i < NP; ++i) {
+        dw_acc[i] = make_float2(0.f, 0.f);
+        db_acc[i] = make_float2(0.f, 0.f);
+        if (COLSUM) cs_acc[i] = make_float2(0.f, 0.f);
     }
     for (long row = (long)blockIdx.x * NW + warp; row < rows; row += (long)gridDim.x * NW) {
         Vec16<T> gy[MAXNV], xv[MAXNV], dv[MAXNV];
@@ -232,7 +250,8 @@ ln_bwd_kernel(T* __restrict__ dinp, float* __restrict__ dweight, float* __restri
             }
         }
         const float m = mean[row], rs = rstd[row];
-        float s1 = 0.f, s2 = 0.f;
+        const float2 rs2 = splat2(rs), mrs2 = splat2(-m * rs);  // nrm = x * rs - m * rs
+        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < MAXNV; ++i) {
             const int idx = (i * 32 + lane) * VN;
@@ -240,23 +259,24 @@ ln_bwd_kernel(T* __restrict__ dinp, float* __restrict__ dweight, float* __restri
 #pragma unroll
                 for (int j4 = 0; j4 < VN / 4; ++j4) {
                     const float4 w4 = *reinterpret_cast<const float4*>(wsm + idx + j4 * 4);
-                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                    const float2 wv[2] = {make_float2(w4.x, w4.y), make_float2(w4.z, w4.w)};
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j4 * 4 + jj;
-                        const float g = gy[i].get(j);
-                        const float nrm = (xv[i].get(j) - m) * rs;
-                        const float dn = wv[jj] * g;
-                        s1 += dn;
-                        s2 += dn * nrm;
-                        db_acc[i * VN + j] += g;
-                        dw_acc[i * VN + j] += nrm * g;
+                    for (int pp = 0; pp < 2; ++pp) {
+                        const int j = j4 * 4 + pp * 2;
+                        const float2 g = make_float2(gy[i].get(j), gy[i].get(j + 1));
+                        const float2 nrm = fma2(make_float2(xv[i].get(j), xv[i].get(j + 1)), rs2, mrs2);
+                        const float2 dn = mul2(wv[pp], g);
+                        s1 = fma2(wv[pp], g, s1);
+                        s2 = fma2(dn, nrm, s2);
+                        db_acc[(i * VN + j) >> 1] = fma2(g, one2, db_acc[(i * VN + j) >> 1]);
+                        dw_acc[(i * VN + j) >> 1] = fma2(nrm, g, dw_acc[(i * VN + j) >> 1]);
                     }
                 }
             }
         }
-        const float dn_mean = warp_sum(s1) / (float)c;
-        const float dnn_mean = warp_sum(s2) / (float)c;
+        const float dn_mean = warp_sum(s1.x + s1.y) / (float)c;
+        const float dnn_mean = warp_sum(s2.x + s2.y) / (float)c;
+        const float2 ndn2 = splat2(-dn_mean), ndnn2 = splat2(-dnn_mean);
 #pragma unroll
         for (int i = 0; i < MAXNV; ++i) {
             const int idx = (i * 32 + lane) * VN;
@@ -264,15 +284,19 @@ ln_bwd_kernel(T* __restrict__ dinp, float* __restrict__ dweight, float* __restri
 #pragma unroll
                 for (int j4 = 0; j4 < VN / 4; ++j4) {
                     const float4 w4 = *reinterpret_cast<const float4*>(wsm + idx + j4 * 4);
-                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                    const float2 wv[2] = {make_float2(w4.x, w4.y), make_float2(w4.z, w4.w)};
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j4 * 4 + jj;
-                        const float nrm = (xv[i].get(j) - m) * rs;
-                        const float dn = wv[jj] * gy[i].get(j);
-                        const float upd = dv[i].get(j) + (dn - dn_mean - nrm * dnn_mean) * rs;
-                        dv[i].set(j, upd);
-                        if (COLSUM) cs_acc[i * VN + j] += dv[i].get(j);  // the value as stored (rounded)
+                    for (int pp = 0; pp < 2; ++pp) {
+                        const int j = j4 * 4 + pp * 2;
+                        const float2 nrm = fma2(make_float2(xv[i].get(j), xv[i].get(j + 1)), rs2, mrs2);
+                        const float2 dnc = fma2(wv[pp], make_float2(gy[i].get(j), gy[i].get(j + 1)), ndn2);  // dn - mean(dn)
+                        // dinp += (dn - mean(dn) - nrm * mean(dn * nrm)) * rstd
+                        const float2 t = fma2(nrm, ndnn2, dnc);
+                        const float2 upd = fma2(t, rs2, make_float2(dv[i].get(j), dv[i].get(j + 1)));
+                        dv[i].set(j, upd.x);
+                        dv[i].set(j + 1, upd.y);
+                        if (COLSUM)  // the value as stored (rounded)
+                            cs_acc[(i * VN + j) >> 1] = fma2(make_float2(dv[i].get(j), dv[i].get(j + 1)), one2, cs_acc[(i * VN + j) >> 1]);
                     }
                 }
                 dv[i].store(dinp + row * c + idx);
@@ -288,7 +312,10 @@ ln_bwd_kernel(T* __restrict__ dinp, float* __restrict__ dweight, float* __restri
             if (idx < c) {
 #pragma unroll
                 for (int j = 0; j < VN; ++j)
-                    red[warp * c + idx + j] = qn == 0 ? dw_acc[i * VN + j] : (qn == 1 ? db_acc[i * VN + j] : cs_acc[COLSUM ? i * VN + j : 0]);
+                {
+                    const float2 v2 = qn == 0 ? dw_acc[(i * VN + j) >> 1] : (qn == 1 ? db_acc[(i * VN + j) >> 1] : cs_acc[COLSUM ? (i * VN + j) >> 1 : 0]);
+                    red[warp * c + idx + j] = (j & 1) ? v2.y : v2.x;
+                }
             }
         }
         __syncthreads();
@@ -588,18 +615,20 @@ int op_layernorm_forward(vitrs_ctx* ctx, T* out, float* mean, float* rstd, const
         VITRS_LAUNCHED(ctx);
         return VITRS_OK;
     }
-    if (grid > 4 * ctx->sm_count) grid = 4 * ctx->sm_count;  // persistent: warps stride over rows
+    const int per_sm = nv <= 4 ? 3 : 1;
+    if (grid > per_sm * ctx->sm_count) grid = per_sm * ctx->sm_count;  // persistent: warps stride over rows
+    const size_t smem = (size_t)2 * c * sizeof(float);  // nv <= 8: at most 16 KB
     if (false) {
     } else if (nv <= 1) {
-        ln_fwd_kernel<T, 1><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+        ln_fwd_kernel<T, 1><<<grid, kThreads, smem, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
     } else if (nv <= 2) {
-        ln_fwd_kernel<T, 2><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+        ln_fwd_kernel<T, 2><<<grid, kThreads, smem, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
     } else if (nv <= 3) {
-        ln_fwd_kernel<T, 3><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+        ln_fwd_kernel<T, 3><<<grid, kThreads, smem, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
     } else if (nv <= 4) {
-        ln_fwd_kernel<T, 4><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+        ln_fwd_kernel<T, 4><<<grid, kThreads, smem, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
     } else {
-        ln_fwd_kernel<T, 8><<<grid, kThreads, 0, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
+        ln_fwd_kernel<T, 8><<<grid, kThreads, smem, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
     }
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
@@ -610,7 +639,7 @@ static int launch_ln_bwd(vitrs_ctx* ctx, T* dinp, float* dw, float* db, const T*
                          const float* mean, const float* rstd, long rows, int c, float* colsum_out) {
     int grid = ceil_div(rows, kThreads / 32);
     if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
-    const size_t smem = (size_t)(kThreads / 32 + 1) * c * sizeof(float);
+    const size_t smem = ((size_t)(kThreads / 32 + 1) * c + 4) * sizeof(float);  // reduction scratch, gains, the constant 1
     if (colsum_out) {
         auto k = ln_bwd_kernel<T, MAXNV, true>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
