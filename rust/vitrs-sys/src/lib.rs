@@ -69,6 +69,11 @@ extern "C" {
     pub fn vitrs_matmul_backward_bf16(ctx: *mut vitrs_ctx, dinp: *mut vitrs_bf16, dweight: *mut f32, dbias: *mut f32,
                                       dout: *const vitrs_bf16, inp: *const vitrs_bf16, weight: *const vitrs_bf16,
                                       b: c_int, t: c_int, c: c_int, oc: c_int) -> c_int;
+    /// one GEMM with a fused epilogue: 1 bias, 2 bias + GELU (second output d2), 3 bias + residual (aux), 4 gelu'(aux)
+    pub fn vitrs_gemm_bf16_fused(ctx: *mut vitrs_ctx, d: *mut vitrs_bf16, d2: *mut vitrs_bf16, aux: *const vitrs_bf16,
+                                 bias: *const f32, a_colsum: *mut f32, a: *const vitrs_bf16, b: *const vitrs_bf16,
+                                 m: c_int, n: c_int, k: c_int, lda: c_int, ldb: c_int, ldd: c_int,
+                                 a_mn_major: c_int, b_mn_major: c_int, epilogue: c_int) -> c_int;
     pub fn vitrs_attention_forward_bf16(ctx: *mut vitrs_ctx, out: *mut vitrs_bf16, lse: *mut f32, inp: *const vitrs_bf16,
                                         b: c_int, t: c_int, c: c_int, nh: c_int, causal: c_int) -> c_int;
     pub fn vitrs_attention_backward_bf16(ctx: *mut vitrs_ctx, dinp: *mut vitrs_bf16, dout: *const vitrs_bf16, out: *const vitrs_bf16,
