@@ -557,6 +557,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 // TMEM: 2 x {S^T 64, dP^T 64} + dV 64 + dK 64 + dQ_0 64 + dQ_1 64 = 512 columns.
 constexpr int kPipeThreads = 384;  // warps 0-3: control (issuer = warp 0 lane 0, TMEM owner = warp 1), 4-7: group A, 8-11: group B
 
+// Sub-tile processed at position t of key tile j.  Iterations alternate between the two SIMT groups; with an even number of
+// sub-tiles of which the last is short (T = 197: 64, 64, 64, 5 queries) the same group would get the short one in every key
+// tile, so odd key tiles swap their last two sub-tiles (0, 1, 3, 2): both groups then see 208 query columns in total.
+__device__ __forceinline__ int sub_at(int j, int t, int nsub) {
+    return ((j & 1) && !(nsub & 1) && t >= nsub - 2) ? 2 * nsub - 3 - t : t;
+}
+
 __device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 __global__ void __launch_bounds__(kPipeThreads, 1)
@@ -625,48 +632,53 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             const uint64_t dK_mn = make_desc(sK, TILE_BYTES, 1024);
             const uint64_t ddS_k = make_desc(sdS, 0, 1024), ddS_mn = make_desc(sdS, TILE_BYTES, 1024);
             auto off = [](uint32_t bytes) { return (uint64_t)(bytes >> 4); };
-            for (int n = 0; n <= N; ++n) {
-                if (n < N) {  // S^T and dP^T of iteration n
-                    const int j = n / NSUB, s_ = n - j * NSUB, bx = n & 1;
-                    const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
-                    if (n >= 2) mbar_wait(x_free + 8 * bx, (uint32_t)(((n >> 1) - 1) & 1));
-                    tc_fence_after();
-                    const uint32_t idesc = make_idesc(TILE, nq16, 0, 0);
-                    const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES), ko = off(j * TILE_BYTES);
+            // S^T and dP^T of iteration n into buffer n & 1.  tcgen05.mma executes in issue order, so the MMAs that overwrite a
+            // buffer need no barrier against the dV MMAs of iteration n - 2 that read P^T from it: they are issued after them.
+            auto issue_scores = [&](int n) {
+                const int j = n / NSUB, s_ = sub_at(j, n - j * NSUB, NSUB), bx = n & 1;
+                const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
+                const uint32_t idesc = make_idesc(TILE, nq16, 0, 0);
+                const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES), ko = off(j * TILE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + bx * 128, dK_k + ko + 2 * k, dQ_k + qo + 2 * k, idesc, k > 0);
+                for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + bx * 128, dK_k + ko + 2 * k, dQ_k + qo + 2 * k, idesc, k > 0);
 #pragma unroll
-                    for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + bx * 128 + 64, dV_k + ko + 2 * k, ddO_k + qo + 2 * k, idesc, k > 0);
-                    umma_commit(s_full + 8 * bx);
-                }
-                if (n >= 1) {  // dV, dK (and dQ) of iteration n-1
-                    const int m = n - 1, j = m / NSUB, s_ = m - j * NSUB, bx = m & 1;
-                    const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
-                    const int nk16 = (min(TILE, T - j * TILE) + 15) & ~15;
-                    const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES);
-                    mbar_wait(p_full + 8 * bx, (uint32_t)((m >> 1) & 1));
+                for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + bx * 128 + 64, dV_k + ko + 2 * k, ddO_k + qo + 2 * k, idesc, k > 0);
+                umma_commit(s_full + 8 * bx);
+            };
+            uint32_t done_mask = 0u;  // sub-tiles of the current key tile whose dS^T is in shared memory
+            issue_scores(0);
+            if (N > 1) issue_scores(1);
+            for (int m = 0; m < N; ++m) {
+                // dV, dK of iteration m, then the scores of m + 2 (the group that finished m is waiting for them), then dQ
+                const int j = m / NSUB, t_ = m - j * NSUB, s_ = sub_at(j, t_, NSUB), bx = m & 1;
+                const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
+                const int nk16 = (min(TILE, T - j * TILE) + 15) & ~15;
+                const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES);
+                if (t_ == 0) done_mask = 0u;
+                mbar_wait(p_full + 8 * bx, (uint32_t)((m >> 1) & 1));
+                tc_fence_after();
+                if (t_ == 0 && j > 0) {  // the previous key tile's dV / dK have been read out
+                    mbar_wait(acc_free, (uint32_t)((j - 1) & 1));
                     tc_fence_after();
-                    if (s_ == 0 && j > 0) {  // the previous key tile's dV / dK have been read out
-                        mbar_wait(acc_free, (uint32_t)((j - 1) & 1));
-                        tc_fence_after();
-                    }
-                    const uint64_t so = off((s_ & 3) * TILE_BYTES);
-                    for (int k16 = 0; k16 < nq16 / 16; ++k16) {
-                        const uint32_t acc = (s_ > 0 || k16 > 0) ? 1u : 0u;
-                        umma_bf16_ts(tmem_base + cDV, tmem_base + bx * 128 + k16 * 8, ddO_mn + qo + 128 * k16, idesc_kk, acc);
-                        umma_bf16(tmem_base + cDK, ddS_k + so + 2 * k16, dQ_mn + qo + 128 * k16, idesc_kk, acc);
-                    }
-                    umma_commit(x_free + 8 * bx);
-                    if ((s_ & 1) || s_ == NSUB - 1) {  // query tile i = s/2 is complete for this key tile: dQ_i += dS K_j
-                        const int i = s_ >> 1;
-                        const uint64_t ao = off((2 * i) * TILE_BYTES), ko = off(j * TILE_BYTES);
-                        for (int k16 = 0; k16 < nk16 / 16; ++k16)
-                            umma_bf16(tmem_base + cDQ + i * HS, ddS_mn + ao + 128 * k16, dK_mn + ko + 128 * k16, idesc_mn, (j > 0 || k16 > 0) ? 1u : 0u);
-                        umma_commit(ds_free + 8 * ((2 * i) & 3));
-                        if (s_ & 1) umma_commit(ds_free + 8 * ((2 * i + 1) & 3));
-                    }
-                    if (s_ == NSUB - 1) umma_commit(acc_full);
                 }
+                const uint64_t so = off((s_ & 3) * TILE_BYTES);
+                for (int k16 = 0; k16 < nq16 / 16; ++k16) {
+                    const uint32_t acc = (t_ > 0 || k16 > 0) ? 1u : 0u;
+                    umma_bf16_ts(tmem_base + cDV, tmem_base + bx * 128 + k16 * 8, ddO_mn + qo + 128 * k16, idesc_kk, acc);
+                    umma_bf16(tmem_base + cDK, ddS_k + so + 2 * k16, dQ_mn + qo + 128 * k16, idesc_kk, acc);
+                }
+                if (m + 2 < N) issue_scores(m + 2);
+                done_mask |= 1u << s_;
+                const int partner = s_ ^ 1;
+                if (partner >= NSUB || ((done_mask >> partner) & 1u)) {  // query tile i = s/2 is complete for this key tile: dQ_i += dS K_j
+                    const int i = s_ >> 1;
+                    const uint64_t ao = off((2 * i) * TILE_BYTES), ko = off(j * TILE_BYTES);
+                    for (int k16 = 0; k16 < nk16 / 16; ++k16)
+                        umma_bf16(tmem_base + cDQ + i * HS, ddS_mn + ao + 128 * k16, dK_mn + ko + 128 * k16, idesc_mn, (j > 0 || k16 > 0) ? 1u : 0u);
+                    umma_commit(ds_free + 8 * ((2 * i) & 3));
+                    if (2 * i + 1 < NSUB) umma_commit(ds_free + 8 * ((2 * i + 1) & 3));
+                }
+                if (t_ == NSUB - 1) umma_commit(acc_full);
             }
             umma_commit(dq_full);
         }
@@ -675,12 +687,34 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         const int g = (warp - 4) >> 2;          // group 0 / 1
         const int r = (warp & 3) * 32 + lane;   // TMEM lane = key within the tile / output row
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-        uint32_t ds_uses = 0;                   // per buffer: how many times this group has written it (2 bits each... counts mod 2 suffice)
+        // dV_j (group 0) / dK_j (group 1): staged through the dead V_j / K_j tile, one TMA store each
+        auto store_acc = [&](int j) {
+            const int key = j * TILE + r;
+            mbar_wait(acc_full, (uint32_t)(j & 1));
+            tc_fence_after();
+            const uint32_t tile = (g == 0 ? sV : sK) + j * TILE_BYTES;  // every MMA that read it has retired (acc_full)
+            const long gcol = (g == 0 ? 2 * C : C) + h * HS;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_off + (g == 0 ? cDV : cDK) + half * 32, v);
+                stage_half_row(tile, r, half, v, (accumulate && key < T) ? dqkv + ((long)b * T + key) * 3 * C + gcol + half * 32 : nullptr);
+            }
+            tc_fence_before();
+            mbar_arrive_cnt(acc_free);  // the accumulators are free; the store below only reads shared memory
+            fence_proxy_async();
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+            if ((warp & 3) == 0 && lane == 0) tma_store_3d(&tm_dqkv, tile, (int)gcol, j * TILE, b);
+        };
+        // The group that owns the first iteration of key tile j + 1 reads out tile j only after that iteration: its scores are
+        // already in tensor memory, whereas acc_full(j) still waits for the other group's last iteration of tile j.
+        int pending = -1;
         for (int j = 0; j < NT; ++j) {
             const int key = j * TILE + r;
-            for (int s_ = 0; s_ < NSUB; ++s_) {
-                const int n = j * NSUB + s_;
+            for (int t_ = 0; t_ < NSUB; ++t_) {
+                const int n = j * NSUB + t_;
                 if ((n & 1) != g) continue;
+                const int s_ = sub_at(j, t_, NSUB);
                 const int nq = min(SUB, T - s_ * SUB), nq16 = (nq + 15) & ~15;
                 const uint32_t xb = tmem_base + lane_off + (uint32_t)(g * 128);
                 mbar_wait(s_full + 8 * g, (uint32_t)((n >> 1) & 1));
@@ -688,7 +722,6 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
                 const int bs = s_ & 3;
                 const uint32_t sbuf = sdS + bs * TILE_BYTES;
                 if (j > 0) mbar_wait(ds_free + 8 * bs, (uint32_t)((j - 1) & 1));  // the MMAs that read this tile last time have retired
-                (void)ds_uses;
                 const int nch = (nq16 + 31) >> 5;
                 for (int ch = 0; ch < nch; ++ch) {
                     uint32_t sv[32], dp[32], pk[16];
@@ -722,25 +755,13 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive_cnt(p_full + 8 * g);
-            }
-            // ---- dV_j (group 0) / dK_j (group 1): staged through the dead V_j / K_j tile, one TMA store each ----
-            mbar_wait(acc_full, (uint32_t)(j & 1));
-            tc_fence_after();
-            {
-                const uint32_t tile = (g == 0 ? sV : sK) + j * TILE_BYTES;  // every MMA that read it has retired (acc_full)
-                const long gcol = (g == 0 ? 2 * C : C) + h * HS;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_off + (g == 0 ? cDV : cDK) + half * 32, v);
-                    stage_half_row(tile, r, half, v, (accumulate && key < T) ? dqkv + ((long)b * T + key) * 3 * C + gcol + half * 32 : nullptr);
+                if (pending >= 0) {
+                    store_acc(pending);
+                    pending = -1;
                 }
-                tc_fence_before();
-                mbar_arrive_cnt(acc_free);  // the accumulators are free; the store below only reads shared memory
-                fence_proxy_async();
-                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-                if ((warp & 3) == 0 && lane == 0) tma_store_3d(&tm_dqkv, tile, (int)gcol, j * TILE, b);
             }
+            if (j + 1 < NT && (((j + 1) * NSUB) & 1) == g) pending = j;
+            else store_acc(j);
         }
         // ---- dQ_0 (group 0) / dQ_1 (group 1) ----
         mbar_wait(dq_full, 0);
