@@ -28,6 +28,8 @@ def to_dev(images, labels):
 
 
 SMALL_HS64 = dict(image_size=64, patch_size=16, channels=128, num_layers=2, num_heads=2, num_classes=16)
+# four 64-wide heads, 272 token rows: the CTA-pair GEMM tiles and the D = rowsum(dO * O) epilogue of the attproj dX GEMM
+MID_HS64 = dict(image_size=64, patch_size=16, channels=256, num_layers=2, num_heads=4, num_classes=16)
 
 
 # init_mode 1 (symmetric weights) is well conditioned: the oracle itself is within ~1e-6 of exact arithmetic and
@@ -106,7 +108,7 @@ def test_inference_forward_and_sgd(vitrs):
     m.close()
 
 
-@pytest.mark.parametrize("cfg_name,b", [("tiny", 8), (SMALL_HS64, 4)])
+@pytest.mark.parametrize("cfg_name,b", [("tiny", 8), (SMALL_HS64, 4), (MID_HS64, 16)])
 def test_bf16_step_within_tolerance(vitrs, cfg_name, b):
     cfg = po.CONFIGS[cfg_name] if isinstance(cfg_name, str) else cfg_name
     ref = po.ViT(cfg_name, seed=1337, init_mode=1)

@@ -1291,14 +1291,25 @@ int op_attention_forward_tc(vitrs_ctx* ctx, bf16* out, float* lse, const bf16* q
     return VITRS_OK;
 }
 
-int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const bf16* out, const bf16* qkv, const float* lse, int b,
-                             int t, int c, int nh, int causal, int accumulate) {
-    if (!tc_shape_ok(dqkv, qkv, t, c, nh) || ((uintptr_t)dout & 15) || ((uintptr_t)out & 15)) return VITRS_ERR_UNSUPPORTED;
+// D[b,h,q] = sum_i dO * O over the head slice (the row term of the softmax backward)
+int op_attention_bwd_prep(vitrs_ctx* ctx, float* dsum, const bf16* dout, const bf16* out, int b, int t, int c, int nh) {
     if (b <= 0) return VITRS_OK;
-    VITRS_TRY(vitrs_ensure_scratch(ctx, (size_t)b * nh * t));
-    float* dsum = ctx->scratch;
     attn_bwd_prep_kernel<<<ceil_div((long)b * t, 8), 256, 0, ctx->stream>>>(dsum, dout, out, b, t, c, nh);
     VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+
+// dsum_ready: D already computed by the producer of dout (the attproj dX GEMM's EPI_ROWDOT epilogue); null -> computed here
+int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const bf16* out, const bf16* qkv, const float* lse, int b,
+                             int t, int c, int nh, int causal, int accumulate, const float* dsum_ready) {
+    if (!tc_shape_ok(dqkv, qkv, t, c, nh) || ((uintptr_t)dout & 15) || ((uintptr_t)out & 15)) return VITRS_ERR_UNSUPPORTED;
+    if (b <= 0) return VITRS_OK;
+    const float* dsum = dsum_ready;
+    if (!dsum) {
+        VITRS_TRY(vitrs_ensure_scratch(ctx, (size_t)b * nh * t));
+        VITRS_TRY(op_attention_bwd_prep(ctx, ctx->scratch, dout, out, b, t, c, nh));
+        dsum = ctx->scratch;
+    }
     const int NT = (t + TILE - 1) / TILE;
     // T <= 256: the one-CTA-per-head kernel (5 matmuls, dQ kept in TMEM) is faster (measured 139.6 vs 143.8 ms per
     // ViT-B/16 step); longer sequences take the two streaming kernels.  VITRS_ATTN_BWD_STREAM forces them (test / A-B aid).

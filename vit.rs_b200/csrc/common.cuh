@@ -178,6 +178,8 @@ enum EpiKind {
     EPI_BIAS_RESIDUAL = 3, // out = acc + bias[n] + aux[m,n]              (proj + residual_forward)
     EPI_GELU_BWD = 4,      // out = acc * gelu'(aux[m,n])                 (fcproj dX + gelu_backward)
     EPI_ACCUM_F32 = 5,     // out(fp32) += acc, atomically (split-K)      (dweight)
+    EPI_ROWDOT = 7,        // out = acc; rowdot[(m / np * N/64 + n/64) * np + m % np] = sum over the 64-column head slice of out * aux
+                           //                                             (attproj dX + D = rowsum(dO * O) of attention_backward)
     EPI_PATCH = 6,         // tok = m % np: out = tok ? acc + bias[n] + pos[tok,n] : cls[n] + pos[0,n]   (patch embedding)
 };
 
@@ -187,11 +189,11 @@ struct Epilogue {
     const float* bias;  // [N] fp32 or null
     const void* aux;    // residual / pre-GELU activations, same dtype and ld as out
     void* out;
-    void* out2;
+    void* out2;         // second bf16 output (EPI_BIAS_GELU) or the fp32 row-dot vector (EPI_ROWDOT)
     long ldo;           // leading dimension of out / out2 / aux
     const float* pos;   // EPI_PATCH: wpe [np, N]
     const float* cls;   // EPI_PATCH: class token [N]
-    int np;             // EPI_PATCH: tokens per image (patches + 1)
+    int np;             // EPI_PATCH, EPI_ROWDOT: tokens per image (patches + 1)
 };
 
 // gemm operand description: element (row, k) of an operand is at base[row*rs + k*ks]
@@ -253,8 +255,9 @@ template <typename T> int op_attention_backward(vitrs_ctx*, T* dqkv, float* dpre
                                                 int nh, int causal);
 // production attention (tensor cores); same contracts
 int op_attention_forward_tc(vitrs_ctx*, bf16* out, float* lse, const bf16* qkv, int b, int t, int c, int nh, int causal);
+int op_attention_bwd_prep(vitrs_ctx*, float* dsum, const bf16* dout, const bf16* out, int b, int t, int c, int nh);
 int op_attention_backward_tc(vitrs_ctx*, bf16* dqkv, const bf16* dout, const bf16* out, const bf16* qkv, const float* lse,
-                             int b, int t, int c, int nh, int causal, int accumulate);
+                             int b, int t, int c, int nh, int causal, int accumulate, const float* dsum_ready = nullptr);
 
 // patch embedding pieces (patch_embed.cu): im2col rows are tokens, [B*T, 3*p*p], CLS rows zero
 template <typename T> int op_im2col(vitrs_ctx*, T* patches, const float* images, int b, int img, int patch);

@@ -120,7 +120,7 @@ template <int KIND>
 __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps& maps, uint32_t stage, uint32_t bar, uint32_t& bar_phase,
                                                uint32_t taddr, int m_base, int n_base, int M, int N, int lane, float2 bias2,
                                                bool aux_issued) {
-    constexpr bool kAux = KIND == EPI_BIAS_RESIDUAL || KIND == EPI_GELU_BWD;
+    constexpr bool kAux = KIND == EPI_BIAS_RESIDUAL || KIND == EPI_GELU_BWD || KIND == EPI_ROWDOT;
     // the staging tile is reusable once the previous TMA store has finished reading it; the residual / pre-GELU box is
     // requested before the accumulator is read so that its latency overlaps the TMEM loads and the bias adds (the first
     // chunk of a tile was requested before the tile's main loop finished: aux_issued)
@@ -151,6 +151,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
             acc[j + 1] += __shfl_sync(0xffffffffu, bias2.y, j >> 1);
         }
     }
+    float rowdot = 0.f;
     if (kAux) {
         mbar_wait(bar, bar_phase);
         bar_phase ^= 1u;
@@ -161,6 +162,15 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
             if (KIND == EPI_BIAS_RESIDUAL) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[c8 * 8 + j] += a[j];
+            } else if (KIND == EPI_ROWDOT) {
+                // the chunk is one head's 64 columns of dO: D = sum dO * O with dO as it is stored (rounded to bf16)
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const __nv_bfloat162 r2 = __floats2bfloat162_rn(acc[c8 * 8 + j], acc[c8 * 8 + j + 1]);
+                    const uint32_t rw = *reinterpret_cast<const uint32_t*>(&r2);
+                    rowdot = fmaf(__uint_as_float(rw << 16), a[j], rowdot);
+                    rowdot = fmaf(__uint_as_float(rw & 0xFFFF0000u), a[j + 1], rowdot);
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; j += 2) {  // packed f32x2 math: this epilogue is instruction-issue-bound
@@ -171,6 +181,13 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
             }
         }
         __syncwarp();  // every lane has read its aux row before the tile is overwritten
+        if (KIND == EPI_ROWDOT) {
+            const long m = (long)m_base + lane;
+            if (m < M) {
+                const long img = m / e.np;
+                reinterpret_cast<float*>(e.out2)[(img * (N >> 6) + (n_base >> 6)) * e.np + (m - img * e.np)] = rowdot;
+            }
+        }
     }
     if (KIND == EPI_PATCH) {
         const long m = (long)m_base + lane;
@@ -449,7 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             const int m_base = m0 + quarter * 32;
             const long m = (long)m_base + lane;
-            const bool has_aux = p.epi.kind == EPI_BIAS_RESIDUAL || p.epi.kind == EPI_GELU_BWD;
+            const bool has_aux = p.epi.kind == EPI_BIAS_RESIDUAL || p.epi.kind == EPI_GELU_BWD || p.epi.kind == EPI_ROWDOT;
             const int nb_first = n0 + chalf * kChunksPerWarp * 64;
             const bool first_live = nb_first < p.N && m_base < p.M;
             float2 bias2[kChunksPerWarp];  // this lane's two bias values of each of the warp's chunks, requested ahead of the accumulator
@@ -505,6 +522,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_BIAS_RESIDUAL: epilogue_chunk<EPI_BIAS_RESIDUAL>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_GELU_BWD: epilogue_chunk<EPI_GELU_BWD>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
+                        case EPI_ROWDOT: epilogue_chunk<EPI_ROWDOT>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_PATCH: epilogue_chunk<EPI_PATCH>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         default: epilogue_chunk<EPI_NONE>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                     }
@@ -606,6 +624,7 @@ static bool tc_eligible(const GemmDesc& g) {
     if (g.epi.aux && !al16(g.epi.aux)) return false;
     if (g.epi.out2 && !al16(g.epi.out2)) return false;
     if (g.M < 1 || g.N < 8 || g.K < 8) return false;
+    if (g.epi.kind == EPI_ROWDOT && (g.N % 64 || g.epi.np < 1 || g.M % g.epi.np || !g.epi.aux || !g.epi.out2)) return false;
     return true;
 }
 
@@ -613,6 +632,17 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return VITRS_OK;
     if (!tc_eligible(g)) {
         if (g.a_colsum) VITRS_TRY(op_colsum<bf16>(ctx, g.a_colsum, reinterpret_cast<const bf16*>(g.A), g.K, g.M, g.a_ks));
+        if (g.epi.kind == EPI_ROWDOT) {  // plain GEMM, then the row dots of every 64-column head slice as a separate pass
+            GemmDesc plain = g;
+            plain.epi.kind = EPI_NONE;
+            plain.epi.aux = nullptr;
+            plain.epi.out2 = nullptr;
+            VITRS_TRY(gemm_simt_bf16(ctx, plain));
+            if (g.N % 64 || g.epi.np < 1 || g.M % g.epi.np || g.epi.ldo != g.N)
+                return vitrs_set_error(ctx, VITRS_ERR_ARG, "EPI_ROWDOT needs N %% 64 == 0, M %% tokens == 0 and a dense output");
+            return op_attention_bwd_prep(ctx, reinterpret_cast<float*>(g.epi.out2), reinterpret_cast<const bf16*>(g.epi.out),
+                                         reinterpret_cast<const bf16*>(g.epi.aux), g.M / g.epi.np, g.epi.np, g.N, g.N / 64);
+        }
         return gemm_simt_bf16(ctx, g);
     }
     const bool a_mn = g.a_ks != 1, b_mn = g.b_ks != 1;
@@ -633,7 +663,7 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     } else {
         // [M, N] bf16 matrices with leading dimension ldo, moved as boxes of 32 rows x 64 columns
         VITRS_TRY(encode_map(ctx, &maps[2], g.epi.out, g.N, g.M, g.epi.ldo, 64, 32));
-        if (g.epi.out2) VITRS_TRY(encode_map(ctx, &maps[3], g.epi.out2, g.N, g.M, g.epi.ldo, 64, 32));
+        if (g.epi.out2 && g.epi.kind != EPI_ROWDOT) VITRS_TRY(encode_map(ctx, &maps[3], g.epi.out2, g.N, g.M, g.epi.ldo, 64, 32));
         else maps[3] = maps[2];
         if (g.epi.aux) VITRS_TRY(encode_map(ctx, &maps[4], g.epi.aux, g.N, g.M, g.epi.ldo, 64, 32));
         else maps[4] = maps[2];

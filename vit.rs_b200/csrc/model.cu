@@ -424,9 +424,22 @@ int backward_bf16(vitrs_model* m) {
         VITRS_TRY(op_layernorm_backward<bf16>(ctx, dres, G(m, P_LN2W) + l * C, G(m, P_LN2B) + l * C, dln, residual2,
                                               P(m, P_LN2W) + l * C, act<float>(m, A_LN2_MEAN) + lbt, act<float>(m, A_LN2_RSTD) + lbt,
                                               rows, C, nullptr));
-        VITRS_TRY((gemm_dx<bf16>(ctx, dln, dres, S(m, P_ATTPROJW) + (long)l * C * C, rows, C, C, EPI_NONE, nullptr, 0)));  // datty
+        // datty = dres . Wattproj; with 64-wide heads the same epilogue also takes D = rowsum(datty * atty) per (image, head,
+        // query), the row term of the softmax backward (it replaces a pass over datty and atty)
+        const bool fuse_d = C == d.NH * 64;
+        if (fuse_d) {
+            VITRS_TRY(vitrs_ensure_scratch(ctx, (size_t)d.B * d.NH * d.T));
+            GemmDesc g = {};
+            g.A = dres; g.a_rs = C; g.a_ks = 1;
+            g.B = S(m, P_ATTPROJW) + (long)l * C * C; g.b_rs = 1; g.b_ks = C;
+            g.M = (int)rows; g.N = C; g.K = C;
+            g.epi.kind = EPI_ROWDOT; g.epi.aux = atty; g.epi.out = dln; g.epi.out2 = ctx->scratch; g.epi.ldo = C; g.epi.np = d.T;
+            VITRS_TRY(gemm_dispatch<bf16>(ctx, g));
+        } else {
+            VITRS_TRY((gemm_dx<bf16>(ctx, dln, dres, S(m, P_ATTPROJW) + (long)l * C * C, rows, C, C, EPI_NONE, nullptr, 0)));
+        }
         VITRS_TRY((gemm_dw<bf16>(ctx, G(m, P_ATTPROJW) + (long)l * C * C, dres, atty, rows, C, C, G(m, P_ATTPROJB) + l * C)));
-        int r = op_attention_backward_tc(ctx, dqkv, dln, atty, qkv, lse, d.B, d.T, C, d.NH, m->cfg.causal, 0);
+        int r = op_attention_backward_tc(ctx, dqkv, dln, atty, qkv, lse, d.B, d.T, C, d.NH, m->cfg.causal, 0, fuse_d ? ctx->scratch : nullptr);
         if (r == VITRS_ERR_UNSUPPORTED) {
             VITRS_CUDA(ctx, cudaMemsetAsync(dqkv, 0, sizeof(bf16) * (size_t)btc * 3, ctx->stream));
             r = op_attention_backward<bf16>(ctx, dqkv, nullptr, nullptr, dln, qkv, nullptr, lse, d.B, d.T, C, d.NH, m->cfg.causal);
