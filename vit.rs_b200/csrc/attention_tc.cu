@@ -577,7 +577,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const uint32_t sdS = sdO + NT * TILE_BYTES;            // 4 x [128 keys][64 queries] bf16, 128B-swizzled
     const uint32_t sStat = sdS + 4 * TILE_BYTES;           // lse*log2e [256], D [256]
     const uint32_t bar0 = sStat + 2 * 256 * 4;
-    const uint32_t bar_load = bar0, s_full = bar0 + 8, x_free = bar0 + 24, p_full = bar0 + 40, ds_free = bar0 + 56,  // [2],[2],[2],[4]
+    const uint32_t bar_load = bar0, s_full = bar0 + 8, bar_load1 = bar0 + 24, p_full = bar0 + 40, ds_free = bar0 + 56,  // [2],[2],[2],[4]
                    acc_full = bar0 + 88, acc_free = bar0 + 96, dq_full = bar0 + 104;
     float* stat = reinterpret_cast<float*>(gen + (sStat - base));
     volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 112);
@@ -591,18 +591,20 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         tma_prefetch_desc(&tm_qkv);
         tma_prefetch_desc(&tm_do);
         mbar_init(bar_load, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(x_free + 8 * i, 1); mbar_init(p_full + 8 * i, 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(bar_load1 + 8 * i, 1); mbar_init(p_full + 8 * i, 128); }
         for (int i = 0; i < 4; ++i) mbar_init(ds_free + 8 * i, 1);
         mbar_init(acc_full, 1);
         mbar_init(acc_free, 256);
         mbar_init(dq_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar_load, (uint32_t)(4 * NT * TILE_BYTES));
+        // the first two iterations need only the first 128 rows of each operand: those are published on their own barrier
         for (int i = 0; i < NT; ++i) {
-            tma_load_3d(sK + i * TILE_BYTES, &tm_qkv, bar_load, C + h * HS, i * TILE, b);
-            tma_load_3d(sQ + i * TILE_BYTES, &tm_qkv, bar_load, h * HS, i * TILE, b);
-            tma_load_3d(sV + i * TILE_BYTES, &tm_qkv, bar_load, 2 * C + h * HS, i * TILE, b);
-            tma_load_3d(sdO + i * TILE_BYTES, &tm_do, bar_load, h * HS, i * TILE, b);
+            const uint32_t bl = i == 0 ? bar_load : bar_load1;
+            mbar_expect_tx(bl, (uint32_t)(4 * TILE_BYTES));
+            tma_load_3d(sK + i * TILE_BYTES, &tm_qkv, bl, C + h * HS, i * TILE, b);
+            tma_load_3d(sQ + i * TILE_BYTES, &tm_qkv, bl, h * HS, i * TILE, b);
+            tma_load_3d(sV + i * TILE_BYTES, &tm_qkv, bl, 2 * C + h * HS, i * TILE, b);
+            tma_load_3d(sdO + i * TILE_BYTES, &tm_do, bl, h * HS, i * TILE, b);
         }
     }
     if (warp == 1) tmem_alloc(smem_u32((const void*)slot), TMEM_COLS);
@@ -634,8 +636,14 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             auto off = [](uint32_t bytes) { return (uint64_t)(bytes >> 4); };
             // S^T and dP^T of iteration n into buffer n & 1.  tcgen05.mma executes in issue order, so the MMAs that overwrite a
             // buffer need no barrier against the dV MMAs of iteration n - 2 that read P^T from it: they are issued after them.
+            bool tile1_ready = false;
             auto issue_scores = [&](int n) {
                 const int j = n / NSUB, s_ = sub_at(j, n - j * NSUB, NSUB), bx = n & 1;
+                if ((j > 0 || s_ >= TILE / SUB) && !tile1_ready) {  // first use of rows >= 128 of Q / dO / K / V
+                    mbar_wait(bar_load1, 0);
+                    tc_fence_after();
+                    tile1_ready = true;
+                }
                 const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
                 const uint32_t idesc = make_idesc(TILE, nq16, 0, 0);
                 const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES), ko = off(j * TILE_BYTES);
