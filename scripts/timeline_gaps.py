@@ -33,7 +33,9 @@ print(f"step span {t1 - t0:.0f} us, kernels {len(step)}, busy {busy:.0f} us, gap
       f"overlap {-sum(g for g in gaps if g < 0):.0f} us, max gap {max(gaps):.1f} us, median gap {sorted(gaps)[len(gaps)//2]:.2f} us")
 agg = collections.defaultdict(lambda: [0.0, 0])
 for e in step:
-    k = e["name"].split("(")[0][-60:]
+    import re
+    nm = e["name"].replace("(anonymous namespace)::", "").replace("void ", "")
+    k = re.split(r"\(", nm)[0][:70]
     agg[k][0] += e["dur"]; agg[k][1] += 1
 for k, (d, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]:
     print(f"{d:10.0f} us {100*d/(t1-t0):5.1f}%  n={n:3d} avg={d/n:8.1f}  {k}")

@@ -495,12 +495,19 @@ int bucket_slices(const vitrs_config& cfg, const size_t* sizes, const size_t* of
 
 int allreduce_bucket(vitrs_model* m, int bucket) {
     if (!m->ctx->nccl_comm || m->mode != VITRS_MODE_BF16) return VITRS_OK;
+    // VITRS_DP_DEFER (tuning aid): every bucket is exchanged after the last gradient kernel instead of behind its block
+    static const bool defer = getenv("VITRS_DP_DEFER") != nullptr;
+    const int last = m->cfg.num_layers + 1;
+    if (defer && bucket != last) return VITRS_OK;
     VITRS_TRY(bucket_begin(m));
-    size_t off[12], cnt[12];
-    float* bufs[12];
-    const int n = bucket_slices(m->cfg, m->param_sizes, m->param_off, bucket, off, cnt);
-    for (int i = 0; i < n; ++i) bufs[i] = m->grads + off[i];
-    return vitrs_nccl_allreduce_group(m->ctx, bufs, cnt, n);
+    for (int bk = defer ? 0 : bucket; bk <= bucket; ++bk) {
+        size_t off[12], cnt[12];
+        float* bufs[12];
+        const int n = bucket_slices(m->cfg, m->param_sizes, m->param_off, bk, off, cnt);
+        for (int i = 0; i < n; ++i) bufs[i] = m->grads + off[i];
+        VITRS_TRY(vitrs_nccl_allreduce_group(m->ctx, bufs, cnt, n));
+    }
+    return VITRS_OK;
 }
 
 // block l: every slice of its bucket is final when the block's backward has been issued (the bias gradients come out of
