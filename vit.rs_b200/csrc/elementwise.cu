@@ -110,7 +110,9 @@ ln_fwd_kernel(T* __restrict__ out, float* __restrict__ mean, float* __restrict__
         wsm[i] = w[i];
         bsm[i] = bias[i];
     }
+    if (threadIdx.x == 0) bsm[c] = 1.0f;
     __syncthreads();
+    const float2 one2 = splat2(bsm[c]);
     const int lane = threadIdx.x & 31;
     const long nwarps = (long)gridDim.x * (kThreads / 32);
     long row = (long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -131,30 +133,36 @@ ln_fwd_kernel(T* __restrict__ out, float* __restrict__ mean, float* __restrict__
                 if (idx < c) nx[i].load(inp + next * c + idx);
             }
         }
-        float xf[MAXNV * VN];  // the row in fp32, converted once
-        float s = 0.f;
+        // packed f32x2 arithmetic: at the SM clock of a power-capped training step this kernel is as much instruction- as
+        // bandwidth-bound (x + y is x * one + y with a multiplier ptxas cannot fold, see ln_bwd_kernel)
+        constexpr int NP = MAXNV * VN / 2;
+        float2 xf[NP];  // the row in fp32, converted once
+        float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < MAXNV; ++i) {
             const bool live = (i * 32 + lane) * VN < c;
 #pragma unroll
-            for (int j = 0; j < VN; ++j) {
-                xf[i * VN + j] = live ? v[i].get(j) : 0.f;
-                s += xf[i * VN + j];
+            for (int j = 0; j < VN; j += 2) {
+                xf[(i * VN + j) >> 1] = live ? make_float2(v[i].get(j), v[i].get(j + 1)) : make_float2(0.f, 0.f);
+                s2 = fma2(xf[(i * VN + j) >> 1], one2, s2);
             }
         }
-        const float m = warp_sum(s) / (float)c;
-        float q = 0.f;
+        const float m = warp_sum(s2.x + s2.y) / (float)c;
+        const float2 nm2 = splat2(-m);
+        float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < MAXNV; ++i) {
             const bool live = (i * 32 + lane) * VN < c;
 #pragma unroll
-            for (int j = 0; j < VN; ++j) {
-                xf[i * VN + j] -= m;
-                q += live ? xf[i * VN + j] * xf[i * VN + j] : 0.f;
+            for (int j = 0; j < VN; j += 2) {
+                const float2 d = fma2(xf[(i * VN + j) >> 1], one2, nm2);
+                xf[(i * VN + j) >> 1] = d;
+                if (live) q2 = fma2(d, d, q2);
             }
         }
-        const float var = warp_sum(q) / (float)c;
+        const float var = warp_sum(q2.x + q2.y) / (float)c;
         const float rs = 1.0f / sqrtf(var + 1e-5f);
+        const float2 rs2 = splat2(rs);
         T* y = out + row * c;
 #pragma unroll
         for (int i = 0; i < MAXNV; ++i) {
@@ -165,10 +173,12 @@ ln_fwd_kernel(T* __restrict__ out, float* __restrict__ mean, float* __restrict__
                 for (int j4 = 0; j4 < VN / 4; ++j4) {
                     const float4 w4 = *reinterpret_cast<const float4*>(wsm + idx + j4 * 4);
                     const float4 b4 = *reinterpret_cast<const float4*>(bsm + idx + j4 * 4);
-                    o.set(j4 * 4 + 0, (rs * xf[i * VN + j4 * 4 + 0]) * w4.x + b4.x);
-                    o.set(j4 * 4 + 1, (rs * xf[i * VN + j4 * 4 + 1]) * w4.y + b4.y);
-                    o.set(j4 * 4 + 2, (rs * xf[i * VN + j4 * 4 + 2]) * w4.z + b4.z);
-                    o.set(j4 * 4 + 3, (rs * xf[i * VN + j4 * 4 + 3]) * w4.w + b4.w);
+                    const float2 o0 = fma2(mul2(rs2, xf[(i * VN + j4 * 4) >> 1]), make_float2(w4.x, w4.y), make_float2(b4.x, b4.y));
+                    const float2 o1 = fma2(mul2(rs2, xf[(i * VN + j4 * 4 + 2) >> 1]), make_float2(w4.z, w4.w), make_float2(b4.z, b4.w));
+                    o.set(j4 * 4 + 0, o0.x);
+                    o.set(j4 * 4 + 1, o0.y);
+                    o.set(j4 * 4 + 2, o1.x);
+                    o.set(j4 * 4 + 3, o1.y);
                 }
                 o.store(y + idx);
             }
@@ -617,7 +627,7 @@ int op_layernorm_forward(vitrs_ctx* ctx, T* out, float* mean, float* rstd, const
     }
     const int per_sm = nv <= 4 ? 3 : 1;
     if (grid > per_sm * ctx->sm_count) grid = per_sm * ctx->sm_count;  // persistent: warps stride over rows
-    const size_t smem = (size_t)2 * c * sizeof(float);  // nv <= 8: at most 16 KB
+    const size_t smem = ((size_t)2 * c + 4) * sizeof(float);  // gains, biases, the constant 1 (nv <= 8: at most 16 KB)
     if (false) {
     } else if (nv <= 1) {
         ln_fwd_kernel<T, 1><<<grid, kThreads, smem, ctx->stream>>>(out, mean, rstd, inp, w, b, rows, c);
