@@ -797,6 +797,319 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     }
 }
 
+// ---- backward, persistent variant of attn_bwd_pipe_kernel: one CTA per SM walks over its (batch, head) pairs ----------
+// A CTA of the kernel above spends 2.9 of its 14.5 us (ViT-B/16) on being launched, allocating tensor memory and waiting for
+// its 128 KB of operands with nothing else resident on the SM (the shared memory it needs excludes a second CTA).  Here the
+// CTA stays, and a loader thread refills each operand tile for the next head as soon as the current head is done with it:
+// K_0 / V_0 once the first key tile's dV / dK have left through them, Q and dO when the head's last MMA has retired, K_1 / V_1
+// after the final stores; dQ leaves through the groups' own dS tiles, so the Q tiles carry no staging.  Row statistics are
+// double-buffered and fetched a head ahead by an otherwise idle warp.  Barrier parities are derived from the running head
+// index G (every barrier completes a fixed number of phases per head).
+__global__ void __launch_bounds__(kPipeThreads, 1)
+attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                        const __grid_constant__ CUtensorMap tm_dqkv, bf16* __restrict__ dqkv, const float* __restrict__ lse,
+                        const float* __restrict__ dsum, int T, int C, int NH, int NT, int accumulate, int total_heads) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sQ = base, sK = sQ + NT * TILE_BYTES, sV = sK + NT * TILE_BYTES, sdO = sV + NT * TILE_BYTES;
+    const uint32_t sdS = sdO + NT * TILE_BYTES;            // 4 x [128 keys][64 queries] bf16, 128B-swizzled
+    const uint32_t sStat = sdS + 4 * TILE_BYTES;           // 2 x {lse*log2e [256], D [256]}
+    const uint32_t bar0 = sStat + 2 * 2 * 256 * 4;
+    const uint32_t load0 = bar0, load1 = bar0 + 8, s_full = bar0 + 16, p_full = bar0 + 32, ds_free = bar0 + 48,  // .., .., [2], [2], [4]
+                   acc_full = bar0 + 80, acc_free = bar0 + 88, dq_full = bar0 + 96, dq_free = bar0 + 104, free_kv = bar0 + 112,  // free_kv[2]
+                   stat_full = bar0 + 128, stat_free = bar0 + 144, q0_free = bar0 + 160;                                           // [2], [2], ..
+    float* stat_all = reinterpret_cast<float*>(gen + (sStat - base));
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 168);
+    constexpr uint32_t TMEM_COLS = 512, cDV = 256, cDK = 320, cDQ = 384;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NSUB = (T + SUB - 1) / SUB;   // 64-query sub-tiles
+    const int N = NT * NSUB;                // iterations per head: n = j * NSUB + t
+    const int nheads = (total_heads - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // heads of this CTA
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_do);
+        tma_prefetch_desc(&tm_dqkv);
+        mbar_init(load0, 1);
+        mbar_init(load1, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(s_full + 8 * i, 1);
+            mbar_init(p_full + 8 * i, 128);
+            mbar_init(free_kv + 8 * i, 2);
+            mbar_init(stat_full + 8 * i, 1);
+            mbar_init(stat_free + 8 * i, 256);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(ds_free + 8 * i, 1);
+        mbar_init(acc_full, 1);
+        mbar_init(acc_free, 256);
+        mbar_init(dq_full, 1);
+        mbar_init(dq_free, 256);
+        mbar_init(q0_free, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32((const void*)slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+    const float scale = 1.0f / sqrtf((float)HS);
+    const float sl2 = kLog2e * scale;
+
+    if (warp == 2) {
+        if (lane == 0) {
+            // ================================ loader ================================
+            for (int G = 0; G < nheads; ++G) {
+                const int bh = (int)blockIdx.x + G * (int)gridDim.x, b = bh / NH, h = bh - b * NH;
+                const uint32_t par = (uint32_t)((G - 1) & 1);  // parity of the previous head's single-phase barriers
+                if (G > 0) mbar_wait(free_kv, par);            // dV_0 / dK_0 of the previous head have left through V_0 / K_0
+                mbar_expect_tx(load0, (uint32_t)(4 * TILE_BYTES));
+                tma_load_3d(sK, &tm_qkv, load0, C + h * HS, 0, b);
+                tma_load_3d(sV, &tm_qkv, load0, 2 * C + h * HS, 0, b);
+                // the first 128 rows of Q and dO are dead once the last key tile is through its first two sub-tiles, well before
+                // the head ends: the next head's first scores can then be issued right behind this head's last MMAs
+                if (G > 0) mbar_wait(q0_free, par);
+                tma_load_3d(sQ, &tm_qkv, load0, h * HS, 0, b);
+                tma_load_3d(sdO, &tm_do, load0, h * HS, 0, b);
+                if (NT > 1) {
+                    if (G > 0) mbar_wait(dq_full, par);        // every MMA of the previous head has retired: the other rows are dead too
+                    mbar_expect_tx(load1, (uint32_t)(4 * TILE_BYTES));
+                    tma_load_3d(sQ + TILE_BYTES, &tm_qkv, load1, h * HS, TILE, b);
+                    tma_load_3d(sdO + TILE_BYTES, &tm_do, load1, h * HS, TILE, b);
+                    if (G > 0) mbar_wait(free_kv + 8, par);
+                    tma_load_3d(sK + TILE_BYTES, &tm_qkv, load1, C + h * HS, TILE, b);
+                    tma_load_3d(sV + TILE_BYTES, &tm_qkv, load1, 2 * C + h * HS, TILE, b);
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ================================ row statistics, one head ahead ================================
+        for (int G = 0; G < nheads; ++G) {
+            const int bh = (int)blockIdx.x + G * (int)gridDim.x, sb = G & 1;
+            if (G >= 2) mbar_wait(stat_free + 8 * sb, (uint32_t)(((G >> 1) - 1) & 1));
+            float* st = stat_all + sb * 512;
+            for (int i = lane; i < 256; i += 32) {
+                st[i] = i < T ? lse[(long)bh * T + i] * kLog2e : 0.f;
+                st[256 + i] = i < T ? dsum[(long)bh * T + i] : 0.f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cnt(stat_full + 8 * sb);
+        }
+    } else if (warp == 0) {
+        if (lane == 0) {
+            // ================================ issuer ================================
+            const uint32_t idesc_kk = make_idesc(TILE, HS, 0, 1);
+            const uint32_t idesc_mn = make_idesc(TILE, HS, 1, 1);
+            const uint64_t dK_k = make_desc(sK, 0, 1024), dV_k = make_desc(sV, 0, 1024);          // K-major A operands (rows = keys)
+            const uint64_t dQ_k = make_desc(sQ, 0, 1024), ddO_k = make_desc(sdO, 0, 1024);        // K-major B operands (rows = queries)
+            const uint64_t dQ_mn = make_desc(sQ, TILE_BYTES, 1024), ddO_mn = make_desc(sdO, TILE_BYTES, 1024);  // MN-major B operands
+            const uint64_t dK_mn = make_desc(sK, TILE_BYTES, 1024);
+            const uint64_t ddS_k = make_desc(sdS, 0, 1024), ddS_mn = make_desc(sdS, TILE_BYTES, 1024);
+            auto off = [](uint32_t bytes) { return (uint64_t)(bytes >> 4); };
+            for (int G = 0; G < nheads; ++G) {
+                const uint32_t gpar = (uint32_t)(G & 1);
+                bool tile1_ready = false, dq_ready = G == 0;
+                uint32_t done_mask = 0u;  // sub-tiles of the current key tile whose dS^T is in shared memory
+                auto issue_scores = [&](int n) {
+                    const int j = n / NSUB, s_ = sub_at(j, n - j * NSUB, NSUB), bx = n & 1;
+                    if ((j > 0 || s_ >= TILE / SUB) && !tile1_ready) {  // first use of rows >= 128 of Q / dO / K / V
+                        mbar_wait(load1, gpar);
+                        tc_fence_after();
+                        tile1_ready = true;
+                    }
+                    const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
+                    const uint32_t idesc = make_idesc(TILE, nq16, 0, 0);
+                    const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES), ko = off(j * TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + bx * 128, dK_k + ko + 2 * k, dQ_k + qo + 2 * k, idesc, k > 0);
+#pragma unroll
+                    for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + bx * 128 + 64, dV_k + ko + 2 * k, ddO_k + qo + 2 * k, idesc, k > 0);
+                    umma_commit(s_full + 8 * bx);
+                };
+                mbar_wait(load0, gpar);
+                tc_fence_after();
+                issue_scores(0);
+                if (N > 1) issue_scores(1);
+                for (int m = 0; m < N; ++m) {
+                    const int j = m / NSUB, t_ = m - j * NSUB, s_ = sub_at(j, t_, NSUB), bx = m & 1;
+                    const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
+                    const int nk16 = (min(TILE, T - j * TILE) + 15) & ~15;
+                    const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES);
+                    if (t_ == 0) done_mask = 0u;
+                    const int per_buf = (N + 1 - bx) >> 1;  // iterations per head on buffer bx
+                    mbar_wait(p_full + 8 * bx, (uint32_t)((G * per_buf + (m >> 1)) & 1));
+                    tc_fence_after();
+                    if (t_ == 0 && G * NT + j > 0) {  // the previous key tile's dV / dK have been read out
+                        mbar_wait(acc_free, (uint32_t)((G * NT + j - 1) & 1));
+                        tc_fence_after();
+                    }
+                    const uint64_t so = off((s_ & 3) * TILE_BYTES);
+                    for (int k16 = 0; k16 < nq16 / 16; ++k16) {
+                        const uint32_t acc = (t_ > 0 || k16 > 0) ? 1u : 0u;
+                        umma_bf16_ts(tmem_base + cDV, tmem_base + bx * 128 + k16 * 8, ddO_mn + qo + 128 * k16, idesc_kk, acc);
+                        umma_bf16(tmem_base + cDK, ddS_k + so + 2 * k16, dQ_mn + qo + 128 * k16, idesc_kk, acc);
+                    }
+                    if (m + 2 < N) issue_scores(m + 2);
+                    done_mask |= 1u << s_;
+                    const int partner = s_ ^ 1;
+                    // last key tile, both sub-tiles of query tile 0 issued: no later MMA of this head reads Q_0 / dO_0
+                    if (j == NT - 1 && s_ < 2 && (partner >= NSUB || ((done_mask >> partner) & 1u))) umma_commit(q0_free);
+                    if (partner >= NSUB || ((done_mask >> partner) & 1u)) {  // query tile i = s/2 is complete for this key tile: dQ_i += dS K_j
+                        if (!dq_ready) {  // the previous head's dQ accumulators have been read out
+                            mbar_wait(dq_free, (uint32_t)((G - 1) & 1));
+                            tc_fence_after();
+                            dq_ready = true;
+                        }
+                        const int i = s_ >> 1;
+                        const uint64_t ao = off((2 * i) * TILE_BYTES), ko = off(j * TILE_BYTES);
+                        for (int k16 = 0; k16 < nk16 / 16; ++k16)
+                            umma_bf16(tmem_base + cDQ + i * HS, ddS_mn + ao + 128 * k16, dK_mn + ko + 128 * k16, idesc_mn, (j > 0 || k16 > 0) ? 1u : 0u);
+                        umma_commit(ds_free + 8 * ((2 * i) & 3));
+                        if (2 * i + 1 < NSUB) umma_commit(ds_free + 8 * ((2 * i + 1) & 3));
+                    }
+                    if (t_ == NSUB - 1) umma_commit(acc_full);
+                }
+                umma_commit(dq_full);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ SIMT groups ================================
+        const int g = (warp - 4) >> 2;          // group 0 / 1
+        const int r = (warp & 3) * 32 + lane;   // TMEM lane = key within the tile / output row
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const bool store_leader = (warp & 3) == 0 && lane == 0;
+        const int per_buf = (N + 1 - g) >> 1;   // iterations per head of this group
+        for (int G = 0; G < nheads; ++G) {
+            const int bh = (int)blockIdx.x + G * (int)gridDim.x, b = bh / NH, h = bh - b * NH;
+            const float* stat = stat_all + (G & 1) * 512;
+            int free_pending = -1;  // leader: key tile whose staging store still has to be confirmed read
+            // dV_j (group 0) / dK_j (group 1): staged through the dead V_j / K_j tile, one TMA store each
+            auto store_acc = [&](int j) {
+                const int key = j * TILE + r;
+                mbar_wait(acc_full, (uint32_t)((G * NT + j) & 1));
+                tc_fence_after();
+                const uint32_t tile = (g == 0 ? sV : sK) + j * TILE_BYTES;  // every MMA that read it has retired (acc_full)
+                const long gcol = (g == 0 ? 2 * C : C) + h * HS;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_off + (g == 0 ? cDV : cDK) + half * 32, v);
+                    stage_half_row(tile, r, half, v, (accumulate && key < T) ? dqkv + ((long)b * T + key) * 3 * C + gcol + half * 32 : nullptr);
+                }
+                tc_fence_before();
+                mbar_arrive_cnt(acc_free);  // the accumulators are free; the store below only reads shared memory
+                fence_proxy_async();
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+                if (store_leader) {
+                    if (free_pending >= 0) {  // an earlier tile's store that no iteration came by to confirm
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        mbar_arrive_cnt(free_kv + 8 * free_pending);
+                    }
+                    tma_store_3d(&tm_dqkv, tile, (int)gcol, j * TILE, b);
+                    free_pending = j;
+                }
+            };
+            // the leader tells the loader that a K / V tile may be refilled once its store has finished reading it
+            auto confirm_free = [&]() {
+                if (store_leader && free_pending >= 0) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_arrive_cnt(free_kv + 8 * free_pending);
+                    free_pending = -1;
+                }
+            };
+            mbar_wait(stat_full + 8 * (G & 1), (uint32_t)((G >> 1) & 1));
+            int pending = -1;
+            for (int j = 0; j < NT; ++j) {
+                const int key = j * TILE + r;
+                for (int t_ = 0; t_ < NSUB; ++t_) {
+                    const int n = j * NSUB + t_;
+                    if ((n & 1) != g) continue;
+                    const int s_ = sub_at(j, t_, NSUB);
+                    const int nq = min(SUB, T - s_ * SUB), nq16 = (nq + 15) & ~15;
+                    const uint32_t xb = tmem_base + lane_off + (uint32_t)(g * 128);
+                    confirm_free();
+                    mbar_wait(s_full + 8 * g, (uint32_t)((G * per_buf + (n >> 1)) & 1));
+                    tc_fence_after();
+                    const int bs = s_ & 3;
+                    const uint32_t sbuf = sdS + bs * TILE_BYTES;
+                    // the MMAs that read this dS tile last time (previous key tile, or the previous head) have retired
+                    if (G * NT + j > 0) mbar_wait(ds_free + 8 * bs, (uint32_t)((G * NT + j - 1) & 1));
+                    const int nch = (nq16 + 31) >> 5;
+                    for (int ch = 0; ch < nch; ++ch) {
+                        uint32_t sv[32], dp[32], pk[16];
+                        tmem_ld32(xb + ch * 32, sv);
+                        tmem_ld32(xb + 64 + ch * 32, dp);
+                        const int q0 = s_ * SUB + ch * 32;             // first query of the chunk (q0 + 31 < 256)
+                        const bool full = key < T && ch * 32 + 32 <= nq;  // warp-uniform except for the key tail: no per-element masks
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const float4 l0 = *reinterpret_cast<const float4*>(stat + q0 + g8 * 8), l1 = *reinterpret_cast<const float4*>(stat + q0 + g8 * 8 + 4);
+                            const float4 d0 = *reinterpret_cast<const float4*>(stat + 256 + q0 + g8 * 8), d1 = *reinterpret_cast<const float4*>(stat + 256 + q0 + g8 * 8 + 4);
+                            const float lq[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                            const float dq[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                            float ds[8], pv[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const int qc = ch * 32 + g8 * 8 + c;
+                                const float e = ex2(__uint_as_float(sv[g8 * 8 + c]) * sl2 - lq[c]);
+                                pv[c] = (full || (key < T && qc < nq)) ? e : 0.f;
+                                ds[c] = pv[c] * (__uint_as_float(dp[g8 * 8 + c]) - dq[c]) * scale;
+                            }
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) pk[g8 * 4 + c] = pack_bf16(pv[2 * c], pv[2 * c + 1]);
+                            st_shared_v4(sw128(sbuf, r, ch * 4 + g8), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
+                                         pack_bf16(ds[6], ds[7]));
+                        }
+                        tmem_st16(xb + ch * 16, pk);  // P^T in place: columns [16ch, 16ch+16) were consumed by chunk <= ch
+                    }
+                    tmem_st_wait();
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive_cnt(p_full + 8 * g);
+                    if (pending >= 0) {
+                        store_acc(pending);
+                        pending = -1;
+                    }
+                }
+                if (j + 1 < NT && (((j + 1) * NSUB) & 1) == g) pending = j;
+                else store_acc(j);
+            }
+            // ---- dQ_0 (group 0) / dQ_1 (group 1), staged through the group's own dS tile (dead: every MMA has retired) ----
+            mbar_wait(dq_full, (uint32_t)(G & 1));
+            tc_fence_after();
+            if (g < NT) {
+                const int q = g * TILE + r;
+                const uint32_t tile = sdS + g * TILE_BYTES;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_off + cDQ + g * HS + half * 32, v);
+                    stage_half_row(tile, r, half, v, (accumulate && q < T) ? dqkv + ((long)b * T + q) * 3 * C + h * HS + half * 32 : nullptr);
+                }
+                fence_proxy_async();
+            }
+            tc_fence_before();
+            mbar_arrive_cnt(dq_free);
+            mbar_arrive_cnt(stat_free + 8 * (G & 1));
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+            if (store_leader) {
+                if (g < NT) tma_store_3d(&tm_dqkv, sdS + g * TILE_BYTES, h * HS, g * TILE, b);
+                // the last key tile's staging store and the dQ store have been read: K / V of that tile and the dS tile are free
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (free_pending >= 0) mbar_arrive_cnt(free_kv + 8 * free_pending);
+                free_pending = -1;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");  // nobody rewrites the dS tile before the store has read it
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // =====================================================================================================
 // Streaming kernels: any sequence length (ViT-B/8: T = 785), two CTAs per SM, every probability operand in
 // tensor memory.  Forward streams 128-key K/V tiles with an online softmax.  Backward is split in two
@@ -1362,6 +1675,20 @@ int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const
         }
         CUtensorMap tm_dq;
         VITRS_TRY(encode_map3d(ctx, &tm_dq, dqkv, 3 * (uint64_t)c, t, b));
+        static const bool persist = getenv("VITRS_ATTN_BWD_NOPERSIST") == nullptr;  // A/B aid: one CTA per (batch, head)
+        if (persist) {
+            const size_t smem_s = smem_p + 2 * 256 * 4 + 128;
+            static size_t conf_s = 0;
+            if (smem_s > conf_s) {
+                VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+                conf_s = smem_s;
+            }
+            const int heads = b * nh, grid = heads < ctx->sm_count ? heads : ctx->sm_count;
+            attn_bwd_persist_kernel<<<grid, kPipeThreads, smem_s, ctx->stream>>>(tm_qkv, tm_do, tm_dq, dqkv, lse, dsum, t, c, nh, NT, accumulate,
+                                                                                 heads);
+            VITRS_LAUNCHED(ctx);
+            return VITRS_OK;
+        }
         attn_bwd_pipe_kernel<<<b * nh, kPipeThreads, smem_p, ctx->stream>>>(tm_qkv, tm_do, tm_dq, dqkv, lse, dsum, t, c, nh, NT, accumulate);
         VITRS_LAUNCHED(ctx);
         return VITRS_OK;
