@@ -10,7 +10,7 @@ $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_ou
 ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-710} -c ${COUNT:-232} --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "list=$?"
 if [ "${FULL:-1}" = "1" ]; then
-  K='regex:gemm_tc_kernel|attn_fwd|attn_bwd_pipe|ln_fwd|ln_bwd|adamw'
+  K='regex:gemm_tc_kernel|attn_fwd|attn_bwd|ln_fwd|ln_bwd|adamw'
   # matches per step: 146 GEMM + 12 + 12 + 25 + 25 + 1 = 221; forward = 1 + 12*7 + 1 = 86
   ncu --set full --clock-control none -k "$K" -s $((3*221+1)) -c 7 -o /tmp/prof_fwd $CMD > gpurun_out/ncu_full1.log 2>&1
   echo "full1=$?"
