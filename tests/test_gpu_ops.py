@@ -232,6 +232,35 @@ def test_attention_bf16(vitrs, causal, b, t, c, nh):
     assert relerr(host(dqkv), wd) <= TOL_BF16
 
 
+@pytest.mark.parametrize("t", [16, 64, 128, 160, 192, 197, 256])
+def test_attention_bf16_many_heads_per_cta(vitrs, t):
+    """768 (batch, head) pairs: the persistent backward kernel walks ~5 heads per CTA (operand tiles refilled for the next head
+    while the current one is still computing).  Reference: fp32 autograd of the same attention on the bf16-rounded inputs —
+    the oracle's O(T^3) backward would take minutes here; its formula is pinned by test_attention_bf16 on small shapes."""
+    b, c, nh = 64, 768, 12
+    g = torch.Generator(device="cuda").manual_seed(t * 7 + b)
+    qkv = (torch.randn(b, t, 3 * c, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    dout = (torch.randn(b, t, c, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    out = torch.zeros(b, t, c, device="cuda", dtype=torch.bfloat16)
+    dqkv = torch.zeros(b, t, 3 * c, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(b * nh * t, device="cuda")
+    vitrs.attention_forward(out, lse, None, qkv, b, t, c, nh, causal=0)
+    vitrs.attention_backward_bf16(dqkv, dout, out, lse, qkv, b, t, c, nh, causal=0)
+    torch.cuda.synchronize()
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x.split(c, dim=2)
+    q, k, v = (z.view(b, t, nh, 64).transpose(1, 2) for z in (q, k, v))
+    att = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    y = (att @ v).transpose(1, 2).reshape(b, t, c)
+    y.backward(dout.float())
+    assert (out.float() - y.detach()).abs().max().item() <= TOL_BF16 * y.abs().max().item()
+    assert (dqkv.float() - x.grad).abs().max().item() <= TOL_BF16 * x.grad.abs().max().item()
+    # the += contract of the ABI: a second call doubles the result (same rounding: bf16 sums of equal values are exact)
+    first = dqkv.clone()
+    vitrs.attention_backward_bf16(dqkv, dout, out, lse, qkv, b, t, c, nh, causal=0)
+    assert (dqkv.float() - 2 * first.float()).abs().max().item() <= 2.0 ** -7 * first.float().abs().max().item()
+
+
 def test_softmax_crossentropy(vitrs):
     b, t, v = 8, 1, 1000
     rng = np.random.default_rng(5)
