@@ -1,6 +1,6 @@
 #!/bin/bash
 # Same-box A/B of two builds of the library (boxes differ by +-3 % under the power cap): alternates
-# build_ab/libvitrs_base.so (A) and the in-tree library (B) over REPS rounds of the training-step bench.
+# build_ab/libvitrs_base.so (A, a copy of an earlier build) and the in-tree library (B) over REPS rounds of the training-step bench.
 mkdir -p gpurun_out
 for r in $(seq 1 ${REPS:-2}); do
   for v in A B; do
