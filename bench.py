@@ -234,6 +234,25 @@ def main():
                "h2d_bytes_per_step": int(world * (h_images[0].numel() * 4 + h_labels[0].numel() * 4)),
                "d2h_bytes_per_step": 4 * world, "ms_per_step": round(ms_e2e / args.steps, 3), "loss": round(last_loss, 5)}
 
+        # the same through the raw-image entry point (uint8 host batches, normalisation fused into im2col): extra key, the
+        # headline `e2e` above keeps the fp32 synthetic images of SURVEY 8-d
+        h_u8 = [torch.randint(0, 256, (per_gpu, 3, img, img), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        for s in range(2):
+            model.train_step_host_u8(h_u8[s % 2], h_labels[s % 2], lr)
+        barrier()
+        model.prefetch_host_u8(h_u8[0], h_labels[0])
+        e0.record()
+        for s in range(args.steps):
+            if s + 1 < args.steps:
+                model.prefetch_host_u8(h_u8[(s + 1) % 2], h_labels[(s + 1) % 2])
+            model.train_step_host_u8(h_u8[s % 2], h_labels[s % 2], lr)
+        e1.record()
+        barrier()
+        ms_u8 = max_over_ranks(e0.elapsed_time(e1))
+        e2e["uint8_images"] = {"value": round(global_batch * args.steps / (ms_u8 / 1e3), 2), "ms_per_step": round(ms_u8 / args.steps, 3),
+                               "h2d_bytes_per_step": int(world * (h_u8[0].numel() + h_labels[0].numel() * 4))}
+        del h_u8
+
     # ---- roofline of the dominant kernel: every tcgen05 GEMM launch of one step, CUDA events per launch ----
     peaks = measured_peaks()
     ctx.profile_begin()

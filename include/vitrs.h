@@ -214,6 +214,19 @@ int vitrs_model_prefetch_host(vitrs_model* m, const float* h_images, const int* 
 int vitrs_model_train_step_host(vitrs_model* m, const float* h_images, const int* h_labels, int b,
                                 float lr, float beta1, float beta2, float eps, float weight_decay,
                                 float* loss_out);
+
+/* ---- raw image batches: the data path in front of the step (the reference takes in-memory
+ * buffers, rusty_vit.rs:269, and has no loader).  Images as datasets store them: uint8, layout 0 = NCHW
+ * [B,3,H,W], layout 1 = NHWC [B,H,W,3] (CIFAR-10 records, decoded JPEGs).  (x / 255 - mean[c]) / std[c] is
+ * applied inside the im2col pass of the patch embedding, so the host sends one byte per sample value.
+ * Default normalisation: mean = std = 0.5 (-> [-1, 1]).  Everything else is as in the fp32 entry points. */
+int vitrs_model_set_input_norm(vitrs_model*, const float* mean3, const float* std3);
+int vitrs_model_forward_u8(vitrs_model*, const uint8_t* images, int layout, const int* labels, int b);
+int vitrs_model_train_step_u8(vitrs_model*, const uint8_t* images, int layout, const int* labels, int b, float lr,
+                              float beta1, float beta2, float eps, float weight_decay);
+int vitrs_model_prefetch_host_u8(vitrs_model*, const uint8_t* h_images, const int* h_labels, int b);
+int vitrs_model_train_step_host_u8(vitrs_model*, const uint8_t* h_images, int layout, const int* h_labels, int b,
+                                   float lr, float beta1, float beta2, float eps, float weight_decay, float* loss_out);
 /* same step with the batch already resident on the device */
 int vitrs_model_train_step(vitrs_model* m, const float* images, const int* labels, int b,
                            float lr, float beta1, float beta2, float eps, float weight_decay);

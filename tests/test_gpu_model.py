@@ -202,3 +202,44 @@ def test_full_size_properties_vit_b16(vitrs):
     logits = m.act("logits").view(b, -1)
     assert torch.equal(logits[0], logits[b - 1])
     m.close()
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_u8_images_match_normalised_fp32(vitrs, layout):
+    """The raw-image entry points (uint8 NCHW / NHWC, normalisation fused into im2col) against the oracle run on the
+    images normalised on the host: fp32 verify mode to 1e-4, and the bf16 host-buffer step against the fp32-image step."""
+    cfg = po.CONFIGS["tiny"]
+    b, img = 8, cfg["image_size"]
+    rng = np.random.default_rng(11 + layout)
+    u8 = rng.integers(0, 256, (b, 3, img, img), dtype=np.uint8)
+    labels = rng.integers(0, cfg["num_classes"], b).astype(np.int32)
+    mean, std = np.array([0.485, 0.456, 0.406], np.float32), np.array([0.229, 0.224, 0.225], np.float32)
+    # the kernel's arithmetic: one FMA per sample with scale = 1 / (255 std), shift = -mean / std
+    norm = (u8.astype(np.float32) * (np.float32(1.0) / (np.float32(255.0) * std))[None, :, None, None]
+            + (-mean / std)[None, :, None, None]).astype(np.float32)
+    want = ((u8.astype(np.float64) / 255.0 - mean[None, :, None, None]) / std[None, :, None, None])
+    assert np.abs(norm - want).max() <= 1e-5  # the fused form is the textbook normalisation
+    dev_u8 = torch.from_numpy(u8 if layout == 0 else np.ascontiguousarray(u8.transpose(0, 2, 3, 1))).cuda()
+    ref = po.ViT("tiny", seed=1337, init_mode=1)
+    ref_loss = ref.forward(norm, labels); ref.zero_grad(); ref.backward()
+    m = vitrs.ViT("tiny", max_batch=b, mode=vitrs.MODE_F32, seed=1337, init_mode=1)
+    m.set_input_norm(mean, std)
+    m.zero_grad(); m.forward_u8(dev_u8, torch.from_numpy(labels).cuda(), layout=layout); m.backward()
+    assert abs(m.mean_loss - ref_loss) <= TOL_F32 * abs(ref_loss)
+    assert relerr(m.act("encoded").cpu().numpy(), ref.act("encoded")) <= TOL_F32
+    assert relerr(m.act("logits").cpu().numpy(), ref.act("logits")) <= TOL_F32
+    for name in ("patchw", "wpe", "qkvw", "headw"):
+        assert relerr(m.grad(name).cpu().numpy(), ref.grad(name)) <= TOL_F32, name
+    m.close()
+    # production mode, host buffers: the uint8 step and the step on the same images normalised to fp32 agree
+    ma = vitrs.ViT("tiny", max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)
+    mb = vitrs.ViT("tiny", max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)
+    ma.set_input_norm(mean, std)
+    h_u8 = dev_u8.cpu().pin_memory()
+    h_lab = torch.from_numpy(labels).pin_memory()
+    for _ in range(3):
+        la = ma.train_step_host_u8(h_u8, h_lab, 1e-3, layout=layout)
+        mb.train_step(torch.from_numpy(norm).cuda(), torch.from_numpy(labels).cuda(), 1e-3)
+        assert abs(la - mb.mean_loss) <= 2e-3
+    assert (ma.params_flat() - mb.params_flat()).abs().max().item() <= 2e-3
+    ma.close(); mb.close()

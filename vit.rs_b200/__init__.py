@@ -126,6 +126,11 @@ _SIGNATURES = {
     "vitrs_model_prefetch_host": (_int, [_vp, _vp, _vp, _int]),
     "vitrs_model_train_step_host": (_int, [_vp, _vp, _vp, _int, _f, _f, _f, _f, _f, C.POINTER(_f)]),
     "vitrs_model_train_step": (_int, [_vp, _vp, _vp, _int, _f, _f, _f, _f, _f]),
+    "vitrs_model_set_input_norm": (_int, [_vp, C.POINTER(_f), C.POINTER(_f)]),
+    "vitrs_model_forward_u8": (_int, [_vp, _vp, _int, _vp, _int]),
+    "vitrs_model_train_step_u8": (_int, [_vp, _vp, _int, _vp, _int, _f, _f, _f, _f, _f]),
+    "vitrs_model_prefetch_host_u8": (_int, [_vp, _vp, _vp, _int]),
+    "vitrs_model_train_step_host_u8": (_int, [_vp, _vp, _int, _vp, _int, _f, _f, _f, _f, _f, C.POINTER(_f)]),
     "vitrs_comm_unique_id": (_int, [_vp, _vp]),
     "vitrs_comm_init": (_int, [_vp, _vp, _int, _int]),
     "vitrs_comm_destroy": (_int, [_vp]),
@@ -513,6 +518,39 @@ class ViT:
         self._keep = (images, targets)
         self.batch_size = b
         self.ctx.check(lib().vitrs_model_train_step(self._h, _ptr(images), _ptr(targets), b, lr, beta1, beta2, eps, weight_decay))
+
+    # ---- raw uint8 image batches (include/vitrs.h: the data path in front of the step) ----
+    NCHW, NHWC = 0, 1
+
+    def set_input_norm(self, mean, std):
+        """Per-channel (x / 255 - mean) / std applied inside the patch embedding's im2col pass."""
+        m3, s3 = (_f * 3)(*[float(x) for x in mean]), (_f * 3)(*[float(x) for x in std])
+        self.ctx.check(lib().vitrs_model_set_input_norm(self._h, m3, s3))
+
+    def forward_u8(self, images, targets, layout=0):
+        """images: cuda uint8 [b,3,H,W] (NCHW) or [b,H,W,3] (NHWC)."""
+        b = images.shape[0]
+        self._keep = (images, targets)
+        self.batch_size = b
+        self.ctx.check(lib().vitrs_model_forward_u8(self._h, _ptr(images), layout, _ptr(targets), b))
+
+    def train_step_u8(self, images, targets, lr, layout=0, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01):
+        b = images.shape[0]
+        self._keep = (images, targets)
+        self.batch_size = b
+        self.ctx.check(lib().vitrs_model_train_step_u8(self._h, _ptr(images), layout, _ptr(targets), b, lr, beta1, beta2, eps, weight_decay))
+
+    def prefetch_host_u8(self, h_images, h_labels):
+        self.ctx.check(lib().vitrs_model_prefetch_host_u8(self._h, _ptr(h_images), _ptr(h_labels), h_images.shape[0]))
+
+    def train_step_host_u8(self, h_images, h_labels, lr, layout=0, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01):
+        """One step from HOST uint8 buffers: a quarter of the fp32 bytes over PCIe, normalised on the device."""
+        out = C.c_float()
+        b = h_images.shape[0]
+        self.batch_size = b
+        self.ctx.check(lib().vitrs_model_train_step_host_u8(self._h, _ptr(h_images), layout, _ptr(h_labels), b, lr, beta1, beta2, eps,
+                                                            weight_decay, C.byref(out)))
+        return out.value
 
     def prefetch_host(self, h_images, h_labels):
         self.ctx.check(lib().vitrs_model_prefetch_host(self._h, _ptr(h_images), _ptr(h_labels), h_images.shape[0]))

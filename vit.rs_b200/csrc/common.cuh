@@ -261,6 +261,8 @@ int op_attention_backward_tc(vitrs_ctx*, bf16* dqkv, const bf16* dout, const bf1
 
 // patch embedding pieces (patch_embed.cu): im2col rows are tokens, [B*T, 3*p*p], CLS rows zero
 template <typename T> int op_im2col(vitrs_ctx*, T* patches, const float* images, int b, int img, int patch);
+template <typename T>
+int op_im2col_u8(vitrs_ctx*, T* patches, const uint8_t* images, int layout, const float* mean, const float* stdev, int b, int img, int patch);
 // dwpe += sum_b denc; dcls += sum_b denc[b,0]; dpatchb += sum over patch tokens
 template <typename T> int op_patch_backward_reduce(vitrs_ctx*, float* dwpe, float* dcls, float* dpatchb, const T* denc,
                                                    int b, int t, int c);

@@ -65,6 +65,9 @@ struct vitrs_model {
     cudaEvent_t ev_bucket, ev_comm_done;
     int batch, has_targets;
     const float* images;  // borrowed device pointer of the current batch
+    const uint8_t* images_u8;  // ... or raw uint8 images (layout u8_layout), normalised inside im2col
+    int u8_layout;
+    float norm_mean[3], norm_std[3];
     const int* labels;
     float dloss_scale;
     int adam_step;
@@ -204,7 +207,8 @@ int forward_f32(vitrs_model* m) {
     const Dims d = dims_of(m);
     const long btc = d.btc;
     float* patches = reinterpret_cast<float*>(m->patches);
-    VITRS_TRY(op_im2col<float>(ctx, patches, m->images, d.B, d.img, d.patch));
+    if (m->images_u8) VITRS_TRY(op_im2col_u8<float>(ctx, patches, m->images_u8, m->u8_layout, m->norm_mean, m->norm_std, d.B, d.img, d.patch));
+    else VITRS_TRY(op_im2col<float>(ctx, patches, m->images, d.B, d.img, d.patch));
     {
         GemmDesc g = {};
         g.A = patches; g.a_rs = d.kdim; g.a_ks = 1;
@@ -335,7 +339,8 @@ int forward_bf16(vitrs_model* m) {
     const int C = d.C, L = d.L;
     const long rows = (long)d.B * d.T;
     bf16* patches = reinterpret_cast<bf16*>(m->patches);
-    VITRS_TRY(op_im2col<bf16>(ctx, patches, m->images, d.B, d.img, d.patch));
+    if (m->images_u8) VITRS_TRY(op_im2col_u8<bf16>(ctx, patches, m->images_u8, m->u8_layout, m->norm_mean, m->norm_std, d.B, d.img, d.patch));
+    else VITRS_TRY(op_im2col<bf16>(ctx, patches, m->images, d.B, d.img, d.patch));
     {
         GemmDesc g = {};
         g.A = patches; g.a_rs = d.kdim; g.a_ks = 1;
@@ -528,6 +533,7 @@ int set_batch(vitrs_model* m, const float* images, const int* labels, int b) {
     VITRS_ARG(ctx, images != nullptr && b >= 1 && b <= m->max_batch);
     m->batch = b;
     m->images = images;
+    m->images_u8 = nullptr;
     m->labels = labels;
     m->has_targets = labels != nullptr;
     return VITRS_OK;
@@ -551,6 +557,7 @@ int vitrs_model_create(vitrs_ctx* ctx, const vitrs_config* cfg_in, int max_batch
     VITRS_CUDA(ctx, cudaSetDevice(ctx->device));
     vitrs_model* m = (vitrs_model*)calloc(1, sizeof(vitrs_model));
     m->ctx = ctx; m->cfg = cfg; m->mode = mode; m->max_batch = max_batch;
+    for (int i = 0; i < 3; ++i) { m->norm_mean[i] = 0.5f; m->norm_std[i] = 0.5f; }  // uint8 -> [-1, 1]
     param_sizes_of(cfg, m->param_sizes);
     size_t off = 0;
     for (int i = 0; i < P_COUNT; ++i) { m->param_off[i] = off; off += m->param_sizes[i]; }
@@ -697,6 +704,30 @@ int vitrs_model_forward(vitrs_model* m, const float* images, const int* labels, 
     return VITRS_OK;
 }
 
+// ---- raw image batches: uint8 samples, normalisation fused into the im2col pass ----
+int vitrs_model_set_input_norm(vitrs_model* m, const float* mean, const float* stdev) {
+    if (!m) return VITRS_ERR_ARG;
+    VITRS_ARG(m->ctx, mean && stdev && stdev[0] > 0.f && stdev[1] > 0.f && stdev[2] > 0.f);
+    for (int i = 0; i < 3; ++i) { m->norm_mean[i] = mean[i]; m->norm_std[i] = stdev[i]; }
+    return VITRS_OK;
+}
+
+int vitrs_model_forward_u8(vitrs_model* m, const uint8_t* images, int layout, const int* labels, int b) {
+    if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_ARG(ctx, images != nullptr && (layout == 0 || layout == 1) && b >= 1 && b <= m->max_batch);
+    m->batch = b;
+    m->images = nullptr;
+    m->images_u8 = images;
+    m->u8_layout = layout;
+    m->labels = labels;
+    m->has_targets = labels != nullptr;
+    VITRS_CUDA(ctx, cudaSetDevice(ctx->device));
+    VITRS_TRY(m->mode == VITRS_MODE_F32 ? forward_f32(m) : forward_bf16(m));
+    if (!m->has_targets) VITRS_TRY(op_fill_const(ctx, m->d_mean_loss, 1, -1.0f));
+    return VITRS_OK;
+}
+
 int vitrs_model_zero_grad(vitrs_model* m) {
     if (!m) return VITRS_ERR_ARG;
     vitrs_ctx* ctx = m->ctx;
@@ -771,6 +802,16 @@ int vitrs_model_train_step(vitrs_model* m, const float* images, const int* label
     return vitrs_model_update(m, lr, beta1, beta2, eps, weight_decay);
 }
 
+int vitrs_model_train_step_u8(vitrs_model* m, const uint8_t* images, int layout, const int* labels, int b, float lr, float beta1,
+                              float beta2, float eps, float weight_decay) {
+    if (!m) return VITRS_ERR_ARG;
+    VITRS_ARG(m->ctx, labels != nullptr);
+    VITRS_TRY(vitrs_model_zero_grad(m));
+    VITRS_TRY(vitrs_model_forward_u8(m, images, layout, labels, b));
+    VITRS_TRY(vitrs_model_backward(m));
+    return vitrs_model_update(m, lr, beta1, beta2, eps, weight_decay);
+}
+
 static int ensure_stage(vitrs_model* m) {
     vitrs_ctx* ctx = m->ctx;
     if (m->stage_images[0]) return VITRS_OK;
@@ -817,6 +858,46 @@ int vitrs_model_train_step_host(vitrs_model* m, const float* h_images, const int
     VITRS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->stage_ready[s], 0));
     m->stage_src[s] = nullptr;
     VITRS_TRY(vitrs_model_train_step(m, m->stage_images[s], m->stage_labels[s], b, lr, beta1, beta2, eps, weight_decay));
+    VITRS_CUDA(ctx, cudaEventRecord(m->stage_free[s], ctx->stream));
+    if (loss_out) VITRS_TRY(vitrs_model_mean_loss(m, loss_out));
+    return VITRS_OK;
+}
+
+// the same two calls for uint8 host batches (a quarter of the bytes over PCIe; the staging slots are shared with the fp32 path)
+int vitrs_model_prefetch_host_u8(vitrs_model* m, const uint8_t* h_images, const int* h_labels, int b) {
+    if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_ARG(ctx, h_images && h_labels && b >= 1 && b <= m->max_batch);
+    VITRS_TRY(ensure_stage(m));
+    const int s = m->stage_next;
+    const size_t img_bytes = (size_t)b * 3 * m->cfg.image_size * m->cfg.image_size;
+    VITRS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, m->stage_free[s], 0));
+    VITRS_CUDA(ctx, cudaMemcpyAsync(m->stage_images[s], h_images, img_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VITRS_CUDA(ctx, cudaMemcpyAsync(m->stage_labels[s], h_labels, sizeof(int) * (size_t)b, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VITRS_CUDA(ctx, cudaEventRecord(m->stage_ready[s], ctx->copy_stream));
+    m->stage_src[s] = h_images;
+    m->stage_batch[s] = b;
+    m->stage_next = s ^ 1;
+    return VITRS_OK;
+}
+
+int vitrs_model_train_step_host_u8(vitrs_model* m, const uint8_t* h_images, int layout, const int* h_labels, int b, float lr,
+                                   float beta1, float beta2, float eps, float weight_decay, float* loss_out) {
+    if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_ARG(ctx, h_images && h_labels && b >= 1 && b <= m->max_batch);
+    VITRS_TRY(ensure_stage(m));
+    int s = -1;
+    for (int i = 0; i < 2; ++i)
+        if (m->stage_src[i] == h_images && m->stage_batch[i] == b) s = i;
+    if (s < 0) {
+        VITRS_TRY(vitrs_model_prefetch_host_u8(m, h_images, h_labels, b));
+        s = m->stage_next ^ 1;
+    }
+    VITRS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->stage_ready[s], 0));
+    m->stage_src[s] = nullptr;
+    VITRS_TRY(vitrs_model_train_step_u8(m, reinterpret_cast<const uint8_t*>(m->stage_images[s]), layout, m->stage_labels[s], b, lr, beta1,
+                                        beta2, eps, weight_decay));
     VITRS_CUDA(ctx, cudaEventRecord(m->stage_free[s], ctx->stream));
     if (loss_out) VITRS_TRY(vitrs_model_mean_loss(m, loss_out));
     return VITRS_OK;
