@@ -105,6 +105,14 @@ extern "C" {
     pub fn vitrs_model_mean_loss(m: *mut vitrs_model, out: *mut f32) -> c_int; // rv:75
     pub fn vitrs_model_train_step_host(m: *mut vitrs_model, h_images: *const f32, h_labels: *const c_int, b: c_int, lr: f32, beta1: f32,
                                        beta2: f32, eps: f32, weight_decay: f32, loss_out: *mut f32) -> c_int;
+    // raw dataset images (uint8; layout 0 = NCHW, 1 = NHWC), normalised on the device inside the patch embedding
+    pub fn vitrs_model_set_input_norm(m: *mut vitrs_model, mean3: *const f32, std3: *const f32) -> c_int;
+    pub fn vitrs_model_forward_u8(m: *mut vitrs_model, images: *const u8, layout: c_int, labels: *const c_int, b: c_int) -> c_int;
+    pub fn vitrs_model_train_step_u8(m: *mut vitrs_model, images: *const u8, layout: c_int, labels: *const c_int, b: c_int, lr: f32,
+                                     beta1: f32, beta2: f32, eps: f32, weight_decay: f32) -> c_int;
+    pub fn vitrs_model_prefetch_host_u8(m: *mut vitrs_model, h_images: *const u8, h_labels: *const c_int, b: c_int) -> c_int;
+    pub fn vitrs_model_train_step_host_u8(m: *mut vitrs_model, h_images: *const u8, layout: c_int, h_labels: *const c_int, b: c_int,
+                                          lr: f32, beta1: f32, beta2: f32, eps: f32, weight_decay: f32, loss_out: *mut f32) -> c_int;
     pub fn vitrs_model_param_view(m: *mut vitrs_model, which: c_int, tensor: c_int, ptr: *mut *mut f32, count: *mut usize) -> c_int;
 }
 
