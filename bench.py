@@ -253,6 +253,18 @@ def main():
                                "h2d_bytes_per_step": int(world * (h_u8[0].numel() + h_labels[0].numel() * 4))}
         del h_u8
 
+    # ---- inference forward (no targets: logits only, rusty_vit.rs:339-350), extra key ------------------------------------
+    for s in range(2):
+        model.forward(d_images[s % 2], None)
+    barrier()
+    e0.record()
+    for s in range(args.steps):
+        model.forward(d_images[s % 2], None)
+    e1.record()
+    barrier()
+    ms_inf = max_over_ranks(e0.elapsed_time(e1))
+    inference = {"value": round(global_batch * args.steps / (ms_inf / 1e3), 2), "unit": "images/s", "ms_per_batch": round(ms_inf / args.steps, 3)}
+
     # ---- roofline of the dominant kernel: every tcgen05 GEMM launch of one step, CUDA events per launch ----
     peaks = measured_peaks()
     ctx.profile_begin()
@@ -296,7 +308,8 @@ def main():
                            "parallelism": f"dp{world}", "train_gflop_per_image": round(flops_per_image / 1e9, 3),
                            "l2_policy": "inputs larger than L2 (activations are GBs per step); no flush needed",
                            "final_loss": round(loss, 5)},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "inference_forward": inference}
         print(json.dumps(line), flush=True)
     model.close()
     if world > 1:

@@ -141,6 +141,7 @@ int vitrs_gemm_bf16(vitrs_ctx*, void* D, const vitrs_bf16* A, const vitrs_bf16* 
  *   2 BIAS_GELU      D = acc + bias[n]; D2 = gelu(D)                 matmul_forward + gelu_forward (:482)
  *   3 BIAS_RESIDUAL  D = acc + bias[n] + aux[m,n]                    matmul_forward + residual_forward (:376)
  *   4 GELU_BWD       D = acc * gelu'(aux[m,n])                       matmul_backward dinp + gelu_backward (:639)
+ *   8 BIAS_GELU_ONLY D = gelu(acc + bias[n])                         the same pair when nothing keeps the pre-activation (inference)
  * D, D2, aux are [M, ldd] bf16; bias may be NULL (kinds 1-3); a_colsum (nullable, MN-major A only) receives
  * a_colsum[m] += sum_k A(m,k), the fused bias gradient of matmul_backward (:548-550). */
 int vitrs_gemm_bf16_fused(vitrs_ctx*, vitrs_bf16* D, vitrs_bf16* D2, const vitrs_bf16* aux, const float* bias,

@@ -61,7 +61,7 @@ def _gelu_grad(x):
     return 0.5 * (1.0 + th) + x * 0.5 * (1.0 - th * th) * 0.7978845608028654 * (1.0 + 3.0 * 0.044715 * x * x)
 
 
-@pytest.mark.parametrize("epi", [1, 2, 3, 4])
+@pytest.mark.parametrize("epi", [1, 2, 3, 4, 8])
 @pytest.mark.parametrize("M,N,K,b_mn", [(256, 512, 768, 0), (200, 192, 192, 0), (129, 264, 72, 1), (1576, 3072, 768, 0), (1000, 768, 3072, 1),
                                         (64, 48, 48, 0), (130, 64, 256, 0)])
 def test_gemm_fused_epilogues(vitrs, M, N, K, b_mn, epi):
@@ -85,6 +85,8 @@ def test_gemm_fused_epilogues(vitrs, M, N, K, b_mn, epi):
         want = acc + bias
     elif epi == 3:
         want = acc + bias + aux.float()
+    elif epi == 8:
+        want = _gelu((acc + bias).to(torch.bfloat16).float())  # gelu_forward of the pre-activation as it would have been stored
     else:
         want = acc * _gelu_grad(aux.float())
     scale = want.abs().max().item()

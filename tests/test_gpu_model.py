@@ -243,3 +243,18 @@ def test_u8_images_match_normalised_fp32(vitrs, layout):
         assert abs(la - mb.mean_loss) <= 2e-3
     assert (ma.params_flat() - mb.params_flat()).abs().max().item() <= 2e-3
     ma.close(); mb.close()
+
+
+def test_bf16_inference_forward_equals_training_forward(vitrs):
+    """forward(images, None) (rusty_vit.rs:339-350: logits only, mean_loss = -1) skips what only backward reads (the pre-GELU
+    activations); its logits are those of the training forward bit for bit."""
+    b = 16
+    m = vitrs.ViT(MID_HS64, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)
+    images, labels = po.synthetic_batch(MID_HS64, b)
+    x, y = to_dev(images, labels)
+    m.forward(x, y)
+    want = m.act("logits").clone()
+    m.forward(x, None)
+    assert m.mean_loss == -1.0
+    assert torch.equal(m.act("logits"), want)
+    m.close()

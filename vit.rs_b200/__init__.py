@@ -356,7 +356,7 @@ def patch_embed_backward(dpatchw, dpatchb, dcls, dwpe, dencoded, images, b, img,
     _call(ctx, "vitrs_patch_embed_backward_f32", dpatchw, dpatchb, dcls, dwpe, dencoded, images, b, img, patch, c)
 
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_GELU_BWD = 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_GELU_BWD, EPI_BIAS_GELU_ONLY = 1, 2, 3, 4, 8
 
 
 def gemm_bf16_fused(D, D2, aux, bias, a_colsum, A, B, M, N, K, lda, ldb, ldd, a_mn_major=0, b_mn_major=0, epilogue=EPI_BIAS, ctx=None):

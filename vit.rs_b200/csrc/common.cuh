@@ -180,6 +180,8 @@ enum EpiKind {
     EPI_ACCUM_F32 = 5,     // out(fp32) += acc, atomically (split-K)      (dweight)
     EPI_ROWDOT = 7,        // out = acc; rowdot[(m / np * N/64 + n/64) * np + m % np] = sum over the 64-column head slice of out * aux
                            //                                             (attproj dX + D = rowsum(dO * O) of attention_backward)
+    EPI_BIAS_GELU_ONLY = 8, // out = gelu(acc + bias[n]) (pre-activation rounded as if stored)   (fc + gelu_forward, inference: no backward
+                           //                                             will ask for the pre-activation)
     EPI_PATCH = 6,         // tok = m % np: out = tok ? acc + bias[n] + pos[tok,n] : cls[n] + pos[0,n]   (patch embedding)
 };
 

@@ -19,6 +19,10 @@ __device__ __forceinline__ float epi_value(const Epilogue& e, long m, int n, flo
             *second = gelu_fwd<FAST>(x);
             break;
         }
+        case EPI_BIAS_GELU_ONLY:
+            if (e.bias) v += __ldg(e.bias + n);
+            v = gelu_fwd<FAST>(to_f32(from_f32<TO>(v)));
+            break;
         case EPI_BIAS_RESIDUAL:
             if (e.bias) v += __ldg(e.bias + n);
             v += aux;

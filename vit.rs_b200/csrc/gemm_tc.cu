@@ -142,13 +142,23 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[32 + j] = __uint_as_float(v[j]);
     }
-    if (KIND == EPI_BIAS || KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_RESIDUAL) {
+    if (KIND == EPI_BIAS || KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_GELU_ONLY || KIND == EPI_BIAS_RESIDUAL) {
         // bias[n_base + 2*lane .. +1] was fetched by this lane before the tile's accumulator was ready (this kernel leaves the
         // L1 no capacity, a global load here costs an L2 round trip per chunk); every lane needs all 64 values: shuffle broadcast
 #pragma unroll
         for (int j = 0; j < 64; j += 2) {
             acc[j] += __shfl_sync(0xffffffffu, bias2.x, j >> 1);
             acc[j + 1] += __shfl_sync(0xffffffffu, bias2.y, j >> 1);
+        }
+    }
+    if (KIND == EPI_BIAS_GELU_ONLY) {
+#pragma unroll
+        for (int j = 0; j < 64; j += 2) {
+            const __nv_bfloat162 r2 = __floats2bfloat162_rn(acc[j], acc[j + 1]);
+            const uint32_t rw = *reinterpret_cast<const uint32_t*>(&r2);
+            const float2 g = gelu_fwd2(make_float2(__uint_as_float(rw << 16), __uint_as_float(rw & 0xFFFF0000u)));
+            acc[j] = g.x;
+            acc[j + 1] = g.y;
         }
     }
     float rowdot = 0.f;
@@ -522,6 +532,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_BIAS_RESIDUAL: epilogue_chunk<EPI_BIAS_RESIDUAL>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_GELU_BWD: epilogue_chunk<EPI_GELU_BWD>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
+                        case EPI_BIAS_GELU_ONLY: epilogue_chunk<EPI_BIAS_GELU_ONLY>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_ROWDOT: epilogue_chunk<EPI_ROWDOT>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_PATCH: epilogue_chunk<EPI_PATCH>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         default: epilogue_chunk<EPI_NONE>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;

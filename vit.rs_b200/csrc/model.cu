@@ -376,8 +376,13 @@ int forward_bf16(vitrs_model* m) {
         VITRS_TRY(op_layernorm_forward<bf16>(ctx, ln2, act<float>(m, A_LN2_MEAN) + lbt, act<float>(m, A_LN2_RSTD) + lbt, residual2,
                                              P(m, P_LN2W) + l * C, P(m, P_LN2B) + l * C, rows, C));
         // fc + gelu_forward (rusty_vit.rs:328-329): both fch and fch_gelu are kept for backward
-        VITRS_TRY((gemm_fwd<bf16>(ctx, fch, ln2, S(m, P_FCW) + (long)l * 4 * C * C, P(m, P_FCB) + l * 4 * C, rows, C, 4 * C,
-                                  EPI_BIAS_GELU, nullptr, fch_gelu)));
+        // (inference — no targets, rusty_vit.rs:339-350 — keeps only the activated output: no backward will read fch)
+        if (m->has_targets)
+            VITRS_TRY((gemm_fwd<bf16>(ctx, fch, ln2, S(m, P_FCW) + (long)l * 4 * C * C, P(m, P_FCB) + l * 4 * C, rows, C, 4 * C,
+                                      EPI_BIAS_GELU, nullptr, fch_gelu)));
+        else
+            VITRS_TRY((gemm_fwd<bf16>(ctx, fch_gelu, ln2, S(m, P_FCW) + (long)l * 4 * C * C, P(m, P_FCB) + l * 4 * C, rows, C, 4 * C,
+                                      EPI_BIAS_GELU_ONLY, nullptr, nullptr)));
         VITRS_TRY((gemm_fwd<bf16>(ctx, residual3, fch_gelu, S(m, P_FCPROJW) + (long)l * C * 4 * C, P(m, P_FCPROJB) + l * C, rows,
                                   4 * C, C, EPI_BIAS_RESIDUAL, residual2, nullptr)));
     }

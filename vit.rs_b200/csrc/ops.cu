@@ -276,7 +276,7 @@ int vitrs_gemm_bf16_fused(vitrs_ctx* ctx, vitrs_bf16* D, vitrs_bf16* D2, const v
                           int b_mn_major, int epilogue) {
     CTX_OR_FAIL(ctx);
     VITRS_ARG(ctx, D && A && B && M >= 0 && N >= 0 && K >= 0);
-    VITRS_ARG(ctx, epilogue >= EPI_BIAS && epilogue <= EPI_GELU_BWD);
+    VITRS_ARG(ctx, (epilogue >= EPI_BIAS && epilogue <= EPI_GELU_BWD) || epilogue == EPI_BIAS_GELU_ONLY);
     VITRS_ARG(ctx, epilogue != EPI_BIAS_GELU || D2);
     VITRS_ARG(ctx, (epilogue != EPI_BIAS_RESIDUAL && epilogue != EPI_GELU_BWD) || aux);
     VITRS_ARG(ctx, !a_colsum || a_mn_major);
