@@ -109,11 +109,13 @@ def run_reference(args, rank):
     from oracle import pyoracle as po
     # size the per-step sample so that the run ends within a few minutes: one calibration image first
     t0 = time.perf_counter()
-    ips1, cores, _ = cpu_oracle_throughput(args.config, 1, 1, 0)
+    # all host threads, stated explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ips1, cores, _ = cpu_oracle_throughput(args.config, 1, 1, 0, threads=threads)
     calib = time.perf_counter() - t0
     budget = 150.0
     per_step = max(1, min(8, int(budget / max(1e-3, (args.steps + args.warmup) / ips1))))
-    ips, cores, sec_per_step = cpu_oracle_throughput(args.config, per_step, args.steps, args.warmup)
+    ips, cores, sec_per_step = cpu_oracle_throughput(args.config, per_step, args.steps, args.warmup, threads=threads)
     line = {"impl": "reference", "metric": METRIC, "value": round(ips, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(sec_per_step * 1e3, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
