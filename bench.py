@@ -294,10 +294,15 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            sample_batch = 1 if args.config in ("b16", "b8") else 2
-            ips, cores, sec = cpu_oracle_throughput(args.config, sample_batch, 1, 0)
+            # one calibration image, then one step sized for about 12 s of CPU work (bounded at 16 images): a batch large
+            # enough for the oracle's threads to spread over
+            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            ips1, cores, sec1 = cpu_oracle_throughput(args.config, 1, 1, 0, threads=threads)
+            sample_batch = max(1, min(16, int(12.0 / max(sec1, 1e-3))))
+            ips, cores, sec = cpu_oracle_throughput(args.config, sample_batch, 1, 0, threads=threads)
             cpu = {"value": round(ips, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"1 step x {sample_batch} image(s), vit-{args.config}, fp32 fwd+bwd+AdamW, {sec:.1f} s"}
+                   "sample": f"1 step x {sample_batch} image(s), vit-{args.config}, fp32 fwd+bwd+AdamW, {sec:.1f} s "
+                             f"(after a {sec1:.1f} s calibration image)"}
         except Exception as e:  # the baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
