@@ -307,8 +307,10 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         if (ch * 32 + 32 <= kend) {
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const float p0 = ex2(__uint_as_float(v[2 * c]) * sl2 - mxs), p1 = ex2(__uint_as_float(v[2 * c + 1]) * sl2 - mxs);
+            const float2 sl22 = splat2(sl2), nmx2 = splat2(-mxs);
+            for (int c = 0; c < 16; ++c) {  // one packed FMA per pair of scores
+                const float2 a = fma2(make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1])), sl22, nmx2);
+                const float p0 = ex2(a.x), p1 = ex2(a.y);
                 s0 += p0;
                 s1 += p1;
                 pk[c] = pack_bf16(p0, p1);
