@@ -5,7 +5,12 @@
 // probabilities from it and uses D = rowsum(dO * O) in place of the reference's O(T^3)
 // softmax-Jacobian loop (tv:583-589).
 //
-// One CTA owns one (batch, head).  Q, K, V (and dO) tiles of 128 tokens x 64 are read straight
+// Kernels in this file (the launchers at the end pick): attn_fwd_tc2_kernel (forward, one CTA per 128-query tile, P in
+// tensor memory), attn_bwd_persist_kernel (backward, persistent and software-pipelined, the default for non-causal T <= 256),
+// attn_bwd_pipe_kernel / attn_bwd_tc_kernel / attn_fwd_tc_kernel (earlier generations, kept for A/B and for causal masks),
+// and the streaming kernels for any sequence length.  The notes below describe the common data flow.
+//
+// One CTA owns one (batch, head) at a time.  Q, K, V (and dO) tiles of 128 tokens x 64 are read straight
 // out of the packed qkv[B,T,3C] activation by 3-D TMA boxes (row pitch 3C, column offset
 // {0,C,2C} + h*64, rows >= T zero-filled), so the reference layout needs no permute kernels.
 //

@@ -11,6 +11,11 @@
 // shared-memory tile is then [k rows][64 mn elements] per TMA box and the UMMA descriptor
 // carries the transpose, so no operand is ever transposed in HBM.
 //
+// Tiles are 256 x 256 and belong to a CTA PAIR (cluster of two = the two SMs of a TPC, tcgen05 cta_group::2): each CTA
+// stages its own 128 rows of A and 128 of the 256 rows of B, one thread of the leader CTA issues the 256 x 256 x 16 MMAs for
+// both, each CTA holds and drains its own 128 accumulator rows.  Per CTA the tensor core then reads a third less shared
+// memory per flop than with 128 x 256 single-CTA tiles (kept for M <= 128 or N <= 128): +11 % on the K = 768 shapes.
+//
 // CTA = 12 warps: warp 0 lane 0 issues TMA, warp 1 lane 0 issues tcgen05.mma and commits,
 // warp 2 owns the TMEM allocation, warps 4-11 are the epilogue (two warps per TMEM lane quarter,
 // each taking half of the tile's 64-column chunks).  Two accumulators live in TMEM (2 x BN
