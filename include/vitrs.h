@@ -54,6 +54,9 @@ int vitrs_ctx_reset_stream(vitrs_ctx* ctx);
 void* vitrs_ctx_stream(vitrs_ctx* ctx);
 int vitrs_ctx_synchronize(vitrs_ctx* ctx);
 const char* vitrs_last_error(vitrs_ctx* ctx);
+/* device-side error flags raised by kernels since the last call, then cleared (bit 0: a class label outside [0, classes));
+ * synchronises.  vitrs_model_mean_loss checks the same flags and fails with VITRS_ERR_ARG. */
+int vitrs_ctx_error_flags(vitrs_ctx* ctx, int* flags);
 /* kernels launched by this library on this context since creation (bench.py: gpu_launches) */
 uint64_t vitrs_launch_count(vitrs_ctx* ctx);
 const char* vitrs_version(void);
@@ -206,7 +209,9 @@ int vitrs_model_backward(vitrs_model* m);
 /* optimizer_step(model, lr) (rusty_vit.rs:949) and its AdamW form */
 int vitrs_model_optimizer_step(vitrs_model* m, float lr);
 int vitrs_model_update(vitrs_model* m, float lr, float beta1, float beta2, float eps, float weight_decay);
-/* mean_loss field (rusty_vit.rs:75): synchronises the stream and reads it back */
+/* mean_loss field (rusty_vit.rs:75): synchronises the stream and reads it back.  A pure local read: under data parallel
+ * forward() has already summed the ranks' losses once (on the comm stream), so it may be read twice, or on one rank only.
+ * Fails with VITRS_ERR_ARG when a label of the batch was outside [0, classes). */
 int vitrs_model_mean_loss(vitrs_model* m, float* out);
 /* one whole training step from HOST buffers (pinned or pageable): H2D copy of images/labels,
  * zero_grad, forward, backward, [all-reduce], AdamW, D2H of the loss.  prefetch stages the
@@ -237,6 +242,12 @@ int vitrs_model_train_step(vitrs_model* m, const float* images, const int* label
  * has no link-time dependency on it.  unique_id is the 128-byte ncclUniqueId made by rank 0. */
 int vitrs_comm_unique_id(vitrs_ctx* ctx, void* id128);
 int vitrs_comm_init(vitrs_ctx* ctx, const void* id128, int rank, int world);
+/* same with an explicit cap on the thread blocks NCCL may use per collective (ncclConfig_t.maxCTAs; 0 = NCCL's default).
+ * vitrs_comm_init uses 8 (env VITRS_NCCL_MAX_CTAS overrides): the persistent GEMM / attention kernels occupy every SM with
+ * one large-shared-memory CTA, so each SM NCCL takes delays a CTA pair of the next GEMM. */
+int vitrs_comm_init_config(vitrs_ctx* ctx, const void* id128, int rank, int world, int max_ctas);
+/* ncclCommGetAsyncError: *nccl_result != 0 (and a VITRS_ERR_NCCL return) when a peer or the fabric failed */
+int vitrs_comm_async_error(vitrs_ctx* ctx, int* nccl_result);
 int vitrs_comm_destroy(vitrs_ctx* ctx);
 int vitrs_comm_world(vitrs_ctx* ctx, int* rank, int* world);
 /* sum all-reduce of the fp32 gradient buffer in reverse-layer buckets on the comm stream;
@@ -246,6 +257,24 @@ int vitrs_model_allreduce_grads(vitrs_model* m);
  * L-1..0 (12 slices each), L+1 = embeddings; offsets/counts (elements, capacity 12) index the flat buffer */
 int vitrs_grad_bucket(const vitrs_config* cfg, int bucket, size_t* offsets, size_t* counts, int* num_slices);
 int vitrs_allreduce_f32(vitrs_ctx* ctx, float* buf, size_t n);
+/* what the gradient exchange of the production mode puts on the wire: 1 (default) = one contiguous bf16 message per bucket
+ * (the bucket's slices are packed into a bucket-major exchange buffer, summed, and unpacked into the fp32 gradient views);
+ * 0 = the fp32 slices themselves, in place (exact sums; twice the bytes, 12 small messages per block) */
+int vitrs_model_set_comm_dtype(vitrs_model* m, int dtype);
+
+/* ---- ZeRO-1 sharded optimiser (the reference's optimizer_step rusty_vit.rs:949-955 and its unused moment
+ * buffers :67-68 generalised): after enable, each bucket of gradients is reduce-scattered (bf16) instead of all-reduced, every
+ * rank keeps the fp32 master weights and both AdamW moments of its 1/world shard only, update() runs AdamW on the shard and
+ * all-gathers the bf16 weights into the shadow the GEMMs read.  The full fp32 parameter view goes stale until
+ * vitrs_model_gather_parameters (save_checkpoint gathers by itself; every rank must call it).  grads views then hold the
+ * rank-local gradients.  Works without a communicator (world 1) as the same code path. */
+int vitrs_model_enable_zero1(vitrs_model* m);
+int vitrs_model_gather_parameters(vitrs_model* m);
+/* bytes of optimiser state (fp32 master weights + AdamW m and v) held by this rank */
+int vitrs_model_optimizer_state_bytes(vitrs_model* m, size_t* bytes);
+/* the partition itself, computable on the host: region [z_off, z_off + z_len) of `bucket` in the bucket-major exchange
+ * buffer (z_len = the bucket's elements padded to a multiple of 8 * world) and the shard length z_len / world */
+int vitrs_zero_partition(const vitrs_config* cfg, int world, int bucket, size_t* z_off, size_t* z_len, size_t* shard);
 
 #ifdef __cplusplus
 }

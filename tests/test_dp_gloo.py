@@ -94,3 +94,78 @@ def test_two_rank_gradients_equal_single_process(vitrs):
     assert abs(loss - ref_loss) < 1e-5
     d = np.abs(params - ref.params_flat())
     assert d.max() < 2e-4 and np.percentile(d, 99.9) < 1e-5
+
+
+def test_zero1_partition_arithmetic(vitrs):
+    """ZeRO-1 host logic (vitrs_zero_partition): the bucket regions tile the exchange buffer, every region is the bucket's
+    elements padded to 8 * world, the world shards of a region are equal, 16-byte aligned, and together cover every gradient
+    element exactly once."""
+    for name in ("tiny", "ti16", "b16"):
+        buckets = vitrs.grad_buckets(name)
+        for world in (1, 2, 4, 8):
+            part = vitrs.zero_partition(name, world)
+            assert len(part) == len(buckets)
+            z = 0
+            for (zo, zl, sh), slices in zip(part, buckets):
+                n = sum(c for _, c in slices)
+                assert zo == z and zl >= n and zl - n < 8 * world and zl % (8 * world) == 0 and sh * world == zl and sh % 8 == 0
+                z += zl
+            total = sum(c for b in buckets for _, c in b)
+            assert z - total < 8 * world * len(buckets)
+
+
+def _zero_worker(rank, world, port, q):
+    """Reduce-scatter + sharded AdamW + all-gather over gloo on the CPU oracle's buffers: the arithmetic of model.cu's ZeRO-1 path."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import __graft_entry__ as ge
+    vitrs = ge.load_package()
+    cfg = po.CONFIGS["tiny"]
+    images, labels = po.synthetic_batch(cfg, B_GLOBAL)
+    per = B_GLOBAL // world
+    sl = slice(rank * per, (rank + 1) * per)
+    m = po.ViT("tiny", seed=1337, init_mode=1)
+    m.set_dloss_scale(1.0 / B_GLOBAL)
+    m.forward(images[sl], labels[sl]); m.zero_grad(); m.backward()
+    grads, params = m.grads_flat(), m.params_flat()
+    buckets, part = vitrs.grad_buckets("tiny"), vitrs.zero_partition("tiny", world)
+    new_params = params.copy()
+    for slices, (zo, zl, sh) in zip(buckets, part):
+        idx = np.concatenate([np.arange(o, o + c) for o, c in slices])        # Z order of this bucket
+        region = np.zeros(zl, np.float32); region[:idx.size] = grads[idx]
+        # gloo has no reduce_scatter: all_reduce and keep this rank's shard (same sums)
+        t = torch.from_numpy(region); dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        g = region[rank * sh:(rank + 1) * sh].copy()
+        pz = np.zeros(zl, np.float32); pz[:idx.size] = params[idx]
+        p = pz[rank * sh:(rank + 1) * sh].copy()
+        mom, var = np.zeros_like(p), np.zeros_like(p)
+        po.adamw_step(p, g, mom, var, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1)         # AdamW on the shard only
+        gathered = [torch.zeros(sh) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(p))
+        full = torch.cat(gathered).numpy()
+        new_params[idx] = full[:idx.size]
+    if rank == 0:
+        q.put(new_params)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_zero1_two_rank_step_equals_single_process(vitrs):
+    cfg = po.CONFIGS["tiny"]
+    images, labels = po.synthetic_batch(cfg, B_GLOBAL)
+    ref = po.ViT("tiny", seed=1337, init_mode=1)
+    ref.forward(images, labels); ref.zero_grad(); ref.backward(); ref.update(1e-3)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_zero_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    params = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d = np.abs(params - ref.params_flat())
+    assert d.max() < 2e-4 and np.percentile(d, 99.9) < 1e-5

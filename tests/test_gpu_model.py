@@ -258,3 +258,115 @@ def test_bf16_inference_forward_equals_training_forward(vitrs):
     assert m.mean_loss == -1.0
     assert torch.equal(m.act("logits"), want)
     m.close()
+
+
+def _write_reference_layout_checkpoint(path, cfg, causal, flat, adam_step=0, m=None, v=None):
+    """A checkpoint written with nothing but numpy / struct, in the layout of rusty_vit.rs:81-129 (Q6 resolved, DEVIATIONS D12):
+    256 x int32 header — slots 2..6 = max_seq_len, vocab (= classes), layers, heads, channels — then fp32 parameters from byte
+    1024 in the reference's tensor order.  Slots 7..12 are this build's ViT fields."""
+    import struct
+    t = (cfg["image_size"] // cfg["patch_size"]) ** 2 + 1
+    header = [0] * 256
+    header[0], header[1] = 20261018, 1
+    header[2:7] = [t, cfg["num_classes"], cfg["num_layers"], cfg["num_heads"], cfg["channels"]]
+    header[7:13] = [cfg["image_size"], cfg["patch_size"], cfg["num_classes"], causal, adam_step, 1 if m is not None else 0]
+    with open(path, "wb") as f:
+        f.write(struct.pack("<256i", *header))
+        assert f.tell() == 1024
+        f.write(np.ascontiguousarray(flat, dtype="<f4").tobytes())
+        if m is not None:
+            f.write(np.ascontiguousarray(m, dtype="<f4").tobytes())
+            f.write(np.ascontiguousarray(v, dtype="<f4").tobytes())
+
+
+def test_checkpoint_interoperates_with_an_independently_written_file(vitrs, tmp_path):
+    """load: a file produced by numpy alone in the documented layout; save: parsed back by numpy alone.  Both bit-exact."""
+    cfg = po.CONFIGS["tiny"]
+    ref = po.ViT("tiny", seed=7, init_mode=1)
+    flat = ref.params_flat().copy()
+    rng = np.random.default_rng(3)
+    mom, var = rng.standard_normal(flat.size).astype(np.float32), rng.random(flat.size).astype(np.float32)
+    # (1) parameters only, as the reference's own save_checkpoint would write them (rusty_vit.rs:912-941)
+    p1 = str(tmp_path / "numpy_params_only.bin")
+    _write_reference_layout_checkpoint(p1, cfg, 0, flat)
+    m = vitrs.ViT.build_from_checkpoint(p1, max_batch=4, mode=vitrs.MODE_F32)
+    assert np.array_equal(m.params_flat().cpu().numpy(), flat)
+    assert not m.adam_m("qkvw").any() and not m.adam_v("qkvw").any()
+    # the loaded model computes what the oracle computes from the same numbers
+    images, labels = po.synthetic_batch(cfg, 4)
+    ref_loss = ref.forward(images, labels)
+    m.forward(*to_dev(images, labels))
+    assert abs(m.mean_loss - ref_loss) <= TOL_F32 * abs(ref_loss)
+    # (2) with AdamW state and a step counter
+    p2 = str(tmp_path / "numpy_full.bin")
+    _write_reference_layout_checkpoint(p2, cfg, 0, flat, adam_step=17, m=mom, v=var)
+    m.load_checkpoint(p2)
+    off = sum(ref.param_sizes[:po.PARAM_NAMES.index("qkvw")])
+    n = ref.param_sizes[po.PARAM_NAMES.index("qkvw")]
+    assert np.array_equal(m.adam_m("qkvw").cpu().numpy(), mom[off:off + n])
+    assert np.array_equal(m.adam_v("qkvw").cpu().numpy(), var[off:off + n])
+    # (3) the reverse: what the library writes, parsed with numpy only
+    p3 = str(tmp_path / "written_by_library.bin")
+    m.save_checkpoint(p3)
+    raw = open(p3, "rb").read()
+    header = np.frombuffer(raw[:1024], dtype="<i4")
+    t = (cfg["image_size"] // cfg["patch_size"]) ** 2 + 1
+    assert list(header[2:7]) == [t, cfg["num_classes"], cfg["num_layers"], cfg["num_heads"], cfg["channels"]]
+    assert header[11] == 17 and header[12] == 1 and len(raw) == 1024 + 3 * 4 * flat.size
+    body = np.frombuffer(raw[1024:], dtype="<f4")
+    assert np.array_equal(body[:flat.size], flat) and np.array_equal(body[flat.size:2 * flat.size], mom)
+    assert np.array_equal(body[2 * flat.size:], var)
+    # (4) a truncated or foreign file is refused and leaves the model untouched
+    bad = str(tmp_path / "truncated.bin")
+    open(bad, "wb").write(raw[:1024 + 4 * flat.size + 40])
+    with pytest.raises(vitrs.VitrsError):
+        m.load_checkpoint(bad)
+    other = dict(cfg, num_heads=2)
+    _write_reference_layout_checkpoint(bad, other, 0, flat)
+    with pytest.raises(vitrs.VitrsError):
+        m.load_checkpoint(bad)
+    assert np.array_equal(m.params_flat().cpu().numpy(), flat)
+    m.close()
+
+
+def test_out_of_range_label_is_reported(vitrs):
+    """A bad dataset label must neither index out of bounds nor pass silently: the loss kernels raise a device flag
+    that mean_loss turns into an error; the next clean batch works again."""
+    cfg = po.CONFIGS["tiny"]
+    images, labels = po.synthetic_batch(cfg, 4)
+    for mode in (vitrs.MODE_BF16, vitrs.MODE_F32):
+        m = vitrs.ViT("tiny", max_batch=4, mode=mode, seed=1337, init_mode=1)
+        bad = labels.copy(); bad[2] = cfg["num_classes"] + 5
+        m.zero_grad(); m.forward(*to_dev(images, bad)); m.backward()
+        with pytest.raises(vitrs.VitrsError):
+            _ = m.mean_loss
+        assert torch.isfinite(m.grads_flat()).all()
+        m.zero_grad(); m.forward(*to_dev(images, labels)); m.backward()
+        assert np.isfinite(m.mean_loss)
+        m.close()
+
+
+def test_zero1_single_rank_equals_replicated_step(vitrs):
+    """ZeRO-1 with world 1 runs the whole sharded code path (pack to the bucket-major exchange buffer, AdamW on the shard with
+    bf16 gradients, unpack of the bf16 weights into the shadow) without a communicator.  Against the replicated step the only
+    difference is the bf16 rounding of the gradients on the wire: AdamW's g / sqrt(v) is scale-free, so after one step every
+    weight moves by ~lr in both; after a few steps the two models still agree to a fraction of lr * steps."""
+    b, lr, steps = 16, 1e-3, 4
+    a = vitrs.ViT(MID_HS64, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)
+    z = vitrs.ViT(MID_HS64, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)
+    full_bytes = z.optimizer_state_bytes
+    z.enable_zero1()
+    assert z.optimizer_state_bytes >= full_bytes and z.optimizer_state_bytes <= full_bytes + 12 * 8 * (MID_HS64["num_layers"] + 2)
+    for s in range(steps):
+        x, y = to_dev(*po.synthetic_batch(MID_HS64, b, step=s))
+        a.train_step(x, y, lr); z.train_step(x, y, lr)
+        assert abs(a.mean_loss - z.mean_loss) <= 2e-3, s
+    z.gather_parameters()
+    d = (a.params_flat() - z.params_flat()).abs()
+    assert d.max().item() <= 2 * lr * steps and d.mean().item() <= 0.1 * lr * steps, (d.max().item(), d.mean().item())
+    # the shadow the GEMMs read is the bf16 image of the gathered masters
+    x, y = to_dev(*po.synthetic_batch(MID_HS64, b, step=9))
+    z.forward(x, None); lz = z.act("logits").clone()
+    z.sync_parameters(); z.forward(x, None)
+    assert torch.equal(z.act("logits"), lz)
+    a.close(); z.close()

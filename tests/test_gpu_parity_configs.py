@@ -1,0 +1,106 @@
+"""bf16 production step against the oracle on the BASELINE.json model configs.
+
+The toy shapes of test_gpu_model.py never reach the kernels the headline run uses.  Here one full
+step (ViT::forward + backward, rusty_vit.rs:269-449) runs on ViT-Ti/16 and ViT-B/16 at T = 197 and
+on a two-block ViT-B/8 slice at T = 785 — the CTA-pair tcgen05 GEMM with every fused epilogue,
+attn_fwd_tc2 / attn_bwd_persist (T <= 256) and the streaming attention kernels (T = 785), EPI_ROWDOT —
+and logits, loss and EVERY parameter gradient are held to the north-star's 2e-2 (tensor-level
+relative error, max |a - b| / max |b|).  The 100-step AdamW loss curve is repeated on an hs = 64,
+T = 197 model so those kernels see 100 consecutive optimiser steps, and one case runs under the
+reference's own all-positive init (rusty_vit.rs:864-903, init_mode 0).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+TOL_BF16 = 2e-2
+
+# ViT-B/8 (T = 785, C = 768, NH = 12) cut to two blocks so the oracle finishes in seconds
+B8_2L = dict(image_size=224, patch_size=8, channels=768, num_layers=2, num_heads=12, num_classes=1000)
+# T = 197 with three 64-wide heads (ViT-Ti/16's block shape), two blocks, 16 classes: the loss-curve model
+TI16_2L = dict(image_size=224, patch_size=16, channels=192, num_layers=2, num_heads=3, num_classes=16)
+MID_HS64 = dict(image_size=64, patch_size=16, channels=256, num_layers=2, num_heads=4, num_classes=16)
+
+
+def relerr(got, want):
+    got, want = np.asarray(got, np.float64).ravel(), np.asarray(want, np.float64).ravel()
+    return np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+
+
+def to_dev(images, labels):
+    return torch.from_numpy(images).cuda(), torch.from_numpy(labels).cuda()
+
+
+def bf16_storage_floor(cfg, ref, images, labels):
+    """Tensor-level relative error of an IDEAL bf16-storage evaluation (fp32 arithmetic, values rounded only where the
+    production mode stores bf16; tests/torch_ref.py) against the fp32 oracle: what the precision itself costs."""
+    from tests import torch_ref
+    p = torch_ref.params_from_flat(ref.params_flat(), cfg, ref.param_sizes, po.PARAM_NAMES)
+    logits, loss, _ = torch_ref.forward_bf16_storage(p, cfg, images, labels)
+    loss.backward()
+    floor = {"logits": relerr(logits.detach().numpy(), ref.act("logits"))}
+    for name in po.PARAM_NAMES:
+        floor["d" + name] = relerr(p[name].grad.numpy(), ref.grad(name))
+    return floor
+
+
+@pytest.mark.parametrize("cfg_name,b,init_mode", [("ti16", 4, 1), ("b16", 2, 1), (B8_2L, 2, 1),
+                                                  ("ti16", 4, 0), (MID_HS64, 16, 0)],
+                         ids=["ti16-b4", "b16-b2", "b8x2-b2", "ti16-b4-refinit", "mid-b16-refinit"])
+def test_bf16_step_matches_oracle_on_model_configs(vitrs, cfg_name, b, init_mode):
+    """init_mode 1 (symmetric weights): logits, loss and every parameter gradient within 2e-2.
+
+    init_mode 0 is the reference's own init, U[0,1)*0.02 (rusty_vit.rs:864-903): every weight is positive, so each
+    matmul output carries a large component common to all its channels that the next LayerNorm removes again; a
+    bf16 tensor holds 8 significant bits of that common component, not of the signal.  The loss still agrees to
+    2e-2, but an IDEAL bf16-storage evaluation (exact arithmetic, rounding only where bf16 is stored) is already
+    2e-2 .. 1.2e-1 away from fp32 on logits and the LayerNorm gradients (DEVIATIONS D14).  There the bar is: no
+    tensor worse than 2e-2 or twice that precision floor, whichever is larger."""
+    cfg = po.CONFIGS[cfg_name] if isinstance(cfg_name, str) else cfg_name
+    ref = po.ViT(cfg_name, seed=1337, init_mode=init_mode)
+    m = vitrs.ViT(cfg_name, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=init_mode)
+    assert np.array_equal(m.params_flat().cpu().numpy(), ref.params_flat())
+    images, labels = po.synthetic_batch(cfg, b)
+    ref_loss = ref.forward(images, labels); ref.zero_grad(); ref.backward()
+    m.zero_grad(); m.forward(*to_dev(images, labels)); m.backward()
+    assert abs(m.mean_loss - ref_loss) <= TOL_BF16 * abs(ref_loss), (m.mean_loss, ref_loss)
+    report = {"logits": relerr(m.act("logits").cpu().numpy(), ref.act("logits"))}
+    for name in po.PARAM_NAMES:
+        report["d" + name] = relerr(m.grad(name).cpu().numpy(), ref.grad(name))
+    bound = {k: TOL_BF16 for k in report}
+    if init_mode == 0:
+        floor = bf16_storage_floor(cfg, ref, images, labels)
+        bound = {k: max(TOL_BF16, 2.0 * floor[k]) for k in report}
+        print("bf16 storage floor", {k: f"{v:.2e}" for k, v in floor.items()})
+    else:
+        for name in ("encoded", "qkv", "atty", "residual2", "fch", "residual3"):
+            got = m.act(name).float().cpu().numpy()
+            report[name] = relerr(got, ref.act(name)[:got.size])
+            bound[name] = TOL_BF16
+    print("gpu vs oracle", {k: f"{v:.2e}" for k, v in report.items()})
+    bad = {k: f"{v:.3e} > {bound[k]:.3e}" for k, v in report.items() if not v <= bound[k]}
+    assert not bad, bad
+    m.close()
+
+
+@pytest.mark.parametrize("cfg,b", [(TI16_2L, 4), (MID_HS64, 16)], ids=["t197-hs64", "mid-hs64"])
+def test_bf16_loss_curve_100_steps_hs64(vitrs, cfg, b):
+    """100 AdamW steps through the tensor-core attention kernels and the CTA-pair GEMM vs the oracle's curve."""
+    steps, lr = 100, 3e-4
+    ref = po.ViT(cfg, seed=1337, init_mode=1)
+    m = vitrs.ViT(cfg, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)
+    ref_curve, got_curve = [], []
+    for step in range(steps):
+        images, labels = po.synthetic_batch(cfg, b, step=step % 8)  # 8 repeating batches: the loss must fall
+        ref_curve.append(ref.forward(images, labels)); ref.zero_grad(); ref.backward(); ref.update(lr)
+        m.train_step(*to_dev(images, labels), lr)
+        got_curve.append(m.mean_loss)
+    ref_curve, got_curve = np.array(ref_curve), np.array(got_curve)
+    assert ref_curve[-4:].mean() < ref_curve[:4].mean() - 0.05, ref_curve
+    dev_ = np.abs(got_curve - ref_curve)
+    msg = f"max {dev_.max():.4f} mean {dev_.mean():.4f} last {got_curve[-4:]} vs {ref_curve[-4:]}"
+    assert dev_.max() <= TOL_BF16 * ref_curve.max(), msg
+    m.close()

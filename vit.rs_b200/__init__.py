@@ -133,7 +133,15 @@ _SIGNATURES = {
     "vitrs_model_train_step_host_u8": (_int, [_vp, _vp, _int, _vp, _int, _f, _f, _f, _f, _f, C.POINTER(_f)]),
     "vitrs_comm_unique_id": (_int, [_vp, _vp]),
     "vitrs_comm_init": (_int, [_vp, _vp, _int, _int]),
+    "vitrs_comm_init_config": (_int, [_vp, _vp, _int, _int, _int]),
+    "vitrs_comm_async_error": (_int, [_vp, C.POINTER(_int)]),
     "vitrs_comm_destroy": (_int, [_vp]),
+    "vitrs_ctx_error_flags": (_int, [_vp, C.POINTER(_int)]),
+    "vitrs_model_set_comm_dtype": (_int, [_vp, _int]),
+    "vitrs_model_enable_zero1": (_int, [_vp]),
+    "vitrs_model_gather_parameters": (_int, [_vp]),
+    "vitrs_model_optimizer_state_bytes": (_int, [_vp, C.POINTER(_sz)]),
+    "vitrs_zero_partition": (_int, [C.POINTER(Config), _int, _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "vitrs_comm_world": (_int, [_vp, C.POINTER(_int), C.POINTER(_int)]),
     "vitrs_model_allreduce_grads": (_int, [_vp]),
     "vitrs_grad_bucket": (_int, [C.POINTER(Config), _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_int)]),
@@ -234,12 +242,40 @@ class Context:
         self.check(lib().vitrs_comm_unique_id(self._h, C.cast(buf, C.c_void_p)))
         return bytes(buf)
 
-    def comm_init(self, uid, rank, world):
+    def comm_init(self, uid, rank, world, max_ctas=None):
+        """max_ctas: cap on the thread blocks NCCL may occupy per collective (None: the library default, 8; 0: NCCL's own)."""
         buf = C.create_string_buffer(uid, 128)
-        self.check(lib().vitrs_comm_init(self._h, C.cast(buf, C.c_void_p), rank, world))
+        if max_ctas is None:
+            self.check(lib().vitrs_comm_init(self._h, C.cast(buf, C.c_void_p), rank, world))
+        else:
+            self.check(lib().vitrs_comm_init_config(self._h, C.cast(buf, C.c_void_p), rank, world, max_ctas))
+
+    def comm_async_error(self):
+        """ncclCommGetAsyncError: 0 when healthy; raises VitrsError otherwise."""
+        r = C.c_int()
+        self.check(lib().vitrs_comm_async_error(self._h, C.byref(r)))
+        return r.value
+
+    def error_flags(self):
+        f = C.c_int()
+        self.check(lib().vitrs_ctx_error_flags(self._h, C.byref(f)))
+        return f.value
 
     def allreduce(self, t):
         self.check(lib().vitrs_allreduce_f32(self._h, _ptr(t), t.numel()))
+
+
+def zero_partition(cfg, world):
+    """The ZeRO-1 partition (host arithmetic only): per bucket (z_off, z_len, shard)."""
+    c = make_config(cfg) if not isinstance(cfg, Config) else cfg
+    out = []
+    for b in range(c.num_layers + 2):
+        zo, zl, sh = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        rc = lib().vitrs_zero_partition(C.byref(c), world, b, C.byref(zo), C.byref(zl), C.byref(sh))
+        if rc != 0:
+            raise VitrsError(f"vitrs_zero_partition failed ({rc})")
+        out.append((zo.value, zl.value, sh.value))
+    return out
 
 
 def grad_buckets(cfg):
@@ -483,6 +519,23 @@ class ViT:
 
     def act(self, name): return self._aview(0, name)
     def grad_act(self, name): return self._aview(1, name)
+
+    def set_comm_dtype(self, dtype):
+        """Gradient exchange payload: "bf16" (default, one packed message per bucket) or "f32" (exact in-place slices)."""
+        self.ctx.check(lib().vitrs_model_set_comm_dtype(self._h, {"f32": 0, "bf16": 1}.get(dtype, dtype)))
+
+    def enable_zero1(self):
+        """ZeRO-1: shard fp32 master weights and AdamW moments 1/world per bucket (include/vitrs.h)."""
+        self.ctx.check(lib().vitrs_model_enable_zero1(self._h))
+
+    def gather_parameters(self):
+        self.ctx.check(lib().vitrs_model_gather_parameters(self._h))
+
+    @property
+    def optimizer_state_bytes(self):
+        n = C.c_size_t()
+        self.ctx.check(lib().vitrs_model_optimizer_state_bytes(self._h, C.byref(n)))
+        return n.value
 
     def set_dloss_scale(self, s):
         self.ctx.check(lib().vitrs_model_set_dloss_scale(self._h, s))

@@ -393,7 +393,7 @@ int op_attention_forward(vitrs_ctx* ctx, T* out, float* preatt, float* att, floa
     const size_t smem = fwd_smem(kWarps * rpw, hs, t);
     if (smem > kMaxSmem) return vitrs_set_error(ctx, VITRS_ERR_UNSUPPORTED, "attention_forward: sequence length %d too long for the SIMT kernel", t);
     auto k = attn_fwd_kernel<T>;
-    VITRS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VITRS_TRY(vitrs_func_smem(ctx, (const void*)k, smem));
     dim3 grid(ceil_div(t, kWarps * rpw), b * nh);
     k<<<grid, kThreads, smem, ctx->stream>>>(out, preatt, att, lse, qkv, t, c, nh, causal, rpw);
     VITRS_LAUNCHED(ctx);
@@ -418,8 +418,8 @@ int op_attention_backward(vitrs_ctx* ctx, T* dqkv, float* dpreatt, float* datt, 
     if (att) {
         auto kq = attn_bwd_q_kernel<T, true>;
         auto kkv = attn_bwd_kv_kernel<T, true>;
-        VITRS_CUDA(ctx, cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
-        VITRS_CUDA(ctx, cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+        VITRS_TRY(vitrs_func_smem(ctx, (const void*)kq, smem_q));
+        VITRS_TRY(vitrs_func_smem(ctx, (const void*)kkv, smem_kv));
         kq<<<grid_q, kThreads, smem_q, ctx->stream>>>(dqkv, dpreatt, datt, dsum, dout, qkv, att, lse, t, c, nh, causal, rpw);
         VITRS_LAUNCHED(ctx);
         kkv<<<grid_kv, kThreads, smem_kv, ctx->stream>>>(dqkv, dsum, dout, qkv, att, lse, t, c, nh, causal);
@@ -427,8 +427,8 @@ int op_attention_backward(vitrs_ctx* ctx, T* dqkv, float* dpreatt, float* datt, 
     } else {
         auto kq = attn_bwd_q_kernel<T, false>;
         auto kkv = attn_bwd_kv_kernel<T, false>;
-        VITRS_CUDA(ctx, cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
-        VITRS_CUDA(ctx, cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+        VITRS_TRY(vitrs_func_smem(ctx, (const void*)kq, smem_q));
+        VITRS_TRY(vitrs_func_smem(ctx, (const void*)kkv, smem_kv));
         kq<<<grid_q, kThreads, smem_q, ctx->stream>>>(dqkv, dpreatt, datt, dsum, dout, qkv, att, lse, t, c, nh, causal, rpw);
         VITRS_LAUNCHED(ctx);
         kkv<<<grid_kv, kThreads, smem_kv, ctx->stream>>>(dqkv, dsum, dout, qkv, att, lse, t, c, nh, causal);

@@ -5,10 +5,11 @@
 // probabilities from it and uses D = rowsum(dO * O) in place of the reference's O(T^3)
 // softmax-Jacobian loop (tv:583-589).
 //
-// Kernels in this file (the launchers at the end pick): attn_fwd_tc2_kernel (forward, one CTA per 128-query tile, P in
-// tensor memory), attn_bwd_persist_kernel (backward, persistent and software-pipelined, the default for non-causal T <= 256),
-// attn_bwd_pipe_kernel / attn_bwd_tc_kernel / attn_fwd_tc_kernel (earlier generations, kept for A/B and for causal masks),
-// and the streaming kernels for any sequence length.  The notes below describe the common data flow.
+// Kernels in this file (the launchers at the end pick): attn_fwd_persist_kernel (forward, 128 < T <= 256: persistent, two
+// softmax groups, operands of the next head prefetched), attn_fwd_tc2_kernel (forward, T <= 128 and causal masks: one CTA per
+// 128-query tile, P in tensor memory), attn_bwd_persist_kernel (backward, persistent and software-pipelined, non-causal
+// T <= 256), attn_bwd_tc_kernel (backward with a causal mask, T <= 256) and the streaming kernels for any sequence length.
+// The notes below describe the common data flow.
 //
 // One CTA owns one (batch, head) at a time.  Q, K, V (and dO) tiles of 128 tokens x 64 are read straight
 // out of the packed qkv[B,T,3C] activation by 3-D TMA boxes (row pitch 3C, column offset
@@ -45,6 +46,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -117,120 +119,6 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
 }
 
 // =============================================== forward ==========================================
-__global__ void __launch_bounds__(kThreads, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, float* __restrict__ lse, int T, int C, int NH,
-                   int causal, int NT, int NK, uint32_t tmem_cols) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-    const int NKB = (NK + 63) >> 6;  // 64-key blocks of the P tile
-    const uint32_t sQ = base, sK = sQ + NT * TILE_BYTES, sV = sK + NT * TILE_BYTES, sP = sV + NT * TILE_BYTES;
-    const uint32_t p_bytes = NKB * TILE_BYTES;
-    const uint32_t bar0 = sP + NT * p_bytes;
-    const uint32_t bar_load = bar0, bar_s = bar0 + 8, bar_o = bar0 + 24;  // bar_s[2], bar_o[2]
-    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 40);
-
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int bh = blockIdx.x, b = bh / NH, h = bh - b * NH;
-    if (tid == 0) {
-        tma_prefetch_desc(&tm_qkv);
-        mbar_init(bar_load, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_s + 8 * i, 1); mbar_init(bar_o + 8 * i, 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) tmem_alloc(smem_u32((const void*)slot), tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *slot;
-
-    if (tid == 0) {
-        mbar_expect_tx(bar_load, (uint32_t)(3 * NT * TILE_BYTES));
-        for (int i = 0; i < NT; ++i) {
-            tma_load_3d(sQ + i * TILE_BYTES, &tm_qkv, bar_load, h * HS, i * TILE, b);
-            tma_load_3d(sK + i * TILE_BYTES, &tm_qkv, bar_load, C + h * HS, i * TILE, b);
-            tma_load_3d(sV + i * TILE_BYTES, &tm_qkv, bar_load, 2 * C + h * HS, i * TILE, b);
-        }
-    }
-    const int grp = warp >> 2;  // query tile handled by this 4-warp group
-    if (grp < NT) {
-        const int r = tid & 127;
-        const bool leader = r == 0;
-        const uint32_t region = tmem_base + (uint32_t)(grp * 256);
-        const uint32_t lane_addr = region + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t sPi = sP + grp * p_bytes;
-        if (leader) {
-            mbar_wait(bar_load, 0);
-            tc_fence_after();
-            const uint32_t idesc = make_idesc(TILE, NK, 0, 0);
-#pragma unroll
-            for (int k = 0; k < HS / 16; ++k)
-                umma_bf16(region, make_desc(sQ + grp * TILE_BYTES + k * 32, 0, 1024), make_desc(sK + k * 32, 0, 1024), idesc, k > 0);
-            umma_commit(bar_s + 8 * grp);
-        }
-        mbar_wait(bar_s + 8 * grp, 0);
-        tc_fence_after();
-        const int q = grp * TILE + r;
-        const int kend = causal ? min(T, q + 1) : T;
-        const int nchunks = (NK + 31) >> 5;
-        const float sl2 = kLog2e / sqrtf((float)HS);
-        float mx = -INFINITY;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            uint32_t v[32];
-            tmem_ld32(lane_addr + ch * 32, v);
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-                if (ch * 32 + c < kend) mx = fmaxf(mx, __uint_as_float(v[c]));
-        }
-        float sum = 0.f;
-        const float mxs = mx * sl2;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            uint32_t v[32];
-            tmem_ld32(lane_addr + ch * 32, v);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                float p[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = ch * 32 + g * 8 + j;
-                    p[j] = k < kend ? ex2(__uint_as_float(v[g * 8 + j]) * sl2 - mxs) : 0.f;
-                    sum += p[j];
-                }
-                const int kcol = ch * 32 + g * 8;
-                st_shared_v4(sw128(sPi + (kcol >> 6) * TILE_BYTES, r, (kcol & 63) >> 3), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]),
-                             pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
-            }
-        }
-        fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core's async proxy
-        tc_fence_before();
-        named_bar_sync(1 + grp, 128);
-        if (leader) {
-            tc_fence_after();
-            const uint32_t idesc = make_idesc(TILE, HS, 0, 1);  // B = V is MN-major: [key rows][64]
-            for (int k16 = 0; k16 < NK / 16; ++k16)
-                umma_bf16(region, make_desc(sPi + (k16 >> 2) * TILE_BYTES + (k16 & 3) * 32, 0, 1024),
-                          make_desc(sV + k16 * 2048, TILE_BYTES, 1024), idesc, k16 > 0);
-            umma_commit(bar_o + 8 * grp);
-        }
-        mbar_wait(bar_o + 8 * grp, 0);
-        tc_fence_after();
-        const float inv = 1.0f / sum;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld32(lane_addr + half * 32, v);
-            if (q < T) store_row32(out + ((long)b * T + q) * C + h * HS + half * 32, v, inv, false);
-        }
-        if (q < T) lse[(long)bh * T + q] = mx * (1.0f / sqrtf((float)HS)) + logf(sum);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, tmem_cols);
-    }
-}
-
 // ---- forward, one CTA per (batch, head, 128-query tile), two CTAs per SM ------------------------------
 // P never leaves tensor memory: the softmax threads overwrite their S row in place with packed bf16
 // (tcgen05.st) and the P.V MMA takes its A operand from TMEM, so a CTA needs only Q_i, K, V in shared
@@ -369,6 +257,239 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ---- forward, persistent (128 < T <= 256, non-causal): one CTA per SM walks over its (batch, head) pairs ----------------
+// The kernel above pays a launch, a tensor-memory allocation and an un-overlapped ~2 us operand fetch per 128-query tile, and
+// fetches K and V of a head once per query tile.  Here the CTA stays resident:
+//   loader (warp 0, one thread)  Q_0 Q_1 K_0 K_1 V_0 V_1 of the NEXT head stream into the other 96 KB stage while this head runs
+//                                (each head's operands cross HBM -> shared memory exactly once);
+//   issuer (warp 1, one thread)  a polling state machine over the two query tiles: S_g = Q_g K^T as soon as group g has given
+//                                its accumulator back and the operands have landed, O_g = P_g V as soon as P_g is packed;
+//   softmax group g (4 warps)    one thread per query row of tile g: max / exp2 / sum from TMEM, P packed to bf16 in place
+//                                (A operand of P.V), O scaled and staged through the dead Q_g tile, one TMA store.
+// Group 1 starts half a period late, so one group's exponentials (the MUFU pipe is the floor of this kernel: T^2 per head)
+// run under the other group's MMA / read-out phases.  Warps whose 32 rows are all beyond T (rows 224..255 at T = 197) skip
+// the arithmetic and only keep the barriers moving.  TMEM: two 256-column regions {S [0,NK) -> P [0,NK/2); O [192,256)}.
+constexpr int kFwdThreads = 320;  // warp 0 loader, warp 1 issuer / TMEM owner, warps 2-5 group 0, warps 6-9 group 1
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+template <bool STAGGER>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
+                        int T, int C, int NH, int NK, int total_heads) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    constexpr uint32_t STAGE = 6 * TILE_BYTES;  // Q_0 Q_1 K_0 K_1 V_0 V_1
+    const uint32_t bar0 = base + 2 * STAGE;
+    const uint32_t full_qk = bar0, full_v = bar0 + 16, s_ready = bar0 + 32, p_ready = bar0 + 48, o_ready = bar0 + 64,
+                   tmem_free = bar0 + 80, stage_free = bar0 + 96;  // two barriers each
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 112);
+    constexpr uint32_t TMEM_COLS = 512, REGION = 256, cO = REGION - HS;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nheads = (total_heads - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // heads of this CTA
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_out);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(full_qk + 8 * i, 1);
+            mbar_init(full_v + 8 * i, 1);
+            mbar_init(s_ready + 8 * i, 1);
+            mbar_init(p_ready + 8 * i, 128);
+            mbar_init(o_ready + 8 * i, 1);
+            mbar_init(tmem_free + 8 * i, 128);
+            mbar_init(stage_free + 8 * i, 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32((const void*)slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================================ loader ================================
+            for (int G = 0; G < nheads; ++G) {
+                const int bh = (int)blockIdx.x + G * (int)gridDim.x, b = bh / NH, h = bh - b * NH;
+                const int st = G & 1;
+                const uint32_t sQ = base + st * STAGE, sK = sQ + 2 * TILE_BYTES, sV = sK + 2 * TILE_BYTES;
+                if (G >= 2) mbar_wait(stage_free + 8 * st, (uint32_t)(((G >> 1) - 1) & 1));  // both groups are done with head G - 2
+                mbar_expect_tx(full_qk + 8 * st, (uint32_t)(4 * TILE_BYTES));
+                tma_load_3d(sK, &tm_qkv, full_qk + 8 * st, C + h * HS, 0, b);
+                tma_load_3d(sQ, &tm_qkv, full_qk + 8 * st, h * HS, 0, b);
+                tma_load_3d(sK + TILE_BYTES, &tm_qkv, full_qk + 8 * st, C + h * HS, TILE, b);
+                tma_load_3d(sQ + TILE_BYTES, &tm_qkv, full_qk + 8 * st, h * HS, TILE, b);
+                mbar_expect_tx(full_v + 8 * st, (uint32_t)(2 * TILE_BYTES));
+                tma_load_3d(sV, &tm_qkv, full_v + 8 * st, 2 * C + h * HS, 0, b);
+                tma_load_3d(sV + TILE_BYTES, &tm_qkv, full_v + 8 * st, 2 * C + h * HS, TILE, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================================ issuer ================================
+            const uint32_t idesc_s = make_idesc(TILE, NK, 0, 0);   // S = Q K^T: both operands K-major
+            const uint32_t idesc_o = make_idesc(TILE, HS, 0, 1);   // O = P V: A = P from TMEM, B = V MN-major
+            int nS[2] = {0, 0}, nPV[2] = {0, 0};
+            while (nPV[0] < nheads || nPV[1] < nheads) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    if (nPV[g] < nS[g]) {
+                        const int G = nPV[g], st = G & 1;
+                        if (mbar_test(p_ready + 8 * g, (uint32_t)(G & 1)) && mbar_test(full_v + 8 * st, (uint32_t)((G >> 1) & 1))) {
+                            tc_fence_after();
+                            const uint32_t region = tmem_base + (uint32_t)g * REGION;
+                            const uint64_t dv = make_desc(base + st * STAGE + 4 * TILE_BYTES, TILE_BYTES, 1024);
+                            for (int k16 = 0; k16 < NK / 16; ++k16) umma_bf16_ts(region + cO, region + k16 * 8, dv + 128 * k16, idesc_o, k16 > 0);
+                            umma_commit(o_ready + 8 * g);
+                            nPV[g] = G + 1;
+                        }
+                    } else if (nS[g] < nheads) {
+                        const int G = nS[g], st = G & 1;
+                        // group 1 enters half a period behind group 0: its first scores wait for group 0's first probabilities
+                        const bool held = STAGGER && g == 1 && G == 0 && nPV[0] == 0 && nheads > 0;
+                        if (!held && (G == 0 || mbar_test(tmem_free + 8 * g, (uint32_t)((G - 1) & 1))) &&
+                            mbar_test(full_qk + 8 * st, (uint32_t)((G >> 1) & 1))) {
+                            tc_fence_after();
+                            const uint32_t sQ = base + st * STAGE;
+                            const uint64_t dq = make_desc(sQ + g * TILE_BYTES, 0, 1024), dk = make_desc(sQ + 2 * TILE_BYTES, 0, 1024);
+#pragma unroll
+                            for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + (uint32_t)g * REGION, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+                            umma_commit(s_ready + 8 * g);
+                            nS[g] = G + 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ================================ softmax groups ================================
+        const int g = (warp - 2) >> 2;
+        const int r = (warp & 3) * 32 + lane;  // TMEM lane = query row within the tile
+        const int q = g * TILE + r;
+        const bool warp_live = g * TILE + (warp & 3) * 32 < T;
+        const bool store_leader = ((warp - 2) & 3) == 0 && lane == 0;
+        const uint32_t lane_addr = tmem_base + (uint32_t)g * REGION + ((uint32_t)((warp & 3) * 32) << 16);
+        const int nchunks = (NK + 31) >> 5;
+        const float scale = 1.0f / sqrtf((float)HS);
+        const float sl2 = kLog2e * scale;
+        int pending_stage = -1;  // leader: stage whose O store still has to be confirmed read
+        for (int G = 0; G < nheads; ++G) {
+            const int bh = (int)blockIdx.x + G * (int)gridDim.x, b = bh / NH, h = bh - b * NH;
+            const int st = G & 1;
+            const uint32_t par = (uint32_t)(G & 1);
+            const uint32_t sO = base + st * STAGE + g * TILE_BYTES;  // the dead Q_g tile of this stage
+            mbar_wait(s_ready + 8 * g, par);
+            tc_fence_after();
+            if (store_leader && pending_stage >= 0) {
+                // the previous head's O store was issued a whole S MMA ago and has read its staging tile by now: tell the loader that
+                // the stage may be refilled (it then has more than a head's time to fetch head G + 1)
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive_cnt(stage_free + 8 * pending_stage);
+                pending_stage = -1;
+            }
+            float mx = -INFINITY, sum = 0.f;
+            if (warp_live) {
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + ch * 32, v);
+                    if (ch * 32 + 32 <= T) {
+                        float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+                        for (int c = 4; c < 32; c += 4) {
+                            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 1])));
+                            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
+                        }
+                        mx = fmaxf(mx, fmaxf(m0, m1));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (ch * 32 + c < T) mx = fmaxf(mx, __uint_as_float(v[c]));
+                    }
+                }
+                const float mxs = mx * sl2;
+                const float2 sl22 = splat2(sl2), nmx2 = splat2(-mxs);
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    uint32_t v[32], pk[16];
+                    tmem_ld32(lane_addr + ch * 32, v);
+                    if (ch * 32 + 32 <= T) {
+                        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {  // one packed FMA per pair of scores
+                            const float2 a = fma2(make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1])), sl22, nmx2);
+                            const float p0 = ex2(a.x), p1 = ex2(a.y);
+                            s0 += p0;
+                            s1 += p1;
+                            pk[c] = pack_bf16(p0, p1);
+                        }
+                        sum += s0 + s1;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const int k = ch * 32 + 2 * c;
+                            const float p0 = k < T ? ex2(__uint_as_float(v[2 * c]) * sl2 - mxs) : 0.f;
+                            const float p1 = k + 1 < T ? ex2(__uint_as_float(v[2 * c + 1]) * sl2 - mxs) : 0.f;
+                            sum += p0 + p1;
+                            pk[c] = pack_bf16(p0, p1);
+                        }
+                    }
+                    tmem_st16(lane_addr + ch * 16, pk);  // in place: columns [16ch, 16ch+16) were consumed by chunk ch/2 <= ch
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            mbar_arrive_cnt(p_ready + 8 * g);
+            mbar_wait(o_ready + 8 * g, par);
+            tc_fence_after();
+            if (warp_live) {
+                const float inv = 1.0f / sum;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + cO + half * 32, v);
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8)
+                        st_shared_v4(sw128(sO, r, half * 4 + g8), pack_bf16(__uint_as_float(v[g8 * 8]) * inv, __uint_as_float(v[g8 * 8 + 1]) * inv),
+                                     pack_bf16(__uint_as_float(v[g8 * 8 + 2]) * inv, __uint_as_float(v[g8 * 8 + 3]) * inv),
+                                     pack_bf16(__uint_as_float(v[g8 * 8 + 4]) * inv, __uint_as_float(v[g8 * 8 + 5]) * inv),
+                                     pack_bf16(__uint_as_float(v[g8 * 8 + 6]) * inv, __uint_as_float(v[g8 * 8 + 7]) * inv));
+                }
+                if (q < T) lse[(long)bh * T + q] = mx * scale + logf(sum);
+            }
+            tc_fence_before();
+            mbar_arrive_cnt(tmem_free + 8 * g);  // S_g of the next head may overwrite this region
+            fence_proxy_async();
+            named_bar_sync(1 + g, 128);
+            if (store_leader) {
+                tma_store_3d(&tm_out, sO, h * HS, g * TILE, b);  // rows >= T are clipped by the tensor map
+                pending_stage = st;
+            }
+        }
+        if (store_leader) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the last stores are complete before shared memory is retired
+            if (pending_stage >= 0) mbar_arrive_cnt(stage_free + 8 * pending_stage);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -553,7 +674,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 }
 
 
-// ---- backward, one CTA per (batch, head), software-pipelined (non-causal, T <= 256) ---------------------
+// ---- backward, software-pipelined and persistent (non-causal, T <= 256) -----------------------------------
 // Same five matmuls as attn_bwd_tc_kernel, but the work is cut into (128-key tile j) x (64-query sub-tile s)
 // iterations and three agents run concurrently:
 //   issuer (one thread)  : S^T / dP^T MMAs of iteration n+1 are in flight while iteration n is in its SIMT phase,
@@ -571,243 +692,11 @@ __device__ __forceinline__ int sub_at(int j, int t, int nsub) {
     return ((j & 1) && !(nsub & 1) && t >= nsub - 2) ? 2 * nsub - 3 - t : t;
 }
 
-__device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-__global__ void __launch_bounds__(kPipeThreads, 1)
-attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                     const __grid_constant__ CUtensorMap tm_dqkv, bf16* __restrict__ dqkv, const float* __restrict__ lse,
-                     const float* __restrict__ dsum, int T, int C, int NH, int NT, int accumulate) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sQ = base, sK = sQ + NT * TILE_BYTES, sV = sK + NT * TILE_BYTES, sdO = sV + NT * TILE_BYTES;
-    const uint32_t sdS = sdO + NT * TILE_BYTES;            // 4 x [128 keys][64 queries] bf16, 128B-swizzled
-    const uint32_t sStat = sdS + 4 * TILE_BYTES;           // lse*log2e [256], D [256]
-    const uint32_t bar0 = sStat + 2 * 256 * 4;
-    const uint32_t bar_load = bar0, s_full = bar0 + 8, bar_load1 = bar0 + 24, p_full = bar0 + 40, ds_free = bar0 + 56,  // [2],[2],[2],[4]
-                   acc_full = bar0 + 88, acc_free = bar0 + 96, dq_full = bar0 + 104;
-    float* stat = reinterpret_cast<float*>(gen + (sStat - base));
-    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 112);
-    constexpr uint32_t TMEM_COLS = 512, cDV = 256, cDK = 320, cDQ = 384;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bh = blockIdx.x, b = bh / NH, h = bh - b * NH;
-    const int NSUB = (T + SUB - 1) / SUB;   // 64-query sub-tiles
-    const int N = NT * NSUB;                // iterations: n = j * NSUB + s
-    if (tid == 0) {
-        tma_prefetch_desc(&tm_qkv);
-        tma_prefetch_desc(&tm_do);
-        mbar_init(bar_load, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(bar_load1 + 8 * i, 1); mbar_init(p_full + 8 * i, 128); }
-        for (int i = 0; i < 4; ++i) mbar_init(ds_free + 8 * i, 1);
-        mbar_init(acc_full, 1);
-        mbar_init(acc_free, 256);
-        mbar_init(dq_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // the first two iterations need only the first 128 rows of each operand: those are published on their own barrier
-        for (int i = 0; i < NT; ++i) {
-            const uint32_t bl = i == 0 ? bar_load : bar_load1;
-            mbar_expect_tx(bl, (uint32_t)(4 * TILE_BYTES));
-            tma_load_3d(sK + i * TILE_BYTES, &tm_qkv, bl, C + h * HS, i * TILE, b);
-            tma_load_3d(sQ + i * TILE_BYTES, &tm_qkv, bl, h * HS, i * TILE, b);
-            tma_load_3d(sV + i * TILE_BYTES, &tm_qkv, bl, 2 * C + h * HS, i * TILE, b);
-            tma_load_3d(sdO + i * TILE_BYTES, &tm_do, bl, h * HS, i * TILE, b);
-        }
-    }
-    if (warp == 1) tmem_alloc(smem_u32((const void*)slot), TMEM_COLS);
-    for (int i = tid; i < 256; i += kPipeThreads) {
-        stat[i] = i < T ? lse[(long)bh * T + i] * kLog2e : 0.f;
-        stat[256 + i] = i < T ? dsum[(long)bh * T + i] : 0.f;
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *slot;
-    const float scale = 1.0f / sqrtf((float)HS);
-    const float sl2 = kLog2e * scale;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ================================ issuer ================================
-            // Every shared-memory descriptor is built once; per-MMA descriptors are the base plus a byte offset >> 4 in the
-            // start-address field (the issuing thread is on the critical path: ~40 MMAs per iteration).
-            mbar_wait(bar_load, 0);
-            tc_fence_after();
-            const uint32_t idesc_kk = make_idesc(TILE, HS, 0, 1);
-            const uint32_t idesc_mn = make_idesc(TILE, HS, 1, 1);
-            const uint64_t dK_k = make_desc(sK, 0, 1024), dV_k = make_desc(sV, 0, 1024);          // K-major A operands (rows = keys)
-            const uint64_t dQ_k = make_desc(sQ, 0, 1024), ddO_k = make_desc(sdO, 0, 1024);        // K-major B operands (rows = queries)
-            const uint64_t dQ_mn = make_desc(sQ, TILE_BYTES, 1024), ddO_mn = make_desc(sdO, TILE_BYTES, 1024);  // MN-major B operands
-            const uint64_t dK_mn = make_desc(sK, TILE_BYTES, 1024);
-            const uint64_t ddS_k = make_desc(sdS, 0, 1024), ddS_mn = make_desc(sdS, TILE_BYTES, 1024);
-            auto off = [](uint32_t bytes) { return (uint64_t)(bytes >> 4); };
-            // S^T and dP^T of iteration n into buffer n & 1.  tcgen05.mma executes in issue order, so the MMAs that overwrite a
-            // buffer need no barrier against the dV MMAs of iteration n - 2 that read P^T from it: they are issued after them.
-            bool tile1_ready = false;
-            auto issue_scores = [&](int n) {
-                const int j = n / NSUB, s_ = sub_at(j, n - j * NSUB, NSUB), bx = n & 1;
-                if ((j > 0 || s_ >= TILE / SUB) && !tile1_ready) {  // first use of rows >= 128 of Q / dO / K / V
-                    mbar_wait(bar_load1, 0);
-                    tc_fence_after();
-                    tile1_ready = true;
-                }
-                const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
-                const uint32_t idesc = make_idesc(TILE, nq16, 0, 0);
-                const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES), ko = off(j * TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + bx * 128, dK_k + ko + 2 * k, dQ_k + qo + 2 * k, idesc, k > 0);
-#pragma unroll
-                for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + bx * 128 + 64, dV_k + ko + 2 * k, ddO_k + qo + 2 * k, idesc, k > 0);
-                umma_commit(s_full + 8 * bx);
-            };
-            uint32_t done_mask = 0u;  // sub-tiles of the current key tile whose dS^T is in shared memory
-            issue_scores(0);
-            if (N > 1) issue_scores(1);
-            for (int m = 0; m < N; ++m) {
-                // dV, dK of iteration m, then the scores of m + 2 (the group that finished m is waiting for them), then dQ
-                const int j = m / NSUB, t_ = m - j * NSUB, s_ = sub_at(j, t_, NSUB), bx = m & 1;
-                const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
-                const int nk16 = (min(TILE, T - j * TILE) + 15) & ~15;
-                const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES);
-                if (t_ == 0) done_mask = 0u;
-                mbar_wait(p_full + 8 * bx, (uint32_t)((m >> 1) & 1));
-                tc_fence_after();
-                if (t_ == 0 && j > 0) {  // the previous key tile's dV / dK have been read out
-                    mbar_wait(acc_free, (uint32_t)((j - 1) & 1));
-                    tc_fence_after();
-                }
-                const uint64_t so = off((s_ & 3) * TILE_BYTES);
-                for (int k16 = 0; k16 < nq16 / 16; ++k16) {
-                    const uint32_t acc = (t_ > 0 || k16 > 0) ? 1u : 0u;
-                    umma_bf16_ts(tmem_base + cDV, tmem_base + bx * 128 + k16 * 8, ddO_mn + qo + 128 * k16, idesc_kk, acc);
-                    umma_bf16(tmem_base + cDK, ddS_k + so + 2 * k16, dQ_mn + qo + 128 * k16, idesc_kk, acc);
-                }
-                if (m + 2 < N) issue_scores(m + 2);
-                done_mask |= 1u << s_;
-                const int partner = s_ ^ 1;
-                if (partner >= NSUB || ((done_mask >> partner) & 1u)) {  // query tile i = s/2 is complete for this key tile: dQ_i += dS K_j
-                    const int i = s_ >> 1;
-                    const uint64_t ao = off((2 * i) * TILE_BYTES), ko = off(j * TILE_BYTES);
-                    for (int k16 = 0; k16 < nk16 / 16; ++k16)
-                        umma_bf16(tmem_base + cDQ + i * HS, ddS_mn + ao + 128 * k16, dK_mn + ko + 128 * k16, idesc_mn, (j > 0 || k16 > 0) ? 1u : 0u);
-                    umma_commit(ds_free + 8 * ((2 * i) & 3));
-                    if (2 * i + 1 < NSUB) umma_commit(ds_free + 8 * ((2 * i + 1) & 3));
-                }
-                if (t_ == NSUB - 1) umma_commit(acc_full);
-            }
-            umma_commit(dq_full);
-        }
-    } else if (warp >= 4) {
-        // ================================ SIMT groups ================================
-        const int g = (warp - 4) >> 2;          // group 0 / 1
-        const int r = (warp & 3) * 32 + lane;   // TMEM lane = key within the tile / output row
-        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-        // dV_j (group 0) / dK_j (group 1): staged through the dead V_j / K_j tile, one TMA store each
-        auto store_acc = [&](int j) {
-            const int key = j * TILE + r;
-            mbar_wait(acc_full, (uint32_t)(j & 1));
-            tc_fence_after();
-            const uint32_t tile = (g == 0 ? sV : sK) + j * TILE_BYTES;  // every MMA that read it has retired (acc_full)
-            const long gcol = (g == 0 ? 2 * C : C) + h * HS;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_off + (g == 0 ? cDV : cDK) + half * 32, v);
-                stage_half_row(tile, r, half, v, (accumulate && key < T) ? dqkv + ((long)b * T + key) * 3 * C + gcol + half * 32 : nullptr);
-            }
-            tc_fence_before();
-            mbar_arrive_cnt(acc_free);  // the accumulators are free; the store below only reads shared memory
-            fence_proxy_async();
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-            if ((warp & 3) == 0 && lane == 0) tma_store_3d(&tm_dqkv, tile, (int)gcol, j * TILE, b);
-        };
-        // The group that owns the first iteration of key tile j + 1 reads out tile j only after that iteration: its scores are
-        // already in tensor memory, whereas acc_full(j) still waits for the other group's last iteration of tile j.
-        int pending = -1;
-        for (int j = 0; j < NT; ++j) {
-            const int key = j * TILE + r;
-            for (int t_ = 0; t_ < NSUB; ++t_) {
-                const int n = j * NSUB + t_;
-                if ((n & 1) != g) continue;
-                const int s_ = sub_at(j, t_, NSUB);
-                const int nq = min(SUB, T - s_ * SUB), nq16 = (nq + 15) & ~15;
-                const uint32_t xb = tmem_base + lane_off + (uint32_t)(g * 128);
-                mbar_wait(s_full + 8 * g, (uint32_t)((n >> 1) & 1));
-                tc_fence_after();
-                const int bs = s_ & 3;
-                const uint32_t sbuf = sdS + bs * TILE_BYTES;
-                if (j > 0) mbar_wait(ds_free + 8 * bs, (uint32_t)((j - 1) & 1));  // the MMAs that read this tile last time have retired
-                const int nch = (nq16 + 31) >> 5;
-                for (int ch = 0; ch < nch; ++ch) {
-                    uint32_t sv[32], dp[32], pk[16];
-                    tmem_ld32(xb + ch * 32, sv);
-                    tmem_ld32(xb + 64 + ch * 32, dp);
-                    const int q0 = s_ * SUB + ch * 32;             // first query of the chunk (q0 + 31 < 256)
-                    const bool full = key < T && ch * 32 + 32 <= nq;  // warp-uniform except for the key tail: no per-element masks
-#pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) {
-                        // lse*log2e and D of the 8 queries: two 16-byte broadcast loads each instead of 16 scalar loads
-                        const float4 l0 = *reinterpret_cast<const float4*>(stat + q0 + g8 * 8), l1 = *reinterpret_cast<const float4*>(stat + q0 + g8 * 8 + 4);
-                        const float4 d0 = *reinterpret_cast<const float4*>(stat + 256 + q0 + g8 * 8), d1 = *reinterpret_cast<const float4*>(stat + 256 + q0 + g8 * 8 + 4);
-                        const float lq[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-                        const float dq[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-                        float ds[8], pv[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const int qc = ch * 32 + g8 * 8 + c;
-                            const float e = ex2(__uint_as_float(sv[g8 * 8 + c]) * sl2 - lq[c]);
-                            pv[c] = (full || (key < T && qc < nq)) ? e : 0.f;
-                            ds[c] = pv[c] * (__uint_as_float(dp[g8 * 8 + c]) - dq[c]) * scale;
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) pk[g8 * 4 + c] = pack_bf16(pv[2 * c], pv[2 * c + 1]);
-                        st_shared_v4(sw128(sbuf, r, ch * 4 + g8), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
-                                     pack_bf16(ds[6], ds[7]));
-                    }
-                    tmem_st16(xb + ch * 16, pk);  // P^T in place: columns [16ch, 16ch+16) were consumed by chunk <= ch
-                }
-                tmem_st_wait();
-                fence_proxy_async();
-                tc_fence_before();
-                mbar_arrive_cnt(p_full + 8 * g);
-                if (pending >= 0) {
-                    store_acc(pending);
-                    pending = -1;
-                }
-            }
-            if (j + 1 < NT && (((j + 1) * NSUB) & 1) == g) pending = j;
-            else store_acc(j);
-        }
-        // ---- dQ_0 (group 0) / dQ_1 (group 1) ----
-        mbar_wait(dq_full, 0);
-        tc_fence_after();
-        if (g < NT) {
-            const int q = g * TILE + r;
-            const uint32_t tile = sQ + g * TILE_BYTES;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_off + cDQ + g * HS + half * 32, v);
-                stage_half_row(tile, r, half, v, (accumulate && q < T) ? dqkv + ((long)b * T + q) * 3 * C + h * HS + half * 32 : nullptr);
-            }
-            fence_proxy_async();
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-            if ((warp & 3) == 0 && lane == 0) tma_store_3d(&tm_dqkv, tile, h * HS, g * TILE, b);
-        }
-        if ((warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
-
-// ---- backward, persistent variant of attn_bwd_pipe_kernel: one CTA per SM walks over its (batch, head) pairs ----------
-// A CTA of the kernel above spends 2.9 of its 14.5 us (ViT-B/16) on being launched, allocating tensor memory and waiting for
-// its 128 KB of operands with nothing else resident on the SM (the shared memory it needs excludes a second CTA).  Here the
-// CTA stays, and a loader thread refills each operand tile for the next head as soon as the current head is done with it:
+// ---- the persistent kernel: one CTA per SM walks over its (batch, head) pairs ----------
+// A one-CTA-per-head version of this pipeline spent 2.9 of its 14.5 us (ViT-B/16) on being launched, allocating tensor memory
+// and waiting for its 128 KB of operands with nothing else resident on the SM (the shared memory it needs excludes a second
+// CTA).  Here the CTA stays, and a loader thread refills each operand tile for the next head as soon as the current head is done with it:
 // K_0 / V_0 once the first key tile's dV / dK have left through them, Q and dO when the head's last MMA has retired, K_1 / V_1
 // after the final stores; dQ leaves through the groups' own dS tiles, so the Q tiles carry no staging.  Row statistics are
 // double-buffered and fetched a head ahead by an otherwise idle warp.  Barrier parities are derived from the running head
@@ -1561,17 +1450,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }
 
 int encode_map3d(vitrs_ctx* ctx, CUtensorMap* map, const void* basep, uint64_t cols, uint64_t rows, uint64_t batch, uint32_t box_rows = TILE) {
-    cuuint64_t dims[3] = {cols, rows, batch};
-    cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
-    cuuint32_t box[3] = {HS, box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(basep), dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-        return vitrs_set_error(ctx, VITRS_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d): cols=%llu rows=%llu batch=%llu", (int)r,
-                               (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)batch);
-    return VITRS_OK;
+    const uint64_t dims[3] = {cols, rows, batch};
+    const uint64_t strides[2] = {cols * 2, rows * cols * 2};
+    const uint32_t box[3] = {HS, box_rows, 1};
+    return vitrs_tensor_map(ctx, map, 3, basep, dims, strides, box);
 }
 
 bool tc_shape_ok(const void* a, const void* b_, int t, int c, int nh) {
@@ -1585,44 +1467,33 @@ int op_attention_forward_tc(vitrs_ctx* ctx, bf16* out, float* lse, const bf16* q
     if (b <= 0) return VITRS_OK;
     CUtensorMap tm, tm_out;
     VITRS_TRY(encode_map3d(ctx, &tm, qkv, 3 * (uint64_t)c, t, b));
+    VITRS_TRY(encode_map3d(ctx, &tm_out, out, (uint64_t)c, t, b));
     const int NT = (t + TILE - 1) / TILE;
     const int NK = (t + 15) & ~15;
-    static const bool use_v1 = getenv("VITRS_ATTN_FWD_V1") != nullptr;  // A/B aid: the two-tiles-per-CTA kernel with P in shared memory
-    static const bool force_stream = getenv("VITRS_ATTN_FWD_STREAM") != nullptr;  // test aid: streaming kernel at any T
-    if (t > 2 * TILE || force_stream) {
-        VITRS_TRY(encode_map3d(ctx, &tm_out, out, (uint64_t)c, t, b));
+    if (t > 2 * TILE || ctx->env_attn_fwd_stream) {  // VITRS_ATTN_FWD_STREAM (test aid): the streaming kernel at any T
         const size_t smem = (size_t)5 * TILE_BYTES + 64 + 1024;
-        static bool configured_s = false;
-        if (!configured_s) {
-            VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured_s = true;
-        }
+        VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_fwd_stream_kernel, smem));
         attn_fwd_stream_kernel<<<b * nh * NT, 128, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, causal);
         VITRS_LAUNCHED(ctx);
         return VITRS_OK;
     }
-    if (!use_v1) {
-        VITRS_TRY(encode_map3d(ctx, &tm_out, out, (uint64_t)c, t, b));
-        const size_t smem = (size_t)(1 + 2 * NT) * TILE_BYTES + 64 + 1024;
-        const uint32_t tmem_cols = NK <= 128 ? 128 : 256;
-        static size_t configured2 = 0;
-        if (smem > configured2) {
-            VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured2 = smem;
+    if (NT == 2 && !causal && !ctx->env_attn_fwd_legacy) {  // VITRS_ATTN_FWD_LEGACY (A/B aid): one CTA per query tile
+        const size_t smem = (size_t)12 * TILE_BYTES + 128 + 1024;
+        const int heads = b * nh, grid = heads < ctx->sm_count ? heads : ctx->sm_count;
+        if (ctx->env_attn_fwd_nostagger) {
+            VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_fwd_persist_kernel<false>, smem));
+            attn_fwd_persist_kernel<false><<<grid, kFwdThreads, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, NK, heads);
+        } else {
+            VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_fwd_persist_kernel<true>, smem));
+            attn_fwd_persist_kernel<true><<<grid, kFwdThreads, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, NK, heads);
         }
-        attn_fwd_tc2_kernel<<<b * nh * NT, 128, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, causal, NT, NK, tmem_cols);
         VITRS_LAUNCHED(ctx);
         return VITRS_OK;
     }
-    const int NKB = (NK + 63) >> 6;
-    const size_t smem = (size_t)NT * 3 * TILE_BYTES + (size_t)NT * NKB * TILE_BYTES + 64 + 1024;
-    const uint32_t tmem_cols = NT == 1 ? 128 : 512;
-    static size_t configured = 0;
-    if (smem > configured) {
-        VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    attn_fwd_tc_kernel<<<b * nh, kThreads, smem, ctx->stream>>>(tm, out, lse, t, c, nh, causal, NT, NK, tmem_cols);
+    const size_t smem = (size_t)(1 + 2 * NT) * TILE_BYTES + 64 + 1024;
+    const uint32_t tmem_cols = NK <= 128 ? 128 : 256;
+    VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_fwd_tc2_kernel, smem));
+    attn_fwd_tc2_kernel<<<b * nh * NT, 128, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, causal, NT, NK, tmem_cols);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
 }
@@ -1649,8 +1520,7 @@ int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const
     const int NT = (t + TILE - 1) / TILE;
     // T <= 256: the one-CTA-per-head kernel (5 matmuls, dQ kept in TMEM) is faster (measured 139.6 vs 143.8 ms per
     // ViT-B/16 step); longer sequences take the two streaming kernels.  VITRS_ATTN_BWD_STREAM forces them (test / A-B aid).
-    static const bool force_stream = getenv("VITRS_ATTN_BWD_STREAM") != nullptr;
-    if (t > 2 * TILE || force_stream) {
+    if (t > 2 * TILE || ctx->env_attn_bwd_stream) {
         CUtensorMap tm_q128, tm_q64, tm_do128, tm_do64, tm_dqkv;
         VITRS_TRY(encode_map3d(ctx, &tm_q128, qkv, 3 * (uint64_t)c, t, b, TILE));
         VITRS_TRY(encode_map3d(ctx, &tm_q64, qkv, 3 * (uint64_t)c, t, b, SUB));
@@ -1659,16 +1529,8 @@ int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const
         VITRS_TRY(encode_map3d(ctx, &tm_dqkv, dqkv, 3 * (uint64_t)c, t, b, TILE));
         const size_t smem_kv = (size_t)2 * TILE_BYTES + 4 * SUB_BYTES + 64 + 2 * (size_t)t * 4 + 1024;
         const size_t smem_q = (size_t)2 * TILE_BYTES + 4 * SUB_BYTES + 64 + 1024;
-        static size_t conf_kv = 0;
-        static bool conf_q = false;
-        if (smem_kv > conf_kv) {
-            VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
-            conf_kv = smem_kv;
-        }
-        if (!conf_q) {
-            VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
-            conf_q = true;
-        }
+        VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_bwd_dkv_kernel, smem_kv));
+        VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_bwd_dq_kernel, smem_q));
         attn_bwd_dkv_kernel<<<b * nh * NT, kThreads, smem_kv, ctx->stream>>>(tm_q128, tm_q64, tm_do64, tm_dqkv, dqkv, lse, dsum, t, c, nh, causal,
                                                                            accumulate);
         VITRS_LAUNCHED(ctx);
@@ -1680,40 +1542,18 @@ int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const
     CUtensorMap tm_qkv, tm_do;
     VITRS_TRY(encode_map3d(ctx, &tm_qkv, qkv, 3 * (uint64_t)c, t, b));
     VITRS_TRY(encode_map3d(ctx, &tm_do, dout, (uint64_t)c, t, b));
-    static const bool use_v1 = getenv("VITRS_ATTN_BWD_V1") != nullptr;  // A/B aid: the unpipelined kernel
-    if (!causal && !use_v1) {
-        const size_t smem_p = (size_t)NT * 4 * TILE_BYTES + 4 * TILE_BYTES + 2 * 256 * 4 + 128 + 1024;
-        static size_t conf_p = 0;
-        if (smem_p > conf_p) {
-            VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-            conf_p = smem_p;
-        }
+    if (!causal) {
+        const size_t smem_s = (size_t)NT * 4 * TILE_BYTES + 4 * TILE_BYTES + 4 * 256 * 4 + 256 + 1024;
+        VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_bwd_persist_kernel, smem_s));
         CUtensorMap tm_dq;
         VITRS_TRY(encode_map3d(ctx, &tm_dq, dqkv, 3 * (uint64_t)c, t, b));
-        static const bool persist = getenv("VITRS_ATTN_BWD_NOPERSIST") == nullptr;  // A/B aid: one CTA per (batch, head)
-        if (persist) {
-            const size_t smem_s = smem_p + 2 * 256 * 4 + 128;
-            static size_t conf_s = 0;
-            if (smem_s > conf_s) {
-                VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-                conf_s = smem_s;
-            }
-            const int heads = b * nh, grid = heads < ctx->sm_count ? heads : ctx->sm_count;
-            attn_bwd_persist_kernel<<<grid, kPipeThreads, smem_s, ctx->stream>>>(tm_qkv, tm_do, tm_dq, dqkv, lse, dsum, t, c, nh, NT, accumulate,
-                                                                                 heads);
-            VITRS_LAUNCHED(ctx);
-            return VITRS_OK;
-        }
-        attn_bwd_pipe_kernel<<<b * nh, kPipeThreads, smem_p, ctx->stream>>>(tm_qkv, tm_do, tm_dq, dqkv, lse, dsum, t, c, nh, NT, accumulate);
+        const int heads = b * nh, grid = heads < ctx->sm_count ? heads : ctx->sm_count;
+        attn_bwd_persist_kernel<<<grid, kPipeThreads, smem_s, ctx->stream>>>(tm_qkv, tm_do, tm_dq, dqkv, lse, dsum, t, c, nh, NT, accumulate, heads);
         VITRS_LAUNCHED(ctx);
         return VITRS_OK;
     }
     const size_t smem = (size_t)NT * 4 * TILE_BYTES + 4 * TILE_BYTES + 2 * 256 * 4 + 64 + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        VITRS_CUDA(ctx, cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_bwd_tc_kernel, smem));
     attn_bwd_tc_kernel<<<b * nh, kThreads, smem, ctx->stream>>>(tm_qkv, tm_do, dqkv, lse, dsum, t, c, nh, causal, NT, accumulate);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;

@@ -16,6 +16,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+struct AdamHyper;
 struct vitrs_ctx {
     int device;
     int sm_count;
@@ -36,8 +37,32 @@ struct vitrs_ctx {
     // NCCL (resolved with dlopen)
     void* nccl_lib;
     void* nccl_comm;
-    int rank, world;
+    int rank, world, nccl_max_ctas;
+    // per-context (= per-device) record of the dynamic shared memory opt-in of each kernel: the attribute belongs to the
+    // device, so a process-wide flag would skip it on a second GPU
+    struct { const void* fn; size_t bytes; } func_smem[96];
+    int func_smem_count;
+    // tensor maps are pure functions of (base, extents, strides, box): encoded once, then served from this table
+    struct vitrs_map_entry* map_cache;
+    int map_cache_used;
+    // diagnostic switches, read once at context creation
+    int env_gemm_cg1, env_gemm_splits, env_dp_defer, env_attn_fwd_stream, env_attn_bwd_stream, env_attn_bwd_overwrite,
+        env_no_map_cache, env_attn_fwd_legacy, env_attn_fwd_nostagger, env_gemm_static;
+    // device-side error flags raised by kernels (bit 0: class label out of range), reported by vitrs_model_mean_loss
+    int* dev_flags;
+    AdamHyper* d_hyper;  // AdamW hyper-parameters of the current step (same allocation as dev_flags)
 };
+
+// collectives on the comm stream (ctx.cu; dtype 0 = fp32, 1 = bf16); no-ops without a communicator
+int vitrs_nccl_allreduce(vitrs_ctx* ctx, const void* send, void* recv, size_t count, int dtype);
+int vitrs_nccl_reduce_scatter(vitrs_ctx* ctx, const void* send, void* recv, size_t recv_count, int dtype);
+int vitrs_nccl_all_gather(vitrs_ctx* ctx, const void* send, void* recv, size_t send_count, int dtype);
+int vitrs_nccl_group(vitrs_ctx* ctx, int begin);
+// opt a kernel in to `bytes` of dynamic shared memory on this context's device (no-op when already done)
+int vitrs_func_smem(vitrs_ctx* ctx, const void* fn, size_t bytes);
+// cached cuTensorMapEncodeTiled: bf16 elements, 128B swizzle, rank 2 or 3; strides in BYTES (rank - 1 of them)
+int vitrs_tensor_map(vitrs_ctx* ctx, CUtensorMap* out, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box);
 
 int vitrs_set_error(vitrs_ctx* ctx, int code, const char* fmt, ...);
 int vitrs_ensure_scratch(vitrs_ctx* ctx, size_t floats);
@@ -242,6 +267,18 @@ template <typename T> int op_cls_scatter_add(vitrs_ctx*, T* dinp, const float* d
 int op_adamw(vitrs_ctx*, float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,
              float eps, float wd, int step, bf16* shadow);
 int op_sgd(vitrs_ctx*, float* p, const float* g, size_t n, float lr, bf16* shadow);
+// AdamW split for CUDA-graph replay and ZeRO-1: hyper-parameters go to device memory once per step, the update reads them
+struct AdamHyper { float lr, b1, b2, eps, wd, step_size, bc2_sqrt, pad; };
+int op_adam_set_hyper(vitrs_ctx*, float lr, float b1, float b2, float eps, float wd, int step, cudaStream_t stream);
+int op_adamw_apply(vitrs_ctx*, float* p, const float* g, float* m, float* v, size_t n, bf16* shadow, cudaStream_t stream);
+int op_adamw_apply_shard(vitrs_ctx*, float* p, bf16* gz, float* m, float* v, size_t n, cudaStream_t stream);
+// slices of one gradient bucket: flat (tensor-major) offsets, lengths, and offsets in the bucket-major exchange buffer
+struct SliceTable { size_t src_off[12], cnt[12], z_off[12]; int n; };
+int op_pack_f32_to_bf16(vitrs_ctx*, bf16* z, const float* flat, const SliceTable&, cudaStream_t);
+int op_unpack_bf16_to_f32(vitrs_ctx*, float* flat, const bf16* z, const SliceTable&, cudaStream_t);
+int op_unpack_bf16_to_bf16(vitrs_ctx*, bf16* flat, const bf16* z, const SliceTable&, cudaStream_t);
+int op_pack_f32_to_f32(vitrs_ctx*, float* z, const float* flat, const SliceTable&, cudaStream_t);
+int op_unpack_f32_to_f32(vitrs_ctx*, float* flat, const float* z, const SliceTable&, cudaStream_t);
 int op_fill_uniform(vitrs_ctx*, float* dst, size_t n, uint64_t seed, uint64_t stream, float lo, float hi);
 int op_fill_const(vitrs_ctx*, float* dst, size_t n, float v);
 int op_scaled_sum(vitrs_ctx*, float* out_accum, const float* inp, long n, float scale);

@@ -424,19 +424,31 @@ __global__ void softmax_fwd_kernel(float* __restrict__ probs, const float* __res
     for (int i = lane; i < v; i += 32) probs[row * v + i] = expf(z[i] - mx) / s;
 }
 
+// A class label outside [0, v) raises bit 0 of *flags (reported by vitrs_ctx_error_flags / vitrs_model_mean_loss) and the row
+// contributes neither a loss nor a target term: a bad dataset label must not read or write out of bounds.
 __global__ void ce_fwd_kernel(float* __restrict__ losses, const float* __restrict__ probs, const int* __restrict__ targets,
-                              long rows, int v) {
+                              long rows, int v, int* __restrict__ flags) {
     const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < rows) losses[r] = -logf(probs[r * v + targets[r]]);
+    if (r >= rows) return;
+    const int tgt = targets[r];
+    if (tgt < 0 || tgt >= v) {
+        atomicOr(flags, 1);
+        losses[r] = 0.f;
+        return;
+    }
+    losses[r] = -logf(probs[r * v + tgt]);
 }
 
 __global__ void ce_softmax_bwd_kernel(float* __restrict__ dlogits, const float* __restrict__ dlosses,
-                                      const float* __restrict__ probs, const int* __restrict__ targets, long rows, int v) {
+                                      const float* __restrict__ probs, const int* __restrict__ targets, long rows, int v,
+                                      int* __restrict__ flags) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * v) return;
     const long r = i / v;
     const int j = (int)(i - r * v);
-    const float ind = (j == targets[r]) ? 1.f : 0.f;
+    const int tgt = targets[r];
+    if (j == 0 && (tgt < 0 || tgt >= v)) atomicOr(flags, 1);
+    const float ind = (j == tgt) ? 1.f : 0.f;
     dlogits[i] += (probs[i] - ind) * dlosses[r];
 }
 
@@ -445,7 +457,7 @@ __global__ void ce_softmax_bwd_kernel(float* __restrict__ dlogits, const float* 
 // dloss = 1/B) must be zeroed by the caller.
 __global__ void head_loss_kernel(float* __restrict__ probs, float* __restrict__ losses, float* __restrict__ mean_loss,
                                  float* __restrict__ dlogits, const float* __restrict__ logits,
-                                 const int* __restrict__ targets, int rows, int v, float dloss) {
+                                 const int* __restrict__ targets, int rows, int v, float dloss, int* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -457,6 +469,10 @@ __global__ void head_loss_kernel(float* __restrict__ probs, float* __restrict__ 
     for (int i = lane; i < v; i += 32) s += expf(z[i] - mx);
     s = warp_sum(s);
     const int tgt = targets ? targets[row] : -1;
+    if (targets && lane == 0 && (tgt < 0 || tgt >= v)) {
+        atomicOr(flags, 1);
+        losses[row] = 0.f;
+    }
     for (int i = lane; i < v; i += 32) {
         float p = expf(z[i] - mx) / s;
         probs[(long)row * v + i] = p;
@@ -489,14 +505,28 @@ __global__ void cls_scatter_kernel(T* __restrict__ dinp, const float* __restrict
 }
 
 // ---- optimiser (tv:737-743; AdamW per D8, torch.optim.AdamW operation order) -----------------
+// Hyper-parameters live in device memory (written by a one-thread kernel per step) so that a captured CUDA graph of the
+// step replays with the current learning rate and bias corrections.  GZ: gradients arrive as bf16 (the reduce-scattered
+// shard of the gradient exchange buffer, ZeRO-1) and the updated bf16 weight goes back to the same place.
+__global__ void adam_set_hyper_kernel(AdamHyper* dst, AdamHyper h) { *dst = h; }
+
+template <bool GZ>
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                             float step_size, float bc2_sqrt, bf16* __restrict__ shadow) {
+                             float* __restrict__ v, size_t n, const AdamHyper* __restrict__ hp, bf16* shadow) {
+    const AdamHyper h = *hp;
+    const float lr = h.lr, b1 = h.b1, b2 = h.b2, eps = h.eps, wd = h.wd, step_size = h.step_size, bc2_sqrt = h.bc2_sqrt;
     const size_t nv = n / 4;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
         float4 pp = reinterpret_cast<float4*>(p)[i];
-        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float4 gg;
+        if (GZ) {
+            const uint2 raw = reinterpret_cast<const uint2*>(shadow)[i];
+            gg.x = __uint_as_float(raw.x << 16); gg.y = __uint_as_float(raw.x & 0xFFFF0000u);
+            gg.z = __uint_as_float(raw.y << 16); gg.w = __uint_as_float(raw.y & 0xFFFF0000u);
+        } else {
+            gg = reinterpret_cast<const float4*>(g)[i];
+        }
         float4 mm = reinterpret_cast<float4*>(m)[i];
         float4 vv = reinterpret_cast<float4*>(v)[i];
         float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
@@ -521,14 +551,53 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
         }
     }
     for (size_t i = nv * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = GZ ? __bfloat162float(shadow[i]) : g[i];
         float pj = p[i] * (1.0f - lr * wd);
-        float mj = b1 * m[i] + (1.0f - b1) * g[i];
-        float vj = b2 * v[i] + (1.0f - b2) * g[i] * g[i];
+        float mj = b1 * m[i] + (1.0f - b1) * gi;
+        float vj = b2 * v[i] + (1.0f - b2) * gi * gi;
         m[i] = mj;
         v[i] = vj;
         pj = pj - step_size * (mj / (sqrtf(vj) / bc2_sqrt + eps));
         p[i] = pj;
         if (shadow) shadow[i] = __float2bfloat16_rn(pj);
+    }
+}
+
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---- gradient exchange buffer ("Z order": bucket-major, slices of a bucket back to back) ---------------------------
+// One launch moves every slice of a bucket between the tensor-major flat buffers and its contiguous region of the
+// exchange buffer (blockIdx.y = slice).  PACK: z[z_off + i] = cvt(flat[src_off + i]); else flat[src_off + i] = cvt(z[z_off + i]).
+template <typename TF, typename TZ, bool PACK>
+__global__ void slice_copy_kernel(TF* __restrict__ flat, TZ* __restrict__ z, const SliceTable tab) {
+    const int sl = blockIdx.y;
+    const size_t cnt = tab.cnt[sl];
+    TF* f = flat + tab.src_off[sl];
+    TZ* zz = z + tab.z_off[sl];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((tab.src_off[sl] | tab.z_off[sl]) & 3) == 0;
+    const size_t nv = vec ? cnt / 4 : 0;
+    for (size_t i = t0; i < nv; i += stride) {
+        float x[4];
+        if (PACK) {
+            if (sizeof(TF) == 4) { const float4 a = reinterpret_cast<const float4*>(f)[i]; x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; }
+            else { const uint2 a = reinterpret_cast<const uint2*>(f)[i]; x[0] = __uint_as_float(a.x << 16); x[1] = __uint_as_float(a.x & 0xFFFF0000u); x[2] = __uint_as_float(a.y << 16); x[3] = __uint_as_float(a.y & 0xFFFF0000u); }
+            if (sizeof(TZ) == 4) reinterpret_cast<float4*>(zz)[i] = make_float4(x[0], x[1], x[2], x[3]);
+            else { uint2 o; o.x = pack2_bf16(x[0], x[1]); o.y = pack2_bf16(x[2], x[3]); reinterpret_cast<uint2*>(zz)[i] = o; }
+        } else {
+            if (sizeof(TZ) == 4) { const float4 a = reinterpret_cast<const float4*>(zz)[i]; x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; }
+            else { const uint2 a = reinterpret_cast<const uint2*>(zz)[i]; x[0] = __uint_as_float(a.x << 16); x[1] = __uint_as_float(a.x & 0xFFFF0000u); x[2] = __uint_as_float(a.y << 16); x[3] = __uint_as_float(a.y & 0xFFFF0000u); }
+            if (sizeof(TF) == 4) reinterpret_cast<float4*>(f)[i] = make_float4(x[0], x[1], x[2], x[3]);
+            else { uint2 o; o.x = pack2_bf16(x[0], x[1]); o.y = pack2_bf16(x[2], x[3]); reinterpret_cast<uint2*>(f)[i] = o; }
+        }
+    }
+    for (size_t i = nv * 4 + t0; i < cnt; i += stride) {
+        if (PACK) zz[i] = from_f32<TZ>(to_f32(f[i]));
+        else f[i] = from_f32<TF>(to_f32(zz[i]));
     }
 }
 
@@ -652,11 +721,11 @@ static int launch_ln_bwd(vitrs_ctx* ctx, T* dinp, float* dw, float* db, const T*
     const size_t smem = ((size_t)(kThreads / 32 + 1) * c + 4) * sizeof(float);  // reduction scratch, gains, the constant 1
     if (colsum_out) {
         auto k = ln_bwd_kernel<T, MAXNV, true>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 48 * 1024) VITRS_TRY(vitrs_func_smem(ctx, (const void*)k, smem));
         k<<<grid, kThreads, smem, ctx->stream>>>(dinp, dw, db, dout, inp, w, mean, rstd, rows, c, colsum_out);
     } else {
         auto k = ln_bwd_kernel<T, MAXNV, false>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 48 * 1024) VITRS_TRY(vitrs_func_smem(ctx, (const void*)k, smem));
         k<<<grid, kThreads, smem, ctx->stream>>>(dinp, dw, db, dout, inp, w, mean, rstd, rows, c, colsum_out);
     }
     VITRS_LAUNCHED(ctx);
@@ -711,21 +780,21 @@ int op_softmax_forward(vitrs_ctx* ctx, float* probs, const float* logits, long r
 }
 int op_crossentropy_forward(vitrs_ctx* ctx, float* losses, const float* probs, const int* targets, long rows, int v) {
     if (rows <= 0) return VITRS_OK;
-    ce_fwd_kernel<<<ceil_div(rows, 128), 128, 0, ctx->stream>>>(losses, probs, targets, rows, v);
+    ce_fwd_kernel<<<ceil_div(rows, 128), 128, 0, ctx->stream>>>(losses, probs, targets, rows, v, ctx->dev_flags);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
 }
 int op_crossentropy_softmax_backward(vitrs_ctx* ctx, float* dlogits, const float* dlosses, const float* probs,
                                      const int* targets, long rows, int v) {
     if (rows <= 0) return VITRS_OK;
-    ce_softmax_bwd_kernel<<<ceil_div(rows * v, 256), 256, 0, ctx->stream>>>(dlogits, dlosses, probs, targets, rows, v);
+    ce_softmax_bwd_kernel<<<ceil_div(rows * v, 256), 256, 0, ctx->stream>>>(dlogits, dlosses, probs, targets, rows, v, ctx->dev_flags);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
 }
 int op_head_loss(vitrs_ctx* ctx, float* probs, float* losses, float* mean_loss, float* dlogits, const float* logits,
                  const int* targets, int rows, int v, float dloss) {
     if (rows <= 0) return VITRS_OK;
-    head_loss_kernel<<<ceil_div(rows, 4), 128, 0, ctx->stream>>>(probs, losses, mean_loss, dlogits, logits, targets, rows, v, dloss);
+    head_loss_kernel<<<ceil_div(rows, 4), 128, 0, ctx->stream>>>(probs, losses, mean_loss, dlogits, logits, targets, rows, v, dloss, ctx->dev_flags);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
 }
@@ -741,16 +810,64 @@ template <typename T> int op_cls_scatter_add(vitrs_ctx* ctx, T* dinp, const floa
     return VITRS_OK;
 }
 
+int op_adam_set_hyper(vitrs_ctx* ctx, float lr, float b1, float b2, float eps, float wd, int step, cudaStream_t stream) {
+    AdamHyper h;
+    const float bc1 = 1.0f - powf(b1, (float)step);
+    const float bc2 = 1.0f - powf(b2, (float)step);
+    h.lr = lr; h.b1 = b1; h.b2 = b2; h.eps = eps; h.wd = wd; h.step_size = lr / bc1; h.bc2_sqrt = sqrtf(bc2); h.pad = 0.f;
+    adam_set_hyper_kernel<<<1, 1, 0, stream>>>(ctx->d_hyper, h);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+// the update with the hyper-parameters last set on this context (graph-capturable: no step-dependent launch argument)
+int op_adamw_apply(vitrs_ctx* ctx, float* p, const float* g, float* m, float* v, size_t n, bf16* shadow, cudaStream_t stream) {
+    if (n == 0) return VITRS_OK;
+    VITRS_ARG(ctx, aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!shadow || ((uintptr_t)shadow & 7) == 0));
+    adamw_kernel<false><<<grid_for((long)(n / 4 + 1), kThreads, ctx->sm_count), kThreads, 0, stream>>>(p, g, m, v, n, ctx->d_hyper, shadow);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
+// ZeRO-1 shard: gradients are the bf16 values at gz (reduce-scattered), which receives the updated bf16 weights
+int op_adamw_apply_shard(vitrs_ctx* ctx, float* p, bf16* gz, float* m, float* v, size_t n, cudaStream_t stream) {
+    if (n == 0) return VITRS_OK;
+    VITRS_ARG(ctx, aligned16(p) && aligned16(m) && aligned16(v) && ((uintptr_t)gz & 7) == 0);
+    adamw_kernel<true><<<grid_for((long)(n / 4 + 1), kThreads, ctx->sm_count), kThreads, 0, stream>>>(p, nullptr, m, v, n, ctx->d_hyper, gz);
+    VITRS_LAUNCHED(ctx);
+    return VITRS_OK;
+}
 int op_adamw(vitrs_ctx* ctx, float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,
              float eps, float wd, int step, bf16* shadow) {
     if (n == 0) return VITRS_OK;
-    VITRS_ARG(ctx, aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!shadow || ((uintptr_t)shadow & 7) == 0));
-    const float bc1 = 1.0f - powf(b1, (float)step);
-    const float bc2 = 1.0f - powf(b2, (float)step);
-    adamw_kernel<<<grid_for((long)(n / 4 + 1), kThreads, ctx->sm_count), kThreads, 0, ctx->stream>>>(
-        p, g, m, v, n, lr, b1, b2, eps, wd, lr / bc1, sqrtf(bc2), shadow);
+    VITRS_TRY(op_adam_set_hyper(ctx, lr, b1, b2, eps, wd, step, ctx->stream));
+    return op_adamw_apply(ctx, p, g, m, v, n, shadow, ctx->stream);
+}
+
+template <typename TF, typename TZ, bool PACK>
+static int slice_copy(vitrs_ctx* ctx, TF* flat, TZ* z, const SliceTable& tab, cudaStream_t stream) {
+    if (tab.n <= 0) return VITRS_OK;
+    size_t mx = 0;
+    for (int i = 0; i < tab.n; ++i) mx = tab.cnt[i] > mx ? tab.cnt[i] : mx;
+    int gx = (int)((mx / 4 + kThreads) / kThreads);
+    if (gx > 4 * ctx->sm_count) gx = 4 * ctx->sm_count;
+    if (gx < 1) gx = 1;
+    slice_copy_kernel<TF, TZ, PACK><<<dim3(gx, tab.n), kThreads, 0, stream>>>(flat, z, tab);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
+}
+int op_pack_f32_to_bf16(vitrs_ctx* ctx, bf16* z, const float* flat, const SliceTable& tab, cudaStream_t s) {
+    return slice_copy<float, bf16, true>(ctx, const_cast<float*>(flat), z, tab, s);
+}
+int op_unpack_bf16_to_f32(vitrs_ctx* ctx, float* flat, const bf16* z, const SliceTable& tab, cudaStream_t s) {
+    return slice_copy<float, bf16, false>(ctx, flat, const_cast<bf16*>(z), tab, s);
+}
+int op_unpack_bf16_to_bf16(vitrs_ctx* ctx, bf16* flat, const bf16* z, const SliceTable& tab, cudaStream_t s) {
+    return slice_copy<bf16, bf16, false>(ctx, flat, const_cast<bf16*>(z), tab, s);
+}
+int op_pack_f32_to_f32(vitrs_ctx* ctx, float* z, const float* flat, const SliceTable& tab, cudaStream_t s) {
+    return slice_copy<float, float, true>(ctx, const_cast<float*>(flat), z, tab, s);
+}
+int op_unpack_f32_to_f32(vitrs_ctx* ctx, float* flat, const float* z, const SliceTable& tab, cudaStream_t s) {
+    return slice_copy<float, float, false>(ctx, flat, const_cast<float*>(z), tab, s);
 }
 int op_sgd(vitrs_ctx* ctx, float* p, const float* g, size_t n, float lr, bf16* shadow) {
     if (n == 0) return VITRS_OK;

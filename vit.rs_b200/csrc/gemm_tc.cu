@@ -568,29 +568,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---- host side --------------------------------------------------------------------------------
 int encode_map(vitrs_ctx* ctx, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_elems,
                uint32_t box_inner, uint32_t box_outer) {
-    cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {outer_stride_elems * 2};
-    cuuint32_t box[2] = {box_inner, box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-        return vitrs_set_error(ctx, VITRS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu stride=%llu box=%ux%u",
-                               (int)r, (unsigned long long)inner, (unsigned long long)outer,
-                               (unsigned long long)outer_stride_elems, box_inner, box_outer);
-    return VITRS_OK;
+    const uint64_t dims[2] = {inner, outer};
+    const uint64_t strides[1] = {outer_stride_elems * 2};
+    const uint32_t box[2] = {box_inner, box_outer};
+    return vitrs_tensor_map(ctx, map, 2, base, dims, strides, box);
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, int CG>
 int launch_tc(vitrs_ctx* ctx, const CUtensorMap* maps, const TcParams& p) {
     using L = SmemLayout<BN, STAGES, CG>;
     auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, CG>;
-    static bool configured = false;
-    if (!configured) {
-        VITRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        configured = true;
-    }
+    VITRS_TRY(vitrs_func_smem(ctx, (const void*)kern, L::TOTAL));
     const int units = p.m_tiles * p.n_tiles * p.splits;
     const int slots = ctx->sm_count / CG;
     const int grid = CG * (units < slots ? units : slots);
@@ -665,9 +653,7 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     const int BN = g.N > 128 ? 256 : 128;
     // a CTA pair per [256 x 256] tile whenever the problem has that many rows
     int CG = (BN == 256 && g.M > BM) ? 2 : 1;
-    if (const char* ov = getenv("VITRS_GEMM_CG")) {  // tuning aid (scripts/bench_gemm.py)
-        if (atoi(ov) == 1) CG = 1;
-    }
+    if (ctx->env_gemm_cg1) CG = 1;  // VITRS_GEMM_CG=1: tuning aid (scripts/bench_gemm.py)
     CUtensorMap maps[5];  // A, B, out, out2, aux
     CUtensorMap &tmA = maps[0], &tmB = maps[1];
     if (!a_mn) VITRS_TRY(encode_map(ctx, &tmA, g.A, g.K, g.M, g.a_rs, BK, BM));
@@ -709,9 +695,7 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
             if (eff >= 0.92) break;
         }
     }
-    if (const char* ov = getenv("VITRS_GEMM_SPLITS")) {  // tuning aid (scripts/exp_dw.py)
-        if (g.epi.kind == EPI_ACCUM_F32 && atoi(ov) > 0) splits = atoi(ov);
-    }
+    if (g.epi.kind == EPI_ACCUM_F32 && ctx->env_gemm_splits > 0) splits = ctx->env_gemm_splits;  // VITRS_GEMM_SPLITS: tuning aid
     p.kb_per_split = ceil_div(p.kb_total, splits);
     p.splits = ceil_div(p.kb_total, p.kb_per_split);
     if (CG == 2) return launch_tc_major<256, 6, 2>(ctx, a_mn, b_mn, maps, p);

@@ -71,6 +71,17 @@ struct vitrs_model {
     const int* labels;
     float dloss_scale;
     int adam_step;
+    // gradient exchange (production mode): bucket-major bf16 buffer ("Z order"), built on first use for the context's world size
+    int comm_dtype;        // 0: fp32 slices all-reduced in place (exact sums), 1: packed bf16 buckets (default)
+    int loss_reduced;      // d_mean_loss[1] holds (or will hold, on the comm stream) the sum over ranks of the local losses
+    int z_world;           // world size the plan below was built for (0 = not built)
+    int z_buckets;
+    size_t *z_off, *z_len, *z_shard, *s_off;  // per bucket: region start / padded length in the exchange buffer, shard length, shard start in zp/zm/zv
+    size_t z_size, s_total;
+    bf16* comm_buf;        // [z_size]
+    // ZeRO-1: fp32 master weights and AdamW moments of this rank's shard of every bucket, in Z order
+    int zero1;
+    float *zp, *zm, *zv;   // [s_total]
 };
 
 namespace {
@@ -469,7 +480,7 @@ int backward_bf16(vitrs_model* m) {
     return VITRS_OK;
 }
 
-// ---- data parallel: bucketed sum all-reduce on the comm stream, overlapped with backward ----------
+// ---- data parallel: bucketed gradient exchange on the comm stream, overlapped with backward ----------
 int bucket_begin(vitrs_model* m) {
     vitrs_ctx* ctx = m->ctx;
     VITRS_CUDA(ctx, cudaEventRecord(m->ev_bucket, ctx->stream));
@@ -503,20 +514,81 @@ int bucket_slices(const vitrs_config& cfg, const size_t* sizes, const size_t* of
     return n;
 }
 
-int allreduce_bucket(vitrs_model* m, int bucket) {
-    if (!m->ctx->nccl_comm || m->mode != VITRS_MODE_BF16) return VITRS_OK;
-    // VITRS_DP_DEFER (tuning aid): every bucket is exchanged after the last gradient kernel instead of behind its block
-    static const bool defer = getenv("VITRS_DP_DEFER") != nullptr;
-    const int last = m->cfg.num_layers + 1;
-    if (defer && bucket != last) return VITRS_OK;
-    VITRS_TRY(bucket_begin(m));
-    for (int bk = defer ? 0 : bucket; bk <= bucket; ++bk) {
+// The exchange buffer holds the buckets back to back, each bucket's slices back to back ("Z order": the layer-major layout
+// SURVEY section 7(v) asks for, as a view for the wire while the named parameter views stay tensor-major).  A bucket's region is
+// padded to a multiple of 8 * world elements so that its world shards are equal and 16-byte aligned (ZeRO-1 reduce-scatter).
+void zplan_sizes(const vitrs_config& cfg, const size_t* sizes, const size_t* offs, int world, int bucket, size_t* len, size_t* shard) {
+    size_t off[12], cnt[12], total = 0;
+    const int n = bucket_slices(cfg, sizes, offs, bucket, off, cnt);
+    for (int i = 0; i < n; ++i) total += cnt[i];
+    const size_t q = (size_t)8 * world;
+    *len = (total + q - 1) / q * q;
+    *shard = *len / world;
+}
+
+int ensure_zplan(vitrs_model* m) {
+    vitrs_ctx* ctx = m->ctx;
+    if (m->z_world == ctx->world && m->comm_buf) return VITRS_OK;
+    VITRS_ARG(ctx, !m->zero1);  // the shards were cut for another world size
+    VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    if (m->comm_buf) VITRS_CUDA(ctx, cudaFree(m->comm_buf));
+    m->comm_buf = nullptr;
+    const int nb = m->cfg.num_layers + 2;
+    free(m->z_off);
+    m->z_off = (size_t*)calloc(4 * (size_t)nb, sizeof(size_t));
+    m->z_len = m->z_off + nb; m->z_shard = m->z_len + nb; m->s_off = m->z_shard + nb;
+    size_t z = 0, sh = 0;
+    for (int b = 0; b < nb; ++b) {
+        zplan_sizes(m->cfg, m->param_sizes, m->param_off, ctx->world, b, &m->z_len[b], &m->z_shard[b]);
+        m->z_off[b] = z; m->s_off[b] = sh;
+        z += m->z_len[b]; sh += m->z_shard[b];
+    }
+    m->z_size = z; m->s_total = sh; m->z_buckets = nb;
+    VITRS_CUDA(ctx, cudaMalloc(&m->comm_buf, z * sizeof(bf16)));
+    VITRS_CUDA(ctx, cudaMemsetAsync(m->comm_buf, 0, z * sizeof(bf16), ctx->comm_stream));  // the padding stays zero for ever
+    m->z_world = ctx->world;
+    return VITRS_OK;
+}
+
+SliceTable table_of(const vitrs_model* m, int bucket, size_t z_base) {
+    SliceTable t;
+    memset(&t, 0, sizeof(t));
+    t.n = bucket_slices(m->cfg, m->param_sizes, m->param_off, bucket, t.src_off, t.cnt);
+    size_t z = z_base;
+    for (int i = 0; i < t.n; ++i) { t.z_off[i] = z; z += t.cnt[i]; }
+    return t;
+}
+
+int exchange_bucket(vitrs_model* m, int bk) {
+    vitrs_ctx* ctx = m->ctx;
+    if (m->comm_dtype == 0 && !m->zero1) {  // exact fp32 sums, slice by slice in place
         size_t off[12], cnt[12];
         float* bufs[12];
         const int n = bucket_slices(m->cfg, m->param_sizes, m->param_off, bk, off, cnt);
         for (int i = 0; i < n; ++i) bufs[i] = m->grads + off[i];
-        VITRS_TRY(vitrs_nccl_allreduce_group(m->ctx, bufs, cnt, n));
+        return vitrs_nccl_allreduce_group(ctx, bufs, cnt, n);
     }
+    // one contiguous bf16 message per bucket (bf16 on the wire in production)
+    const SliceTable tab = table_of(m, bk, m->z_off[bk]);
+    bf16* region = m->comm_buf + m->z_off[bk];
+    VITRS_TRY(op_pack_f32_to_bf16(ctx, m->comm_buf, m->grads, tab, ctx->comm_stream));
+    if (m->zero1) {
+        // each rank receives the sum of its 1/world shard; AdamW runs on the shard in update()
+        return vitrs_nccl_reduce_scatter(ctx, region, region + (size_t)ctx->rank * m->z_shard[bk], m->z_shard[bk], 1);
+    }
+    VITRS_TRY(vitrs_nccl_allreduce(ctx, region, region, m->z_len[bk], 1));
+    return op_unpack_bf16_to_f32(ctx, m->grads, m->comm_buf, tab, ctx->comm_stream);
+}
+
+int allreduce_bucket(vitrs_model* m, int bucket) {
+    if (m->mode != VITRS_MODE_BF16 || (!m->ctx->nccl_comm && !m->zero1)) return VITRS_OK;
+    // VITRS_DP_DEFER (tuning aid): every bucket is exchanged after the last gradient kernel instead of behind its block
+    const bool defer = m->ctx->env_dp_defer != 0;
+    const int last = m->cfg.num_layers + 1;
+    if (defer && bucket != last) return VITRS_OK;
+    if (m->comm_dtype != 0 || m->zero1) VITRS_TRY(ensure_zplan(m));
+    VITRS_TRY(bucket_begin(m));
+    for (int bk = defer ? 0 : bucket; bk <= bucket; ++bk) VITRS_TRY(exchange_bucket(m, bk));
     return VITRS_OK;
 }
 
@@ -527,10 +599,97 @@ int allreduce_tail(vitrs_model* m, bool head) { return allreduce_bucket(m, head 
 
 int comm_join(vitrs_model* m) {
     vitrs_ctx* ctx = m->ctx;
-    if (!ctx->nccl_comm) return VITRS_OK;
+    if (!ctx->nccl_comm && !m->zero1) return VITRS_OK;
     VITRS_CUDA(ctx, cudaEventRecord(m->ev_comm_done, ctx->comm_stream));
     VITRS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->ev_comm_done, 0));
     return VITRS_OK;
+}
+
+// The local value is sum(losses) * dloss_scale; under data parallel the global mean is the sum over ranks.  It is reduced ONCE
+// per forward, out of place, on the comm stream, so vitrs_model_mean_loss stays a pure local read (no collective hides in a
+// getter: reading twice, or on one rank only, is safe).
+int reduce_loss(vitrs_model* m) {
+    vitrs_ctx* ctx = m->ctx;
+    m->loss_reduced = 0;
+    if (!ctx->nccl_comm || !m->has_targets) return VITRS_OK;
+    VITRS_TRY(bucket_begin(m));
+    VITRS_TRY(vitrs_nccl_allreduce(ctx, m->d_mean_loss, m->d_mean_loss + 1, 1, 0));
+    m->loss_reduced = 1;
+    return VITRS_OK;
+}
+
+// ---- ZeRO-1: fp32 master weights and AdamW moments sharded 1/world per bucket ---------------------
+// (re)cut the shards from the full tensor-major buffers params / m / v, then drop the full moment buffers
+int zero_shard_from_full(vitrs_model* m) {
+    vitrs_ctx* ctx = m->ctx;
+    m->zero1 = 0;
+    VITRS_TRY(ensure_zplan(m));
+    VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!m->zp) {
+        VITRS_CUDA(ctx, cudaMalloc(&m->zp, m->s_total * sizeof(float)));
+        VITRS_CUDA(ctx, cudaMalloc(&m->zm, m->s_total * sizeof(float)));
+        VITRS_CUDA(ctx, cudaMalloc(&m->zv, m->s_total * sizeof(float)));
+    }
+    float* tmp = nullptr;
+    VITRS_CUDA(ctx, cudaMalloc(&tmp, m->z_size * sizeof(float)));
+    float* full[3] = {m->params, m->m, m->v};
+    float* shard[3] = {m->zp, m->zm, m->zv};
+    for (int k = 0; k < 3; ++k) {
+        if (!full[k]) {  // moments already dropped: they stay as they are
+            continue;
+        }
+        VITRS_CUDA(ctx, cudaMemsetAsync(tmp, 0, m->z_size * sizeof(float), ctx->comm_stream));
+        for (int b = 0; b < m->z_buckets; ++b) {
+            const SliceTable tab = table_of(m, b, m->z_off[b]);
+            VITRS_TRY(op_pack_f32_to_f32(ctx, tmp, full[k], tab, ctx->comm_stream));
+            VITRS_CUDA(ctx, cudaMemcpyAsync(shard[k] + m->s_off[b], tmp + m->z_off[b] + (size_t)ctx->rank * m->z_shard[b],
+                                            m->z_shard[b] * sizeof(float), cudaMemcpyDeviceToDevice, ctx->comm_stream));
+        }
+    }
+    VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    VITRS_CUDA(ctx, cudaFree(tmp));
+    if (m->m) { VITRS_CUDA(ctx, cudaFree(m->m)); m->m = nullptr; }
+    if (m->v) { VITRS_CUDA(ctx, cudaFree(m->v)); m->v = nullptr; }
+    m->zero1 = 1;
+    return VITRS_OK;
+}
+
+// all-gather one sharded fp32 array (zp / zm / zv) into a full tensor-major buffer
+int zero_gather_full(vitrs_model* m, const float* shards, float* full) {
+    vitrs_ctx* ctx = m->ctx;
+    float* tmp = nullptr;
+    VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VITRS_CUDA(ctx, cudaMalloc(&tmp, m->z_size * sizeof(float)));
+    for (int b = 0; b < m->z_buckets; ++b) {
+        float* region = tmp + m->z_off[b];
+        float* mine = region + (size_t)ctx->rank * m->z_shard[b];
+        VITRS_CUDA(ctx, cudaMemcpyAsync(mine, shards + m->s_off[b], m->z_shard[b] * sizeof(float), cudaMemcpyDeviceToDevice, ctx->comm_stream));
+        VITRS_TRY(vitrs_nccl_all_gather(ctx, mine, region, m->z_shard[b], 0));
+        VITRS_TRY(op_unpack_f32_to_f32(ctx, full, tmp, table_of(m, b, m->z_off[b]), ctx->comm_stream));
+    }
+    VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    VITRS_CUDA(ctx, cudaFree(tmp));
+    return VITRS_OK;
+}
+
+// AdamW on this rank's shard of every bucket (gradients: the reduce-scattered bf16 sums sitting in the exchange buffer), then
+// the updated bf16 weights are all-gathered in place and scattered into the tensor-major shadow the GEMMs read
+int zero_update(vitrs_model* m) {
+    vitrs_ctx* ctx = m->ctx;
+    VITRS_TRY(bucket_begin(m));  // the comm stream continues behind whatever the compute stream has issued (hyper-parameters)
+    for (int b = 0; b < m->z_buckets; ++b) {
+        bf16* mine = m->comm_buf + m->z_off[b] + (size_t)ctx->rank * m->z_shard[b];
+        VITRS_TRY(op_adamw_apply_shard(ctx, m->zp + m->s_off[b], mine, m->zm + m->s_off[b], m->zv + m->s_off[b], m->z_shard[b], ctx->comm_stream));
+    }
+    VITRS_TRY(vitrs_nccl_group(ctx, 1));
+    for (int b = 0; b < m->z_buckets; ++b) {
+        bf16* region = m->comm_buf + m->z_off[b];
+        VITRS_TRY(vitrs_nccl_all_gather(ctx, region + (size_t)ctx->rank * m->z_shard[b], region, m->z_shard[b], 1));
+    }
+    VITRS_TRY(vitrs_nccl_group(ctx, 0));
+    for (int b = 0; b < m->z_buckets; ++b)
+        VITRS_TRY(op_unpack_bf16_to_bf16(ctx, m->shadow, m->comm_buf, table_of(m, b, m->z_off[b]), ctx->comm_stream));
+    return comm_join(m);
 }
 
 int set_batch(vitrs_model* m, const float* images, const int* labels, int b) {
@@ -562,6 +721,7 @@ int vitrs_model_create(vitrs_ctx* ctx, const vitrs_config* cfg_in, int max_batch
     VITRS_CUDA(ctx, cudaSetDevice(ctx->device));
     vitrs_model* m = (vitrs_model*)calloc(1, sizeof(vitrs_model));
     m->ctx = ctx; m->cfg = cfg; m->mode = mode; m->max_batch = max_batch;
+    m->comm_dtype = mode == VITRS_MODE_BF16 ? 1 : 0;
     for (int i = 0; i < 3; ++i) { m->norm_mean[i] = 0.5f; m->norm_std[i] = 0.5f; }  // uint8 -> [-1, 1]
     param_sizes_of(cfg, m->param_sizes);
     size_t off = 0;
@@ -609,8 +769,8 @@ int vitrs_model_create(vitrs_ctx* ctx, const vitrs_config* cfg_in, int max_batch
         MODEL_CUDA(cudaMalloc(&m->dlogits, sizeof(float) * B * V));
         MODEL_CUDA(cudaMalloc(&m->dlnf, sizeof(float) * B * C));
     }
-    MODEL_CUDA(cudaMalloc(&m->d_mean_loss, sizeof(float)));
-    MODEL_CUDA(cudaMallocHost(&m->h_mean_loss, sizeof(float)));
+    MODEL_CUDA(cudaMalloc(&m->d_mean_loss, 2 * sizeof(float)));  // [0] local, [1] summed over ranks
+    MODEL_CUDA(cudaMallocHost(&m->h_mean_loss, 2 * sizeof(float)));  // [0] loss, [1] device error flags
     *m->h_mean_loss = -1.0f;
     for (int i = 0; i < 2; ++i) {
         MODEL_CUDA(cudaEventCreateWithFlags(&m->stage_ready[i], cudaEventDisableTiming));
@@ -633,6 +793,8 @@ int vitrs_model_destroy(vitrs_model* m) {
     cudaFree(m->lse); cudaFree(m->cls_rows); cudaFree(m->dcls_rows); cudaFree(m->patches);
     cudaFree(m->dres); cudaFree(m->dln); cudaFree(m->dbig); cudaFree(m->dlogits); cudaFree(m->dlnf);
     cudaFree(m->d_mean_loss);
+    cudaFree(m->comm_buf); cudaFree(m->zp); cudaFree(m->zm); cudaFree(m->zv);
+    free(m->z_off);
     if (m->h_mean_loss) cudaFreeHost(m->h_mean_loss);
     for (int i = 0; i < 2; ++i) {
         cudaFree(m->stage_images[i]); cudaFree(m->stage_labels[i]);
@@ -656,15 +818,21 @@ int vitrs_model_init_parameters(vitrs_model* m, uint64_t seed, int init_mode) {
     if (!m) return VITRS_ERR_ARG;
     vitrs_ctx* ctx = m->ctx;
     VITRS_CUDA(ctx, cudaMemsetAsync(m->params, 0, m->num_params * sizeof(float), ctx->stream));
-    VITRS_CUDA(ctx, cudaMemsetAsync(m->m, 0, m->num_params * sizeof(float), ctx->stream));
-    VITRS_CUDA(ctx, cudaMemsetAsync(m->v, 0, m->num_params * sizeof(float), ctx->stream));
+    if (m->m) VITRS_CUDA(ctx, cudaMemsetAsync(m->m, 0, m->num_params * sizeof(float), ctx->stream));
+    if (m->v) VITRS_CUDA(ctx, cudaMemsetAsync(m->v, 0, m->num_params * sizeof(float), ctx->stream));
     m->adam_step = 0;
     const float lo = init_mode == 1 ? -0.02f : 0.0f, hi = 0.02f;
     const int weight_ids[] = {P_PATCHW, P_CLS, P_WPE, P_QKVW, P_ATTPROJW, P_FCW, P_FCPROJW, P_HEADW};
     for (int id : weight_ids) VITRS_TRY(op_fill_uniform(ctx, P(m, id), m->param_sizes[id], seed, (uint64_t)id, lo, hi));
     const int gain_ids[] = {P_LN1W, P_LN2W, P_LNFW};
     for (int id : gain_ids) VITRS_TRY(op_fill_const(ctx, P(m, id), m->param_sizes[id], 1.0f));
-    return refresh_shadow(m);
+    VITRS_TRY(refresh_shadow(m));
+    if (m->zero1) {
+        VITRS_CUDA(ctx, cudaMemsetAsync(m->zm, 0, m->s_total * sizeof(float), ctx->stream));
+        VITRS_CUDA(ctx, cudaMemsetAsync(m->zv, 0, m->s_total * sizeof(float), ctx->stream));
+        return zero_shard_from_full(m);
+    }
+    return VITRS_OK;
 }
 
 size_t vitrs_model_num_parameters(vitrs_model* m) { return m ? m->num_params : 0; }
@@ -673,6 +841,8 @@ int vitrs_model_param_view(vitrs_model* m, int which, int tensor, float** ptr, s
     if (!m) return VITRS_ERR_ARG;
     VITRS_ARG(m->ctx, which >= 0 && which <= 3 && tensor >= 0 && tensor < P_COUNT && ptr);
     float* base = which == 0 ? m->params : which == 1 ? m->grads : which == 2 ? m->m : m->v;
+    if (!base)  // ZeRO-1 keeps the moments as shards only
+        return vitrs_set_error(m->ctx, VITRS_ERR_UNSUPPORTED, "the AdamW moments are sharded (ZeRO-1): no full view");
     *ptr = base + m->param_off[tensor];
     if (count) *count = m->param_sizes[tensor];
     return VITRS_OK;
@@ -697,7 +867,9 @@ int vitrs_model_set_dloss_scale(vitrs_model* m, float scale) {
 // weights changed behind the model's back (tests writing through param_view): rebuild the bf16 shadow
 int vitrs_model_sync_parameters(vitrs_model* m) {
     if (!m) return VITRS_ERR_ARG;
-    return refresh_shadow(m);
+    VITRS_TRY(refresh_shadow(m));
+    if (m->zero1) return zero_shard_from_full(m);  // the master shards follow the full view
+    return VITRS_OK;
 }
 
 int vitrs_model_forward(vitrs_model* m, const float* images, const int* labels, int b) {
@@ -706,7 +878,7 @@ int vitrs_model_forward(vitrs_model* m, const float* images, const int* labels, 
     VITRS_CUDA(m->ctx, cudaSetDevice(m->ctx->device));
     VITRS_TRY(m->mode == VITRS_MODE_F32 ? forward_f32(m) : forward_bf16(m));
     if (!m->has_targets) VITRS_TRY(op_fill_const(m->ctx, m->d_mean_loss, 1, -1.0f));  // rusty_vit.rs:348-350
-    return VITRS_OK;
+    return reduce_loss(m);
 }
 
 // ---- raw image batches: uint8 samples, normalisation fused into the im2col pass ----
@@ -730,7 +902,7 @@ int vitrs_model_forward_u8(vitrs_model* m, const uint8_t* images, int layout, co
     VITRS_CUDA(ctx, cudaSetDevice(ctx->device));
     VITRS_TRY(m->mode == VITRS_MODE_F32 ? forward_f32(m) : forward_bf16(m));
     if (!m->has_targets) VITRS_TRY(op_fill_const(ctx, m->d_mean_loss, 1, -1.0f));
-    return VITRS_OK;
+    return reduce_loss(m);
 }
 
 int vitrs_model_zero_grad(vitrs_model* m) {
@@ -772,14 +944,17 @@ int vitrs_model_allreduce_grads(vitrs_model* m) {
 
 int vitrs_model_optimizer_step(vitrs_model* m, float lr) {
     if (!m) return VITRS_ERR_ARG;
+    VITRS_ARG(m->ctx, !m->zero1);  // the reference's SGD works on the full replicated buffers
     return op_sgd(m->ctx, m->params, m->grads, m->num_params, lr, m->shadow);
 }
 
 int vitrs_model_update(vitrs_model* m, float lr, float beta1, float beta2, float eps, float weight_decay) {
     if (!m) return VITRS_ERR_ARG;
+    vitrs_ctx* ctx = m->ctx;
     m->adam_step += 1;
-    return op_adamw(m->ctx, m->params, m->grads, m->m, m->v, m->num_params, lr, beta1, beta2, eps, weight_decay, m->adam_step,
-                    m->shadow);
+    VITRS_TRY(op_adam_set_hyper(ctx, lr, beta1, beta2, eps, weight_decay, m->adam_step, ctx->stream));
+    if (m->zero1) return zero_update(m);
+    return op_adamw_apply(ctx, m->params, m->grads, m->m, m->v, m->num_params, m->shadow, ctx->stream);
 }
 
 int vitrs_model_mean_loss(vitrs_model* m, float* out) {
@@ -787,13 +962,66 @@ int vitrs_model_mean_loss(vitrs_model* m, float* out) {
     vitrs_ctx* ctx = m->ctx;
     VITRS_ARG(ctx, out != nullptr);
     if (m->batch == 0) { *out = -1.0f; return VITRS_OK; }
-    if (ctx->nccl_comm && m->has_targets) {
-        // the local value is sum(losses) / B_global when a dloss scale is set: the global mean is the sum over ranks
-        VITRS_TRY(vitrs_allreduce_f32(ctx, m->d_mean_loss, 1));
-    }
-    VITRS_CUDA(ctx, cudaMemcpyAsync(m->h_mean_loss, m->d_mean_loss, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    // a pure local read: under data parallel the sum over ranks was taken once, by forward, on the comm stream
+    const int reduced = m->loss_reduced && m->has_targets;
+    if (reduced) VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    VITRS_CUDA(ctx, cudaMemcpyAsync(m->h_mean_loss, m->d_mean_loss + (reduced ? 1 : 0), sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VITRS_CUDA(ctx, cudaMemcpyAsync(m->h_mean_loss + 1, ctx->dev_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *out = *m->h_mean_loss;
+    *out = m->h_mean_loss[0];
+    if (reinterpret_cast<const int*>(m->h_mean_loss)[1] & 1) {  // raised by the loss kernels
+        VITRS_CUDA(ctx, cudaMemsetAsync(ctx->dev_flags, 0, sizeof(int), ctx->stream));
+        return vitrs_set_error(ctx, VITRS_ERR_ARG, "a class label of the batch is outside [0, %d)", m->cfg.num_classes);
+    }
+    return VITRS_OK;
+}
+
+// ---- gradient exchange options / ZeRO-1 ---------------------------------------------------------------------------------
+int vitrs_model_set_comm_dtype(vitrs_model* m, int dtype) {
+    if (!m) return VITRS_ERR_ARG;
+    VITRS_ARG(m->ctx, (dtype == 0 || dtype == 1) && m->mode == VITRS_MODE_BF16);
+    m->comm_dtype = dtype;
+    return VITRS_OK;
+}
+
+int vitrs_model_enable_zero1(vitrs_model* m) {
+    if (!m) return VITRS_ERR_ARG;
+    VITRS_ARG(m->ctx, m->mode == VITRS_MODE_BF16);
+    if (m->zero1) return VITRS_OK;
+    return zero_shard_from_full(m);
+}
+
+// ZeRO-1: all-gather the fp32 master weights into the full parameter view (checkpoints, inspection).  No-op otherwise.
+int vitrs_model_gather_parameters(vitrs_model* m) {
+    if (!m) return VITRS_ERR_ARG;
+    if (!m->zero1) return VITRS_OK;
+    return zero_gather_full(m, m->zp, m->params);
+}
+
+// bytes of optimiser state (fp32 master weights + both AdamW moments) this rank holds
+int vitrs_model_optimizer_state_bytes(vitrs_model* m, size_t* bytes) {
+    if (!m || !bytes) return VITRS_ERR_ARG;
+    *bytes = (m->zero1 ? m->s_total : m->num_params) * 3 * sizeof(float);
+    return VITRS_OK;
+}
+
+// host-only description of the ZeRO-1 partition (no device needed): region offset / padded length of `bucket` in the exchange
+// buffer and the length of each rank's shard, for `world` ranks
+int vitrs_zero_partition(const vitrs_config* cfg_in, int world, int bucket, size_t* z_off, size_t* z_len, size_t* shard) {
+    if (!cfg_in || world < 1) return VITRS_ERR_ARG;
+    vitrs_config cfg = *cfg_in;
+    cfg.max_seq_len = tokens(cfg);
+    if (bucket < 0 || bucket > cfg.num_layers + 1) return VITRS_ERR_ARG;
+    size_t sizes[P_COUNT], offs[P_COUNT], off = 0, z = 0, len = 0, sh = 0;
+    param_sizes_of(cfg, sizes);
+    for (int i = 0; i < P_COUNT; ++i) { offs[i] = off; off += sizes[i]; }
+    for (int b = 0; b <= bucket; ++b) {
+        z += len;
+        zplan_sizes(cfg, sizes, offs, world, b, &len, &sh);
+    }
+    if (z_off) *z_off = z;
+    if (z_len) *z_len = len;
+    if (shard) *shard = sh;
     return VITRS_OK;
 }
 
@@ -912,59 +1140,100 @@ int vitrs_model_train_step_host_u8(vitrs_model* m, const uint8_t* h_images, int 
 // header[0] magic, [1] version, [2..6] max_seq_len, vocab(=classes), layers, heads, channels (the
 // reference's slots), [7..10] image, patch, classes, causal, [11] adam step, [12] has m/v.
 #define VITRS_CKPT_MAGIC 20261018
+#define VITRS_CKPT_VERSION 1
 int vitrs_model_save_checkpoint(vitrs_model* m, const char* path) {
     if (!m) return VITRS_ERR_ARG;
     vitrs_ctx* ctx = m->ctx;
     VITRS_ARG(ctx, path != nullptr);
+    VITRS_CUDA(ctx, cudaSetDevice(ctx->device));
     VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    FILE* f = fopen(path, "wb");
-    if (!f) return vitrs_set_error(ctx, VITRS_ERR_ARG, "cannot open %s for writing", path);
-    int32_t header[256] = {0};
-    header[0] = VITRS_CKPT_MAGIC; header[1] = 1;
-    header[2] = m->cfg.max_seq_len; header[3] = m->cfg.num_classes; header[4] = m->cfg.num_layers;
-    header[5] = m->cfg.num_heads; header[6] = m->cfg.channels; header[7] = m->cfg.image_size;
-    header[8] = m->cfg.patch_size; header[9] = m->cfg.num_classes; header[10] = m->cfg.causal;
-    header[11] = m->adam_step; header[12] = 1;
-    bool ok = fwrite(header, sizeof(int32_t), 256, f) == 256;
+    // ZeRO-1: every rank takes part in gathering the shards; the full moments live in temporaries for the duration of the write
+    float *full_m = m->m, *full_v = m->v;
+    if (m->zero1) {
+        VITRS_TRY(zero_gather_full(m, m->zp, m->params));
+        VITRS_CUDA(ctx, cudaMalloc(&full_m, m->num_params * sizeof(float)));
+        VITRS_CUDA(ctx, cudaMalloc(&full_v, m->num_params * sizeof(float)));
+        VITRS_TRY(zero_gather_full(m, m->zm, full_m));
+        VITRS_TRY(zero_gather_full(m, m->zv, full_v));
+    }
+    bool ok = true;
     float* host = (float*)malloc(m->num_params * sizeof(float));
-    float* srcs[3] = {m->params, m->m, m->v};
-    for (int k = 0; k < 3 && ok; ++k) {
-        if (cudaMemcpy(host, srcs[k], m->num_params * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
-        else ok = fwrite(host, sizeof(float), m->num_params, f) == m->num_params;
+    FILE* f = host ? fopen(path, "wb") : nullptr;
+    if (f) {
+        int32_t header[256] = {0};
+        header[0] = VITRS_CKPT_MAGIC; header[1] = VITRS_CKPT_VERSION;
+        header[2] = m->cfg.max_seq_len; header[3] = m->cfg.num_classes; header[4] = m->cfg.num_layers;
+        header[5] = m->cfg.num_heads; header[6] = m->cfg.channels; header[7] = m->cfg.image_size;
+        header[8] = m->cfg.patch_size; header[9] = m->cfg.num_classes; header[10] = m->cfg.causal;
+        header[11] = m->adam_step; header[12] = 1;
+        ok = fwrite(header, sizeof(int32_t), 256, f) == 256;
+        float* srcs[3] = {m->params, full_m, full_v};
+        for (int k = 0; k < 3 && ok; ++k) {
+            if (cudaMemcpy(host, srcs[k], m->num_params * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+            else ok = fwrite(host, sizeof(float), m->num_params, f) == m->num_params;
+        }
+        ok = fclose(f) == 0 && ok;
     }
     free(host);
-    fclose(f);
+    if (m->zero1) { cudaFree(full_m); cudaFree(full_v); }
+    if (!host) return vitrs_set_error(ctx, VITRS_ERR_ARG, "out of host memory for %s", path);
+    if (!f) return vitrs_set_error(ctx, VITRS_ERR_ARG, "cannot open %s for writing", path);
     return ok ? VITRS_OK : vitrs_set_error(ctx, VITRS_ERR_CUDA, "short write to %s", path);
 }
 
+// Everything is validated and read into host memory BEFORE the first byte of device state changes: a truncated or foreign file
+// leaves the model exactly as it was.  Files written by the reference's layout (header slots 2..6, fp32 parameters from byte
+// 1024 in tensor order, nothing else) load with zeroed moments.
 int vitrs_model_load_checkpoint(vitrs_model* m, const char* path) {
     if (!m) return VITRS_ERR_ARG;
     vitrs_ctx* ctx = m->ctx;
     VITRS_ARG(ctx, path != nullptr);
+    VITRS_CUDA(ctx, cudaSetDevice(ctx->device));
     FILE* f = fopen(path, "rb");
     if (!f) return vitrs_set_error(ctx, VITRS_ERR_ARG, "cannot open %s", path);
     int32_t header[256];
     if (fread(header, sizeof(int32_t), 256, f) != 256) { fclose(f); return vitrs_set_error(ctx, VITRS_ERR_ARG, "%s: short header", path); }
-    if (header[0] != VITRS_CKPT_MAGIC || header[2] != m->cfg.max_seq_len || header[4] != m->cfg.num_layers ||
-        header[5] != m->cfg.num_heads || header[6] != m->cfg.channels || header[8] != m->cfg.patch_size ||
-        header[9] != m->cfg.num_classes) {
+    if (header[0] != VITRS_CKPT_MAGIC || header[1] != VITRS_CKPT_VERSION) {
+        fclose(f);
+        return vitrs_set_error(ctx, VITRS_ERR_ARG, "%s: magic %d / version %d, expected %d / %d", path, header[0], header[1],
+                               VITRS_CKPT_MAGIC, VITRS_CKPT_VERSION);
+    }
+    if (header[2] != m->cfg.max_seq_len || header[4] != m->cfg.num_layers || header[5] != m->cfg.num_heads ||
+        header[6] != m->cfg.channels || header[7] != m->cfg.image_size || header[8] != m->cfg.patch_size ||
+        header[9] != m->cfg.num_classes || header[10] != m->cfg.causal || header[11] < 0) {
         fclose(f);
         return vitrs_set_error(ctx, VITRS_ERR_ARG, "%s: header does not match the model configuration", path);
     }
-    VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    float* host = (float*)malloc(m->num_params * sizeof(float));
-    float* dsts[3] = {m->params, m->m, m->v};
     const int sections = header[12] ? 3 : 1;
-    bool ok = true;
-    for (int k = 0; k < sections && ok; ++k) {
-        ok = fread(host, sizeof(float), m->num_params, f) == m->num_params &&
-             cudaMemcpy(dsts[k], host, m->num_params * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    const long want = 1024 + (long)sections * (long)m->num_params * 4;
+    fseek(f, 0, SEEK_END);
+    const long have = ftell(f);
+    fseek(f, 1024, SEEK_SET);
+    if (have != want) {
+        fclose(f);
+        return vitrs_set_error(ctx, VITRS_ERR_ARG, "%s: %ld bytes, expected %ld (%d section(s) of %zu fp32)", path, have, want, sections,
+                               m->num_params);
     }
-    free(host);
+    float* host = (float*)malloc((size_t)sections * m->num_params * sizeof(float));
+    if (!host) { fclose(f); return vitrs_set_error(ctx, VITRS_ERR_ARG, "out of host memory for %s", path); }
+    const bool ok = fread(host, sizeof(float), (size_t)sections * m->num_params, f) == (size_t)sections * m->num_params;
     fclose(f);
-    if (!ok) return vitrs_set_error(ctx, VITRS_ERR_ARG, "%s: short read", path);
+    if (!ok) { free(host); return vitrs_set_error(ctx, VITRS_ERR_ARG, "%s: short read", path); }
+    VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t bytes = m->num_params * sizeof(float);
+    if (m->zero1) {  // the shards are re-cut from full buffers
+        if (!m->m) VITRS_CUDA(ctx, cudaMalloc(&m->m, bytes));
+        if (!m->v) VITRS_CUDA(ctx, cudaMalloc(&m->v, bytes));
+    }
+    cudaError_t e = cudaMemcpy(m->params, host, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = sections == 3 ? cudaMemcpy(m->m, host + m->num_params, bytes, cudaMemcpyHostToDevice) : cudaMemset(m->m, 0, bytes);
+    if (e == cudaSuccess) e = sections == 3 ? cudaMemcpy(m->v, host + 2 * m->num_params, bytes, cudaMemcpyHostToDevice) : cudaMemset(m->v, 0, bytes);
+    free(host);
+    if (e != cudaSuccess) return vitrs_set_error(ctx, VITRS_ERR_CUDA, "%s: copy to the device failed: %s", path, cudaGetErrorString(e));
     m->adam_step = header[11];
-    return refresh_shadow(m);
+    VITRS_TRY(refresh_shadow(m));
+    if (m->zero1) return zero_shard_from_full(m);
+    return VITRS_OK;
 }
 
 }  // extern "C"

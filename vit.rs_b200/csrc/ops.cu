@@ -7,8 +7,11 @@
 
 namespace {
 
-#define CTX_OR_FAIL(ctx) \
-    if (!(ctx)) return VITRS_ERR_ARG
+// every op entry point: a context is mandatory (no CPU fallback) and its device becomes current (a process may hold
+// contexts on several GPUs)
+#define CTX_OR_FAIL(ctx)                 \
+    if (!(ctx)) return VITRS_ERR_ARG;    \
+    VITRS_CUDA(ctx, cudaSetDevice((ctx)->device))
 
 // out[M, oc] = inp[M, c] . weight[oc, c]^T (+ bias)                       (train_vit.rs:384-398)
 template <typename T>
@@ -236,7 +239,7 @@ int vitrs_attention_backward_bf16(vitrs_ctx* ctx, vitrs_bf16* dinp, const vitrs_
     CTX_OR_FAIL(ctx);
     VITRS_ARG(ctx, dinp && dout && lse && inp);
     // the reference's `+=` contract; VITRS_ATTN_BWD_OVERWRITE (benchmark aid) times the overwrite path the fused model step uses
-    static const int accumulate = getenv("VITRS_ATTN_BWD_OVERWRITE") ? 0 : 1;
+    const int accumulate = ctx->env_attn_bwd_overwrite ? 0 : 1;
     int r = out ? op_attention_backward_tc(ctx, B16(dinp), CB16(dout), CB16(out), CB16(inp), lse, b, t, c, nh, causal, accumulate)
                 : VITRS_ERR_UNSUPPORTED;
     if (r == VITRS_ERR_UNSUPPORTED)
