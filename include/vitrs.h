@@ -254,8 +254,10 @@ int vitrs_comm_world(vitrs_ctx* ctx, int* rank, int* world);
  * called by train_step when a communicator exists, exported for tests */
 int vitrs_model_allreduce_grads(vitrs_model* m);
 /* the bucket schedule itself, computable on the host: bucket 0 = final LayerNorm + head, 1..L = blocks
- * L-1..0 (12 slices each), L+1 = embeddings; offsets/counts (elements, capacity 12) index the flat buffer */
-int vitrs_grad_bucket(const vitrs_config* cfg, int bucket, size_t* offsets, size_t* counts, int* num_slices);
+ * L-1..0 (12 slices each), L+1 = embeddings; offsets/counts (elements, capacity 12) index the flat buffer; big (nullable,
+ * capacity 12): 1 for the GEMM weight matrices (read through the bf16 shadow; sharded by ZeRO-1), 0 for the tensors the
+ * kernels read in fp32 (gains, biases, embeddings, class head; always replicated) */
+int vitrs_grad_bucket(const vitrs_config* cfg, int bucket, size_t* offsets, size_t* counts, int* big, int* num_slices);
 int vitrs_allreduce_f32(vitrs_ctx* ctx, float* buf, size_t n);
 /* what the gradient exchange of the production mode puts on the wire: 1 (default) = one contiguous bf16 message per bucket
  * (the bucket's slices are packed into a bucket-major exchange buffer, summed, and unpacked into the fp32 gradient views);
@@ -263,9 +265,10 @@ int vitrs_allreduce_f32(vitrs_ctx* ctx, float* buf, size_t n);
 int vitrs_model_set_comm_dtype(vitrs_model* m, int dtype);
 
 /* ---- ZeRO-1 sharded optimiser (the reference's optimizer_step rusty_vit.rs:949-955 and its unused moment
- * buffers :67-68 generalised): after enable, each bucket of gradients is reduce-scattered (bf16) instead of all-reduced, every
- * rank keeps the fp32 master weights and both AdamW moments of its 1/world shard only, update() runs AdamW on the shard and
- * all-gathers the bf16 weights into the shadow the GEMMs read.  The full fp32 parameter view goes stale until
+ * buffers :67-68 generalised): after enable, the GEMM weight matrices of each bucket (98.7 % of ViT-B/16's parameters) are
+ * reduce-scattered (bf16) instead of all-reduced, every rank keeps their fp32 master weights and both AdamW moments for its
+ * 1/world shard only, update() runs AdamW on the shard and all-gathers the bf16 weights into the shadow the GEMMs read.  The
+ * tensors the kernels read in fp32 (gains, biases, embeddings, class head) stay replicated: all-reduced and updated everywhere.  The full fp32 parameter view goes stale until
  * vitrs_model_gather_parameters (save_checkpoint gathers by itself; every rank must call it).  grads views then hold the
  * rank-local gradients.  Works without a communicator (world 1) as the same code path. */
 int vitrs_model_enable_zero1(vitrs_model* m);
@@ -273,8 +276,9 @@ int vitrs_model_gather_parameters(vitrs_model* m);
 /* bytes of optimiser state (fp32 master weights + AdamW m and v) held by this rank */
 int vitrs_model_optimizer_state_bytes(vitrs_model* m, size_t* bytes);
 /* the partition itself, computable on the host: region [z_off, z_off + z_len) of `bucket` in the bucket-major exchange
- * buffer (z_len = the bucket's elements padded to a multiple of 8 * world) and the shard length z_len / world */
-int vitrs_zero_partition(const vitrs_config* cfg, int world, int bucket, size_t* z_off, size_t* z_len, size_t* shard);
+ * buffer; its first z_big elements are the bucket's big slices padded to a multiple of 8 * world and cut into world shards
+ * of `shard` elements, the rest are its small slices (padded to 8), which stay replicated */
+int vitrs_zero_partition(const vitrs_config* cfg, int world, int bucket, size_t* z_off, size_t* z_len, size_t* z_big, size_t* shard);
 
 #ifdef __cplusplus
 }

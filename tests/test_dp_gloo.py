@@ -55,7 +55,7 @@ def test_bucket_schedule_covers_every_gradient_once(vitrs):
     for name in ("tiny", "ti16", "b16"):
         buckets = vitrs.grad_buckets(name)
         cfg = vitrs.CONFIGS[name]
-        assert len(buckets) == cfg["num_layers"] + 2 and all(len(b) == 12 for b in buckets[1:-1])
+        assert len(buckets) == cfg["num_layers"] + 2 and all(len(b) == 12 for b in buckets[1:-1]) and len(buckets[-1]) == 2
         n = po.ViT(name).num_parameters if name == "tiny" else None
         cover = {}
         total = 0
@@ -97,25 +97,29 @@ def test_two_rank_gradients_equal_single_process(vitrs):
 
 
 def test_zero1_partition_arithmetic(vitrs):
-    """ZeRO-1 host logic (vitrs_zero_partition): the bucket regions tile the exchange buffer, every region is the bucket's
-    elements padded to 8 * world, the world shards of a region are equal, 16-byte aligned, and together cover every gradient
-    element exactly once."""
+    """ZeRO-1 host logic (vitrs_zero_partition): the bucket regions tile the exchange buffer; a region is the bucket's big slices
+    (GEMM weight matrices) padded to 8 * world and cut into world equal, 16-byte aligned shards, followed by its small slices
+    (replicated) padded to 8; together the regions cover every gradient element exactly once."""
     for name in ("tiny", "ti16", "b16"):
-        buckets = vitrs.grad_buckets(name)
+        buckets = vitrs.grad_buckets(name, with_kind=True)
         for world in (1, 2, 4, 8):
             part = vitrs.zero_partition(name, world)
             assert len(part) == len(buckets)
             z = 0
-            for (zo, zl, sh), slices in zip(part, buckets):
-                n = sum(c for _, c in slices)
-                assert zo == z and zl >= n and zl - n < 8 * world and zl % (8 * world) == 0 and sh * world == zl and sh % 8 == 0
+            for (zo, zl, zb, sh), slices in zip(part, buckets):
+                nb = sum(c for _, c, big in slices if big)
+                ns = sum(c for _, c, big in slices if not big)
+                assert zo == z and zb >= nb and zb - nb < 8 * world and zb % (8 * world) == 0 and sh * world == zb and sh % 8 == 0
+                assert zl - zb >= ns and zl - zb - ns < 8
                 z += zl
-            total = sum(c for b in buckets for _, c in b)
-            assert z - total < 8 * world * len(buckets)
+        big = sum(c for b in buckets for _, c, k in b if k)
+        total = sum(c for b in buckets for _, c, _ in b)
+        assert big / total > (0.9 if name != "tiny" else 0.5)  # what ZeRO-1 shards: the bulk of the model
 
 
 def _zero_worker(rank, world, port, q):
-    """Reduce-scatter + sharded AdamW + all-gather over gloo on the CPU oracle's buffers: the arithmetic of model.cu's ZeRO-1 path."""
+    """Reduce-scatter + sharded AdamW + all-gather over gloo on the CPU oracle's buffers: the arithmetic of model.cu's ZeRO-1
+    path (big slices sharded in Z order; small slices all-reduced and updated on every rank)."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.set_num_threads(1)
@@ -130,22 +134,33 @@ def _zero_worker(rank, world, port, q):
     m.set_dloss_scale(1.0 / B_GLOBAL)
     m.forward(images[sl], labels[sl]); m.zero_grad(); m.backward()
     grads, params = m.grads_flat(), m.params_flat()
-    buckets, part = vitrs.grad_buckets("tiny"), vitrs.zero_partition("tiny", world)
+    buckets, part = vitrs.grad_buckets("tiny", with_kind=True), vitrs.zero_partition("tiny", world)
     new_params = params.copy()
-    for slices, (zo, zl, sh) in zip(buckets, part):
-        idx = np.concatenate([np.arange(o, o + c) for o, c in slices])        # Z order of this bucket
-        region = np.zeros(zl, np.float32); region[:idx.size] = grads[idx]
-        # gloo has no reduce_scatter: all_reduce and keep this rank's shard (same sums)
-        t = torch.from_numpy(region); dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        g = region[rank * sh:(rank + 1) * sh].copy()
-        pz = np.zeros(zl, np.float32); pz[:idx.size] = params[idx]
-        p = pz[rank * sh:(rank + 1) * sh].copy()
-        mom, var = np.zeros_like(p), np.zeros_like(p)
-        po.adamw_step(p, g, mom, var, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1)         # AdamW on the shard only
-        gathered = [torch.zeros(sh) for _ in range(world)]
-        dist.all_gather(gathered, torch.from_numpy(p))
-        full = torch.cat(gathered).numpy()
-        new_params[idx] = full[:idx.size]
+    hp = (1e-3, 0.9, 0.999, 1e-8, 0.01, 1)
+    for slices, (zo, zl, zb, sh) in zip(buckets, part):
+        big = [np.arange(o, o + c) for o, c, k in slices if k]
+        small = [np.arange(o, o + c) for o, c, k in slices if not k]
+        if big:
+            idx = np.concatenate(big)                                          # Z order of the bucket's big part
+            region = np.zeros(zb, np.float32); region[:idx.size] = grads[idx]
+            # gloo has no reduce_scatter: all_reduce and keep this rank's shard (the same sums)
+            dist.all_reduce(torch.from_numpy(region), op=dist.ReduceOp.SUM)
+            g = region[rank * sh:(rank + 1) * sh].copy()
+            pz = np.zeros(zb, np.float32); pz[:idx.size] = params[idx]
+            p = pz[rank * sh:(rank + 1) * sh].copy()
+            mom, var = np.zeros_like(p), np.zeros_like(p)
+            po.adamw_step(p, g, mom, var, *hp)                                  # AdamW on the shard only
+            gathered = [torch.zeros(sh) for _ in range(world)]
+            dist.all_gather(gathered, torch.from_numpy(p))
+            new_params[idx] = torch.cat(gathered).numpy()[:idx.size]
+        if small:
+            idx = np.concatenate(small)
+            g = grads[idx].copy()
+            dist.all_reduce(torch.from_numpy(g), op=dist.ReduceOp.SUM)
+            p = params[idx].copy()
+            mom, var = np.zeros_like(p), np.zeros_like(p)
+            po.adamw_step(p, g, mom, var, *hp)                                  # replicated
+            new_params[idx] = p
     if rank == 0:
         q.put(new_params)
     dist.barrier()

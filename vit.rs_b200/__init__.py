@@ -141,10 +141,10 @@ _SIGNATURES = {
     "vitrs_model_enable_zero1": (_int, [_vp]),
     "vitrs_model_gather_parameters": (_int, [_vp]),
     "vitrs_model_optimizer_state_bytes": (_int, [_vp, C.POINTER(_sz)]),
-    "vitrs_zero_partition": (_int, [C.POINTER(Config), _int, _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "vitrs_zero_partition": (_int, [C.POINTER(Config), _int, _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "vitrs_comm_world": (_int, [_vp, C.POINTER(_int), C.POINTER(_int)]),
     "vitrs_model_allreduce_grads": (_int, [_vp]),
-    "vitrs_grad_bucket": (_int, [C.POINTER(Config), _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_int)]),
+    "vitrs_grad_bucket": (_int, [C.POINTER(Config), _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_int), C.POINTER(_int)]),
     "vitrs_allreduce_f32": (_int, [_vp, _vp, _sz]),
 }
 # the two-mode operator families share argument lists
@@ -266,28 +266,29 @@ class Context:
 
 
 def zero_partition(cfg, world):
-    """The ZeRO-1 partition (host arithmetic only): per bucket (z_off, z_len, shard)."""
+    """The ZeRO-1 partition (host arithmetic only): per bucket (z_off, z_len, z_big, shard)."""
     c = make_config(cfg) if not isinstance(cfg, Config) else cfg
     out = []
     for b in range(c.num_layers + 2):
-        zo, zl, sh = C.c_size_t(), C.c_size_t(), C.c_size_t()
-        rc = lib().vitrs_zero_partition(C.byref(c), world, b, C.byref(zo), C.byref(zl), C.byref(sh))
+        zo, zl, zb, sh = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        rc = lib().vitrs_zero_partition(C.byref(c), world, b, C.byref(zo), C.byref(zl), C.byref(zb), C.byref(sh))
         if rc != 0:
             raise VitrsError(f"vitrs_zero_partition failed ({rc})")
-        out.append((zo.value, zl.value, sh.value))
+        out.append((zo.value, zl.value, zb.value, sh.value))
     return out
 
 
-def grad_buckets(cfg):
-    """The gradient-exchange schedule (host arithmetic only): list of buckets, each a list of (offset, count)."""
+def grad_buckets(cfg, with_kind=False):
+    """The gradient-exchange schedule (host arithmetic only): list of buckets, each a list of (offset, count)
+    — or (offset, count, big) with with_kind: big = a GEMM weight matrix (sharded by ZeRO-1)."""
     c = make_config(cfg) if not isinstance(cfg, Config) else cfg
     out = []
     for b in range(c.num_layers + 2):
-        off, cnt, n = (C.c_size_t * 12)(), (C.c_size_t * 12)(), C.c_int()
-        rc = lib().vitrs_grad_bucket(C.byref(c), b, off, cnt, C.byref(n))
+        off, cnt, big, n = (C.c_size_t * 12)(), (C.c_size_t * 12)(), (C.c_int * 12)(), C.c_int()
+        rc = lib().vitrs_grad_bucket(C.byref(c), b, off, cnt, big, C.byref(n))
         if rc != 0:
             raise VitrsError(f"vitrs_grad_bucket failed ({rc})")
-        out.append([(off[i], cnt[i]) for i in range(n.value)])
+        out.append([(off[i], cnt[i], big[i]) if with_kind else (off[i], cnt[i]) for i in range(n.value)])
     return out
 
 

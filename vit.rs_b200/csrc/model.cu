@@ -76,12 +76,15 @@ struct vitrs_model {
     int loss_reduced;      // d_mean_loss[1] holds (or will hold, on the comm stream) the sum over ranks of the local losses
     int z_world;           // world size the plan below was built for (0 = not built)
     int z_buckets;
-    size_t *z_off, *z_len, *z_shard, *s_off;  // per bucket: region start / padded length in the exchange buffer, shard length, shard start in zp/zm/zv
+    size_t *z_off, *z_len, *z_big, *z_shard, *s_off;  // per bucket: region start / length in the exchange buffer, length of its big (sharded)
+                                                      // part, shard length, shard start in zp / zm / zv
     size_t z_size, s_total;
     bf16* comm_buf;        // [z_size]
     // ZeRO-1: fp32 master weights and AdamW moments of this rank's shard of every bucket, in Z order
     int zero1;
     float *zp, *zm, *zv;   // [s_total]
+    float *m_small, *v_small;  // replicated moments of the small tensors, compact (small_runs)
+    size_t small_total;
 };
 
 namespace {
@@ -491,17 +494,24 @@ int bucket_begin(vitrs_model* m) {
 // Bucket b of the gradient exchange, in the order backward completes them: 0 = final LayerNorm + head,
 // 1..L = blocks L-1..0 (the block's 12 slices of the tensor-major buffer), L+1 = patch / cls / position
 // embeddings.  Returns the slice count; offsets / counts are in elements of the flat gradient buffer.
-int bucket_slices(const vitrs_config& cfg, const size_t* sizes, const size_t* offs, int bucket, size_t* out_off, size_t* out_cnt) {
+// big[i] = 1 for the GEMM weight matrices (patchw, qkvw, attprojw, fcw, fcprojw: 98.7 % of ViT-B/16), which the kernels
+// read through the bf16 shadow and ZeRO-1 shards; every other tensor (gains, biases, embeddings, the class head) is read in
+// fp32 by the kernels and stays replicated.
+int bucket_slices(const vitrs_config& cfg, const size_t* sizes, const size_t* offs, int bucket, size_t* out_off, size_t* out_cnt,
+                  int* big = nullptr) {
     const int L = cfg.num_layers;
+    int dummy[12];
+    if (!big) big = dummy;
     if (bucket == 0) {  // lnfw, lnfb, headw, headb are contiguous
         out_off[0] = offs[P_LNFW];
         out_cnt[0] = sizes[P_LNFW] + sizes[P_LNFB] + sizes[P_HEADW] + sizes[P_HEADB];
+        big[0] = 0;
         return 1;
     }
-    if (bucket == L + 1) {  // patchw, patchb, cls, wpe are contiguous
-        out_off[0] = offs[P_PATCHW];
-        out_cnt[0] = offs[P_LN1W];
-        return 1;
+    if (bucket == L + 1) {  // patchw | patchb, cls, wpe (contiguous)
+        out_off[0] = offs[P_PATCHW]; out_cnt[0] = sizes[P_PATCHW]; big[0] = 1;
+        out_off[1] = offs[P_PATCHB]; out_cnt[1] = offs[P_LN1W] - offs[P_PATCHB]; big[1] = 0;
+        return 2;
     }
     const int l = L - bucket;
     int n = 0;
@@ -509,21 +519,24 @@ int bucket_slices(const vitrs_config& cfg, const size_t* sizes, const size_t* of
         const size_t per = sizes[i] / L;
         out_off[n] = offs[i] + (size_t)l * per;
         out_cnt[n] = per;
+        big[n] = i == P_QKVW || i == P_ATTPROJW || i == P_FCW || i == P_FCPROJW;
         ++n;
     }
     return n;
 }
 
-// The exchange buffer holds the buckets back to back, each bucket's slices back to back ("Z order": the layer-major layout
-// SURVEY section 7(v) asks for, as a view for the wire while the named parameter views stay tensor-major).  A bucket's region is
-// padded to a multiple of 8 * world elements so that its world shards are equal and 16-byte aligned (ZeRO-1 reduce-scatter).
-void zplan_sizes(const vitrs_config& cfg, const size_t* sizes, const size_t* offs, int world, int bucket, size_t* len, size_t* shard) {
-    size_t off[12], cnt[12], total = 0;
-    const int n = bucket_slices(cfg, sizes, offs, bucket, off, cnt);
-    for (int i = 0; i < n; ++i) total += cnt[i];
+// The exchange buffer holds the buckets back to back ("Z order": the layer-major layout SURVEY section 7(v) asks for, as a view
+// for the wire while the named parameter views stay tensor-major).  Inside a bucket's region the big slices come first, padded
+// to a multiple of 8 * world elements so that the world shards are equal and 16-byte aligned (ZeRO-1 reduce-scatter), then
+// the small slices, padded to 8.
+void zplan_sizes(const vitrs_config& cfg, const size_t* sizes, const size_t* offs, int world, int bucket, size_t* big_len, size_t* small_len) {
+    size_t off[12], cnt[12], tb = 0, ts = 0;
+    int big[12];
+    const int n = bucket_slices(cfg, sizes, offs, bucket, off, cnt, big);
+    for (int i = 0; i < n; ++i) (big[i] ? tb : ts) += cnt[i];
     const size_t q = (size_t)8 * world;
-    *len = (total + q - 1) / q * q;
-    *shard = *len / world;
+    *big_len = (tb + q - 1) / q * q;
+    *small_len = (ts + 7) / 8 * 8;
 }
 
 int ensure_zplan(vitrs_model* m) {
@@ -535,11 +548,14 @@ int ensure_zplan(vitrs_model* m) {
     m->comm_buf = nullptr;
     const int nb = m->cfg.num_layers + 2;
     free(m->z_off);
-    m->z_off = (size_t*)calloc(4 * (size_t)nb, sizeof(size_t));
-    m->z_len = m->z_off + nb; m->z_shard = m->z_len + nb; m->s_off = m->z_shard + nb;
+    m->z_off = (size_t*)calloc(5 * (size_t)nb, sizeof(size_t));
+    m->z_len = m->z_off + nb; m->z_big = m->z_len + nb; m->z_shard = m->z_big + nb; m->s_off = m->z_shard + nb;
     size_t z = 0, sh = 0;
     for (int b = 0; b < nb; ++b) {
-        zplan_sizes(m->cfg, m->param_sizes, m->param_off, ctx->world, b, &m->z_len[b], &m->z_shard[b]);
+        size_t small = 0;
+        zplan_sizes(m->cfg, m->param_sizes, m->param_off, ctx->world, b, &m->z_big[b], &small);
+        m->z_len[b] = m->z_big[b] + small;
+        m->z_shard[b] = m->z_big[b] / ctx->world;
         m->z_off[b] = z; m->s_off[b] = sh;
         z += m->z_len[b]; sh += m->z_shard[b];
     }
@@ -550,12 +566,22 @@ int ensure_zplan(vitrs_model* m) {
     return VITRS_OK;
 }
 
-SliceTable table_of(const vitrs_model* m, int bucket, size_t z_base) {
+// which: 0 = every slice, 1 = the big slices only, 2 = the small slices only (offsets in the exchange buffer are the same)
+SliceTable table_of(const vitrs_model* m, int bucket, int which = 0) {
     SliceTable t;
     memset(&t, 0, sizeof(t));
-    t.n = bucket_slices(m->cfg, m->param_sizes, m->param_off, bucket, t.src_off, t.cnt);
-    size_t z = z_base;
-    for (int i = 0; i < t.n; ++i) { t.z_off[i] = z; z += t.cnt[i]; }
+    size_t off[12], cnt[12];
+    int big[12];
+    const int n = bucket_slices(m->cfg, m->param_sizes, m->param_off, bucket, off, cnt, big);
+    size_t zb = m->z_off[bucket], zs = m->z_off[bucket] + m->z_big[bucket];
+    for (int i = 0; i < n; ++i) {
+        size_t& z = big[i] ? zb : zs;
+        if (which == 0 || (which == 1) == (big[i] != 0)) {
+            t.src_off[t.n] = off[i]; t.cnt[t.n] = cnt[i]; t.z_off[t.n] = z;
+            t.n++;
+        }
+        z += cnt[i];
+    }
     return t;
 }
 
@@ -569,15 +595,20 @@ int exchange_bucket(vitrs_model* m, int bk) {
         return vitrs_nccl_allreduce_group(ctx, bufs, cnt, n);
     }
     // one contiguous bf16 message per bucket (bf16 on the wire in production)
-    const SliceTable tab = table_of(m, bk, m->z_off[bk]);
     bf16* region = m->comm_buf + m->z_off[bk];
-    VITRS_TRY(op_pack_f32_to_bf16(ctx, m->comm_buf, m->grads, tab, ctx->comm_stream));
+    VITRS_TRY(op_pack_f32_to_bf16(ctx, m->comm_buf, m->grads, table_of(m, bk), ctx->comm_stream));
     if (m->zero1) {
-        // each rank receives the sum of its 1/world shard; AdamW runs on the shard in update()
-        return vitrs_nccl_reduce_scatter(ctx, region, region + (size_t)ctx->rank * m->z_shard[bk], m->z_shard[bk], 1);
+        // big slices: each rank receives the sum of its 1/world shard (AdamW runs on the shard in update()); small slices
+        // stay replicated: summed everywhere and unpacked into the fp32 gradient views
+        const size_t small = m->z_len[bk] - m->z_big[bk];
+        VITRS_TRY(vitrs_nccl_group(ctx, 1));
+        if (m->z_shard[bk]) VITRS_TRY(vitrs_nccl_reduce_scatter(ctx, region, region + (size_t)ctx->rank * m->z_shard[bk], m->z_shard[bk], 1));
+        if (small) VITRS_TRY(vitrs_nccl_allreduce(ctx, region + m->z_big[bk], region + m->z_big[bk], small, 1));
+        VITRS_TRY(vitrs_nccl_group(ctx, 0));
+        return op_unpack_bf16_to_f32(ctx, m->grads, m->comm_buf, table_of(m, bk, 2), ctx->comm_stream);
     }
     VITRS_TRY(vitrs_nccl_allreduce(ctx, region, region, m->z_len[bk], 1));
-    return op_unpack_bf16_to_f32(ctx, m->grads, m->comm_buf, tab, ctx->comm_stream);
+    return op_unpack_bf16_to_f32(ctx, m->grads, m->comm_buf, table_of(m, bk), ctx->comm_stream);
 }
 
 int allreduce_bucket(vitrs_model* m, int bucket) {
@@ -618,33 +649,59 @@ int reduce_loss(vitrs_model* m) {
     return VITRS_OK;
 }
 
-// ---- ZeRO-1: fp32 master weights and AdamW moments sharded 1/world per bucket ---------------------
+// ---- ZeRO-1: fp32 master weights and AdamW moments of the GEMM weight matrices sharded 1/world per bucket ------
+// The small tensors (everything the kernels read in fp32) keep replicated fp32 weights in the parameter view and replicated
+// moments in two compact arrays; they are five contiguous runs of the tensor-major buffer.
+struct SmallRun { size_t off, cnt, soff; };
+int small_runs(const vitrs_model* m, SmallRun* r) {
+    const int first[5] = {P_PATCHB, P_QKVB, P_ATTPROJB, P_FCB, P_FCPROJB}, last[5] = {P_LN1B, P_QKVB, P_LN2B, P_FCB, P_HEADB};
+    size_t so = 0;
+    for (int i = 0; i < 5; ++i) {
+        r[i].off = m->param_off[first[i]];
+        r[i].cnt = m->param_off[last[i]] + m->param_sizes[last[i]] - r[i].off;
+        r[i].soff = so;
+        so += (r[i].cnt + 3) / 4 * 4;  // 16-byte aligned starts
+    }
+    return 5;
+}
+
 // (re)cut the shards from the full tensor-major buffers params / m / v, then drop the full moment buffers
 int zero_shard_from_full(vitrs_model* m) {
     vitrs_ctx* ctx = m->ctx;
     m->zero1 = 0;
     VITRS_TRY(ensure_zplan(m));
     VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SmallRun runs[5];
+    small_runs(m, runs);
+    const size_t small_total = runs[4].soff + (runs[4].cnt + 3) / 4 * 4;
     if (!m->zp) {
-        VITRS_CUDA(ctx, cudaMalloc(&m->zp, m->s_total * sizeof(float)));
-        VITRS_CUDA(ctx, cudaMalloc(&m->zm, m->s_total * sizeof(float)));
-        VITRS_CUDA(ctx, cudaMalloc(&m->zv, m->s_total * sizeof(float)));
+        VITRS_CUDA(ctx, cudaMalloc(&m->zp, (m->s_total + 4) * sizeof(float)));
+        VITRS_CUDA(ctx, cudaMalloc(&m->zm, (m->s_total + 4) * sizeof(float)));
+        VITRS_CUDA(ctx, cudaMalloc(&m->zv, (m->s_total + 4) * sizeof(float)));
+        VITRS_CUDA(ctx, cudaMalloc(&m->m_small, small_total * sizeof(float)));
+        VITRS_CUDA(ctx, cudaMalloc(&m->v_small, small_total * sizeof(float)));
+        VITRS_CUDA(ctx, cudaMemsetAsync(m->m_small, 0, small_total * sizeof(float), ctx->comm_stream));
+        VITRS_CUDA(ctx, cudaMemsetAsync(m->v_small, 0, small_total * sizeof(float), ctx->comm_stream));
+        m->small_total = small_total;
     }
     float* tmp = nullptr;
     VITRS_CUDA(ctx, cudaMalloc(&tmp, m->z_size * sizeof(float)));
     float* full[3] = {m->params, m->m, m->v};
     float* shard[3] = {m->zp, m->zm, m->zv};
+    float* small[3] = {nullptr, m->m_small, m->v_small};
     for (int k = 0; k < 3; ++k) {
-        if (!full[k]) {  // moments already dropped: they stay as they are
-            continue;
-        }
+        if (!full[k]) continue;  // moments already dropped: they stay as they are
         VITRS_CUDA(ctx, cudaMemsetAsync(tmp, 0, m->z_size * sizeof(float), ctx->comm_stream));
         for (int b = 0; b < m->z_buckets; ++b) {
-            const SliceTable tab = table_of(m, b, m->z_off[b]);
-            VITRS_TRY(op_pack_f32_to_f32(ctx, tmp, full[k], tab, ctx->comm_stream));
+            if (!m->z_shard[b]) continue;
+            VITRS_TRY(op_pack_f32_to_f32(ctx, tmp, full[k], table_of(m, b, 1), ctx->comm_stream));
             VITRS_CUDA(ctx, cudaMemcpyAsync(shard[k] + m->s_off[b], tmp + m->z_off[b] + (size_t)ctx->rank * m->z_shard[b],
                                             m->z_shard[b] * sizeof(float), cudaMemcpyDeviceToDevice, ctx->comm_stream));
         }
+        if (small[k])
+            for (int i = 0; i < 5; ++i)
+                VITRS_CUDA(ctx, cudaMemcpyAsync(small[k] + runs[i].soff, full[k] + runs[i].off, runs[i].cnt * sizeof(float),
+                                                cudaMemcpyDeviceToDevice, ctx->comm_stream));
     }
     VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
     VITRS_CUDA(ctx, cudaFree(tmp));
@@ -654,41 +711,57 @@ int zero_shard_from_full(vitrs_model* m) {
     return VITRS_OK;
 }
 
-// all-gather one sharded fp32 array (zp / zm / zv) into a full tensor-major buffer
-int zero_gather_full(vitrs_model* m, const float* shards, float* full) {
+// all-gather one sharded fp32 array (zp / zm / zv) into the big slices of a full tensor-major buffer; `small` (nullable): the
+// compact replicated array that fills the small runs
+int zero_gather_full(vitrs_model* m, const float* shards, const float* small, float* full) {
     vitrs_ctx* ctx = m->ctx;
     float* tmp = nullptr;
     VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     VITRS_CUDA(ctx, cudaMalloc(&tmp, m->z_size * sizeof(float)));
     for (int b = 0; b < m->z_buckets; ++b) {
+        if (!m->z_shard[b]) continue;
         float* region = tmp + m->z_off[b];
         float* mine = region + (size_t)ctx->rank * m->z_shard[b];
         VITRS_CUDA(ctx, cudaMemcpyAsync(mine, shards + m->s_off[b], m->z_shard[b] * sizeof(float), cudaMemcpyDeviceToDevice, ctx->comm_stream));
         VITRS_TRY(vitrs_nccl_all_gather(ctx, mine, region, m->z_shard[b], 0));
-        VITRS_TRY(op_unpack_f32_to_f32(ctx, full, tmp, table_of(m, b, m->z_off[b]), ctx->comm_stream));
+        VITRS_TRY(op_unpack_f32_to_f32(ctx, full, tmp, table_of(m, b, 1), ctx->comm_stream));
+    }
+    if (small) {
+        SmallRun runs[5];
+        small_runs(m, runs);
+        for (int i = 0; i < 5; ++i)
+            VITRS_CUDA(ctx, cudaMemcpyAsync(full + runs[i].off, small + runs[i].soff, runs[i].cnt * sizeof(float), cudaMemcpyDeviceToDevice,
+                                            ctx->comm_stream));
     }
     VITRS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
     VITRS_CUDA(ctx, cudaFree(tmp));
     return VITRS_OK;
 }
 
-// AdamW on this rank's shard of every bucket (gradients: the reduce-scattered bf16 sums sitting in the exchange buffer), then
-// the updated bf16 weights are all-gathered in place and scattered into the tensor-major shadow the GEMMs read
+// AdamW on this rank's shard of every bucket (gradients: the reduce-scattered bf16 sums sitting in the exchange buffer), the
+// updated bf16 weights all-gathered in place and scattered into the tensor-major shadow the GEMMs read; the small tensors are
+// updated in place, replicated, from the summed fp32 gradients
 int zero_update(vitrs_model* m) {
     vitrs_ctx* ctx = m->ctx;
     VITRS_TRY(bucket_begin(m));  // the comm stream continues behind whatever the compute stream has issued (hyper-parameters)
     for (int b = 0; b < m->z_buckets; ++b) {
+        if (!m->z_shard[b]) continue;
         bf16* mine = m->comm_buf + m->z_off[b] + (size_t)ctx->rank * m->z_shard[b];
         VITRS_TRY(op_adamw_apply_shard(ctx, m->zp + m->s_off[b], mine, m->zm + m->s_off[b], m->zv + m->s_off[b], m->z_shard[b], ctx->comm_stream));
     }
     VITRS_TRY(vitrs_nccl_group(ctx, 1));
     for (int b = 0; b < m->z_buckets; ++b) {
         bf16* region = m->comm_buf + m->z_off[b];
-        VITRS_TRY(vitrs_nccl_all_gather(ctx, region + (size_t)ctx->rank * m->z_shard[b], region, m->z_shard[b], 1));
+        if (m->z_shard[b]) VITRS_TRY(vitrs_nccl_all_gather(ctx, region + (size_t)ctx->rank * m->z_shard[b], region, m->z_shard[b], 1));
     }
     VITRS_TRY(vitrs_nccl_group(ctx, 0));
+    SmallRun runs[5];
+    small_runs(m, runs);
+    for (int i = 0; i < 5; ++i)
+        VITRS_TRY(op_adamw_apply(ctx, m->params + runs[i].off, m->grads + runs[i].off, m->m_small + runs[i].soff, m->v_small + runs[i].soff,
+                                 runs[i].cnt, m->shadow + runs[i].off, ctx->comm_stream));
     for (int b = 0; b < m->z_buckets; ++b)
-        VITRS_TRY(op_unpack_bf16_to_bf16(ctx, m->shadow, m->comm_buf, table_of(m, b, m->z_off[b]), ctx->comm_stream));
+        if (m->z_shard[b]) VITRS_TRY(op_unpack_bf16_to_bf16(ctx, m->shadow, m->comm_buf, table_of(m, b, 1), ctx->comm_stream));
     return comm_join(m);
 }
 
@@ -793,7 +866,7 @@ int vitrs_model_destroy(vitrs_model* m) {
     cudaFree(m->lse); cudaFree(m->cls_rows); cudaFree(m->dcls_rows); cudaFree(m->patches);
     cudaFree(m->dres); cudaFree(m->dln); cudaFree(m->dbig); cudaFree(m->dlogits); cudaFree(m->dlnf);
     cudaFree(m->d_mean_loss);
-    cudaFree(m->comm_buf); cudaFree(m->zp); cudaFree(m->zm); cudaFree(m->zv);
+    cudaFree(m->comm_buf); cudaFree(m->zp); cudaFree(m->zm); cudaFree(m->zv); cudaFree(m->m_small); cudaFree(m->v_small);
     free(m->z_off);
     if (m->h_mean_loss) cudaFreeHost(m->h_mean_loss);
     for (int i = 0; i < 2; ++i) {
@@ -925,7 +998,7 @@ int vitrs_model_backward(vitrs_model* m) {
 }
 
 // host-only description of the bucketed exchange (no device needed): slices of bucket `bucket` for `cfg`
-int vitrs_grad_bucket(const vitrs_config* cfg_in, int bucket, size_t* offsets, size_t* counts, int* num_slices) {
+int vitrs_grad_bucket(const vitrs_config* cfg_in, int bucket, size_t* offsets, size_t* counts, int* big, int* num_slices) {
     if (!cfg_in || !offsets || !counts || !num_slices) return VITRS_ERR_ARG;
     vitrs_config cfg = *cfg_in;
     cfg.max_seq_len = tokens(cfg);
@@ -933,7 +1006,7 @@ int vitrs_grad_bucket(const vitrs_config* cfg_in, int bucket, size_t* offsets, s
     size_t sizes[P_COUNT], offs[P_COUNT], off = 0;
     param_sizes_of(cfg, sizes);
     for (int i = 0; i < P_COUNT; ++i) { offs[i] = off; off += sizes[i]; }
-    *num_slices = bucket_slices(cfg, sizes, offs, bucket, offsets, counts);
+    *num_slices = bucket_slices(cfg, sizes, offs, bucket, offsets, counts, big);
     return VITRS_OK;
 }
 
@@ -995,33 +1068,35 @@ int vitrs_model_enable_zero1(vitrs_model* m) {
 int vitrs_model_gather_parameters(vitrs_model* m) {
     if (!m) return VITRS_ERR_ARG;
     if (!m->zero1) return VITRS_OK;
-    return zero_gather_full(m, m->zp, m->params);
+    return zero_gather_full(m, m->zp, nullptr, m->params);  // the small tensors are current in the view already
 }
 
 // bytes of optimiser state (fp32 master weights + both AdamW moments) this rank holds
 int vitrs_model_optimizer_state_bytes(vitrs_model* m, size_t* bytes) {
     if (!m || !bytes) return VITRS_ERR_ARG;
-    *bytes = (m->zero1 ? m->s_total : m->num_params) * 3 * sizeof(float);
+    // ZeRO-1: sharded master / m / v of the big tensors + replicated fp32 weights / m / v of the small ones
+    *bytes = m->zero1 ? (m->s_total + m->small_total) * 3 * sizeof(float) : m->num_params * 3 * sizeof(float);
     return VITRS_OK;
 }
 
 // host-only description of the ZeRO-1 partition (no device needed): region offset / padded length of `bucket` in the exchange
 // buffer and the length of each rank's shard, for `world` ranks
-int vitrs_zero_partition(const vitrs_config* cfg_in, int world, int bucket, size_t* z_off, size_t* z_len, size_t* shard) {
+int vitrs_zero_partition(const vitrs_config* cfg_in, int world, int bucket, size_t* z_off, size_t* z_len, size_t* z_big, size_t* shard) {
     if (!cfg_in || world < 1) return VITRS_ERR_ARG;
     vitrs_config cfg = *cfg_in;
     cfg.max_seq_len = tokens(cfg);
     if (bucket < 0 || bucket > cfg.num_layers + 1) return VITRS_ERR_ARG;
-    size_t sizes[P_COUNT], offs[P_COUNT], off = 0, z = 0, len = 0, sh = 0;
+    size_t sizes[P_COUNT], offs[P_COUNT], off = 0, z = 0, big = 0, small = 0;
     param_sizes_of(cfg, sizes);
     for (int i = 0; i < P_COUNT; ++i) { offs[i] = off; off += sizes[i]; }
     for (int b = 0; b <= bucket; ++b) {
-        z += len;
-        zplan_sizes(cfg, sizes, offs, world, b, &len, &sh);
+        z += big + small;
+        zplan_sizes(cfg, sizes, offs, world, b, &big, &small);
     }
     if (z_off) *z_off = z;
-    if (z_len) *z_len = len;
-    if (shard) *shard = sh;
+    if (z_len) *z_len = big + small;
+    if (z_big) *z_big = big;
+    if (shard) *shard = big / world;
     return VITRS_OK;
 }
 
@@ -1150,11 +1225,11 @@ int vitrs_model_save_checkpoint(vitrs_model* m, const char* path) {
     // ZeRO-1: every rank takes part in gathering the shards; the full moments live in temporaries for the duration of the write
     float *full_m = m->m, *full_v = m->v;
     if (m->zero1) {
-        VITRS_TRY(zero_gather_full(m, m->zp, m->params));
+        VITRS_TRY(zero_gather_full(m, m->zp, nullptr, m->params));
         VITRS_CUDA(ctx, cudaMalloc(&full_m, m->num_params * sizeof(float)));
         VITRS_CUDA(ctx, cudaMalloc(&full_v, m->num_params * sizeof(float)));
-        VITRS_TRY(zero_gather_full(m, m->zm, full_m));
-        VITRS_TRY(zero_gather_full(m, m->zv, full_v));
+        VITRS_TRY(zero_gather_full(m, m->zm, m->m_small, full_m));
+        VITRS_TRY(zero_gather_full(m, m->zv, m->v_small, full_v));
     }
     bool ok = true;
     float* host = (float*)malloc(m->num_params * sizeof(float));
