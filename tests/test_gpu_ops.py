@@ -346,3 +346,27 @@ def test_empty_inputs_are_noops(vitrs):
     vitrs.matmul_forward(z, z, one, None, 0, 3, 2, 2)
     vitrs.layernorm_forward(z, z, z, z, one, one, 0, 3, 4)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("t,peak_key", [(197, 150), (256, 255), (160, 40)])
+def test_attention_bf16_late_peak_moves_the_exponent_reference(vitrs, t, peak_key):
+    """The persistent forward takes its exponent reference from the first 32 keys and moves it when a later key is more than
+    2^12 times more probable (attention_tc.cu, single-pass softmax).  Here one late key scores ~15 nats above every other for
+    every query, so each row goes through that rescale path; the result must still be the exact softmax (oracle)."""
+    b, c, nh = 2, 128, 2
+    rng = np.random.default_rng(t)
+    x = (rng.standard_normal((b, t, 3, nh, 64)) * 0.5).astype(f32)
+    u = np.full(64, 1.0 / 8.0, f32)                     # unit vector
+    x[:, :, 0] += 10.0 * u                               # every query has a component 10 along u
+    x[:, peak_key, 1] = 12.0 * u                         # one key has 12 along u: q.k / sqrt(64) = 15
+    hq, qkv = prep(x.reshape(-1), torch.bfloat16)
+    out = torch.zeros(b * t * c, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(b * nh * t, device="cuda")
+    vitrs.attention_forward(out, lse, None, qkv, b, t, c, nh, causal=0)
+    wo, wp, wa = np.zeros(b * t * c, f32), np.zeros(b * nh * t * t, f32), np.zeros(b * nh * t * t, f32)
+    po.attention_forward(wo, wp, wa, hq, b, t, c, nh, causal=0)
+    assert relerr(host(out), wo) <= TOL_BF16
+    pre = wp.reshape(b * nh, t, t).astype(np.float64)
+    want_lse = np.log(np.exp(pre - pre.max(-1, keepdims=True)).sum(-1)) + pre.max(-1)
+    assert np.abs(host(lse).reshape(b * nh, t) - want_lse).max() <= 2e-2
+    assert (wa.reshape(b * nh, t, t)[:, :, peak_key] > 0.9).all()  # the case is what it claims to be

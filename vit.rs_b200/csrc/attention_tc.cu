@@ -272,6 +272,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 // Group 1 starts half a period late, so one group's exponentials (the MUFU pipe is the floor of this kernel: T^2 per head)
 // run under the other group's MMA / read-out phases.  Warps whose 32 rows are all beyond T (rows 224..255 at T = 197) skip
 // the arithmetic and only keep the barriers moving.  TMEM: two 256-column regions {S [0,NK) -> P [0,NK/2); O [192,256)}.
+constexpr float kTau = 12.f;  // probabilities may exceed 1 by up to 2^kTau before the exponent reference is moved
 constexpr int kFwdThreads = 320;  // warp 0 loader, warp 1 issuer / TMEM owner, warps 2-5 group 0, warps 6-9 group 1
 
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
@@ -403,35 +404,59 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                 mbar_arrive_cnt(stage_free + 8 * pending_stage);
                 pending_stage = -1;
             }
-            float mx = -INFINITY, sum = 0.f;
+            // One pass over the scores.  Tensor-memory reads (64 B / clock / SM) are the floor of this kernel, so the row maximum is
+            // not taken in a pass of its own: the exponent reference m_ref (an integer, log2 domain) is the first chunk's maximum
+            // rounded up, every probability is 2^(s - m_ref), and a later chunk whose maximum exceeds m_ref by more than kTau
+            // (rare: a key more than 8 nats above the first 32) moves the reference and rescales the probabilities already
+            // written by an exact power of two.  P <= 2^kTau keeps every sum far inside fp32 / bf16 range; the result is the
+            // softmax itself, whatever the reference.
+            float m_ref = 0.f, sum = 0.f;
             if (warp_live) {
-                for (int ch = 0; ch < nchunks; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_addr + ch * 32, v);
-                    if (ch * 32 + 32 <= T) {
+                uint32_t va[32], vb[32];
+                auto process = [&](int ch, uint32_t (&v)[32]) {
+                    const int k0 = ch * 32;
+                    const bool full = k0 + 32 <= T;
+                    float cm;
+                    if (full) {
                         float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
 #pragma unroll
                         for (int c = 4; c < 32; c += 4) {
                             m0 = fmaxf(m0, fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 1])));
                             m1 = fmaxf(m1, fmaxf(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
                         }
-                        mx = fmaxf(mx, fmaxf(m0, m1));
+                        cm = fmaxf(m0, m1);
                     } else {
+                        cm = -INFINITY;
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
-                            if (ch * 32 + c < T) mx = fmaxf(mx, __uint_as_float(v[c]));
+                            if (k0 + c < T) cm = fmaxf(cm, __uint_as_float(v[c]));
                     }
-                }
-                const float mxs = mx * sl2;
-                const float2 sl22 = splat2(sl2), nmx2 = splat2(-mxs);
-                for (int ch = 0; ch < nchunks; ++ch) {
-                    uint32_t v[32], pk[16];
-                    tmem_ld32(lane_addr + ch * 32, v);
-                    if (ch * 32 + 32 <= T) {
+                    const float cm2 = cm * sl2;
+                    if (ch == 0) {
+                        m_ref = ceilf(cm2);
+                    } else if (__any_sync(0xffffffffu, cm2 > m_ref + kTau)) {
+                        // rare: move the reference up and rescale what was written (warp-uniform branch, per-lane factor)
+                        const float new_ref = cm2 > m_ref + kTau ? ceilf(cm2) : m_ref;
+                        const float f = ex2(m_ref - new_ref);  // 2^(integer <= 0): exact
+                        tmem_st_wait();
+                        for (int blk = 0; blk < ch; ++blk) {
+                            uint32_t pk[16];
+                            tmem_ld16(lane_addr + blk * 16, pk);
+#pragma unroll
+                            for (int c = 0; c < 16; ++c)
+                                pk[c] = pack_bf16(__uint_as_float(pk[c] << 16) * f, __uint_as_float(pk[c] & 0xFFFF0000u) * f);
+                            tmem_st16(lane_addr + blk * 16, pk);
+                        }
+                        sum *= f;
+                        m_ref = new_ref;
+                    }
+                    uint32_t pk[16];
+                    if (full) {
+                        const float2 sl22 = splat2(sl2), nref2 = splat2(-m_ref);
                         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                         for (int c = 0; c < 16; ++c) {  // one packed FMA per pair of scores
-                            const float2 a = fma2(make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1])), sl22, nmx2);
+                            const float2 a = fma2(make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1])), sl22, nref2);
                             const float p0 = ex2(a.x), p1 = ex2(a.y);
                             s0 += p0;
                             s1 += p1;
@@ -441,14 +466,27 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                     } else {
 #pragma unroll
                         for (int c = 0; c < 16; ++c) {
-                            const int k = ch * 32 + 2 * c;
-                            const float p0 = k < T ? ex2(__uint_as_float(v[2 * c]) * sl2 - mxs) : 0.f;
-                            const float p1 = k + 1 < T ? ex2(__uint_as_float(v[2 * c + 1]) * sl2 - mxs) : 0.f;
+                            const int k = k0 + 2 * c;
+                            const float p0 = k < T ? ex2(__uint_as_float(v[2 * c]) * sl2 - m_ref) : 0.f;
+                            const float p1 = k + 1 < T ? ex2(__uint_as_float(v[2 * c + 1]) * sl2 - m_ref) : 0.f;
                             sum += p0 + p1;
                             pk[c] = pack_bf16(p0, p1);
                         }
                     }
-                    tmem_st16(lane_addr + ch * 16, pk);  // in place: columns [16ch, 16ch+16) were consumed by chunk ch/2 <= ch
+                    tmem_st16(lane_addr + ch * 16, pk);  // in place: columns [16ch, 16ch+16) hold scores of chunk ch/2 <= ch, consumed
+                };
+                // the next chunk's load is in flight while this chunk is exponentiated
+                tmem_ld32_issue(lane_addr, va);
+                tmem_ld_wait32(va);
+                for (int ch = 0; ch < nchunks; ch += 2) {
+                    if (ch + 1 < nchunks) tmem_ld32_issue(lane_addr + (ch + 1) * 32, vb);
+                    process(ch, va);
+                    if (ch + 1 < nchunks) {
+                        tmem_ld_wait32(vb);
+                        if (ch + 2 < nchunks) tmem_ld32_issue(lane_addr + (ch + 2) * 32, va);
+                        process(ch + 1, vb);
+                        if (ch + 2 < nchunks) tmem_ld_wait32(va);
+                    }
                 }
                 tmem_st_wait();
             }
@@ -469,7 +507,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                                      pack_bf16(__uint_as_float(v[g8 * 8 + 4]) * inv, __uint_as_float(v[g8 * 8 + 5]) * inv),
                                      pack_bf16(__uint_as_float(v[g8 * 8 + 6]) * inv, __uint_as_float(v[g8 * 8 + 7]) * inv));
                 }
-                if (q < T) lse[(long)bh * T + q] = mx * scale + logf(sum);
+                if (q < T) lse[(long)bh * T + q] = (m_ref + __log2f(sum)) * (1.0f / kLog2e);
             }
             tc_fence_before();
             mbar_arrive_cnt(tmem_free + 8 * g);  // S_g of the next head may overwrite this region
