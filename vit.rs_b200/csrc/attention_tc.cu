@@ -265,13 +265,15 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 // fetches K and V of a head once per query tile.  Here the CTA stays resident:
 //   loader (warp 0, one thread)  Q_0 Q_1 K_0 K_1 V_0 V_1 of the NEXT head stream into the other 96 KB stage while this head runs
 //                                (each head's operands cross HBM -> shared memory exactly once);
-//   issuer (warp 1, one thread)  a polling state machine over the two query tiles: S_g = Q_g K^T as soon as group g has given
-//                                its accumulator back and the operands have landed, O_g = P_g V as soon as P_g is packed;
+//   issuer (warp 1, one thread)  a polling state machine over the two query tiles: O_g = P_g V as soon as P_g is packed, with the
+//                                next head's S_g = Q_g K^T queued right behind it (in-order tensor pipe), except for the few
+//                                score columns that alias the O accumulator, which follow when the group has read O out;
 //   softmax group g (4 warps)    one thread per query row of tile g: max / exp2 / sum from TMEM, P packed to bf16 in place
 //                                (A operand of P.V), O scaled and staged through the dead Q_g tile, one TMA store.
 // Group 1 starts half a period late, so one group's exponentials (the MUFU pipe is the floor of this kernel: T^2 per head)
 // run under the other group's MMA / read-out phases.  Warps whose 32 rows are all beyond T (rows 224..255 at T = 197) skip
 // the arithmetic and only keep the barriers moving.  TMEM: two 256-column regions {S [0,NK) -> P [0,NK/2); O [192,256)}.
+constexpr int kMainCols = 192;  // score columns that do not overlap the O accumulator at [192, 256)
 constexpr float kTau = 12.f;  // probabilities may exceed 1 by up to 2^kTau before the exponent reference is moved
 constexpr int kFwdThreads = 320;  // warp 0 loader, warp 1 issuer / TMEM owner, warps 2-5 group 0, warps 6-9 group 1
 
@@ -296,9 +298,9 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     constexpr uint32_t STAGE = 6 * TILE_BYTES;  // Q_0 Q_1 K_0 K_1 V_0 V_1
     const uint32_t bar0 = base + 2 * STAGE;
-    const uint32_t full_qk = bar0, full_v = bar0 + 16, s_ready = bar0 + 32, p_ready = bar0 + 48, o_ready = bar0 + 64,
-                   tmem_free = bar0 + 80, stage_free = bar0 + 96;  // two barriers each
-    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 112);
+    const uint32_t full_qk = bar0, full_v = bar0 + 16, s_main = bar0 + 32, p_ready = bar0 + 48, o_ready = bar0 + 64,
+                   tmem_free = bar0 + 80, stage_free = bar0 + 96, s_tail = bar0 + 112;  // two barriers each
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 128);
     constexpr uint32_t TMEM_COLS = 512, REGION = 256, cO = REGION - HS;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -309,7 +311,8 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         for (int i = 0; i < 2; ++i) {
             mbar_init(full_qk + 8 * i, 1);
             mbar_init(full_v + 8 * i, 1);
-            mbar_init(s_ready + 8 * i, 1);
+            mbar_init(s_main + 8 * i, 1);
+            mbar_init(s_tail + 8 * i, 1);
             mbar_init(p_ready + 8 * i, 128);
             mbar_init(o_ready + 8 * i, 1);
             mbar_init(tmem_free + 8 * i, 128);
@@ -344,13 +347,27 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     } else if (warp == 1) {
         if (lane == 0) {
             // ================================ issuer ================================
-            const uint32_t idesc_s = make_idesc(TILE, NK, 0, 0);   // S = Q K^T: both operands K-major
+            // S = Q K^T (both operands K-major) is issued in two pieces.  Columns [0, kMainCols) of the next head go out right behind
+            // this head's P.V MMAs: tcgen05.mma executes in issue order, so overwriting the probabilities the P.V MMAs are still
+            // reading needs no barrier, and the O accumulator at [192, 256) is untouched.  The few columns that overlap O
+            // (keys >= 192) follow once the group has read O out.  The group thus finds its next scores waiting when it comes back.
+            const int n_main = NK < kMainCols ? NK : kMainCols, n_tail = NK - n_main;
+            const uint32_t idesc_main = make_idesc(TILE, n_main, 0, 0);
+            const uint32_t idesc_tail = make_idesc(TILE, n_tail > 0 ? n_tail : 16, 0, 0);
             const uint32_t idesc_o = make_idesc(TILE, HS, 0, 1);   // O = P V: A = P from TMEM, B = V MN-major
-            int nS[2] = {0, 0}, nPV[2] = {0, 0};
+            int nMain[2] = {0, 0}, nTail[2] = {0, 0}, nPV[2] = {0, 0};
+            auto issue_main = [&](int g, int G) {
+                const uint32_t sQ = base + (G & 1) * STAGE;
+                const uint64_t dq = make_desc(sQ + g * TILE_BYTES, 0, 1024), dk = make_desc(sQ + 2 * TILE_BYTES, 0, 1024);
+#pragma unroll
+                for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + (uint32_t)g * REGION, dq + 2 * k, dk + 2 * k, idesc_main, k > 0);
+                umma_commit(s_main + 8 * g);
+                nMain[g] = G + 1;
+            };
             while (nPV[0] < nheads || nPV[1] < nheads) {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    if (nPV[g] < nS[g]) {
+                    if (nPV[g] < nTail[g]) {
                         const int G = nPV[g], st = G & 1;
                         if (mbar_test(p_ready + 8 * g, (uint32_t)(G & 1)) && mbar_test(full_v + 8 * st, (uint32_t)((G >> 1) & 1))) {
                             tc_fence_after();
@@ -359,20 +376,36 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                             for (int k16 = 0; k16 < NK / 16; ++k16) umma_bf16_ts(region + cO, region + k16 * 8, dv + 128 * k16, idesc_o, k16 > 0);
                             umma_commit(o_ready + 8 * g);
                             nPV[g] = G + 1;
+                            // the next head's main scores right behind, if its operands have landed
+                            if (G + 1 < nheads && mbar_test(full_qk + 8 * ((G + 1) & 1), (uint32_t)(((G + 1) >> 1) & 1))) {
+                                tc_fence_after();
+                                issue_main(g, G + 1);
+                            }
                         }
-                    } else if (nS[g] < nheads) {
-                        const int G = nS[g], st = G & 1;
+                    }
+                    if (nMain[g] < nheads && nMain[g] == nPV[g]) {  // (not issued behind P.V: first head, or operands were late)
+                        const int G = nMain[g];
                         // group 1 enters half a period behind group 0: its first scores wait for group 0's first probabilities
-                        const bool held = STAGGER && g == 1 && G == 0 && nPV[0] == 0 && nheads > 0;
-                        if (!held && (G == 0 || mbar_test(tmem_free + 8 * g, (uint32_t)((G - 1) & 1))) &&
-                            mbar_test(full_qk + 8 * st, (uint32_t)((G >> 1) & 1))) {
+                        const bool held = STAGGER && g == 1 && G == 0 && nPV[0] == 0;
+                        if (!held && mbar_test(full_qk + 8 * (G & 1), (uint32_t)((G >> 1) & 1))) {
                             tc_fence_after();
-                            const uint32_t sQ = base + st * STAGE;
-                            const uint64_t dq = make_desc(sQ + g * TILE_BYTES, 0, 1024), dk = make_desc(sQ + 2 * TILE_BYTES, 0, 1024);
+                            issue_main(g, G);
+                        }
+                    }
+                    if (nTail[g] < nMain[g]) {
+                        const int G = nTail[g];
+                        if (G == 0 || mbar_test(tmem_free + 8 * g, (uint32_t)((G - 1) & 1))) {  // O of the previous head has been read out
+                            if (n_tail > 0) {
+                                tc_fence_after();
+                                const uint32_t sQ = base + (G & 1) * STAGE;
+                                const uint64_t dq = make_desc(sQ + g * TILE_BYTES, 0, 1024);
+                                const uint64_t dk = make_desc(sQ + 2 * TILE_BYTES + (kMainCols / 8) * 1024, 0, 1024);  // key rows >= kMainCols
 #pragma unroll
-                            for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + (uint32_t)g * REGION, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
-                            umma_commit(s_ready + 8 * g);
-                            nS[g] = G + 1;
+                                for (int k = 0; k < HS / 16; ++k)
+                                    umma_bf16(tmem_base + (uint32_t)g * REGION + kMainCols, dq + 2 * k, dk + 2 * k, idesc_tail, k > 0);
+                            }
+                            umma_commit(s_tail + 8 * g);
+                            nTail[g] = G + 1;
                         }
                     }
                 }
@@ -395,7 +428,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             const int st = G & 1;
             const uint32_t par = (uint32_t)(G & 1);
             const uint32_t sO = base + st * STAGE + g * TILE_BYTES;  // the dead Q_g tile of this stage
-            mbar_wait(s_ready + 8 * g, par);
+            mbar_wait(s_main + 8 * g, par);
             tc_fence_after();
             if (store_leader && pending_stage >= 0) {
                 // the previous head's O store was issued a whole S MMA ago and has read its staging tile by now: tell the loader that
@@ -475,20 +508,33 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                     }
                     tmem_st16(lane_addr + ch * 16, pk);  // in place: columns [16ch, 16ch+16) hold scores of chunk ch/2 <= ch, consumed
                 };
-                // the next chunk's load is in flight while this chunk is exponentiated
-                tmem_ld32_issue(lane_addr, va);
+                // the next chunk's load is in flight while this chunk is exponentiated; the columns from kMainCols on arrive with
+                // the second piece of the score MMA (see the issuer)
+                bool tail_ready = false;
+                auto issue_load = [&](int ch, uint32_t (&v)[32]) {
+                    if (!tail_ready && ch * 32 + 32 > kMainCols) {
+                        mbar_wait(s_tail + 8 * g, par);
+                        tc_fence_after();
+                        tail_ready = true;
+                    }
+                    tmem_ld32_issue(lane_addr + ch * 32, v);
+                };
+                issue_load(0, va);
                 tmem_ld_wait32(va);
                 for (int ch = 0; ch < nchunks; ch += 2) {
-                    if (ch + 1 < nchunks) tmem_ld32_issue(lane_addr + (ch + 1) * 32, vb);
+                    if (ch + 1 < nchunks) issue_load(ch + 1, vb);
                     process(ch, va);
                     if (ch + 1 < nchunks) {
                         tmem_ld_wait32(vb);
-                        if (ch + 2 < nchunks) tmem_ld32_issue(lane_addr + (ch + 2) * 32, va);
+                        if (ch + 2 < nchunks) issue_load(ch + 2, va);
                         process(ch + 1, vb);
                         if (ch + 2 < nchunks) tmem_ld_wait32(va);
                     }
                 }
                 tmem_st_wait();
+                if (!tail_ready) mbar_wait(s_tail + 8 * g, par);  // (keeps the barrier's phase in step when no column needed it)
+            } else {
+                mbar_wait(s_tail + 8 * g, par);
             }
             tc_fence_before();
             mbar_arrive_cnt(p_ready + 8 * g);
