@@ -136,6 +136,10 @@ def main():
     ap.add_argument("--config", default="b16", choices=["tiny", "ti16", "s16", "b16", "b8"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 1024 for b16/s16, 256 for ti16/b8)")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--comm", default="bf16", choices=["bf16", "f32"], help="gradient exchange payload (N > 1)")
+    ap.add_argument("--zero1", action="store_true", help="ZeRO-1: reduce-scatter, AdamW on the shard, all-gather of the bf16 weights")
+    ap.add_argument("--nccl-max-ctas", type=int, default=-1, help="cap on NCCL thread blocks per collective (-1: library default)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (global batch 1024 split over the ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -162,7 +166,7 @@ def main():
     if world > 1:
         uid = [ctx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(uid[0], rank, world)
+        ctx.comm_init(uid[0], rank, world, max_ctas=None if args.nccl_max_ctas < 0 else args.nccl_max_ctas)
 
     cfg = pkg.CONFIGS[args.config]
     per_gpu = args.batch or {"b16": 1024, "s16": 1024, "ti16": 256, "b8": 256, "tiny": 8}[args.config]
@@ -170,6 +174,10 @@ def main():
     mode = pkg.MODE_BF16 if args.mode == "bf16" else pkg.MODE_F32
     model = pkg.ViT(args.config, max_batch=per_gpu, mode=mode, seed=1337, init_mode=1, ctx=ctx)
     model.set_dloss_scale(1.0 / global_batch)
+    if mode == pkg.MODE_BF16:
+        model.set_comm_dtype(args.comm)
+    if args.zero1:
+        model.enable_zero1()
     lr = 1e-4
 
     # synthetic data: images U[-1,1) from the shared counter generator, labels uniform; two batches
@@ -306,17 +314,39 @@ def main():
         except Exception as e:  # the baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
+    # ---- strong scaling (BASELINE's "batch 1024" read as the GLOBAL batch): same model, 1024 / N images per rank ----
+    strong = None
+    if world > 1 and not args.no_strong and args.config in ("b16", "s16") and per_gpu % world == 0:
+        sb = per_gpu // world
+        model.set_dloss_scale(1.0 / per_gpu)
+        xs = [d_images[i][:sb].contiguous() for i in range(2)]
+        ys = [d_labels[i][:sb].contiguous() for i in range(2)]
+        for s_ in range(3):
+            model.train_step(xs[s_ % 2], ys[s_ % 2], lr)
+        barrier()
+        e0.record()
+        for s_ in range(args.steps):
+            model.train_step(xs[s_ % 2], ys[s_ % 2], lr)
+        e1.record()
+        barrier()
+        ms_strong = max_over_ranks(e0.elapsed_time(e1))
+        strong = {"global_batch": per_gpu, "per_gpu_batch": sb, "value": round(per_gpu * args.steps / (ms_strong / 1e3), 2), "unit": UNIT,
+                  "ms_per_step": round(ms_strong / args.steps, 3)}
+        model.set_dloss_scale(1.0 / global_batch)
+
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.mode, "data": "synthetic",
                 "config": {"workload": f"vit-{args.config} {img}x{img} train step (fwd+bwd+AdamW), per-GPU batch {per_gpu}",
                            "global_batch": global_batch, "per_gpu_batch": per_gpu, "tokens": (img // cfg['patch_size']) ** 2 + 1,
-                           "parallelism": f"dp{world}", "train_gflop_per_image": round(flops_per_image / 1e9, 3),
+                           "parallelism": f"dp{world}" + ("+zero1" if args.zero1 else ""), "grad_exchange": args.comm if world > 1 else None,
+                           "train_gflop_per_image": round(flops_per_image / 1e9, 3),
                            "l2_policy": "inputs larger than L2 (activations are GBs per step); no flush needed",
                            "final_loss": round(loss, 5)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "inference_forward": inference}
+                "inference_forward": inference, "strong_scaling": strong,
+                "optimizer_state_bytes_per_rank": model.optimizer_state_bytes}
         print(json.dumps(line), flush=True)
     model.close()
     if world > 1:
