@@ -51,6 +51,7 @@ struct vitrs_ctx {
     // device-side error flags raised by kernels (bit 0: class label out of range), reported by vitrs_model_mean_loss
     int* dev_flags;
     AdamHyper* d_hyper;  // AdamW hyper-parameters of the current step (same allocation as dev_flags)
+    unsigned int* gemm_sched;  // {next unit, drained clusters} of the GEMM's dynamic tile scheduler (same allocation)
 };
 
 // collectives on the comm stream (ctx.cu; dtype 0 = fp32, 1 = bf16); no-ops without a communicator

@@ -168,6 +168,7 @@ extern "C" int vitrs_ctx_create(vitrs_ctx** out, int device) {
         return VITRS_ERR_CUDA;
     }
     ctx->d_hyper = reinterpret_cast<AdamHyper*>(ctx->dev_flags + 16);
+    ctx->gemm_sched = reinterpret_cast<unsigned int*>(ctx->dev_flags + 8);
     *out = ctx;
     return VITRS_OK;
 }

@@ -571,33 +571,34 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
 // ---- gradient exchange buffer ("Z order": bucket-major, slices of a bucket back to back) ---------------------------
 // One launch moves every slice of a bucket between the tensor-major flat buffers and its contiguous region of the
 // exchange buffer (blockIdx.y = slice).  PACK: z[z_off + i] = cvt(flat[src_off + i]); else flat[src_off + i] = cvt(z[z_off + i]).
-template <typename TF, typename TZ, bool PACK>
-__global__ void slice_copy_kernel(TF* __restrict__ flat, TZ* __restrict__ z, const SliceTable tab) {
-    const int sl = blockIdx.y;
-    const size_t cnt = tab.cnt[sl];
-    TF* f = flat + tab.src_off[sl];
-    TZ* zz = z + tab.z_off[sl];
+template <typename TF, typename TZ, bool PACK, int VEC>
+__global__ void slice_copy_kernel(TF* __restrict__ flat, TZ* __restrict__ z, const SliceTable tab, size_t total_units) {
+    // the slices form one virtual array of units (VEC elements each: 4 when every slice is 4-aligned, else 1); a thread walks
+    // it with a grid stride and finds the slice of a unit in the (<= 12 entry) table
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool vec = ((tab.src_off[sl] | tab.z_off[sl]) & 3) == 0;
-    const size_t nv = vec ? cnt / 4 : 0;
-    for (size_t i = t0; i < nv; i += stride) {
-        float x[4];
-        if (PACK) {
-            if (sizeof(TF) == 4) { const float4 a = reinterpret_cast<const float4*>(f)[i]; x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; }
-            else { const uint2 a = reinterpret_cast<const uint2*>(f)[i]; x[0] = __uint_as_float(a.x << 16); x[1] = __uint_as_float(a.x & 0xFFFF0000u); x[2] = __uint_as_float(a.y << 16); x[3] = __uint_as_float(a.y & 0xFFFF0000u); }
-            if (sizeof(TZ) == 4) reinterpret_cast<float4*>(zz)[i] = make_float4(x[0], x[1], x[2], x[3]);
-            else { uint2 o; o.x = pack2_bf16(x[0], x[1]); o.y = pack2_bf16(x[2], x[3]); reinterpret_cast<uint2*>(zz)[i] = o; }
+    for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < total_units; u += stride) {
+        size_t local = u;
+        int sl = 0;
+        while (sl + 1 < tab.n && local >= tab.cnt[sl] / VEC) { local -= tab.cnt[sl] / VEC; ++sl; }
+        TF* f = flat + tab.src_off[sl] + local * VEC;
+        TZ* zz = z + tab.z_off[sl] + local * VEC;
+        if (VEC == 4) {
+            float x[4];
+            if (PACK) {
+                if (sizeof(TF) == 4) { const float4 a = *reinterpret_cast<const float4*>(f); x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; }
+                else { const uint2 a = *reinterpret_cast<const uint2*>(f); x[0] = __uint_as_float(a.x << 16); x[1] = __uint_as_float(a.x & 0xFFFF0000u); x[2] = __uint_as_float(a.y << 16); x[3] = __uint_as_float(a.y & 0xFFFF0000u); }
+                if (sizeof(TZ) == 4) *reinterpret_cast<float4*>(zz) = make_float4(x[0], x[1], x[2], x[3]);
+                else { uint2 o; o.x = pack2_bf16(x[0], x[1]); o.y = pack2_bf16(x[2], x[3]); *reinterpret_cast<uint2*>(zz) = o; }
+            } else {
+                if (sizeof(TZ) == 4) { const float4 a = *reinterpret_cast<const float4*>(zz); x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; }
+                else { const uint2 a = *reinterpret_cast<const uint2*>(zz); x[0] = __uint_as_float(a.x << 16); x[1] = __uint_as_float(a.x & 0xFFFF0000u); x[2] = __uint_as_float(a.y << 16); x[3] = __uint_as_float(a.y & 0xFFFF0000u); }
+                if (sizeof(TF) == 4) *reinterpret_cast<float4*>(f) = make_float4(x[0], x[1], x[2], x[3]);
+                else { uint2 o; o.x = pack2_bf16(x[0], x[1]); o.y = pack2_bf16(x[2], x[3]); *reinterpret_cast<uint2*>(f) = o; }
+            }
         } else {
-            if (sizeof(TZ) == 4) { const float4 a = reinterpret_cast<const float4*>(zz)[i]; x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; }
-            else { const uint2 a = reinterpret_cast<const uint2*>(zz)[i]; x[0] = __uint_as_float(a.x << 16); x[1] = __uint_as_float(a.x & 0xFFFF0000u); x[2] = __uint_as_float(a.y << 16); x[3] = __uint_as_float(a.y & 0xFFFF0000u); }
-            if (sizeof(TF) == 4) reinterpret_cast<float4*>(f)[i] = make_float4(x[0], x[1], x[2], x[3]);
-            else { uint2 o; o.x = pack2_bf16(x[0], x[1]); o.y = pack2_bf16(x[2], x[3]); reinterpret_cast<uint2*>(f)[i] = o; }
+            if (PACK) *zz = from_f32<TZ>(to_f32(*f));
+            else *f = from_f32<TF>(to_f32(*zz));
         }
-    }
-    for (size_t i = nv * 4 + t0; i < cnt; i += stride) {
-        if (PACK) zz[i] = from_f32<TZ>(to_f32(f[i]));
-        else f[i] = from_f32<TF>(to_f32(zz[i]));
     }
 }
 
@@ -845,12 +846,18 @@ int op_adamw(vitrs_ctx* ctx, float* p, const float* g, float* m, float* v, size_
 template <typename TF, typename TZ, bool PACK>
 static int slice_copy(vitrs_ctx* ctx, TF* flat, TZ* z, const SliceTable& tab, cudaStream_t stream) {
     if (tab.n <= 0) return VITRS_OK;
-    size_t mx = 0;
-    for (int i = 0; i < tab.n; ++i) mx = tab.cnt[i] > mx ? tab.cnt[i] : mx;
-    int gx = (int)((mx / 4 + kThreads) / kThreads);
-    if (gx > 4 * ctx->sm_count) gx = 4 * ctx->sm_count;
-    if (gx < 1) gx = 1;
-    slice_copy_kernel<TF, TZ, PACK><<<dim3(gx, tab.n), kThreads, 0, stream>>>(flat, z, tab);
+    size_t total = 0;
+    bool vec = true;
+    for (int i = 0; i < tab.n; ++i) {
+        total += tab.cnt[i];
+        vec = vec && ((tab.cnt[i] | tab.src_off[i] | tab.z_off[i]) & 3) == 0;
+    }
+    if (total == 0) return VITRS_OK;
+    const size_t units = vec ? total / 4 : total;
+    int gx = (int)((units + kThreads - 1) / kThreads);
+    if (gx > 8 * ctx->sm_count) gx = 8 * ctx->sm_count;
+    if (vec) slice_copy_kernel<TF, TZ, PACK, 4><<<gx, kThreads, 0, stream>>>(flat, z, tab, units);
+    else slice_copy_kernel<TF, TZ, PACK, 1><<<gx, kThreads, 0, stream>>>(flat, z, tab, units);
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
 }

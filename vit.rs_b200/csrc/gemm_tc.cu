@@ -37,11 +37,32 @@ constexpr int kThreads = 384;
 constexpr int kEpilogueWarp0 = 4;
 constexpr int kEpilogueWarps = 8;
 constexpr int kColsumWarps = 4;  // epilogue warps that also sum the A tiles (fused bias gradient)
+constexpr int kSchedSlots = 4;   // depth of the per-CTA tile queue (the producer runs up to two tiles ahead of the epilogue)
+
+// Tile scheduler.  Work units are handed out by one thread of the cluster's leader CTA (warp 3) through a small queue in the
+// shared memory of every CTA of the cluster: the unit number travels with st.async and completes the transaction count of that
+// CTA's `full` barrier, every consumer role (TMA producer, MMA issuer, the epilogue warps, of both CTAs of a pair) arrives on
+// the leader's `empty` barrier once it has read the slot.  With a global counter (p.sched) the units go to whichever cluster
+// asks first, so a cluster that starts late — its SMs were held by a collective's CTAs when the grid launched — simply takes
+// fewer tiles instead of becoming the tail of the whole launch (measured at 2 ranks: GEMMs that overlap an NCCL kernel ran
+// +40 % with the static stride).  Without a counter the same queue carries the static stride.
+__device__ __forceinline__ void sched_publish(uint32_t full_cluster_addr, uint32_t slot_cluster_addr, uint32_t unit) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], 4;" ::"r"(full_cluster_addr) : "memory");
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(slot_cluster_addr), "r"(unit),
+                 "r"(full_cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 
 struct TcParams {
     int M, N, K;
     int m_tiles, n_tiles, kb_total, kb_per_split, splits;
     float* a_colsum;  // MN-major A only: a_colsum[m] += sum_k A(m, k)  (the bias gradient of matmul_backward, tv:548-550)
+    unsigned int* sched;  // [0] next unit, [1] clusters that have drained the queue (dynamic tile scheduler); null = static stride
     Epilogue epi;
 };
 
@@ -55,7 +76,8 @@ struct SmemLayout {
     static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;  // 8 epilogue warps x [32 rows][128 B]
     static constexpr int STAGING_BYTES = kEpilogueWarps * 32 * 128;
     static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+    static constexpr int SCHED_OFFSET = BAR_OFFSET + 256;  // tile queue: kSchedSlots x {full, empty} barriers + kSchedSlots unit numbers
+    static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;  // barriers + tile queue + alignment slack
 };
 
 // ---- epilogue: one warp, its 32 accumulator rows, one 64-column chunk ------------------------------
@@ -273,6 +295,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto aux_bar = [&](int w) { return bar_base + 8u * (3 * STAGES + 4 + w); };  // one per epilogue warp
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (3 * STAGES + 4 + kEpilogueWarps));
     static_assert(8 * (3 * STAGES + 4 + kEpilogueWarps) + 4 <= 256, "barrier block");
+    const uint32_t sched_base = smem_base + L::SCHED_OFFSET;
+    auto sfull_bar = [&](int s) { return sched_base + 8u * s; };
+    auto sempty_bar = [&](int s) { return sched_base + 8u * (kSchedSlots + s); };  // used in the leader CTA only
+    auto sunit_slot = [&](int s) { return sched_base + 16u * kSchedSlots + 4u * s; };
     // CTA pair: rank 0 (the leader) issues the MMAs and owns the full / tempty barriers; both CTAs load, both run epilogues
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     const bool colsum = A_MN && p.a_colsum != nullptr;
@@ -301,6 +327,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(tempty_bar(a), CG * kEpilogueWarps);  // one arrive per epilogue warp (of both CTAs of a pair)
         }
         for (int w = 0; w < kEpilogueWarps; ++w) mbar_init(aux_bar(w), 1);
+        for (int q = 0; q < kSchedSlots; ++q) {
+            mbar_init(sfull_bar(q), 1);
+            // consumers per CTA: TMA producer + 8 epilogue warps, plus the MMA issuer in the leader
+            mbar_init(sempty_bar(q), CG == 2 ? 2 * (1 + kEpilogueWarps) + 1 : 2 + kEpilogueWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -325,6 +356,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int tiles = p.m_tiles * p.n_tiles;  // tiles of CG*128 rows
     const int total_units = tiles * p.splits;
     const int unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
+    // consumer side of the tile queue: the it-th unit of this CTA (>= total_units: the queue is drained)
+    const uint32_t sempty_leader0 = CG == 2 ? mapa_shared(sempty_bar(0), 0) : sempty_bar(0);
+    auto next_unit = [&](int it) -> int {
+        const int q = it % kSchedSlots;
+        mbar_wait(sfull_bar(q), (uint32_t)((it / kSchedSlots) & 1));
+        const int unit = (int)ld_shared_u32(sunit_slot(q));
+        if (CG == 2) mbar_arrive_cluster(sempty_leader0 + 8u * q);
+        else mbar_arrive(sempty_bar(q));
+        return unit;
+    };
     constexpr int TM = BM * CG;
     const int m_rank = (int)rank * BM, n_rank = (int)rank * (BN / CG);  // this CTA's share of the operand tiles
 
@@ -336,7 +377,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (CG == 2) tma_load_2d_pair(dst, map, bar, c0, c1);
             else tma_load_2d(dst, map, bar, c0, c1);
         };
-        for (int unit = unit0; unit < total_units; unit += unit_step) {
+        for (int it = 0;; ++it) {
+            const int unit = next_unit(it);
+            if (unit >= total_units) break;
             // split-major: consecutive units (= concurrently running CTAs) walk the same K range, so every
             // operand slab is fetched from HBM once and shared through L2
             const int split = unit / tiles, tile = unit - split * tiles;
@@ -376,7 +419,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
-        for (int unit = unit0; unit < total_units; unit += unit_step) {
+        for (int it = 0;; ++it) {
+            const int unit = next_unit(it);
+            if (unit >= total_units) break;
             const int split = unit / tiles;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -408,6 +453,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             else umma_commit(tfull_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+    } else if (warp == 3 && lane == 0 && rank == 0) {
+        // ===== tile scheduler (one thread of the cluster's leader) =====
+        uint32_t full_addr[CG], slot_addr[CG];
+        for (int i = 0;; ++i) {
+            const int q = i % kSchedSlots;
+            if (i >= kSchedSlots) mbar_wait(sempty_bar(q), (uint32_t)(((i / kSchedSlots) - 1) & 1));
+            const uint32_t unit = p.sched ? atomicAdd(p.sched, 1u) : (uint32_t)(unit0 + i * unit_step);
+#pragma unroll
+            for (int r = 0; r < CG; ++r) {
+                full_addr[r] = CG == 2 ? mapa_shared(sfull_bar(q), (uint32_t)r) : sfull_bar(q);
+                slot_addr[r] = CG == 2 ? mapa_shared(sunit_slot(q), (uint32_t)r) : sunit_slot(q);
+                sched_publish(full_addr[r], slot_addr[r], unit);
+            }
+            if (unit >= (uint32_t)total_units) {
+                // the queue of this cluster is drained; the last cluster to get here re-arms the counter for the next launch
+                if (p.sched && atomicAdd(p.sched + 1, 1u) == (unsigned int)unit_step - 1u) {
+                    p.sched[1] = 0u;
+                    __threadfence();
+                    p.sched[0] = 0u;
+                }
+                break;
+            }
+        }
     } else if (warp >= kEpilogueWarp0) {
         // ===== epilogue: TMEM -> registers -> global =====
         const int ew = warp - kEpilogueWarp0;       // 0..7
@@ -423,7 +491,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int cs_stage = 0;        // column-sum consumer: walks the stage ring in step with the MMA warp
         uint32_t cs_phase = 0;
         const uint32_t tempty_remote0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : 0u;
-        for (int unit = unit0; unit < total_units; unit += unit_step) {
+        for (int it = 0;; ++it) {
+            int unit = 0;
+            if (lane == 0) unit = next_unit(it);
+            unit = __shfl_sync(0xffffffffu, unit, 0);
+            if (unit >= total_units) break;
             const int tile = unit % tiles;
             const int m0 = (tile / p.n_tiles) * TM + m_rank, n0 = (tile % p.n_tiles) * BN;
             if (colsum && (ew & 2)) {
@@ -678,6 +750,7 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     p.kb_total = ceil_div(g.K, BK);
     p.epi = g.epi;
     p.a_colsum = g.a_colsum;
+    p.sched = ctx->env_gemm_static ? nullptr : ctx->gemm_sched;  // VITRS_GEMM_STATIC: the static stride (A/B aid)
     int splits = 1;
     const int tiles = p.m_tiles * p.n_tiles;
     const int slots = ctx->sm_count / CG;  // tiles in flight
