@@ -39,10 +39,10 @@ constexpr int kEpilogueWarps = 8;
 constexpr int kColsumWarps = 4;  // epilogue warps that also sum the A tiles (fused bias gradient)
 constexpr int kSchedSlots = 4;   // depth of the per-CTA tile queue (the producer runs up to two tiles ahead of the epilogue)
 
-// Tile scheduler.  Work units are handed out by one thread of the cluster's leader CTA (warp 3) through a small queue in the
-// shared memory of every CTA of the cluster: the unit number travels with st.async and completes the transaction count of that
-// CTA's `full` barrier, every consumer role (TMA producer, MMA issuer, the epilogue warps, of both CTAs of a pair) arrives on
-// the leader's `empty` barrier once it has read the slot.  With a global counter (p.sched) the units go to whichever cluster
+// Tile scheduler.  Work units are handed out by the TMA producer thread of the cluster's leader CTA through a small queue in
+// the shared memory of every CTA of the cluster: the unit number travels with st.async and completes the transaction count of
+// that CTA's `full` barrier, every other role (the peer's producer, the MMA issuer, the epilogue warps of both CTAs) arrives
+// on the leader's `empty` barrier once it has read the slot.  With a global counter (p.sched) the units go to whichever cluster
 // asks first, so a cluster that starts late — its SMs were held by a collective's CTAs when the grid launched — simply takes
 // fewer tiles instead of becoming the tail of the whole launch (measured at 2 ranks: GEMMs that overlap an NCCL kernel ran
 // +40 % with the static stride).  Without a counter the same queue carries the static stride.
@@ -329,8 +329,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int w = 0; w < kEpilogueWarps; ++w) mbar_init(aux_bar(w), 1);
         for (int q = 0; q < kSchedSlots; ++q) {
             mbar_init(sfull_bar(q), 1);
-            // consumers per CTA: TMA producer + 8 epilogue warps, plus the MMA issuer in the leader
-            mbar_init(sempty_bar(q), CG == 2 ? 2 * (1 + kEpilogueWarps) + 1 : 2 + kEpilogueWarps);
+            // consumers: 8 epilogue warps per CTA, the MMA issuer of the leader, the TMA producer of the peer
+            mbar_init(sempty_bar(q), CG == 2 ? 2 * kEpilogueWarps + 2 : kEpilogueWarps + 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -378,8 +378,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             else tma_load_2d(dst, map, bar, c0, c1);
         };
         for (int it = 0;; ++it) {
-            const int unit = next_unit(it);
-            if (unit >= total_units) break;
+            int unit;
+            if (rank == 0) {
+                // The leader's producer is the cluster's tile scheduler: it asks for the next unit only when it has issued every
+                // load of the previous one (a deeper look-ahead would hoard units: with ~1 unit per cluster, as in the split-K
+                // weight-gradient GEMMs, the clusters that start first would take several and leave the others idle).
+                const int q = it % kSchedSlots;
+                if (it >= kSchedSlots) mbar_wait(sempty_bar(q), (uint32_t)(((it / kSchedSlots) - 1) & 1));
+                unit = p.sched ? (int)atomicAdd(p.sched, 1u) : unit0 + it * unit_step;
+#pragma unroll
+                for (int r = 0; r < CG; ++r)
+                    sched_publish(CG == 2 ? mapa_shared(sfull_bar(q), (uint32_t)r) : sfull_bar(q),
+                                  CG == 2 ? mapa_shared(sunit_slot(q), (uint32_t)r) : sunit_slot(q), (uint32_t)unit);
+                if (unit >= total_units) {
+                    // this cluster is done asking; the last cluster to get here re-arms the counter for the next launch
+                    if (p.sched && atomicAdd(p.sched + 1, 1u) == (unsigned int)unit_step - 1u) {
+                        p.sched[1] = 0u;
+                        __threadfence();
+                        p.sched[0] = 0u;
+                    }
+                    break;
+                }
+            } else {
+                unit = next_unit(it);
+                if (unit >= total_units) break;
+            }
             // split-major: consecutive units (= concurrently running CTAs) walk the same K range, so every
             // operand slab is fetched from HBM once and shared through L2
             const int split = unit / tiles, tile = unit - split * tiles;
@@ -452,29 +475,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (CG == 2) umma_commit_pair(tfull_bar(acc));
             else umma_commit(tfull_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-        }
-    } else if (warp == 3 && lane == 0 && rank == 0) {
-        // ===== tile scheduler (one thread of the cluster's leader) =====
-        uint32_t full_addr[CG], slot_addr[CG];
-        for (int i = 0;; ++i) {
-            const int q = i % kSchedSlots;
-            if (i >= kSchedSlots) mbar_wait(sempty_bar(q), (uint32_t)(((i / kSchedSlots) - 1) & 1));
-            const uint32_t unit = p.sched ? atomicAdd(p.sched, 1u) : (uint32_t)(unit0 + i * unit_step);
-#pragma unroll
-            for (int r = 0; r < CG; ++r) {
-                full_addr[r] = CG == 2 ? mapa_shared(sfull_bar(q), (uint32_t)r) : sfull_bar(q);
-                slot_addr[r] = CG == 2 ? mapa_shared(sunit_slot(q), (uint32_t)r) : sunit_slot(q);
-                sched_publish(full_addr[r], slot_addr[r], unit);
-            }
-            if (unit >= (uint32_t)total_units) {
-                // the queue of this cluster is drained; the last cluster to get here re-arms the counter for the next launch
-                if (p.sched && atomicAdd(p.sched + 1, 1u) == (unsigned int)unit_step - 1u) {
-                    p.sched[1] = 0u;
-                    __threadfence();
-                    p.sched[0] = 0u;
-                }
-                break;
-            }
         }
     } else if (warp >= kEpilogueWarp0) {
         // ===== epilogue: TMEM -> registers -> global =====
