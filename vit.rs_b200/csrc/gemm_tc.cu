@@ -377,15 +377,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (CG == 2) tma_load_2d_pair(dst, map, bar, c0, c1);
             else tma_load_2d(dst, map, bar, c0, c1);
         };
+        // The leader's producer is the cluster's tile scheduler.  With many units per cluster it asks for unit i + 1 when it starts
+        // loading unit i, so the counter's round trip hides under the loads (asking only when unit i is loaded cost the forward
+        // GEMMs 16 %: this thread is the one that must never bubble).  With few units per cluster — the split-K weight-gradient
+        // GEMMs have about one — any look-ahead would hoard: the clusters that start first would take two units each and leave
+        // the others idle; there it asks on demand.
+        const bool lookahead = total_units >= 4 * unit_step;
+        auto fetch = [&](int it) -> int { return p.sched ? (int)atomicAdd(p.sched, 1u) : unit0 + it * unit_step; };
+        int prefetched = (rank == 0 && lookahead) ? fetch(0) : 0;
         for (int it = 0;; ++it) {
             int unit;
             if (rank == 0) {
-                // The leader's producer is the cluster's tile scheduler: it asks for the next unit only when it has issued every
-                // load of the previous one (a deeper look-ahead would hoard units: with ~1 unit per cluster, as in the split-K
-                // weight-gradient GEMMs, the clusters that start first would take several and leave the others idle).
                 const int q = it % kSchedSlots;
                 if (it >= kSchedSlots) mbar_wait(sempty_bar(q), (uint32_t)(((it / kSchedSlots) - 1) & 1));
-                unit = p.sched ? (int)atomicAdd(p.sched, 1u) : unit0 + it * unit_step;
+                unit = lookahead ? prefetched : fetch(it);
+                if (lookahead && unit < total_units) prefetched = fetch(it + 1);
 #pragma unroll
                 for (int r = 0; r < CG; ++r)
                     sched_publish(CG == 2 ? mapa_shared(sfull_bar(q), (uint32_t)r) : sfull_bar(q),
