@@ -81,6 +81,7 @@ struct vitrs_model {
     size_t z_size, s_total;
     bf16* comm_buf;        // [z_size]
     // ZeRO-1: fp32 master weights and AdamW moments of this rank's shard of every bucket, in Z order
+    unsigned long long unpack_pending;  // buckets whose summed gradients still sit in the exchange buffer (bit per bucket)
     int zero1;
     float *zp, *zm, *zv;   // [s_total]
     float *m_small, *v_small;  // replicated moments of the small tensors, compact (small_runs)
@@ -585,6 +586,11 @@ SliceTable table_of(const vitrs_model* m, int bucket, int which = 0) {
     return t;
 }
 
+// Gradient exchange of one bucket.  The pack runs on the COMPUTE stream, right behind the kernels that produced the bucket's
+// gradients, where it has the whole GPU (28 MB in, 14 MB out: ~10 us); only the collective itself goes to the comm stream, and
+// the unpack of every bucket waits for comm_join.  (Packing and unpacking on the comm stream cost 45-95 us per bucket EACH:
+// those kernels can only run on SMs the persistent GEMMs are not holding, and their 1184 blocks delayed the next GEMM's
+// clusters by about as long as the collective itself — measured, profiles/r2_timeline_dp2_*.txt.)
 int exchange_bucket(vitrs_model* m, int bk) {
     vitrs_ctx* ctx = m->ctx;
     if (m->comm_dtype == 0 && !m->zero1) {  // exact fp32 sums, slice by slice in place
@@ -592,11 +598,14 @@ int exchange_bucket(vitrs_model* m, int bk) {
         float* bufs[12];
         const int n = bucket_slices(m->cfg, m->param_sizes, m->param_off, bk, off, cnt);
         for (int i = 0; i < n; ++i) bufs[i] = m->grads + off[i];
+        VITRS_TRY(bucket_begin(m));
         return vitrs_nccl_allreduce_group(ctx, bufs, cnt, n);
     }
     // one contiguous bf16 message per bucket (bf16 on the wire in production)
     bf16* region = m->comm_buf + m->z_off[bk];
-    VITRS_TRY(op_pack_f32_to_bf16(ctx, m->comm_buf, m->grads, table_of(m, bk), ctx->comm_stream));
+    VITRS_TRY(op_pack_f32_to_bf16(ctx, m->comm_buf, m->grads, table_of(m, bk), ctx->stream));
+    VITRS_TRY(bucket_begin(m));
+    m->unpack_pending |= 1ull << bk;
     if (m->zero1) {
         // big slices: each rank receives the sum of its 1/world shard (AdamW runs on the shard in update()); small slices
         // stay replicated: summed everywhere and unpacked into the fp32 gradient views
@@ -604,11 +613,9 @@ int exchange_bucket(vitrs_model* m, int bk) {
         VITRS_TRY(vitrs_nccl_group(ctx, 1));
         if (m->z_shard[bk]) VITRS_TRY(vitrs_nccl_reduce_scatter(ctx, region, region + (size_t)ctx->rank * m->z_shard[bk], m->z_shard[bk], 1));
         if (small) VITRS_TRY(vitrs_nccl_allreduce(ctx, region + m->z_big[bk], region + m->z_big[bk], small, 1));
-        VITRS_TRY(vitrs_nccl_group(ctx, 0));
-        return op_unpack_bf16_to_f32(ctx, m->grads, m->comm_buf, table_of(m, bk, 2), ctx->comm_stream);
+        return vitrs_nccl_group(ctx, 0);
     }
-    VITRS_TRY(vitrs_nccl_allreduce(ctx, region, region, m->z_len[bk], 1));
-    return op_unpack_bf16_to_f32(ctx, m->grads, m->comm_buf, table_of(m, bk), ctx->comm_stream);
+    return vitrs_nccl_allreduce(ctx, region, region, m->z_len[bk], 1);
 }
 
 int allreduce_bucket(vitrs_model* m, int bucket) {
@@ -618,7 +625,6 @@ int allreduce_bucket(vitrs_model* m, int bucket) {
     const int last = m->cfg.num_layers + 1;
     if (defer && bucket != last) return VITRS_OK;
     if (m->comm_dtype != 0 || m->zero1) VITRS_TRY(ensure_zplan(m));
-    VITRS_TRY(bucket_begin(m));
     for (int bk = defer ? 0 : bucket; bk <= bucket; ++bk) VITRS_TRY(exchange_bucket(m, bk));
     return VITRS_OK;
 }
@@ -633,6 +639,12 @@ int comm_join(vitrs_model* m) {
     if (!ctx->nccl_comm && !m->zero1) return VITRS_OK;
     VITRS_CUDA(ctx, cudaEventRecord(m->ev_comm_done, ctx->comm_stream));
     VITRS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->ev_comm_done, 0));
+    // the summed bf16 gradients go back into the fp32 views (ZeRO-1: of the small, replicated slices only)
+    for (int bk = 0; bk < m->z_buckets && m->unpack_pending; ++bk) {
+        if (!((m->unpack_pending >> bk) & 1ull)) continue;
+        VITRS_TRY(op_unpack_bf16_to_f32(ctx, m->grads, m->comm_buf, table_of(m, bk, m->zero1 ? 2 : 0), ctx->stream));
+    }
+    m->unpack_pending = 0;
     return VITRS_OK;
 }
 
@@ -786,7 +798,7 @@ int vitrs_model_create(vitrs_ctx* ctx, const vitrs_config* cfg_in, int max_batch
     vitrs_config cfg = *cfg_in;
     VITRS_ARG(ctx, cfg.patch_size > 0 && cfg.image_size % cfg.patch_size == 0 && cfg.patch_size % 4 == 0);
     VITRS_ARG(ctx, cfg.channels > 0 && cfg.num_heads > 0 && cfg.channels % cfg.num_heads == 0 && cfg.channels % 8 == 0);
-    VITRS_ARG(ctx, cfg.num_layers >= 1 && cfg.num_classes >= 1);
+    VITRS_ARG(ctx, cfg.num_layers >= 1 && cfg.num_layers <= 62 && cfg.num_classes >= 1);  // (one bit per gradient bucket)
     VITRS_ARG(ctx, cfg.max_seq_len == 0 || cfg.max_seq_len == tokens(cfg));
     cfg.max_seq_len = tokens(cfg);
     cfg.vocab_size = cfg.num_classes;
