@@ -1,122 +1,37 @@
-//! `extern "C"` declarations for `libvitrs.so` (include/vitrs.h) — the thin FFI crate the
-//! north-star asks for.  Source only: this image has no Rust toolchain, so the same ABI is
-//! exercised from C++ (csrc/model.cu) and from ctypes (vit.rs_b200/__init__.py, tests/).
+//! Thin FFI crate over `libvitrs.so` (include/vitrs.h) — the boundary the north-star asks for.
 //!
-//! Every function mirrors one reference item; the reference line is given beside it
-//! (tv = train_vit.rs, rv = rusty_vit.rs).  Pointers are DEVICE pointers, calls are
-//! asynchronous on the context's stream, the return value is 0 or a negative status.
-#![allow(non_camel_case_types)]
-use std::os::raw::{c_char, c_int, c_void};
-
-#[repr(C)]
-pub struct vitrs_ctx { _private: [u8; 0] }
-#[repr(C)]
-pub struct vitrs_model { _private: [u8; 0] }
-pub type vitrs_bf16 = u16;
+//! `ffi` holds one `extern "C"` declaration per exported symbol, generated from the header
+//! (scripts/gen_rust_ffi.py; tests/test_abi.py keeps it current).  This file adds the mirror of
+//! the reference's model surface on top: `ViT::{build_from_checkpoint, forward, backward}`
+//! (rusty_vit.rs:79,269,354), `optimizer_step` (rusty_vit.rs:949) and the train loop's step
+//! (train_vit.rs:65-86), with the same names and argument meaning, device-resident.
+//!
+//! Source only: this image has no Rust toolchain, so the same ABI is exercised from C++
+//! (csrc/model.cu) and from ctypes (vit.rs_b200/__init__.py, tests/).  Pointers passed to
+//! `forward` / `train_step` are DEVICE pointers; the `_host` calls take host slices.
+pub mod ffi;
+pub use ffi::*;
+use std::ffi::{CStr, CString};
+use std::os::raw::c_int;
 
 pub const VITRS_OK: c_int = 0;
+pub const VITRS_ERR_CUDA: c_int = -1;
+pub const VITRS_ERR_ARG: c_int = -2;
+pub const VITRS_ERR_UNSUPPORTED: c_int = -3;
+pub const VITRS_ERR_NCCL: c_int = -4;
 pub const VITRS_MODE_F32: c_int = 0;
 pub const VITRS_MODE_BF16: c_int = 1;
+pub const VITRS_NUM_PARAMETER_TENSORS: usize = 20;
+pub const VITRS_NUM_ACTIVATION_TENSORS: usize = 23;
 
-/// `ViTConfig` (rv:10-16 / tv:56-63) plus the ViT fields (DEVIATIONS D7).
-#[repr(C)]
-#[derive(Clone, Copy, Debug, Default)]
-pub struct vitrs_config {
-    pub max_seq_len: c_int,
-    pub vocab_size: c_int,
-    pub num_layers: c_int,
-    pub num_heads: c_int,
-    pub channels: c_int,
-    pub image_size: c_int,
-    pub patch_size: c_int,
-    pub num_classes: c_int,
-    pub causal: c_int,
+/// AdamW hyper-parameters of `ViT::update` (DEVIATIONS D8; the reference's `optimizer_step` is plain SGD).
+#[derive(Clone, Copy, Debug)]
+pub struct AdamW { pub lr: f32, pub beta1: f32, pub beta2: f32, pub eps: f32, pub weight_decay: f32 }
+impl Default for AdamW {
+    fn default() -> Self { AdamW { lr: 1e-3, beta1: 0.9, beta2: 0.999, eps: 1e-8, weight_decay: 0.0 } }
 }
 
-extern "C" {
-    pub fn vitrs_ctx_create(out: *mut *mut vitrs_ctx, device: c_int) -> c_int;
-    pub fn vitrs_ctx_destroy(ctx: *mut vitrs_ctx) -> c_int;
-    pub fn vitrs_ctx_synchronize(ctx: *mut vitrs_ctx) -> c_int;
-    pub fn vitrs_last_error(ctx: *mut vitrs_ctx) -> *const c_char;
-    pub fn vitrs_malloc(ctx: *mut vitrs_ctx, ptr: *mut *mut c_void, bytes: usize) -> c_int;
-    pub fn vitrs_free(ctx: *mut vitrs_ctx, ptr: *mut c_void) -> c_int;
-    pub fn vitrs_memcpy_h2d(ctx: *mut vitrs_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
-    pub fn vitrs_memcpy_d2h(ctx: *mut vitrs_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
-
-    // ---- L1 operators, fp32 verify mode (reference line each replaces) ----
-    pub fn vitrs_residual_forward_f32(ctx: *mut vitrs_ctx, out: *mut f32, inp1: *const f32, inp2: *const f32, n: c_int) -> c_int; // tv:376
-    pub fn vitrs_matmul_forward_f32(ctx: *mut vitrs_ctx, out: *mut f32, inp: *const f32, weight: *const f32, bias: *const f32,
-                                    b: c_int, t: c_int, c: c_int, oc: c_int) -> c_int; // tv:384
-    pub fn vitrs_attention_forward_f32(ctx: *mut vitrs_ctx, out: *mut f32, preatt: *mut f32, att: *mut f32, inp: *const f32,
-                                       b: c_int, t: c_int, c: c_int, nh: c_int, causal: c_int) -> c_int; // tv:400
-    pub fn vitrs_layernorm_forward_f32(ctx: *mut vitrs_ctx, out: *mut f32, mean: *mut f32, rstd: *mut f32, inp: *const f32,
-                                       weight: *const f32, bias: *const f32, b: c_int, t: c_int, c: c_int) -> c_int; // tv:453
-    pub fn vitrs_gelu_forward_f32(ctx: *mut vitrs_ctx, out: *mut f32, inp: *const f32, n: c_int) -> c_int; // tv:482
-    pub fn vitrs_softmax_forward_f32(ctx: *mut vitrs_ctx, probs: *mut f32, logits: *const f32, b: c_int, t: c_int, v: c_int) -> c_int; // tv:493
-    pub fn vitrs_residual_backward_f32(ctx: *mut vitrs_ctx, dinp1: *mut f32, dinp2: *mut f32, dout: *const f32, n: c_int) -> c_int; // tv:521
-    pub fn vitrs_matmul_backward_f32(ctx: *mut vitrs_ctx, dinp: *mut f32, dweight: *mut f32, dbias: *mut f32, dout: *const f32,
-                                     inp: *const f32, weight: *const f32, b: c_int, t: c_int, c: c_int, oc: c_int) -> c_int; // tv:530
-    pub fn vitrs_attention_backward_f32(ctx: *mut vitrs_ctx, dinp: *mut f32, dpreatt: *mut f32, datt: *mut f32, dout: *const f32,
-                                        inp: *const f32, att: *const f32, b: c_int, t: c_int, c: c_int, nh: c_int, causal: c_int) -> c_int; // tv:559
-    pub fn vitrs_layernorm_backward_f32(ctx: *mut vitrs_ctx, dinp: *mut f32, dweight: *mut f32, dbias: *mut f32, dout: *const f32,
-                                        inp: *const f32, weight: *const f32, mean: *const f32, rstd: *const f32,
-                                        b: c_int, t: c_int, c: c_int) -> c_int; // tv:603
-    pub fn vitrs_gelu_backward_f32(ctx: *mut vitrs_ctx, dinp: *mut f32, inp: *const f32, dout: *const f32, n: c_int) -> c_int; // tv:639
-
-    // ---- bf16 production mode: same names with _bf16 (activations / weights bf16, stats and parameter gradients fp32) ----
-    pub fn vitrs_matmul_forward_bf16(ctx: *mut vitrs_ctx, out: *mut vitrs_bf16, inp: *const vitrs_bf16, weight: *const vitrs_bf16,
-                                     bias: *const f32, b: c_int, t: c_int, c: c_int, oc: c_int) -> c_int;
-    pub fn vitrs_matmul_backward_bf16(ctx: *mut vitrs_ctx, dinp: *mut vitrs_bf16, dweight: *mut f32, dbias: *mut f32,
-                                      dout: *const vitrs_bf16, inp: *const vitrs_bf16, weight: *const vitrs_bf16,
-                                      b: c_int, t: c_int, c: c_int, oc: c_int) -> c_int;
-    /// one GEMM with a fused epilogue: 1 bias, 2 bias + GELU (second output d2), 3 bias + residual (aux), 4 gelu'(aux)
-    pub fn vitrs_gemm_bf16_fused(ctx: *mut vitrs_ctx, d: *mut vitrs_bf16, d2: *mut vitrs_bf16, aux: *const vitrs_bf16,
-                                 bias: *const f32, a_colsum: *mut f32, a: *const vitrs_bf16, b: *const vitrs_bf16,
-                                 m: c_int, n: c_int, k: c_int, lda: c_int, ldb: c_int, ldd: c_int,
-                                 a_mn_major: c_int, b_mn_major: c_int, epilogue: c_int) -> c_int;
-    pub fn vitrs_attention_forward_bf16(ctx: *mut vitrs_ctx, out: *mut vitrs_bf16, lse: *mut f32, inp: *const vitrs_bf16,
-                                        b: c_int, t: c_int, c: c_int, nh: c_int, causal: c_int) -> c_int;
-    pub fn vitrs_attention_backward_bf16(ctx: *mut vitrs_ctx, dinp: *mut vitrs_bf16, dout: *const vitrs_bf16, out: *const vitrs_bf16,
-                                         lse: *const f32, inp: *const vitrs_bf16, b: c_int, t: c_int, c: c_int, nh: c_int,
-                                         causal: c_int) -> c_int;
-    pub fn vitrs_layernorm_forward_bf16(ctx: *mut vitrs_ctx, out: *mut vitrs_bf16, mean: *mut f32, rstd: *mut f32,
-                                        inp: *const vitrs_bf16, weight: *const f32, bias: *const f32, b: c_int, t: c_int, c: c_int) -> c_int;
-    pub fn vitrs_layernorm_backward_bf16(ctx: *mut vitrs_ctx, dinp: *mut vitrs_bf16, dweight: *mut f32, dbias: *mut f32,
-                                         dout: *const vitrs_bf16, inp: *const vitrs_bf16, weight: *const f32, mean: *const f32,
-                                         rstd: *const f32, b: c_int, t: c_int, c: c_int) -> c_int;
-
-    // ---- optimiser: optimizer_step (rv:949) and its AdamW form ----
-    pub fn vitrs_sgd_step(ctx: *mut vitrs_ctx, params: *mut f32, grads: *const f32, n: usize, lr: f32, shadow: *mut vitrs_bf16) -> c_int;
-    pub fn vitrs_adamw_step(ctx: *mut vitrs_ctx, params: *mut f32, grads: *const f32, m: *mut f32, v: *mut f32, n: usize, lr: f32,
-                            beta1: f32, beta2: f32, eps: f32, weight_decay: f32, step: c_int, shadow: *mut vitrs_bf16) -> c_int;
-
-    // ---- L2 model: struct ViT / impl ViT (rv:63-450) ----
-    pub fn vitrs_model_create(ctx: *mut vitrs_ctx, cfg: *const vitrs_config, max_batch: c_int, mode: c_int, out: *mut *mut vitrs_model) -> c_int;
-    pub fn vitrs_model_destroy(m: *mut vitrs_model) -> c_int;
-    pub fn vitrs_model_init_parameters(m: *mut vitrs_model, seed: u64, init_mode: c_int) -> c_int; // rv:864
-    pub fn vitrs_model_load_checkpoint(m: *mut vitrs_model, path: *const c_char) -> c_int; // rv:79
-    pub fn vitrs_model_save_checkpoint(m: *mut vitrs_model, path: *const c_char) -> c_int; // rv:912
-    pub fn vitrs_model_num_parameters(m: *mut vitrs_model) -> usize;
-    pub fn vitrs_model_forward(m: *mut vitrs_model, images: *const f32, labels: *const c_int, b: c_int) -> c_int; // rv:269
-    pub fn vitrs_model_zero_grad(m: *mut vitrs_model) -> c_int;
-    pub fn vitrs_model_backward(m: *mut vitrs_model) -> c_int; // rv:354
-    pub fn vitrs_model_optimizer_step(m: *mut vitrs_model, lr: f32) -> c_int; // rv:949
-    pub fn vitrs_model_update(m: *mut vitrs_model, lr: f32, beta1: f32, beta2: f32, eps: f32, weight_decay: f32) -> c_int;
-    pub fn vitrs_model_mean_loss(m: *mut vitrs_model, out: *mut f32) -> c_int; // rv:75
-    pub fn vitrs_model_train_step_host(m: *mut vitrs_model, h_images: *const f32, h_labels: *const c_int, b: c_int, lr: f32, beta1: f32,
-                                       beta2: f32, eps: f32, weight_decay: f32, loss_out: *mut f32) -> c_int;
-    // raw dataset images (uint8; layout 0 = NCHW, 1 = NHWC), normalised on the device inside the patch embedding
-    pub fn vitrs_model_set_input_norm(m: *mut vitrs_model, mean3: *const f32, std3: *const f32) -> c_int;
-    pub fn vitrs_model_forward_u8(m: *mut vitrs_model, images: *const u8, layout: c_int, labels: *const c_int, b: c_int) -> c_int;
-    pub fn vitrs_model_train_step_u8(m: *mut vitrs_model, images: *const u8, layout: c_int, labels: *const c_int, b: c_int, lr: f32,
-                                     beta1: f32, beta2: f32, eps: f32, weight_decay: f32) -> c_int;
-    pub fn vitrs_model_prefetch_host_u8(m: *mut vitrs_model, h_images: *const u8, h_labels: *const c_int, b: c_int) -> c_int;
-    pub fn vitrs_model_train_step_host_u8(m: *mut vitrs_model, h_images: *const u8, layout: c_int, h_labels: *const c_int, b: c_int,
-                                          lr: f32, beta1: f32, beta2: f32, eps: f32, weight_decay: f32, loss_out: *mut f32) -> c_int;
-    pub fn vitrs_model_param_view(m: *mut vitrs_model, which: c_int, tensor: c_int, ptr: *mut *mut f32, count: *mut usize) -> c_int;
-}
-
-/// Safe-ish mirror of the reference's `ViT` (rv:63-76): same method names, device-resident.
+/// Mirror of the reference's `ViT` (rusty_vit.rs:63-76): same method names, device-resident.
 pub struct ViT {
     ctx: *mut vitrs_ctx,
     model: *mut vitrs_model,
@@ -124,39 +39,97 @@ pub struct ViT {
     pub mean_loss: f32,
 }
 
+unsafe fn err(ctx: *mut vitrs_ctx) -> String { CStr::from_ptr(vitrs_last_error(ctx)).to_string_lossy().into_owned() }
+
+macro_rules! check {
+    ($self:ident, $call:expr) => {
+        if unsafe { $call } != VITRS_OK { return Err(unsafe { err($self.ctx) }); }
+    };
+}
+
 impl ViT {
-    /// `ViT::build_from_checkpoint` (rv:79): allocate for `config`, then read the llm.c-style file.
-    pub fn build_from_checkpoint(config: vitrs_config, max_batch: i32, path: &str) -> Result<ViT, String> {
+    /// Allocate a model for `config` on `device` and initialise it (rusty_vit.rs:864 `init_parameters`).
+    pub fn new(config: vitrs_config, device: i32, max_batch: i32, mode: c_int, seed: u64) -> Result<ViT, String> {
         unsafe {
             let mut ctx = std::ptr::null_mut();
-            if vitrs_ctx_create(&mut ctx, 0) != VITRS_OK { return Err("no sm_100 device (there is no CPU fallback)".into()); }
+            if vitrs_ctx_create(&mut ctx, device) != VITRS_OK { return Err("no sm_100 device (there is no CPU fallback)".into()); }
             let mut model = std::ptr::null_mut();
-            if vitrs_model_create(ctx, &config, max_batch, VITRS_MODE_BF16, &mut model) != VITRS_OK { return Err(err(ctx)); }
-            let c = std::ffi::CString::new(path).unwrap();
-            if vitrs_model_load_checkpoint(model, c.as_ptr()) != VITRS_OK { return Err(err(ctx)); }
+            if vitrs_model_create(ctx, &config, max_batch, mode, &mut model) != VITRS_OK { let e = err(ctx); vitrs_ctx_destroy(ctx); return Err(e); }
+            if vitrs_model_init_parameters(model, seed, 0) != VITRS_OK { return Err(err(ctx)); }
             Ok(ViT { ctx, model, config, mean_loss: -1.0 })
         }
     }
-    /// `vit.forward(inputs, targets, b, t)` (rv:269): device images [b,3,H,W] fp32, device labels [b] (null => logits only).
+    /// `ViT::build_from_checkpoint` (rusty_vit.rs:79): allocate for `config`, then read the llm.c-style file.
+    pub fn build_from_checkpoint(config: vitrs_config, max_batch: i32, path: &str) -> Result<ViT, String> {
+        let v = ViT::new(config, 0, max_batch, VITRS_MODE_BF16, 0)?;
+        let c = CString::new(path).map_err(|e| e.to_string())?;
+        check!(v, vitrs_model_load_checkpoint(v.model, c.as_ptr()));
+        Ok(v)
+    }
+    pub fn save_checkpoint(&mut self, path: &str) -> Result<(), String> {
+        let c = CString::new(path).map_err(|e| e.to_string())?;
+        check!(self, vitrs_model_save_checkpoint(self.model, c.as_ptr()));
+        Ok(())
+    }
+    /// `vit.forward(inputs, targets, b, t)` (rusty_vit.rs:269): device images [b,3,H,W] fp32, device labels [b] (null => logits only).
     pub fn forward(&mut self, images: *const f32, targets: *const c_int, b: i32) -> Result<(), String> {
-        unsafe {
-            if vitrs_model_forward(self.model, images, targets, b) != VITRS_OK { return Err(err(self.ctx)); }
-            if vitrs_model_mean_loss(self.model, &mut self.mean_loss) != VITRS_OK { return Err(err(self.ctx)); }
-        }
+        check!(self, vitrs_model_forward(self.model, images, targets, b));
+        check!(self, vitrs_model_mean_loss(self.model, &mut self.mean_loss));
         Ok(())
     }
-    /// `vit.backward()` (rv:354); gradients accumulate, so zero them once per step first.
-    pub fn backward(&mut self) -> Result<(), String> {
-        unsafe { if vitrs_model_backward(self.model) != VITRS_OK { return Err(err(self.ctx)); } }
+    /// `vit.backward()` (rusty_vit.rs:354); gradients accumulate, so zero them once per step first.
+    pub fn backward(&mut self) -> Result<(), String> { check!(self, vitrs_model_backward(self.model)); Ok(()) }
+    pub fn zero_grad(&mut self) -> Result<(), String> { check!(self, vitrs_model_zero_grad(self.model)); Ok(()) }
+    /// AdamW form of `optimizer_step` (under data parallel the gradient exchange has already been queued by `backward`).
+    pub fn update(&mut self, o: &AdamW) -> Result<(), String> {
+        check!(self, vitrs_model_update(self.model, o.lr, o.beta1, o.beta2, o.eps, o.weight_decay));
         Ok(())
     }
-    pub fn zero_grad(&mut self) { unsafe { vitrs_model_zero_grad(self.model); } }
+    /// One step of the train loop (train_vit.rs:65-86: forward, zero_grad, backward, update) from HOST slices;
+    /// returns the mean loss.  `images` is [b,3,H,W] fp32, `labels` is [b].
+    pub fn train_step_host(&mut self, images: &[f32], labels: &[c_int], o: &AdamW) -> Result<f32, String> {
+        let b = labels.len() as c_int;
+        let per = 3 * (self.config.image_size as usize).pow(2);
+        if images.len() != per * labels.len() { return Err("images.len() != b * 3 * H * W".into()); }
+        check!(self, vitrs_model_train_step_host(self.model, images.as_ptr(), labels.as_ptr(), b, o.lr, o.beta1, o.beta2, o.eps,
+                                                   o.weight_decay, &mut self.mean_loss));
+        Ok(self.mean_loss)
+    }
+    /// The same from raw dataset bytes (uint8; layout 0 = NCHW, 1 = NHWC), normalised on the device.
+    pub fn train_step_host_u8(&mut self, images: &[u8], layout: c_int, labels: &[c_int], o: &AdamW) -> Result<f32, String> {
+        check!(self, vitrs_model_train_step_host_u8(self.model, images.as_ptr(), layout, labels.as_ptr(), labels.len() as c_int, o.lr, o.beta1,
+                                                      o.beta2, o.eps, o.weight_decay, &mut self.mean_loss));
+        Ok(self.mean_loss)
+    }
+    /// Join a data-parallel job: `id128` is the 128-byte NCCL unique id made by rank 0 (`unique_id`) and broadcast by the host.
+    pub fn init_data_parallel(&mut self, id128: &[u8; 128], rank: i32, world: i32, global_batch: i32) -> Result<(), String> {
+        check!(self, vitrs_comm_init(self.ctx, id128.as_ptr() as *const _, rank, world));
+        check!(self, vitrs_model_set_dloss_scale(self.model, 1.0 / global_batch as f32));
+        Ok(())
+    }
+    pub fn unique_id(&mut self) -> Result<[u8; 128], String> {
+        let mut id = [0u8; 128];
+        check!(self, vitrs_comm_unique_id(self.ctx, id.as_mut_ptr() as *mut _));
+        Ok(id)
+    }
+    /// `ncclCommGetAsyncError`: Err when a peer or the fabric has failed since the last call.
+    pub fn comm_health(&mut self) -> Result<(), String> {
+        let mut r: c_int = 0;
+        check!(self, vitrs_comm_async_error(self.ctx, &mut r));
+        Ok(())
+    }
+    /// ZeRO-1: shard the fp32 master weights and AdamW moments of the GEMM weights over the ranks.
+    pub fn enable_zero1(&mut self) -> Result<(), String> { check!(self, vitrs_model_enable_zero1(self.model)); Ok(()) }
+    pub fn num_parameters(&self) -> usize { unsafe { vitrs_model_num_parameters(self.model) } }
+    pub fn synchronize(&mut self) -> Result<(), String> { check!(self, vitrs_ctx_synchronize(self.ctx)); Ok(()) }
+    pub fn raw(&self) -> (*mut vitrs_ctx, *mut vitrs_model) { (self.ctx, self.model) }
 }
 
-/// `optimizer_step(model, lr)` (rv:949).
-pub fn optimizer_step(model: &mut ViT, lr: f32) { unsafe { vitrs_model_optimizer_step(model.model, lr); } }
-
-unsafe fn err(ctx: *mut vitrs_ctx) -> String { std::ffi::CStr::from_ptr(vitrs_last_error(ctx)).to_string_lossy().into_owned() }
+/// `optimizer_step(model, lr)` (rusty_vit.rs:949): SGD over the flat parameter buffer.
+pub fn optimizer_step(model: &mut ViT, lr: f32) -> Result<(), String> {
+    check!(model, vitrs_model_optimizer_step(model.model, lr));
+    Ok(())
+}
 
 impl Drop for ViT {
     fn drop(&mut self) { unsafe { vitrs_model_destroy(self.model); vitrs_ctx_destroy(self.ctx); } }

@@ -33,6 +33,22 @@ def test_library_exports_every_declared_symbol(vitrs):
     assert extra == [], extra
 
 
+def test_rust_crate_declares_every_symbol():
+    """rust/vitrs-sys/src/ffi.rs is generated from the header (scripts/gen_rust_ffi.py): it must be current and complete."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "scripts", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    want = gen.render(gen.parse_header(HEADER))
+    have = open(os.path.join(ROOT, "rust", "vitrs-sys", "src", "ffi.rs")).read()
+    assert have == want, "stale: python scripts/gen_rust_ffi.py > rust/vitrs-sys/src/ffi.rs"
+    assert sorted(re.findall(r"pub fn (vitrs_[a-z0-9_]+)\(", have)) == declared_symbols()
+    # the wrapper only calls what ffi.rs declares
+    wrapper = open(os.path.join(ROOT, "rust", "vitrs-sys", "src", "lib.rs")).read()
+    used = set(re.findall(r"\b(vitrs_[a-z0-9_]+)\(", wrapper))
+    assert used <= set(declared_symbols()), sorted(used - set(declared_symbols()))
+
+
 def test_library_has_no_oracle_or_torch_dependency(vitrs):
     out = subprocess.run(["ldd", vitrs.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out and "torch" not in out and "libnccl" not in out  # NCCL is dlopen'ed at comm_init
