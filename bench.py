@@ -275,6 +275,38 @@ def main():
     ms_inf = max_over_ranks(e0.elapsed_time(e1))
     inference = {"value": round(global_batch * args.steps / (ms_inf / 1e3), 2), "unit": "images/s", "ms_per_batch": round(ms_inf / args.steps, 3)}
 
+    # the same through the inference engine (vitrs_infer_*: ping-pong workspace, CUDA-graph replay) incl. small-batch latency
+    # from HOST buffers (H2D + forward + D2H of the logits, synchronised): the serving figures of SURVEY 8-f.3
+    if world == 1 and mode == pkg.MODE_BF16:
+        eng = pkg.InferenceEngine(model, max_batch=per_gpu)
+        for s in range(3):
+            eng.forward(d_images[s % 2])
+        barrier()
+        e0.record()
+        for s in range(args.steps):
+            eng.forward(d_images[s % 2])
+        e1.record()
+        barrier()
+        ms_eng = e0.elapsed_time(e1)
+        inference["engine"] = {"value": round(per_gpu * args.steps / (ms_eng / 1e3), 2), "ms_per_batch": round(ms_eng / args.steps, 3),
+                               "workspace_bytes": eng.stats()["workspace_bytes"], "latency_ms_host_to_host": {}}
+        import numpy as np
+        for lb in (1, 8, 64):
+            if lb > per_gpu:
+                continue
+            hx = np.ascontiguousarray(d_images[0][:lb].cpu().numpy())
+            out = np.empty((lb, cfg["num_classes"]), dtype=np.float32)
+            for _ in range(5):
+                eng.forward_host(hx, out)
+            ts = []
+            for _ in range(30):
+                t0 = time.perf_counter()
+                eng.forward_host(hx, out)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            ts.sort()
+            inference["engine"]["latency_ms_host_to_host"][str(lb)] = {"median": round(ts[len(ts) // 2], 3), "p90": round(ts[int(len(ts) * 0.9)], 3)}
+        eng.close()
+
     # ---- roofline of the dominant kernel: every tcgen05 GEMM launch of one step, CUDA events per launch ----
     peaks = measured_peaks()
     ctx.profile_begin()

@@ -237,6 +237,28 @@ int vitrs_model_train_step_host_u8(vitrs_model*, const uint8_t* h_images, int la
 int vitrs_model_train_step(vitrs_model* m, const float* images, const int* labels, int b,
                            float lr, float beta1, float beta2, float eps, float weight_decay);
 
+/* ---- inference engine: ViT::forward without targets (rusty_vit.rs:339-350, logits only) ---------------------
+ * Borrows the parameters of a production-mode model (which must outlive it; create that model with max_batch 1 when it only
+ * serves) and owns a ping-pong workspace instead of the [L, ...] activation arena of the training forward: two [M,C] residual
+ * streams, [M,C] LayerNorm output, [M,3C] qkv, [M,C] attention output, [M,4C] MLP buffer — independent of the layer count
+ * (ViT-B/16, batch 1024: 3.7 GB against 59.5 GB).  After one eager run per (batch, input pointer, input kind) the launch
+ * sequence is replayed as a CUDA graph.  Same kernels as the training forward: logits are bit-identical to
+ * vitrs_model_forward(labels = NULL).  Images: fp32 NCHW, or uint8 (layout 0 = NCHW, 1 = NHWC, normalised on the device with
+ * the model's vitrs_model_set_input_norm constants). */
+typedef struct vitrs_infer vitrs_infer;
+int vitrs_infer_create(vitrs_model* m, int max_batch, vitrs_infer** out);
+int vitrs_infer_destroy(vitrs_infer* e);
+/* device images -> device logits / probabilities [b, classes] fp32 (vitrs_infer_outputs), asynchronous on the context's stream */
+int vitrs_infer_forward(vitrs_infer* e, const float* images, int b);
+int vitrs_infer_forward_u8(vitrs_infer* e, const uint8_t* images, int layout, int b);
+int vitrs_infer_outputs(vitrs_infer* e, float** logits, float** probs);
+/* host images -> host logits: H2D copy, forward, D2H copy, synchronised (the serving call; latency figures of bench.py) */
+int vitrs_infer_forward_host(vitrs_infer* e, const float* h_images, int b, float* h_logits);
+int vitrs_infer_forward_host_u8(vitrs_infer* e, const uint8_t* h_images, int layout, int b, float* h_logits);
+/* 0 = launch kernel by kernel every time (A/B aid); default 1 */
+int vitrs_infer_set_graph(vitrs_infer* e, int enabled);
+int vitrs_infer_stats(vitrs_infer* e, size_t* workspace_bytes, uint64_t* graph_replays);
+
 /* ---- data parallel (not in the reference) ------------------------------------
  * NCCL is resolved at run time from the already-loaded libnccl.so.2 (dlopen), so the library
  * has no link-time dependency on it.  unique_id is the 128-byte ncclUniqueId made by rank 0. */

@@ -370,3 +370,60 @@ def test_zero1_single_rank_equals_replicated_step(vitrs):
     z.sync_parameters(); z.forward(x, None)
     assert torch.equal(z.act("logits"), lz)
     a.close(); z.close()
+
+
+def test_inference_engine_equals_training_forward_and_replays_graphs(vitrs):
+    """vitrs_infer_* (rusty_vit.rs:339-350): a workspace that does not grow with the layer count, the forward replayed as a
+    CUDA graph, logits bit-equal to the training forward's — for fp32 and uint8 device batches, host batches and two batch sizes."""
+    b = 16
+    m = vitrs.ViT(MID_HS64, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)
+    images, labels = po.synthetic_batch(MID_HS64, b)
+    x, y = to_dev(images, labels)
+    m.forward(x, y)
+    want = m.act("logits").clone().view(b, -1)
+    want_probs = m.act("probs").clone().view(b, -1)
+    eng = vitrs.InferenceEngine(m, max_batch=b)
+    for call in range(4):  # call 0 runs eagerly and records, 1.. replay the graph
+        logits, probs = eng.forward(x)
+        assert torch.equal(logits, want), call
+        assert torch.equal(probs, want_probs), call
+    assert eng.stats()["graph_replays"] == 3
+    # another batch size gets its own graph; the first one stays valid
+    half, _ = eng.forward(x[:5].contiguous())
+    assert torch.equal(half, want[:5])
+    half, _ = eng.forward(x[:5].contiguous())  # (a new tensor: new pointer, new graph or eager — same result)
+    assert torch.equal(half, want[:5])
+    logits, _ = eng.forward(x)
+    assert torch.equal(logits, want)
+    # host entry point: H2D, replay, D2H
+    for _ in range(3):
+        assert np.array_equal(eng.forward_host(images), want.cpu().numpy())
+    # graph off: the same kernels launched one by one
+    eager = vitrs.InferenceEngine(m, max_batch=b, use_graph=False)
+    logits, _ = eager.forward(x)
+    assert torch.equal(logits, want)
+    assert eager.stats()["graph_replays"] == 0
+    # uint8 batches, normalised inside the im2col pass: equal to the model's own uint8 forward
+    u8 = torch.randint(0, 256, (b, 64, 64, 3), dtype=torch.uint8, device="cuda")
+    m.forward_u8(u8, None, layout=vitrs.ViT.NHWC)
+    want_u8 = m.act("logits").clone().view(b, -1)
+    for _ in range(3):
+        logits, _ = eng.forward_u8(u8, layout=vitrs.ViT.NHWC)
+        assert torch.equal(logits, want_u8)
+    assert np.array_equal(eng.forward_host_u8(u8.cpu().numpy(), layout=vitrs.ViT.NHWC), want_u8.cpu().numpy())
+    # the weights are borrowed: an optimiser step on the model changes what the engine computes
+    m.train_step(x, y, 1e-2)
+    m.forward(x, None)
+    after = m.act("logits").clone().view(b, -1)
+    logits, _ = eng.forward(x)
+    assert torch.equal(logits, after) and not torch.equal(after, want)
+    # workspace: no factor L (the training arena of the same model has one)
+    deep = dict(MID_HS64, num_layers=6)
+    m6 = vitrs.ViT(deep, max_batch=1, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)
+    eng6 = vitrs.InferenceEngine(m6, max_batch=b)
+    assert eng6.stats()["workspace_bytes"] == eng.stats()["workspace_bytes"]
+    lg6, _ = eng6.forward(x)  # engine batch 16 on a model created for batch 1
+    assert torch.isfinite(lg6).all()
+    for e in (eng, eager, eng6):
+        e.close()
+    m.close(); m6.close()

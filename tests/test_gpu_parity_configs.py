@@ -116,3 +116,21 @@ def test_bf16_loss_curve_100_steps_hs64(vitrs, cfg, b):
     msg = f"max {dev_.max():.4f} mean {dev_.mean():.4f} last {got_curve[-4:]} vs {ref_curve[-4:]}"
     assert dev_.max() <= TOL_BF16 * ref_curve.max(), msg
     m.close()
+
+
+@pytest.mark.parametrize("cfg_name,b", [("b16", 2), ("ti16", 4)], ids=["b16-b2", "ti16-b4"])
+def test_inference_engine_logits_match_oracle(vitrs, cfg_name, b):
+    """The graph-replayed, activation-free forward (vitrs_infer_*, rusty_vit.rs:339-350) against the oracle's logits at 2e-2."""
+    ref = po.ViT(cfg_name, seed=1337, init_mode=1)
+    m = vitrs.ViT(cfg_name, max_batch=1, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)  # a serving model: no batch-sized arena
+    eng = vitrs.InferenceEngine(m, max_batch=b)
+    images, labels = po.synthetic_batch(po.CONFIGS[cfg_name], b)
+    ref.forward(images, None)
+    want = ref.act("logits").reshape(b, -1)
+    x = torch.from_numpy(images).cuda()
+    for call in range(3):
+        logits, probs = eng.forward(x)
+        assert relerr(logits.cpu().numpy(), want) <= TOL_BF16, call
+    assert np.abs(probs.sum(dim=1).cpu().numpy() - 1.0).max() < 1e-5
+    assert relerr(eng.forward_host(images), want) <= TOL_BF16
+    eng.close(); m.close()

@@ -146,6 +146,15 @@ _SIGNATURES = {
     "vitrs_model_allreduce_grads": (_int, [_vp]),
     "vitrs_grad_bucket": (_int, [C.POINTER(Config), _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_int), C.POINTER(_int)]),
     "vitrs_allreduce_f32": (_int, [_vp, _vp, _sz]),
+    "vitrs_infer_create": (_int, [_vp, _int, C.POINTER(C.c_void_p)]),
+    "vitrs_infer_destroy": (_int, [_vp]),
+    "vitrs_infer_forward": (_int, [_vp, _vp, _int]),
+    "vitrs_infer_forward_u8": (_int, [_vp, _vp, _int, _int]),
+    "vitrs_infer_outputs": (_int, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "vitrs_infer_forward_host": (_int, [_vp, _vp, _int, _vp]),
+    "vitrs_infer_forward_host_u8": (_int, [_vp, _vp, _int, _int, _vp]),
+    "vitrs_infer_set_graph": (_int, [_vp, _int]),
+    "vitrs_infer_stats": (_int, [_vp, C.POINTER(_sz), C.POINTER(_u64)]),
 }
 # the two-mode operator families share argument lists
 for _m in ("f32", "bf16"):
@@ -617,3 +626,69 @@ class ViT:
         self.ctx.check(lib().vitrs_model_train_step_host(self._h, _ptr(h_images), _ptr(h_labels), b, lr, beta1, beta2, eps,
                                                          weight_decay, C.byref(out)))
         return out.value
+
+
+class InferenceEngine:
+    """ViT::forward without targets (rusty_vit.rs:339-350) as a serving object: borrows `model`'s parameters, owns a ping-pong
+    workspace (no [L, ...] activation arena) and replays the forward as a CUDA graph (include/vitrs.h: vitrs_infer_*)."""
+
+    def __init__(self, model, max_batch, use_graph=True):
+        self.model = model  # keeps the parameters alive
+        self.ctx = model.ctx
+        self.max_batch = max_batch
+        self.num_classes = model.cfg_dict["num_classes"]
+        self._h = C.c_void_p()
+        self.ctx.check(lib().vitrs_infer_create(model._h, max_batch, C.byref(self._h)))
+        if not use_graph:
+            self.ctx.check(lib().vitrs_infer_set_graph(self._h, 0))
+
+    def close(self):
+        if self._h:
+            lib().vitrs_infer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _outputs(self, b):
+        lg, pr = C.c_void_p(), C.c_void_p()
+        self.ctx.check(lib().vitrs_infer_outputs(self._h, C.byref(lg), C.byref(pr)))
+        n = b * self.num_classes
+        return (_tensor_view(lg.value, n, 4, self.ctx.device, self).view(b, self.num_classes),
+                _tensor_view(pr.value, n, 4, self.ctx.device, self).view(b, self.num_classes))
+
+    def forward(self, images):
+        """images: cuda fp32 [b,3,H,W]; returns (logits, probs) views [b, classes] (valid until the next call)."""
+        b = images.shape[0]
+        self._keep = images
+        self.ctx.check(lib().vitrs_infer_forward(self._h, _ptr(images), b))
+        return self._outputs(b)
+
+    def forward_u8(self, images, layout=0):
+        b = images.shape[0]
+        self._keep = images
+        self.ctx.check(lib().vitrs_infer_forward_u8(self._h, _ptr(images), layout, b))
+        return self._outputs(b)
+
+    def forward_host(self, h_images, h_logits=None):
+        """Host images (numpy / pinned torch, fp32 NCHW) -> host logits [b, classes]: H2D, graph replay, D2H, synchronised."""
+        import numpy as np
+        b = h_images.shape[0]
+        out = h_logits if h_logits is not None else np.empty((b, self.num_classes), dtype=np.float32)
+        self.ctx.check(lib().vitrs_infer_forward_host(self._h, _ptr(h_images), b, _ptr(out)))
+        return out
+
+    def forward_host_u8(self, h_images, layout=0, h_logits=None):
+        import numpy as np
+        b = h_images.shape[0]
+        out = h_logits if h_logits is not None else np.empty((b, self.num_classes), dtype=np.float32)
+        self.ctx.check(lib().vitrs_infer_forward_host_u8(self._h, _ptr(h_images), layout, b, _ptr(out)))
+        return out
+
+    def stats(self):
+        ws, rep = C.c_size_t(), C.c_uint64()
+        self.ctx.check(lib().vitrs_infer_stats(self._h, C.byref(ws), C.byref(rep)))
+        return {"workspace_bytes": ws.value, "graph_replays": rep.value}
