@@ -259,6 +259,24 @@ int vitrs_infer_forward_host_u8(vitrs_infer* e, const uint8_t* h_images, int lay
 int vitrs_infer_set_graph(vitrs_infer* e, int enabled);
 int vitrs_infer_stats(vitrs_infer* e, size_t* workspace_bytes, uint64_t* graph_replays);
 
+/* ---- record loader: the reader + loader thread in front of vitrs_model_train_step_host_u8 ------------------
+ * The reference's loop takes in-memory buffers (rusty_vit.rs:269) and has no reader.  Files hold fixed-size records in the
+ * CIFAR binary layout: `label_bytes` label bytes (CIFAR-10: 1; CIFAR-100: 2, the last one is used), then 3 x H x W uint8 samples,
+ * channel-major.  A loader thread assembles (optionally shuffled: a function of seed and epoch only) batches into a ring of four
+ * pinned host slots; ctx may be NULL for pageable slots (tools, CPU tests).  The files are read whole at open. */
+typedef struct vitrs_loader vitrs_loader;
+int vitrs_loader_open(vitrs_ctx* ctx, const char* const* paths, int num_paths, int image_size, int label_bytes, int batch,
+                      int shuffle, uint64_t seed, int drop_last, vitrs_loader** out);
+int vitrs_loader_close(vitrs_loader* loader);
+int vitrs_loader_info(vitrs_loader* loader, size_t* num_records, int* batches_per_epoch, int* num_classes_seen);
+/* blocks until the next batch is assembled: uint8 NCHW images [b,3,H,W] and int labels [b] in host memory that stays valid
+ * until the call after the next one; epoch (nullable) counts passes over the files */
+int vitrs_loader_next(vitrs_loader* loader, const uint8_t** h_images, const int** h_labels, int* b, uint64_t* epoch);
+/* one AdamW training step on the loader's next batch; the batch after it, when already assembled, is staged on the copy stream so
+ * its H2D transfer overlaps this step */
+int vitrs_model_train_step_loader(vitrs_model* m, vitrs_loader* loader, float lr, float beta1, float beta2, float eps,
+                                  float weight_decay, float* loss_out, int* batch_out);
+
 /* ---- data parallel (not in the reference) ------------------------------------
  * NCCL is resolved at run time from the already-loaded libnccl.so.2 (dlopen), so the library
  * has no link-time dependency on it.  unique_id is the 128-byte ncclUniqueId made by rank 0. */

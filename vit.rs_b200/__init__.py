@@ -146,6 +146,11 @@ _SIGNATURES = {
     "vitrs_model_allreduce_grads": (_int, [_vp]),
     "vitrs_grad_bucket": (_int, [C.POINTER(Config), _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_int), C.POINTER(_int)]),
     "vitrs_allreduce_f32": (_int, [_vp, _vp, _sz]),
+    "vitrs_loader_open": (_int, [_vp, C.POINTER(C.c_char_p), _int, _int, _int, _int, _int, _u64, _int, C.POINTER(C.c_void_p)]),
+    "vitrs_loader_close": (_int, [_vp]),
+    "vitrs_loader_info": (_int, [_vp, C.POINTER(_sz), C.POINTER(_int), C.POINTER(_int)]),
+    "vitrs_loader_next": (_int, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(_int), C.POINTER(_u64)]),
+    "vitrs_model_train_step_loader": (_int, [_vp, _vp, _f, _f, _f, _f, _f, C.POINTER(_f), C.POINTER(_int)]),
     "vitrs_infer_create": (_int, [_vp, _int, C.POINTER(C.c_void_p)]),
     "vitrs_infer_destroy": (_int, [_vp]),
     "vitrs_infer_forward": (_int, [_vp, _vp, _int]),
@@ -692,3 +697,51 @@ class InferenceEngine:
         ws, rep = C.c_size_t(), C.c_uint64()
         self.ctx.check(lib().vitrs_infer_stats(self._h, C.byref(ws), C.byref(rep)))
         return {"workspace_bytes": ws.value, "graph_replays": rep.value}
+
+
+class RecordLoader:
+    """CIFAR-layout record files -> shuffled uint8 batches assembled by a native loader thread into pinned host slots
+    (include/vitrs.h: vitrs_loader_*).  ctx=None uses pageable memory (no GPU needed)."""
+
+    def __init__(self, paths, image_size, batch, label_bytes=1, shuffle=True, seed=0, drop_last=True, ctx=None, pinned=True):
+        paths = [paths] if isinstance(paths, str) else list(paths)
+        self.ctx = ctx if ctx is not None else (default_context() if pinned else None)
+        self.image_size, self.batch = image_size, batch
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        self._h = C.c_void_p()
+        rc = lib().vitrs_loader_open(self.ctx._h if self.ctx else None, arr, len(paths), image_size, label_bytes, batch, int(shuffle), seed,
+                                     int(drop_last), C.byref(self._h))
+        if rc != 0:
+            raise VitrsError(f"vitrs_loader_open failed ({rc})" + (f": {lib().vitrs_last_error(self.ctx._h).decode()}" if self.ctx else ""))
+        n, bpe, ncls = C.c_size_t(), C.c_int(), C.c_int()
+        lib().vitrs_loader_info(self._h, C.byref(n), C.byref(bpe), C.byref(ncls))
+        self.num_records, self.batches_per_epoch, self.num_classes_seen = n.value, bpe.value, ncls.value
+
+    def next(self):
+        """(images uint8 [b,3,H,W], labels int32 [b], epoch) as numpy views of the loader's slot: valid until the call after the next."""
+        pi, pl, b, ep = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_uint64()
+        rc = lib().vitrs_loader_next(self._h, C.byref(pi), C.byref(pl), C.byref(b), C.byref(ep))
+        if rc != 0:
+            raise VitrsError(f"vitrs_loader_next failed ({rc})")
+        n = b.value
+        img = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint8)), shape=(n, 3, self.image_size, self.image_size))
+        lab = np.ctypeslib.as_array(C.cast(pl, C.POINTER(C.c_int32)), shape=(n,))
+        return img, lab, ep.value
+
+    def train_step(self, model, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01):
+        """One AdamW step of `model` on the next batch (vitrs_model_train_step_loader); returns (loss, batch size)."""
+        loss, b = C.c_float(), C.c_int()
+        model.ctx.check(lib().vitrs_model_train_step_loader(model._h, self._h, lr, beta1, beta2, eps, weight_decay, C.byref(loss), C.byref(b)))
+        model.batch_size = b.value
+        return loss.value, b.value
+
+    def close(self):
+        if self._h:
+            lib().vitrs_loader_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

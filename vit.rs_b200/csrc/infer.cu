@@ -33,6 +33,7 @@ struct vitrs_infer {
     float *lse, *mean, *rstd, *cls_rows, *lnf, *lnf_mean, *lnf_rstd, *logits, *probs;
     void* stage;          // device staging of the host entry points: [max_batch, 3, H, W] fp32 (uint8 batches use its first quarter)
     float* h_logits;      // pinned [max_batch, V]
+    cudaStream_t cap_stream;  // capture happens here: the context may run on the legacy default stream, which cannot be captured
     InferGraph graphs[8];
     uint64_t tick, graph_replays;
 };
@@ -102,9 +103,12 @@ int capture_graph(vitrs_infer* e, const void* src, int kind, int b) {
     if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
     const uint64_t before = ctx->launches;
     cudaGraph_t graph = nullptr;
-    VITRS_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    VITRS_CUDA(ctx, cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    cudaStream_t run_stream = ctx->stream;
+    ctx->stream = e->cap_stream;  // the launchers read the context's stream; the graph itself replays on any stream
     const int rc = forward_once(e, src, kind, b);
-    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    ctx->stream = run_stream;
+    const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
     if (rc != VITRS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess) return vitrs_set_error(ctx, VITRS_ERR_CUDA, "stream capture of the inference forward failed: %s", cudaGetErrorString(ce));
     slot->launches = ctx->launches - before;
@@ -162,7 +166,8 @@ int vitrs_infer_create(vitrs_model* m, int max_batch, vitrs_infer** out) {
     e->workspace_bytes = off[15];
     const size_t img_bytes = B * 3 * cfg.image_size * cfg.image_size * sizeof(float);
     if (cudaMalloc(&e->ws, e->workspace_bytes) != cudaSuccess || cudaMalloc(&e->stage, img_bytes) != cudaSuccess ||
-        cudaMallocHost(&e->h_logits, B * V * sizeof(float)) != cudaSuccess) {
+        cudaMallocHost(&e->h_logits, B * V * sizeof(float)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
         const int rc = vitrs_set_error(ctx, VITRS_ERR_CUDA, "inference workspace (%zu + %zu bytes): %s", e->workspace_bytes, img_bytes,
                                        cudaGetErrorString(cudaGetLastError()));
         cudaFree(e->ws); cudaFree(e->stage);
@@ -187,6 +192,7 @@ int vitrs_infer_destroy(vitrs_infer* e) {
     cudaFree(e->ws);
     cudaFree(e->stage);
     if (e->h_logits) cudaFreeHost(e->h_logits);
+    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
     free(e);
     return VITRS_OK;
 }

@@ -1,0 +1,224 @@
+// loader.cu — the data path in front of the step.  The reference's train loop takes in-memory buffers
+// (`inputs: &[usize]`, rusty_vit.rs:269) and has no reader; this is the piece a training job needs in its place: a reader of
+// fixed-size image records (the CIFAR-10 / CIFAR-100 binary layout: `label_bytes` label bytes, then 3 x H x W uint8 samples,
+// channel-major) and a loader thread that assembles shuffled batches into a ring of pinned host slots, so that
+// vitrs_model_train_step_loader finds the next batch ready, stages the one after it on the copy stream and never waits on
+// the file system.  Pixels stay uint8 until the im2col pass of the patch embedding normalises them on the device.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+constexpr int kSlots = 4;
+
+inline uint64_t splitmix64(uint64_t& s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+}  // namespace
+
+struct vitrs_loader {
+    vitrs_ctx* ctx;  // NULL: pageable slots (tools and CPU tests); otherwise pinned
+    std::vector<uint8_t> data;  // every record of every file, back to back
+    size_t record_bytes, image_bytes, num_records;
+    int label_bytes, batch, shuffle, drop_last, num_classes_seen;
+    uint64_t seed;
+    // ring of host slots: the loader thread fills `filled`, the consumer hands slots back through `released`
+    uint8_t* images[kSlots];
+    int* labels[kSlots];
+    int count[kSlots];
+    uint64_t epoch_of[kSlots];
+    uint64_t produced, consumed, released;  // slot sequence numbers (slot = n % kSlots)
+    int prefetched;                          // 1: slot `consumed` has already been staged on the device by the previous step
+    bool stop;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::thread worker;
+};
+
+namespace {
+
+void fill_loop(vitrs_loader* L) {
+    std::vector<uint32_t> order(L->num_records);
+    uint64_t epoch = 0;
+    for (;;) {
+        for (size_t i = 0; i < L->num_records; ++i) order[i] = (uint32_t)i;
+        if (L->shuffle) {  // Fisher-Yates from a per-epoch stream: the order is a function of (seed, epoch) only
+            uint64_t s = L->seed * 0x100000001B3ull + epoch;
+            for (size_t i = L->num_records - 1; i > 0; --i) {
+                const size_t j = (size_t)(splitmix64(s) % (i + 1));
+                const uint32_t t = order[i]; order[i] = order[j]; order[j] = t;
+            }
+        }
+        for (size_t at = 0; at < L->num_records; at += (size_t)L->batch) {
+            const size_t n = L->num_records - at < (size_t)L->batch ? L->num_records - at : (size_t)L->batch;
+            if (n < (size_t)L->batch && L->drop_last) break;
+            int slot;
+            {
+                std::unique_lock<std::mutex> lk(L->mu);
+                L->cv.wait(lk, [&] { return L->stop || L->produced - L->released < (uint64_t)kSlots; });
+                if (L->stop) return;
+                slot = (int)(L->produced % kSlots);
+            }
+            for (size_t k = 0; k < n; ++k) {
+                const uint8_t* rec = L->data.data() + (size_t)order[at + k] * L->record_bytes;
+                L->labels[slot][k] = rec[L->label_bytes - 1];  // CIFAR-100: (coarse, fine) -> the fine label
+                memcpy(L->images[slot] + k * L->image_bytes, rec + L->label_bytes, L->image_bytes);
+            }
+            {
+                std::lock_guard<std::mutex> lk(L->mu);
+                L->count[slot] = (int)n;
+                L->epoch_of[slot] = epoch;
+                L->produced++;
+            }
+            L->cv.notify_all();
+        }
+        ++epoch;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int vitrs_loader_open(vitrs_ctx* ctx, const char* const* paths, int num_paths, int image_size, int label_bytes, int batch, int shuffle,
+                      uint64_t seed, int drop_last, vitrs_loader** out) {
+    if (!out || !paths || num_paths < 1 || image_size < 1 || label_bytes < 1 || label_bytes > 4 || batch < 1) {
+        if (ctx) vitrs_set_error(ctx, VITRS_ERR_ARG, "vitrs_loader_open: bad argument");
+        return VITRS_ERR_ARG;
+    }
+    *out = nullptr;
+    vitrs_loader* L = new vitrs_loader();
+    L->ctx = ctx;
+    L->image_bytes = (size_t)3 * image_size * image_size;
+    L->record_bytes = L->image_bytes + label_bytes;
+    L->label_bytes = label_bytes; L->batch = batch; L->shuffle = shuffle; L->drop_last = drop_last; L->seed = seed;
+    auto fail = [&](int code, const char* what, const char* path) {
+        if (ctx) vitrs_set_error(ctx, code, "vitrs_loader_open: %s (%s)", what, path);
+        delete L;
+        return code;
+    };
+    for (int i = 0; i < num_paths; ++i) {
+        FILE* f = fopen(paths[i], "rb");
+        if (!f) return fail(VITRS_ERR_ARG, "cannot open", paths[i]);
+        fseek(f, 0, SEEK_END);
+        const long bytes = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (bytes <= 0 || (size_t)bytes % L->record_bytes != 0) {
+            fclose(f);
+            return fail(VITRS_ERR_ARG, "file size is not a whole number of records", paths[i]);
+        }
+        const size_t at = L->data.size();
+        L->data.resize(at + (size_t)bytes);
+        const size_t got = fread(L->data.data() + at, 1, (size_t)bytes, f);
+        fclose(f);
+        if (got != (size_t)bytes) return fail(VITRS_ERR_ARG, "short read", paths[i]);
+    }
+    L->num_records = L->data.size() / L->record_bytes;
+    if (drop_last && L->num_records < (size_t)batch) return fail(VITRS_ERR_ARG, "fewer records than one batch", paths[0]);
+    int max_label = 0;
+    for (size_t r = 0; r < L->num_records; ++r) {
+        const int lb = L->data[r * L->record_bytes + label_bytes - 1];
+        if (lb > max_label) max_label = lb;
+    }
+    L->num_classes_seen = max_label + 1;
+    for (int s = 0; s < kSlots; ++s) {
+        const size_t ib = L->image_bytes * batch, lb = sizeof(int) * (size_t)batch;
+        if (ctx) {
+            cudaSetDevice(ctx->device);
+            if (cudaMallocHost(&L->images[s], ib) != cudaSuccess || cudaMallocHost(&L->labels[s], lb) != cudaSuccess)
+                return fail(VITRS_ERR_CUDA, "cudaMallocHost of a batch slot failed", paths[0]);
+        } else {
+            L->images[s] = (uint8_t*)malloc(ib);
+            L->labels[s] = (int*)malloc(lb);
+        }
+    }
+    L->worker = std::thread(fill_loop, L);
+    *out = L;
+    return VITRS_OK;
+}
+
+int vitrs_loader_close(vitrs_loader* L) {
+    if (!L) return VITRS_OK;
+    {
+        std::lock_guard<std::mutex> lk(L->mu);
+        L->stop = true;
+    }
+    L->cv.notify_all();
+    if (L->worker.joinable()) L->worker.join();
+    for (int s = 0; s < kSlots; ++s) {
+        if (L->ctx) { cudaFreeHost(L->images[s]); cudaFreeHost(L->labels[s]); }
+        else { free(L->images[s]); free(L->labels[s]); }
+    }
+    delete L;
+    return VITRS_OK;
+}
+
+int vitrs_loader_info(vitrs_loader* L, size_t* num_records, int* batches_per_epoch, int* num_classes_seen) {
+    if (!L) return VITRS_ERR_ARG;
+    if (num_records) *num_records = L->num_records;
+    if (batches_per_epoch)
+        *batches_per_epoch = (int)(L->drop_last ? L->num_records / L->batch : (L->num_records + L->batch - 1) / L->batch);
+    if (num_classes_seen) *num_classes_seen = L->num_classes_seen;
+    return VITRS_OK;
+}
+
+// Blocks until the next batch is assembled; the pointers stay valid until the call after the next one (the slot of batch n is
+// handed back to the loader thread when batch n + 1 is taken).
+int vitrs_loader_next(vitrs_loader* L, const uint8_t** h_images, const int** h_labels, int* b, uint64_t* epoch) {
+    if (!L || !h_images || !h_labels || !b) return VITRS_ERR_ARG;
+    std::unique_lock<std::mutex> lk(L->mu);
+    if (L->consumed > 0 && L->released < L->consumed - 1) {  // batch n - 2 is dead now
+        L->released = L->consumed - 1;
+        L->cv.notify_all();
+    }
+    L->cv.wait(lk, [&] { return L->produced > L->consumed; });
+    const int slot = (int)(L->consumed % kSlots);
+    *h_images = L->images[slot];
+    *h_labels = L->labels[slot];
+    *b = L->count[slot];
+    if (epoch) *epoch = L->epoch_of[slot];
+    L->consumed++;
+    return VITRS_OK;
+}
+
+// One training step fed by the loader: take the next batch, stage the one after it (if already assembled) on the copy stream so
+// that its H2D transfer overlaps this step, run the uint8 host step (H2D / step / D2H of the loss).
+int vitrs_model_train_step_loader(vitrs_model* m, vitrs_loader* L, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                  float* loss_out, int* batch_out) {
+    if (!m || !L) return VITRS_ERR_ARG;
+    const uint8_t* img;
+    const int* lab;
+    int b;
+    VITRS_TRY(vitrs_loader_next(L, &img, &lab, &b, nullptr));
+    if (batch_out) *batch_out = b;
+    const uint8_t* nimg = nullptr;
+    const int* nlab = nullptr;
+    int nb = 0;
+    {
+        std::lock_guard<std::mutex> lk(L->mu);
+        if (L->produced > L->consumed) {  // peek: do not consume
+            const int slot = (int)(L->consumed % kSlots);
+            nimg = L->images[slot]; nlab = L->labels[slot]; nb = L->count[slot];
+        }
+    }
+    // the batch being consumed now was staged by the previous call when it was already there (prefetch_host_u8 matches by pointer)
+    if (!L->prefetched) VITRS_TRY(vitrs_model_prefetch_host_u8(m, img, lab, b));
+    L->prefetched = 0;
+    if (nimg) {
+        VITRS_TRY(vitrs_model_prefetch_host_u8(m, nimg, nlab, nb));
+        L->prefetched = 1;
+    }
+    return vitrs_model_train_step_host_u8(m, img, 0 /* NCHW records */, lab, b, lr, beta1, beta2, eps, weight_decay, loss_out);
+}
+
+}  // extern "C"
