@@ -28,6 +28,36 @@
 
 #include "tc_ptx.cuh"
 
+// Diagnostic build only (make trace -> libvitrs_trace.so, scripts/attn_trace.py): CTA 0 stamps its SM clock at the pipeline's
+// hand-over points so the critical path of the persistent kernels can be read off a timeline.  Compiled out otherwise.
+#ifdef VITRS_ATTN_TRACE
+// per-warp rows of 2048 stamps, written with plain stores (an atomic cursor would cost the stamping warp a round trip to L2)
+__device__ unsigned long long g_attn_trace[16 * 2048];
+#define TR_DECL unsigned int tr_i__ = 0;
+#define TR(ev, a)                                                                                                              \
+    do {                                                                                                                       \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_i__ < 2048u)                                                       \
+            g_attn_trace[((threadIdx.x >> 5) << 11) + tr_i__++] = ((unsigned long long)clock64() << 24) |                        \
+                                                                  ((unsigned long long)(threadIdx.x >> 5) << 16) |               \
+                                                                  ((unsigned long long)(ev) << 8) | (unsigned long long)((a) & 255); \
+    } while (0)
+extern "C" int vitrs_debug_trace_read(unsigned long long* out, unsigned int* n) {
+    static unsigned long long host[16 * 2048];
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(host));
+    unsigned int cnt = 0;
+    for (int i = 0; i < 16 * 2048; ++i)
+        if (host[i]) { if (out) out[cnt] = host[i]; ++cnt; }
+    memset(host, 0, sizeof(host));
+    cudaMemcpyToSymbol(g_attn_trace, host, sizeof(host));
+    *n = cnt;
+    return 0;
+}
+#else
+#define TR_DECL
+#define TR(ev, a)
+#endif
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -289,6 +319,9 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 
+// the same for a converged warp: one answer for all lanes (a completed phase stays completed, so "any lane saw it" is exact)
+__device__ __forceinline__ bool mbar_test_warp(uint32_t bar, uint32_t parity) { return __any_sync(0xffffffffu, mbar_test(bar, parity)); }
+
 template <bool STAGGER>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
@@ -303,7 +336,9 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 128);
     constexpr uint32_t TMEM_COLS = 512, REGION = 256, cO = REGION - HS;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches stay converged
+    TR_DECL
     const int nheads = (total_heads - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // heads of this CTA
     if (tid == 0) {
         tma_prefetch_desc(&tm_qkv);
@@ -324,7 +359,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot, 0);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -345,8 +380,8 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ================================ issuer ================================
+        {
+            // ================================ issuer (whole warp converged, tcgen05 instructions on the elected lane) ================
             // S = Q K^T (both operands K-major) is issued in two pieces.  Columns [0, kMainCols) of the next head go out right behind
             // this head's P.V MMAs: tcgen05.mma executes in issue order, so overwriting the probabilities the P.V MMAs are still
             // reading needs no barrier, and the O accumulator at [192, 256) is untouched.  The few columns that overlap O
@@ -359,25 +394,33 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             auto issue_main = [&](int g, int G) {
                 const uint32_t sQ = base + (G & 1) * STAGE;
                 const uint64_t dq = make_desc(sQ + g * TILE_BYTES, 0, 1024), dk = make_desc(sQ + 2 * TILE_BYTES, 0, 1024);
+                if (elect_one()) {  // one elected region per batch: the MMAs go out back to back (scripts/exp_mma_rate.cu)
 #pragma unroll
-                for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + (uint32_t)g * REGION, dq + 2 * k, dk + 2 * k, idesc_main, k > 0);
-                umma_commit(s_main + 8 * g);
+                    for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + (uint32_t)g * REGION, dq + 2 * k, dk + 2 * k, idesc_main, k > 0);
+                    umma_commit(s_main + 8 * g);
+                }
+                __syncwarp();
                 nMain[g] = G + 1;
+                TR(52 + g, G);
             };
             while (nPV[0] < nheads || nPV[1] < nheads) {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     if (nPV[g] < nTail[g]) {
                         const int G = nPV[g], st = G & 1;
-                        if (mbar_test(p_ready + 8 * g, (uint32_t)(G & 1)) && mbar_test(full_v + 8 * st, (uint32_t)((G >> 1) & 1))) {
+                        if (mbar_test_warp(p_ready + 8 * g, (uint32_t)(G & 1)) && mbar_test_warp(full_v + 8 * st, (uint32_t)((G >> 1) & 1))) {
                             tc_fence_after();
                             const uint32_t region = tmem_base + (uint32_t)g * REGION;
                             const uint64_t dv = make_desc(base + st * STAGE + 4 * TILE_BYTES, TILE_BYTES, 1024);
-                            for (int k16 = 0; k16 < NK / 16; ++k16) umma_bf16_ts(region + cO, region + k16 * 8, dv + 128 * k16, idesc_o, k16 > 0);
-                            umma_commit(o_ready + 8 * g);
+                            if (elect_one()) {
+                                for (int k16 = 0; k16 < NK / 16; ++k16) umma_bf16_ts(region + cO, region + k16 * 8, dv + 128 * k16, idesc_o, k16 > 0);
+                                umma_commit(o_ready + 8 * g);
+                            }
+                            __syncwarp();
                             nPV[g] = G + 1;
+                            TR(50 + g, G);
                             // the next head's main scores right behind, if its operands have landed
-                            if (G + 1 < nheads && mbar_test(full_qk + 8 * ((G + 1) & 1), (uint32_t)(((G + 1) >> 1) & 1))) {
+                            if (G + 1 < nheads && mbar_test_warp(full_qk + 8 * ((G + 1) & 1), (uint32_t)(((G + 1) >> 1) & 1))) {
                                 tc_fence_after();
                                 issue_main(g, G + 1);
                             }
@@ -387,25 +430,29 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                         const int G = nMain[g];
                         // group 1 enters half a period behind group 0: its first scores wait for group 0's first probabilities
                         const bool held = STAGGER && g == 1 && G == 0 && nPV[0] == 0;
-                        if (!held && mbar_test(full_qk + 8 * (G & 1), (uint32_t)((G >> 1) & 1))) {
+                        if (!held && mbar_test_warp(full_qk + 8 * (G & 1), (uint32_t)((G >> 1) & 1))) {
                             tc_fence_after();
                             issue_main(g, G);
                         }
                     }
                     if (nTail[g] < nMain[g]) {
                         const int G = nTail[g];
-                        if (G == 0 || mbar_test(tmem_free + 8 * g, (uint32_t)((G - 1) & 1))) {  // O of the previous head has been read out
-                            if (n_tail > 0) {
-                                tc_fence_after();
-                                const uint32_t sQ = base + (G & 1) * STAGE;
-                                const uint64_t dq = make_desc(sQ + g * TILE_BYTES, 0, 1024);
-                                const uint64_t dk = make_desc(sQ + 2 * TILE_BYTES + (kMainCols / 8) * 1024, 0, 1024);  // key rows >= kMainCols
+                        if (G == 0 || mbar_test_warp(tmem_free + 8 * g, (uint32_t)((G - 1) & 1))) {  // O of the previous head has been read out
+                            tc_fence_after();
+                            const uint32_t sQ = base + (G & 1) * STAGE;
+                            const uint64_t dq = make_desc(sQ + g * TILE_BYTES, 0, 1024);
+                            const uint64_t dk = make_desc(sQ + 2 * TILE_BYTES + (kMainCols / 8) * 1024, 0, 1024);  // key rows >= kMainCols
+                            if (elect_one()) {
+                                if (n_tail > 0) {
 #pragma unroll
-                                for (int k = 0; k < HS / 16; ++k)
-                                    umma_bf16(tmem_base + (uint32_t)g * REGION + kMainCols, dq + 2 * k, dk + 2 * k, idesc_tail, k > 0);
+                                    for (int k = 0; k < HS / 16; ++k)
+                                        umma_bf16(tmem_base + (uint32_t)g * REGION + kMainCols, dq + 2 * k, dk + 2 * k, idesc_tail, k > 0);
+                                }
+                                umma_commit(s_tail + 8 * g);
                             }
-                            umma_commit(s_tail + 8 * g);
+                            __syncwarp();
                             nTail[g] = G + 1;
+                            TR(54 + g, G);
                         }
                     }
                 }
@@ -428,8 +475,10 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             const int st = G & 1;
             const uint32_t par = (uint32_t)(G & 1);
             const uint32_t sO = base + st * STAGE + g * TILE_BYTES;  // the dead Q_g tile of this stage
+            TR(41, G);
             mbar_wait(s_main + 8 * g, par);
             tc_fence_after();
+            TR(42, G);
             if (store_leader && pending_stage >= 0) {
                 // the previous head's O store was issued a whole S MMA ago and has read its staging tile by now: tell the loader that
                 // the stage may be refilled (it then has more than a head's time to fetch head G + 1)
@@ -538,8 +587,10 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             }
             tc_fence_before();
             mbar_arrive_cnt(p_ready + 8 * g);
+            TR(43, G);
             mbar_wait(o_ready + 8 * g, par);
             tc_fence_after();
+            TR(44, G);
             if (warp_live) {
                 const float inv = 1.0f / sum;
 #pragma unroll
@@ -557,8 +608,10 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             }
             tc_fence_before();
             mbar_arrive_cnt(tmem_free + 8 * g);  // S_g of the next head may overwrite this region
+            TR(45, G);
             fence_proxy_async();
             named_bar_sync(1 + g, 128);
+            TR(46, G);
             if (store_leader) {
                 tma_store_3d(&tm_out, sO, h * HS, g * TILE, b);  // rows >= T are clipped by the tensor map
                 pending_stage = st;
@@ -803,7 +856,9 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 168);
     constexpr uint32_t TMEM_COLS = 512, cDV = 256, cDK = 320, cDQ = 384;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches stay converged
+    TR_DECL
     const int NSUB = (T + SUB - 1) / SUB;   // 64-query sub-tiles
     const int N = NT * NSUB;                // iterations per head: n = j * NSUB + t
     const int nheads = (total_heads - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // heads of this CTA
@@ -832,7 +887,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot, 0);
     const float scale = 1.0f / sqrtf((float)HS);
     const float sl2 = kLog2e * scale;
 
@@ -842,13 +897,16 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             for (int G = 0; G < nheads; ++G) {
                 const int bh = (int)blockIdx.x + G * (int)gridDim.x, b = bh / NH, h = bh - b * NH;
                 const uint32_t par = (uint32_t)((G - 1) & 1);  // parity of the previous head's single-phase barriers
+                TR(30, G);
                 if (G > 0) mbar_wait(free_kv, par);            // dV_0 / dK_0 of the previous head have left through V_0 / K_0
+                TR(31, G);
                 mbar_expect_tx(load0, (uint32_t)(4 * TILE_BYTES));
                 tma_load_3d(sK, &tm_qkv, load0, C + h * HS, 0, b);
                 tma_load_3d(sV, &tm_qkv, load0, 2 * C + h * HS, 0, b);
                 // the first 128 rows of Q and dO are dead once the last key tile is through its first two sub-tiles, well before
                 // the head ends: the next head's first scores can then be issued right behind this head's last MMAs
                 if (G > 0) mbar_wait(q0_free, par);
+                TR(32, G);
                 tma_load_3d(sQ, &tm_qkv, load0, h * HS, 0, b);
                 tma_load_3d(sdO, &tm_do, load0, h * HS, 0, b);
                 if (NT > 1) {
@@ -856,7 +914,9 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                     mbar_expect_tx(load1, (uint32_t)(4 * TILE_BYTES));
                     tma_load_3d(sQ + TILE_BYTES, &tm_qkv, load1, h * HS, TILE, b);
                     tma_load_3d(sdO + TILE_BYTES, &tm_do, load1, h * HS, TILE, b);
+                    TR(33, G);
                     if (G > 0) mbar_wait(free_kv + 8, par);
+                    TR(34, G);
                     tma_load_3d(sK + TILE_BYTES, &tm_qkv, load1, C + h * HS, TILE, b);
                     tma_load_3d(sV + TILE_BYTES, &tm_qkv, load1, 2 * C + h * HS, TILE, b);
                 }
@@ -876,27 +936,36 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             if (lane == 0) mbar_arrive_cnt(stat_full + 8 * sb);
         }
     } else if (warp == 0) {
-        if (lane == 0) {
-            // ================================ issuer ================================
+        {
+            // ================================ issuer (whole warp converged, tcgen05 instructions on the elected lane) ================
             const uint32_t idesc_kk = make_idesc(TILE, HS, 0, 1);
             const uint32_t idesc_mn = make_idesc(TILE, HS, 1, 1);
             const uint64_t dK_k = make_desc(sK, 0, 1024), dV_k = make_desc(sV, 0, 1024);          // K-major A operands (rows = keys)
             const uint64_t dQ_k = make_desc(sQ, 0, 1024), ddO_k = make_desc(sdO, 0, 1024);        // K-major B operands (rows = queries)
             const uint64_t dQ_mn = make_desc(sQ, TILE_BYTES, 1024), ddO_mn = make_desc(sdO, TILE_BYTES, 1024);  // MN-major B operands
             const uint64_t dK_mn = make_desc(sK, TILE_BYTES, 1024);
-            const uint64_t ddS_k = make_desc(sdS, 0, 1024), ddS_mn = make_desc(sdS, TILE_BYTES, 1024);
+            const uint64_t ddS_mn = make_desc(sdS, TILE_BYTES, 1024);  // (dK takes dS^T from tensor memory)
             auto off = [](uint32_t bytes) { return (uint64_t)(bytes >> 4); };
+            // Every wait is taken by the converged warp; the tcgen05 instructions of one step then go out from ONE elected region,
+            // back to back (measured, scripts/exp_mma_rate.cu: an elect per MMA costs 76 cycles per MMA whatever its size, a
+            // threadIdx test 94; inside one region a 128x64x16 MMA with A in tensor memory takes 42 and with A in shared memory 74).
             for (int G = 0; G < nheads; ++G) {
                 const uint32_t gpar = (uint32_t)(G & 1);
                 bool tile1_ready = false, dq_ready = G == 0;
                 uint32_t done_mask = 0u;  // sub-tiles of the current key tile whose dS^T is in shared memory
-                auto issue_scores = [&](int n) {
-                    const int j = n / NSUB, s_ = sub_at(j, n - j * NSUB, NSUB), bx = n & 1;
-                    if ((j > 0 || s_ >= TILE / SUB) && !tile1_ready) {  // first use of rows >= 128 of Q / dO / K / V
+                auto needs_tile1 = [&](int n) {  // iteration n is the first to touch rows >= 128 of Q / dO / K / V
+                    const int j = n / NSUB, s_ = sub_at(j, n - j * NSUB, NSUB);
+                    return j > 0 || s_ >= TILE / SUB;
+                };
+                auto wait_tile1 = [&](int n) {
+                    if (n < N && !tile1_ready && needs_tile1(n)) {
                         mbar_wait(load1, gpar);
                         tc_fence_after();
                         tile1_ready = true;
                     }
+                };
+                auto issue_scores = [&](int n) {  // (elected lane) S^T = K_j Q_s^T and dP^T = V_j dO_s^T of iteration n
+                    const int j = n / NSUB, s_ = sub_at(j, n - j * NSUB, NSUB), bx = n & 1;
                     const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
                     const uint32_t idesc = make_idesc(TILE, nq16, 0, 0);
                     const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES), ko = off(j * TILE_BYTES);
@@ -906,10 +975,17 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                     for (int k = 0; k < HS / 16; ++k) umma_bf16(tmem_base + bx * 128 + 64, dV_k + ko + 2 * k, ddO_k + qo + 2 * k, idesc, k > 0);
                     umma_commit(s_full + 8 * bx);
                 };
+                TR(22, G);
                 mbar_wait(load0, gpar);
                 tc_fence_after();
-                issue_scores(0);
-                if (N > 1) issue_scores(1);
+                TR(23, G);
+                wait_tile1(0);
+                wait_tile1(1);
+                if (elect_one()) {
+                    issue_scores(0);
+                    if (N > 1) issue_scores(1);
+                }
+                __syncwarp();
                 for (int m = 0; m < N; ++m) {
                     const int j = m / NSUB, t_ = m - j * NSUB, s_ = sub_at(j, t_, NSUB), bx = m & 1;
                     const int nq16 = (min(SUB, T - s_ * SUB) + 15) & ~15;
@@ -917,39 +993,44 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                     const uint64_t qo = off((s_ >> 1) * TILE_BYTES + (s_ & 1) * SUB_BYTES);
                     if (t_ == 0) done_mask = 0u;
                     const int per_buf = (N + 1 - bx) >> 1;  // iterations per head on buffer bx
-                    mbar_wait(p_full + 8 * bx, (uint32_t)((G * per_buf + (m >> 1)) & 1));
-                    tc_fence_after();
-                    if (t_ == 0 && G * NT + j > 0) {  // the previous key tile's dV / dK have been read out
-                        mbar_wait(acc_free, (uint32_t)((G * NT + j - 1) & 1));
-                        tc_fence_after();
-                    }
-                    const uint64_t so = off((s_ & 3) * TILE_BYTES);
-                    for (int k16 = 0; k16 < nq16 / 16; ++k16) {
-                        const uint32_t acc = (t_ > 0 || k16 > 0) ? 1u : 0u;
-                        umma_bf16_ts(tmem_base + cDV, tmem_base + bx * 128 + k16 * 8, ddO_mn + qo + 128 * k16, idesc_kk, acc);
-                        umma_bf16(tmem_base + cDK, ddS_k + so + 2 * k16, dQ_mn + qo + 128 * k16, idesc_kk, acc);
-                    }
-                    if (m + 2 < N) issue_scores(m + 2);
                     done_mask |= 1u << s_;
                     const int partner = s_ ^ 1;
-                    // last key tile, both sub-tiles of query tile 0 issued: no later MMA of this head reads Q_0 / dO_0
-                    if (j == NT - 1 && s_ < 2 && (partner >= NSUB || ((done_mask >> partner) & 1u))) umma_commit(q0_free);
-                    if (partner >= NSUB || ((done_mask >> partner) & 1u)) {  // query tile i = s/2 is complete for this key tile: dQ_i += dS K_j
-                        if (!dq_ready) {  // the previous head's dQ accumulators have been read out
-                            mbar_wait(dq_free, (uint32_t)((G - 1) & 1));
-                            tc_fence_after();
-                            dq_ready = true;
-                        }
-                        const int i = s_ >> 1;
-                        const uint64_t ao = off((2 * i) * TILE_BYTES), ko = off(j * TILE_BYTES);
-                        for (int k16 = 0; k16 < nk16 / 16; ++k16)
-                            umma_bf16(tmem_base + cDQ + i * HS, ddS_mn + ao + 128 * k16, dK_mn + ko + 128 * k16, idesc_mn, (j > 0 || k16 > 0) ? 1u : 0u);
-                        umma_commit(ds_free + 8 * ((2 * i) & 3));
-                        if (2 * i + 1 < NSUB) umma_commit(ds_free + 8 * ((2 * i + 1) & 3));
+                    const bool pair_done = partner >= NSUB || ((done_mask >> partner) & 1u);  // query tile i = s/2 complete for this key tile
+                    TR(20, m);
+                    mbar_wait(p_full + 8 * bx, (uint32_t)((G * per_buf + (m >> 1)) & 1));
+                    TR(21, m);
+                    if (t_ == 0 && G * NT + j > 0) mbar_wait(acc_free, (uint32_t)((G * NT + j - 1) & 1));  // previous key tile's dV / dK read out
+                    wait_tile1(m + 2);
+                    if (pair_done && !dq_ready) {  // the previous head's dQ accumulators have been read out
+                        mbar_wait(dq_free, (uint32_t)((G - 1) & 1));
+                        dq_ready = true;
                     }
-                    if (t_ == NSUB - 1) umma_commit(acc_full);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        // dV_j += P^T dO_s and dK_j += dS^T Q_s: both A operands are the bf16 tiles the group packed in place in tensor memory
+                        for (int k16 = 0; k16 < nq16 / 16; ++k16) {
+                            const uint32_t acc = (t_ > 0 || k16 > 0) ? 1u : 0u;
+                            umma_bf16_ts(tmem_base + cDV, tmem_base + bx * 128 + k16 * 8, ddO_mn + qo + 128 * k16, idesc_kk, acc);
+                            umma_bf16_ts(tmem_base + cDK, tmem_base + bx * 128 + 64 + k16 * 8, dQ_mn + qo + 128 * k16, idesc_kk, acc);
+                        }
+                        if (m + 2 < N) issue_scores(m + 2);
+                        // last key tile, both sub-tiles of query tile 0 issued: no later MMA of this head reads Q_0 / dO_0
+                        if (j == NT - 1 && s_ < 2 && pair_done) umma_commit(q0_free);
+                        if (pair_done) {  // dQ_i += dS K_j: A = dS^T read MN-major from the groups' shared tiles
+                            const int i = s_ >> 1;
+                            const uint64_t ao = off((2 * i) * TILE_BYTES), ko = off(j * TILE_BYTES);
+                            for (int k16 = 0; k16 < nk16 / 16; ++k16)
+                                umma_bf16(tmem_base + cDQ + i * HS, ddS_mn + ao + 128 * k16, dK_mn + ko + 128 * k16, idesc_mn, (j > 0 || k16 > 0) ? 1u : 0u);
+                            umma_commit(ds_free + 8 * ((2 * i) & 3));
+                            if (2 * i + 1 < NSUB) umma_commit(ds_free + 8 * ((2 * i + 1) & 3));
+                        }
+                        if (t_ == NSUB - 1) umma_commit(acc_full);
+                    }
+                    __syncwarp();
+                    TR(24, m);
                 }
-                umma_commit(dq_full);
+                if (elect_one()) umma_commit(dq_full);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -959,15 +1040,52 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const bool store_leader = (warp & 3) == 0 && lane == 0;
         const int per_buf = (N + 1 - g) >> 1;   // iterations per head of this group
+        int free_pending = -1;   // leader: key tile whose staging store still has to be confirmed read
+        int dq_pending = -1;     // head whose dQ_g accumulator this group still has to read out (deferred into the next head)
+        bool dq_store_inflight = false;  // the dQ store may still be reading its staging tile (dS tile 2 + g)
+        const uint32_t dq_stage = sdS + (2 + g) * TILE_BYTES;
+        // dQ_g of head Gd leaves through dS tile 2 + g.  It is read out one iteration INTO the next head: the issuer needs the dQ
+        // accumulators back only for that head's first dQ MMA (iteration 1), so the read-out runs under the issue of iteration 0
+        // instead of holding up the head turn-around (which already has to wait for the last key tile's dV / dK to be read).
+        // The tile is free: its last dQ MMA of head Gd has retired (dq_full), and this group is the first to write it again
+        // (sub-tile 2 + g of the next head comes after this point in the group's own program order).
+        auto drain_dq = [&](int Gd) {
+            const int bhd = (int)blockIdx.x + Gd * (int)gridDim.x, bd = bhd / NH, hd = bhd - bd * NH;
+            TR(8, Gd);
+            mbar_wait(dq_full, (uint32_t)(Gd & 1));
+            tc_fence_after();
+            TR(9, Gd);
+            if (dq_store_inflight) {  // (sequences whose sub-tiles never reach tile 2 + g: the previous dQ store has read the tile)
+                if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+            }
+            if (g < NT) {
+                const int q = g * TILE + r;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_off + cDQ + g * HS + half * 32, v);
+                    stage_half_row(dq_stage, r, half, v, (accumulate && q < T) ? dqkv + ((long)bd * T + q) * 3 * C + hd * HS + half * 32 : nullptr);
+                }
+                fence_proxy_async();
+            }
+            tc_fence_before();
+            mbar_arrive_cnt(dq_free);
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+            if (store_leader && g < NT) tma_store_3d(&tm_dqkv, dq_stage, hd * HS, g * TILE, bd);
+            dq_store_inflight = g < NT;
+            TR(10, Gd);
+        };
         for (int G = 0; G < nheads; ++G) {
             const int bh = (int)blockIdx.x + G * (int)gridDim.x, b = bh / NH, h = bh - b * NH;
             const float* stat = stat_all + (G & 1) * 512;
-            int free_pending = -1;  // leader: key tile whose staging store still has to be confirmed read
             // dV_j (group 0) / dK_j (group 1): staged through the dead V_j / K_j tile, one TMA store each
             auto store_acc = [&](int j) {
                 const int key = j * TILE + r;
+                TR(5, j);
                 mbar_wait(acc_full, (uint32_t)((G * NT + j) & 1));
                 tc_fence_after();
+                TR(6, j);
                 const uint32_t tile = (g == 0 ? sV : sK) + j * TILE_BYTES;  // every MMA that read it has retired (acc_full)
                 const long gcol = (g == 0 ? 2 * C : C) + h * HS;
 #pragma unroll
@@ -988,6 +1106,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                     tma_store_3d(&tm_dqkv, tile, (int)gcol, j * TILE, b);
                     free_pending = j;
                 }
+                TR(7, j);
             };
             // the leader tells the loader that a K / V tile may be refilled once its store has finished reading it
             auto confirm_free = [&]() {
@@ -997,6 +1116,8 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                     free_pending = -1;
                 }
             };
+            TR(1, G);
+            if (dq_pending >= 0 && per_buf == 0) { drain_dq(dq_pending); dq_pending = -1; }
             mbar_wait(stat_full + 8 * (G & 1), (uint32_t)((G >> 1) & 1));
             int pending = -1;
             for (int j = 0; j < NT; ++j) {
@@ -1008,15 +1129,22 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                     const int nq = min(SUB, T - s_ * SUB), nq16 = (nq + 15) & ~15;
                     const uint32_t xb = tmem_base + lane_off + (uint32_t)(g * 128);
                     confirm_free();
+                    TR(2, n);
                     mbar_wait(s_full + 8 * g, (uint32_t)((G * per_buf + (n >> 1)) & 1));
                     tc_fence_after();
                     const int bs = s_ & 3;
                     const uint32_t sbuf = sdS + bs * TILE_BYTES;
+                    if (dq_store_inflight && bs == 2 + g) {  // (group-uniform) the previous head's dQ store has read its staging tile
+                        if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+                        dq_store_inflight = false;
+                    }
                     // the MMAs that read this dS tile last time (previous key tile, or the previous head) have retired
                     if (G * NT + j > 0) mbar_wait(ds_free + 8 * bs, (uint32_t)((G * NT + j - 1) & 1));
+                    TR(3, n);
                     const int nch = (nq16 + 31) >> 5;
                     for (int ch = 0; ch < nch; ++ch) {
-                        uint32_t sv[32], dp[32], pk[16];
+                        uint32_t sv[32], dp[32], pk[16], dk[16];
                         tmem_ld32(xb + ch * 32, sv);
                         tmem_ld32(xb + 64 + ch * 32, dp);
                         const int q0 = s_ * SUB + ch * 32;             // first query of the chunk (q0 + 31 < 256)
@@ -1044,16 +1172,21 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                                 ds[c + 1] = d2.y;
                             }
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) pk[g8 * 4 + c] = pack_bf16(pv[2 * c], pv[2 * c + 1]);
-                            st_shared_v4(sw128(sbuf, r, ch * 4 + g8), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
-                                         pack_bf16(ds[6], ds[7]));
+                            for (int c = 0; c < 4; ++c) {
+                                pk[g8 * 4 + c] = pack_bf16(pv[2 * c], pv[2 * c + 1]);
+                                dk[g8 * 4 + c] = pack_bf16(ds[2 * c], ds[2 * c + 1]);
+                            }
+                            st_shared_v4(sw128(sbuf, r, ch * 4 + g8), dk[g8 * 4], dk[g8 * 4 + 1], dk[g8 * 4 + 2], dk[g8 * 4 + 3]);
                         }
-                        tmem_st16(xb + ch * 16, pk);  // P^T in place: columns [16ch, 16ch+16) were consumed by chunk <= ch
+                        tmem_st16(xb + ch * 16, pk);       // P^T in place: columns [16ch, 16ch+16) were consumed by chunk <= ch
+                        tmem_st16(xb + 64 + ch * 16, dk);  // dS^T likewise over dP^T: the A operand of dK (shared memory keeps the copy dQ reads)
                     }
                     tmem_st_wait();
                     fence_proxy_async();
                     tc_fence_before();
                     mbar_arrive_cnt(p_full + 8 * g);
+                    TR(4, n);
+                    if (dq_pending >= 0) { drain_dq(dq_pending); dq_pending = -1; }
                     if (pending >= 0) {
                         store_acc(pending);
                         pending = -1;
@@ -1062,33 +1195,12 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                 if (j + 1 < NT && (((j + 1) * NSUB) & 1) == g) pending = j;
                 else store_acc(j);
             }
-            // ---- dQ_0 (group 0) / dQ_1 (group 1), staged through the group's own dS tile (dead: every MMA has retired) ----
-            mbar_wait(dq_full, (uint32_t)(G & 1));
-            tc_fence_after();
-            if (g < NT) {
-                const int q = g * TILE + r;
-                const uint32_t tile = sdS + g * TILE_BYTES;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_off + cDQ + g * HS + half * 32, v);
-                    stage_half_row(tile, r, half, v, (accumulate && q < T) ? dqkv + ((long)b * T + q) * 3 * C + h * HS + half * 32 : nullptr);
-                }
-                fence_proxy_async();
-            }
-            tc_fence_before();
-            mbar_arrive_cnt(dq_free);
-            mbar_arrive_cnt(stat_free + 8 * (G & 1));
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-            if (store_leader) {
-                if (g < NT) tma_store_3d(&tm_dqkv, sdS + g * TILE_BYTES, h * HS, g * TILE, b);
-                // the last key tile's staging store and the dQ store have been read: K / V of that tile and the dS tile are free
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                if (free_pending >= 0) mbar_arrive_cnt(free_kv + 8 * free_pending);
-                free_pending = -1;
-            }
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");  // nobody rewrites the dS tile before the store has read it
+            mbar_arrive_cnt(stat_free + 8 * (G & 1));  // this head's row statistics are no longer read
+            dq_pending = G;
+            if (per_buf == 0) confirm_free();  // (a group without iterations passes no other point that releases K / V to the loader)
         }
+        if (dq_pending >= 0) drain_dq(dq_pending);
+        if (store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every store is complete before shared memory is retired
     }
     tc_fence_before();
     __syncthreads();

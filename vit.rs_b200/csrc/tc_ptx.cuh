@@ -58,6 +58,19 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a CONVERGED warp (elect.sync): the issuing warp runs its control flow with all 32 lanes so that loop counters,
+// descriptors and barrier addresses stay in uniform registers, and only the tcgen05 instruction itself is predicated on the
+// elected lane.  (A `if (lane == 0)` region instead makes every operand a per-thread value that ptxas moves back to uniform
+// registers around each UTCHMMA with an R2UR + vote loop: ~10 instructions per MMA on a warp that shares its scheduler.)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 // arrive on an mbarrier when every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
