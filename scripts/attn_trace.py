@@ -39,7 +39,7 @@ names = {1: "head", 2: "wait s_full", 3: "got s_full+ds_free", 4: "P/dS done", 5
 print(f"{n.value} stamps, span {ev[-1][0] - t0} cycles, heads per CTA = {b * nh / 148:.1f}")
 # print the full timeline of a steady-state window: from the 3rd 'head'(1)/(41) event of the first SIMT warp
 lo = int(os.environ.get("FROM", 0)); hi = int(os.environ.get("TO", 60000))
-warps = [int(w) for w in os.environ.get("WARPS", "0,2,4,8" if which == "bwd" else "1,2,6").split(",")]
+warps = [int(w) for w in os.environ.get("WARPS", "0,4,8,12" if which == "bwd" else "1,2,6").split(",")]
 last = {}
 for clk, w, e, a in ev:
     rel = clk - t0

@@ -820,7 +820,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 //                          in place in tensor memory (A operand of dV), dS^T goes to one of four shared tiles that
 //                          serve as the K-major A operand of dK and, pairwise, as the MN-major A operand of dQ
 // TMEM: 2 x {S^T 64, dP^T 64} + dV 64 + dK 64 + dQ_0 64 + dQ_1 64 = 512 columns.
-constexpr int kPipeThreads = 384;  // warps 0-3: control (issuer = warp 0 lane 0, TMEM owner = warp 1), 4-7: group A, 8-11: group B
+constexpr int kPipeThreads = 512;  // warps 0-3: control (issuer = warp 0, TMEM owner = warp 1), 4-7: group A, 8-11: group B, 12-15: read-out
 
 // Sub-tile processed at position t of key tile j.  Iterations alternate between the two SIMT groups; with an even number of
 // sub-tiles of which the last is short (T = 197: 64, 64, 64, 5 queries) the same group would get the short one in every key
@@ -847,13 +847,14 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sQ = base, sK = sQ + NT * TILE_BYTES, sV = sK + NT * TILE_BYTES, sdO = sV + NT * TILE_BYTES;
     const uint32_t sdS = sdO + NT * TILE_BYTES;            // 4 x [128 keys][64 queries] bf16, 128B-swizzled
-    const uint32_t sStat = sdS + 4 * TILE_BYTES;           // 2 x {lse*log2e [256], D [256]}
+    const uint32_t sDQ = sdS + 4 * TILE_BYTES;             // staging tile of the dQ stores
+    const uint32_t sStat = sDQ + TILE_BYTES;               // 2 x {lse*log2e [256], D [256]}
     const uint32_t bar0 = sStat + 2 * 2 * 256 * 4;
     const uint32_t load0 = bar0, load1 = bar0 + 8, s_full = bar0 + 16, p_full = bar0 + 32, ds_free = bar0 + 48,  // .., .., [2], [2], [4]
                    acc_full = bar0 + 80, acc_free = bar0 + 88, dq_full = bar0 + 96, dq_free = bar0 + 104, free_kv = bar0 + 112,  // free_kv[2]
-                   stat_full = bar0 + 128, stat_free = bar0 + 144, q0_free = bar0 + 160;                                           // [2], [2], ..
+                   stat_full = bar0 + 128, stat_free = bar0 + 144, q0_free = bar0 + 160, load2 = bar0 + 168;                       // [2], [2], .., ..
     float* stat_all = reinterpret_cast<float*>(gen + (sStat - base));
-    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 168);
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 176);
     constexpr uint32_t TMEM_COLS = 512, cDV = 256, cDK = 320, cDQ = 384;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -868,18 +869,19 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         tma_prefetch_desc(&tm_dqkv);
         mbar_init(load0, 1);
         mbar_init(load1, 1);
+        mbar_init(load2, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(s_full + 8 * i, 1);
             mbar_init(p_full + 8 * i, 128);
-            mbar_init(free_kv + 8 * i, 2);
+            mbar_init(free_kv + 8 * i, 1);
             mbar_init(stat_full + 8 * i, 1);
             mbar_init(stat_free + 8 * i, 256);
         }
         for (int i = 0; i < 4; ++i) mbar_init(ds_free + 8 * i, 1);
         mbar_init(acc_full, 1);
-        mbar_init(acc_free, 256);
+        mbar_init(acc_free, 128);
         mbar_init(dq_full, 1);
-        mbar_init(dq_free, 256);
+        mbar_init(dq_free, 128);
         mbar_init(q0_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -911,14 +913,17 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                 tma_load_3d(sdO, &tm_do, load0, h * HS, 0, b);
                 if (NT > 1) {
                     if (G > 0) mbar_wait(dq_full, par);        // every MMA of the previous head has retired: the other rows are dead too
-                    mbar_expect_tx(load1, (uint32_t)(4 * TILE_BYTES));
+                    // rows >= 128 of Q / dO (first needed by the third sub-tile of key tile 0) and K_1 / V_1 (first needed by key
+                    // tile 1) complete on barriers of their own: K_1 / V_1 wait for the read-out group's stores of the previous head
+                    mbar_expect_tx(load1, (uint32_t)(2 * TILE_BYTES));
                     tma_load_3d(sQ + TILE_BYTES, &tm_qkv, load1, h * HS, TILE, b);
                     tma_load_3d(sdO + TILE_BYTES, &tm_do, load1, h * HS, TILE, b);
                     TR(33, G);
                     if (G > 0) mbar_wait(free_kv + 8, par);
                     TR(34, G);
-                    tma_load_3d(sK + TILE_BYTES, &tm_qkv, load1, C + h * HS, TILE, b);
-                    tma_load_3d(sV + TILE_BYTES, &tm_qkv, load1, 2 * C + h * HS, TILE, b);
+                    mbar_expect_tx(load2, (uint32_t)(2 * TILE_BYTES));
+                    tma_load_3d(sK + TILE_BYTES, &tm_qkv, load2, C + h * HS, TILE, b);
+                    tma_load_3d(sV + TILE_BYTES, &tm_qkv, load2, 2 * C + h * HS, TILE, b);
                 }
             }
         }
@@ -951,18 +956,20 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             // threadIdx test 94; inside one region a 128x64x16 MMA with A in tensor memory takes 42 and with A in shared memory 74).
             for (int G = 0; G < nheads; ++G) {
                 const uint32_t gpar = (uint32_t)(G & 1);
-                bool tile1_ready = false, dq_ready = G == 0;
+                bool q1_ready = false, kv1_ready = false, dq_ready = G == 0;
                 uint32_t done_mask = 0u;  // sub-tiles of the current key tile whose dS^T is in shared memory
-                auto needs_tile1 = [&](int n) {  // iteration n is the first to touch rows >= 128 of Q / dO / K / V
+                auto wait_tile1 = [&](int n) {  // operands iteration n is the first to touch: rows >= 128 of Q / dO, K_1 / V_1
+                    if (n >= N) return;
                     const int j = n / NSUB, s_ = sub_at(j, n - j * NSUB, NSUB);
-                    return j > 0 || s_ >= TILE / SUB;
-                };
-                auto wait_tile1 = [&](int n) {
-                    if (n < N && !tile1_ready && needs_tile1(n)) {
+                    if (!q1_ready && s_ >= TILE / SUB) {
                         mbar_wait(load1, gpar);
-                        tc_fence_after();
-                        tile1_ready = true;
+                        q1_ready = true;
                     }
+                    if (!kv1_ready && j > 0) {
+                        mbar_wait(load2, gpar);
+                        kv1_ready = true;
+                    }
+                    tc_fence_after();
                 };
                 auto issue_scores = [&](int n) {  // (elected lane) S^T = K_j Q_s^T and dP^T = V_j dO_s^T of iteration n
                     const int j = n / NSUB, s_ = sub_at(j, n - j * NSUB, NSUB), bx = n & 1;
@@ -1033,93 +1040,114 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                 __syncwarp();
             }
         }
-    } else if (warp >= 4) {
-        // ================================ SIMT groups ================================
-        const int g = (warp - 4) >> 2;          // group 0 / 1
-        const int r = (warp & 3) * 32 + lane;   // TMEM lane = key within the tile / output row
+    } else if (warp >= 12) {
+        // ================================ read-out group (warps 12-15, one per TMEM lane quarter) ================================
+        // Takes every accumulator out of tensor memory so that the SIMT groups never leave their iterations: dV_j / dK_j when a key
+        // tile completes (acc_full), dQ_0 / dQ_1 when the head completes (dq_full).  The accumulators are handed back to the
+        // issuer (acc_free / dq_free) as soon as their values sit in registers; conversion, staging and the TMA stores follow
+        // off the critical path.  dV_j / dK_j leave through the dead V_j / K_j tiles, dQ through a staging tile of its own.
+        const int r = (warp & 3) * 32 + lane;
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-        const bool store_leader = (warp & 3) == 0 && lane == 0;
-        const int per_buf = (N + 1 - g) >> 1;   // iterations per head of this group
-        int free_pending = -1;   // leader: key tile whose staging store still has to be confirmed read
-        int dq_pending = -1;     // head whose dQ_g accumulator this group still has to read out (deferred into the next head)
-        bool dq_store_inflight = false;  // the dQ store may still be reading its staging tile (dS tile 2 + g)
-        const uint32_t dq_stage = sdS + (2 + g) * TILE_BYTES;
-        // dQ_g of head Gd leaves through dS tile 2 + g.  It is read out one iteration INTO the next head: the issuer needs the dQ
-        // accumulators back only for that head's first dQ MMA (iteration 1), so the read-out runs under the issue of iteration 0
-        // instead of holding up the head turn-around (which already has to wait for the last key tile's dV / dK to be read).
-        // The tile is free: its last dQ MMA of head Gd has retired (dq_full), and this group is the first to write it again
-        // (sub-tile 2 + g of the next head comes after this point in the group's own program order).
-        auto drain_dq = [&](int Gd) {
-            const int bhd = (int)blockIdx.x + Gd * (int)gridDim.x, bd = bhd / NH, hd = bhd - bd * NH;
-            TR(8, Gd);
-            mbar_wait(dq_full, (uint32_t)(Gd & 1));
-            tc_fence_after();
-            TR(9, Gd);
-            if (dq_store_inflight) {  // (sequences whose sub-tiles never reach tile 2 + g: the previous dQ store has read the tile)
-                if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-            }
-            if (g < NT) {
-                const int q = g * TILE + r;
+        const bool leader = warp == 12 && lane == 0;
+        bool stage_busy = false;  // (group-uniform) a dQ store may still be reading the staging tile
+        auto pack32 = [&](uint32_t (&v)[32], uint32_t (&o)[16]) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_off + cDQ + g * HS + half * 32, v);
-                    stage_half_row(dq_stage, r, half, v, (accumulate && q < T) ? dqkv + ((long)bd * T + q) * 3 * C + hd * HS + half * 32 : nullptr);
+            for (int c = 0; c < 16; ++c) o[c] = pack_bf16(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+        };
+        // 64 packed bf16 values (this thread's row of a [128][64] tile) -> (+ what global memory holds) -> swizzled staging tile
+        auto stage_row = [&](uint32_t tile, const uint32_t (&lo)[16], const uint32_t (&hi)[16], const bf16* old) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) w[c] = half == 0 ? lo[g4 * 4 + c] : hi[g4 * 4 + c];
+                    if (old) {
+                        Vec16<bf16> o;
+                        o.load(old + half * 32 + g4 * 8);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            w[c] = pack_bf16(__uint_as_float(w[c] << 16) + o.get(2 * c), __uint_as_float(w[c] & 0xFFFF0000u) + o.get(2 * c + 1));
+                    }
+                    st_shared_v4(sw128(tile, r, half * 4 + g4), w[0], w[1], w[2], w[3]);
                 }
-                fence_proxy_async();
             }
-            tc_fence_before();
-            mbar_arrive_cnt(dq_free);
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-            if (store_leader && g < NT) tma_store_3d(&tm_dqkv, dq_stage, hd * HS, g * TILE, bd);
-            dq_store_inflight = g < NT;
-            TR(10, Gd);
+        };
+        auto read64 = [&](uint32_t col, uint32_t (&lo)[16], uint32_t (&hi)[16]) {  // 64 fp32 accumulator columns -> packed bf16
+            uint32_t v[32];
+            tmem_ld32(tmem_base + lane_off + col, v);
+            pack32(v, lo);
+            tmem_ld32(tmem_base + lane_off + col + 32, v);
+            pack32(v, hi);
         };
         for (int G = 0; G < nheads; ++G) {
             const int bh = (int)blockIdx.x + G * (int)gridDim.x, b = bh / NH, h = bh - b * NH;
-            const float* stat = stat_all + (G & 1) * 512;
-            // dV_j (group 0) / dK_j (group 1): staged through the dead V_j / K_j tile, one TMA store each
-            auto store_acc = [&](int j) {
+            for (int j = 0; j < NT; ++j) {
                 const int key = j * TILE + r;
+                uint32_t vlo[16], vhi[16], klo[16], khi[16];
                 TR(5, j);
                 mbar_wait(acc_full, (uint32_t)((G * NT + j) & 1));
                 tc_fence_after();
                 TR(6, j);
-                const uint32_t tile = (g == 0 ? sV : sK) + j * TILE_BYTES;  // every MMA that read it has retired (acc_full)
-                const long gcol = (g == 0 ? 2 * C : C) + h * HS;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_off + (g == 0 ? cDV : cDK) + half * 32, v);
-                    stage_half_row(tile, r, half, v, (accumulate && key < T) ? dqkv + ((long)b * T + key) * 3 * C + gcol + half * 32 : nullptr);
-                }
+                read64(cDV, vlo, vhi);
+                read64(cDK, klo, khi);
                 tc_fence_before();
-                mbar_arrive_cnt(acc_free);  // the accumulators are free; the store below only reads shared memory
+                mbar_arrive_cnt(acc_free);  // the next key tile's dV / dK MMAs may start
+                const bf16* old = (accumulate && key < T) ? dqkv + ((long)b * T + key) * 3 * C + h * HS : nullptr;
+                // every MMA that read K_j / V_j has retired (acc_full covers the key tile's scores and its dQ MMAs)
+                stage_row(sV + j * TILE_BYTES, vlo, vhi, old ? old + 2 * C : nullptr);
+                stage_row(sK + j * TILE_BYTES, klo, khi, old ? old + C : nullptr);
                 fence_proxy_async();
-                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-                if (store_leader) {
-                    if (free_pending >= 0) {  // an earlier tile's store that no iteration came by to confirm
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        mbar_arrive_cnt(free_kv + 8 * free_pending);
-                    }
-                    tma_store_3d(&tm_dqkv, tile, (int)gcol, j * TILE, b);
-                    free_pending = j;
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (leader) {
+                    tma_store_3d(&tm_dqkv, sV + j * TILE_BYTES, 2 * C + h * HS, j * TILE, b);
+                    tma_store_3d(&tm_dqkv, sK + j * TILE_BYTES, C + h * HS, j * TILE, b);
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // (also covers an earlier dQ store)
+                    mbar_arrive_cnt(free_kv + 8 * j);  // the loader may refill K_j / V_j for the next head
                 }
+                stage_busy = false;  // (the leader has just waited for every earlier store's reads; the others pass bar 2 before staging again)
                 TR(7, j);
-            };
-            // the leader tells the loader that a K / V tile may be refilled once its store has finished reading it
-            auto confirm_free = [&]() {
-                if (store_leader && free_pending >= 0) {
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    mbar_arrive_cnt(free_kv + 8 * free_pending);
-                    free_pending = -1;
-                }
-            };
+            }
+            // ---- dQ_0, dQ_1 ----
+            {
+                uint32_t alo[16], ahi[16], blo[16], bhi[16];
+                TR(8, G);
+                mbar_wait(dq_full, (uint32_t)(G & 1));
+                tc_fence_after();
+                TR(9, G);
+                read64(cDQ, alo, ahi);
+                if (NT > 1) read64(cDQ + HS, blo, bhi);
+                tc_fence_before();
+                mbar_arrive_cnt(dq_free);  // the next head's dQ MMAs may start
+                auto store_dq = [&](int i, const uint32_t (&lo)[16], const uint32_t (&hi)[16]) {
+                    const int q = i * TILE + r;
+                    if (stage_busy) {
+                        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
+                    }
+                    stage_row(sDQ, lo, hi, (accumulate && q < T) ? dqkv + ((long)b * T + q) * 3 * C + h * HS : nullptr);
+                    fence_proxy_async();
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (leader) tma_store_3d(&tm_dqkv, sDQ, h * HS, i * TILE, b);
+                    stage_busy = true;
+                };
+                store_dq(0, alo, ahi);
+                if (NT > 1) store_dq(1, blo, bhi);
+                TR(10, G);
+            }
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every store is complete before shared memory is retired
+    } else if (warp >= 4) {
+        // ================================ SIMT groups ================================
+        const int g = (warp - 4) >> 2;          // group 0 / 1
+        const int r = (warp & 3) * 32 + lane;   // TMEM lane = key within the tile
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const int per_buf = (N + 1 - g) >> 1;   // iterations per head of this group
+        for (int G = 0; G < nheads; ++G) {
+            const float* stat = stat_all + (G & 1) * 512;
             TR(1, G);
-            if (dq_pending >= 0 && per_buf == 0) { drain_dq(dq_pending); dq_pending = -1; }
             mbar_wait(stat_full + 8 * (G & 1), (uint32_t)((G >> 1) & 1));
-            int pending = -1;
             for (int j = 0; j < NT; ++j) {
                 const int key = j * TILE + r;
                 for (int t_ = 0; t_ < NSUB; ++t_) {
@@ -1128,17 +1156,11 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                     const int s_ = sub_at(j, t_, NSUB);
                     const int nq = min(SUB, T - s_ * SUB), nq16 = (nq + 15) & ~15;
                     const uint32_t xb = tmem_base + lane_off + (uint32_t)(g * 128);
-                    confirm_free();
                     TR(2, n);
                     mbar_wait(s_full + 8 * g, (uint32_t)((G * per_buf + (n >> 1)) & 1));
                     tc_fence_after();
                     const int bs = s_ & 3;
                     const uint32_t sbuf = sdS + bs * TILE_BYTES;
-                    if (dq_store_inflight && bs == 2 + g) {  // (group-uniform) the previous head's dQ store has read its staging tile
-                        if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-                        dq_store_inflight = false;
-                    }
                     // the MMAs that read this dS tile last time (previous key tile, or the previous head) have retired
                     if (G * NT + j > 0) mbar_wait(ds_free + 8 * bs, (uint32_t)((G * NT + j - 1) & 1));
                     TR(3, n);
@@ -1186,21 +1208,10 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                     tc_fence_before();
                     mbar_arrive_cnt(p_full + 8 * g);
                     TR(4, n);
-                    if (dq_pending >= 0) { drain_dq(dq_pending); dq_pending = -1; }
-                    if (pending >= 0) {
-                        store_acc(pending);
-                        pending = -1;
-                    }
                 }
-                if (j + 1 < NT && (((j + 1) * NSUB) & 1) == g) pending = j;
-                else store_acc(j);
             }
             mbar_arrive_cnt(stat_free + 8 * (G & 1));  // this head's row statistics are no longer read
-            dq_pending = G;
-            if (per_buf == 0) confirm_free();  // (a group without iterations passes no other point that releases K / V to the loader)
         }
-        if (dq_pending >= 0) drain_dq(dq_pending);
-        if (store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every store is complete before shared memory is retired
     }
     tc_fence_before();
     __syncthreads();
@@ -1232,7 +1243,8 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 56);
     constexpr uint32_t TMEM_COLS = 256, cO = 192;  // S [0,128) -> P packed [0,64); O [192,256)
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: warp 0 issues the tcgen05 instructions converged
     const int NT = (T + TILE - 1) / TILE;
     const int qt = blockIdx.x % NT, bh = blockIdx.x / NT, b = bh / NH, h = bh - b * NH;
     const int NJ = causal ? qt + 1 : NT;
@@ -1249,7 +1261,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot, 0);
     if (tid == 0) {
         mbar_expect_tx(bar_q, TILE_BYTES);
         tma_load_3d(sQ, &tm_qkv, bar_q, h * HS, qt * TILE, b);
@@ -1273,15 +1285,18 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         const uint32_t ph = (uint32_t)((j >> 1) & 1);
         const int k0 = j * TILE;
         const int nk16 = (min(TILE, T - k0) + 15) & ~15;
-        if (tid == 0) {
+        if (warp == 0) {  // waits by the converged warp, the MMAs back to back from one elected region (scripts/exp_mma_rate.cu)
             if (j == 0) mbar_wait(bar_q, 0);
             mbar_wait(bar_k + 8 * buf, ph);
             tc_fence_after();
             const uint32_t idesc = make_idesc(TILE, nk16, 0, 0);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < HS / 16; ++k)
-                umma_bf16(tmem_base, make_desc(sQ + k * 32, 0, 1024), make_desc(sK + buf * TILE_BYTES + k * 32, 0, 1024), idesc, k > 0);
-            umma_commit(bar_s);
+                for (int k = 0; k < HS / 16; ++k)
+                    umma_bf16(tmem_base, make_desc(sQ + k * 32, 0, 1024), make_desc(sK + buf * TILE_BYTES + k * 32, 0, 1024), idesc, k > 0);
+                umma_commit(bar_s);
+            }
+            __syncwarp();
         }
         mbar_wait(bar_s, (uint32_t)(j & 1));
         tc_fence_after();
@@ -1342,14 +1357,17 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         tmem_st_wait();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_v + 8 * buf, j == 1 ? 0u : ph);
             const uint32_t idesc = make_idesc(TILE, HS, 0, 1);
-            for (int k16 = 0; k16 < nk16 / 16; ++k16)
-                umma_bf16_ts(tmem_base + cO, tmem_base + k16 * 8, make_desc(sV + buf * TILE_BYTES + k16 * 2048, TILE_BYTES, 1024), idesc,
-                             (j > 0 || k16 > 0) ? 1u : 0u);
-            umma_commit(bar_o);
+            if (elect_one()) {
+                for (int k16 = 0; k16 < nk16 / 16; ++k16)
+                    umma_bf16_ts(tmem_base + cO, tmem_base + k16 * 8, make_desc(sV + buf * TILE_BYTES + k16 * 2048, TILE_BYTES, 1024), idesc,
+                                 (j > 0 || k16 > 0) ? 1u : 0u);
+                umma_commit(bar_o);
+            }
+            __syncwarp();
         }
     }
     mbar_wait(bar_o, (uint32_t)((NJ - 1) & 1));
@@ -1394,7 +1412,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     float* stat = reinterpret_cast<float*>(gen + (bar0 - base) + 64);  // lse*log2e [T], D [T]
     constexpr uint32_t TMEM_COLS = 256, cST = 0, cDPT = 64, cDV = 128, cDK = 192;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: warp 0 issues the tcgen05 instructions converged
     const int NT = (T + TILE - 1) / TILE, NS = (T + SUB - 1) / SUB;
     const int jt = blockIdx.x % NT, bh = blockIdx.x / NT, b = bh / NH, h = bh - b * NH;
     const int s0 = causal ? (jt * TILE) / SUB : 0;
@@ -1411,7 +1430,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot, 0);
     const bool leader = tid == 0;
     auto load_sub = [&](int s, int buf) {
         mbar_expect_tx(bar_q + 8 * buf, 2 * SUB_BYTES);
@@ -1435,18 +1454,21 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
         const int it = s - s0, buf = it & 1;
         const uint32_t ph = (uint32_t)((it >> 1) & 1);
         const int nq = min(SUB, T - s * SUB), nq16 = (nq + 15) & ~15;
-        if (leader) {
+        if (warp == 0) {
             if (it == 0) mbar_wait(bar_kv, 0);
             mbar_wait(bar_q + 8 * buf, ph);
             tc_fence_after();
             const uint32_t idesc = make_idesc(TILE, nq16, 0, 0);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < HS / 16; ++k)  // S^T = K_j Q_s^T
-                umma_bf16(tmem_base + cST, make_desc(sK + k * 32, 0, 1024), make_desc(sQ + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
+                for (int k = 0; k < HS / 16; ++k)  // S^T = K_j Q_s^T
+                    umma_bf16(tmem_base + cST, make_desc(sK + k * 32, 0, 1024), make_desc(sQ + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
 #pragma unroll
-            for (int k = 0; k < HS / 16; ++k)  // dP^T = V_j dO_s^T
-                umma_bf16(tmem_base + cDPT, make_desc(sV + k * 32, 0, 1024), make_desc(sdO + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
-            umma_commit(bar_s);  // also covers the dV / dK MMAs of the previous sub-tile
+                for (int k = 0; k < HS / 16; ++k)  // dP^T = V_j dO_s^T
+                    umma_bf16(tmem_base + cDPT, make_desc(sV + k * 32, 0, 1024), make_desc(sdO + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
+                umma_commit(bar_s);  // also covers the dV / dK MMAs of the previous sub-tile
+            }
+            __syncwarp();
         }
         mbar_wait(bar_s, (uint32_t)(it & 1));
         tc_fence_after();
@@ -1482,17 +1504,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
         tmem_st_wait();
         tc_fence_before();
         __syncthreads();
-        if (leader) {
+        if (warp == 0) {
             tc_fence_after();
             const uint32_t idesc = make_idesc(TILE, HS, 0, 1);  // A from TMEM, B MN-major
-            for (int k16 = 0; k16 < nq16 / 16; ++k16) {
-                const uint32_t acc = (it > 0 || k16 > 0) ? 1u : 0u;
-                umma_bf16_ts(tmem_base + cDV, tmem_base + cST + k16 * 8, make_desc(sdO + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc, acc);
-                umma_bf16_ts(tmem_base + cDK, tmem_base + cDPT + k16 * 8, make_desc(sQ + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc, acc);
+            if (elect_one()) {
+                for (int k16 = 0; k16 < nq16 / 16; ++k16) {
+                    const uint32_t acc = (it > 0 || k16 > 0) ? 1u : 0u;
+                    umma_bf16_ts(tmem_base + cDV, tmem_base + cST + k16 * 8, make_desc(sdO + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc, acc);
+                    umma_bf16_ts(tmem_base + cDK, tmem_base + cDPT + k16 * 8, make_desc(sQ + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc, acc);
+                }
+                if (s + 1 == NS) umma_commit(bar_acc);
             }
+            __syncwarp();
         }
     }
-    if (leader) umma_commit(bar_acc);
     mbar_wait(bar_acc, 0);
     tc_fence_after();
     {
@@ -1531,7 +1556,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 40);
     constexpr uint32_t TMEM_COLS = 256, cS = 0, cDP = 64, cDQ = 128;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: warp 0 issues the tcgen05 instructions converged
     const int NT = (T + TILE - 1) / TILE;
     const int qt = blockIdx.x % NT, bh = blockIdx.x / NT, b = bh / NH, h = bh - b * NH;
     const int kmax = causal ? min(T, (qt + 1) * TILE) : T;  // keys this query tile can see
@@ -1545,7 +1571,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot, 0);
     const bool leader = tid == 0;
     auto load_sub = [&](int s, int buf) {
         mbar_expect_tx(bar_kv + 8 * buf, 2 * SUB_BYTES);
@@ -1571,18 +1597,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int buf = s & 1;
         const uint32_t ph = (uint32_t)((s >> 1) & 1);
         const int nk = min(SUB, T - s * SUB), nk16 = (nk + 15) & ~15;
-        if (leader) {
+        if (warp == 0) {
             if (s == 0) mbar_wait(bar_qdo, 0);
             mbar_wait(bar_kv + 8 * buf, ph);
             tc_fence_after();
             const uint32_t idesc = make_idesc(TILE, nk16, 0, 0);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < HS / 16; ++k)  // S = Q_i K_s^T
-                umma_bf16(tmem_base + cS, make_desc(sQ + k * 32, 0, 1024), make_desc(sK + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
+                for (int k = 0; k < HS / 16; ++k)  // S = Q_i K_s^T
+                    umma_bf16(tmem_base + cS, make_desc(sQ + k * 32, 0, 1024), make_desc(sK + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
 #pragma unroll
-            for (int k = 0; k < HS / 16; ++k)  // dP = dO_i V_s^T
-                umma_bf16(tmem_base + cDP, make_desc(sdO + k * 32, 0, 1024), make_desc(sV + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
-            umma_commit(bar_s);  // also covers the dQ MMAs of the previous sub-tile
+                for (int k = 0; k < HS / 16; ++k)  // dP = dO_i V_s^T
+                    umma_bf16(tmem_base + cDP, make_desc(sdO + k * 32, 0, 1024), make_desc(sV + buf * SUB_BYTES + k * 32, 0, 1024), idesc, k > 0);
+                umma_commit(bar_s);  // also covers the dQ MMAs of the previous sub-tile
+            }
+            __syncwarp();
         }
         mbar_wait(bar_s, (uint32_t)(s & 1));
         tc_fence_after();
@@ -1615,15 +1644,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tmem_st_wait();
         tc_fence_before();
         __syncthreads();
-        if (leader) {
+        if (warp == 0) {
             tc_fence_after();
             const uint32_t idesc = make_idesc(TILE, HS, 0, 1);
-            for (int k16 = 0; k16 < nk16 / 16; ++k16)  // dQ_i += dS K_s
-                umma_bf16_ts(tmem_base + cDQ, tmem_base + cS + k16 * 8, make_desc(sK + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc,
-                             (s > 0 || k16 > 0) ? 1u : 0u);
+            if (elect_one()) {
+                for (int k16 = 0; k16 < nk16 / 16; ++k16)  // dQ_i += dS K_s
+                    umma_bf16_ts(tmem_base + cDQ, tmem_base + cS + k16 * 8, make_desc(sK + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc,
+                                 (s > 0 || k16 > 0) ? 1u : 0u);
+                if (s + 1 == NS) umma_commit(bar_acc);
+            }
+            __syncwarp();
         }
     }
-    if (leader) umma_commit(bar_acc);
     mbar_wait(bar_acc, 0);
     tc_fence_after();
     {
@@ -1739,7 +1771,7 @@ int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const
     VITRS_TRY(encode_map3d(ctx, &tm_qkv, qkv, 3 * (uint64_t)c, t, b));
     VITRS_TRY(encode_map3d(ctx, &tm_do, dout, (uint64_t)c, t, b));
     if (!causal) {
-        const size_t smem_s = (size_t)NT * 4 * TILE_BYTES + 4 * TILE_BYTES + 4 * 256 * 4 + 256 + 1024;
+        const size_t smem_s = (size_t)NT * 4 * TILE_BYTES + 5 * TILE_BYTES + 4 * 256 * 4 + 256 + 1024;
         VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_bwd_persist_kernel, smem_s));
         CUtensorMap tm_dq;
         VITRS_TRY(encode_map3d(ctx, &tm_dq, dqkv, 3 * (uint64_t)c, t, b));
