@@ -26,6 +26,24 @@ sys.path.insert(0, ROOT)
 METRIC = "ViT train images/sec (fwd+bwd+AdamW)"
 UNIT = "images/s"
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on stdout when the box sets
+# NCCL_DEBUG), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved real stdout.
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def isolate_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
 
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -124,7 +142,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": round(ips, 4), "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{args.steps} steps x {per_step} image(s), vit-{args.config}, fp32 fwd+bwd+AdamW"},
             "e2e": {"value": round(ips, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -144,6 +162,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "vitrs" else args.warmup
+    isolate_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -379,7 +398,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "inference_forward": inference, "strong_scaling": strong,
                 "optimizer_state_bytes_per_rank": model.optimizer_state_bytes}
-        print(json.dumps(line), flush=True)
+        emit(line)
     model.close()
     if world > 1:
         dist.destroy_process_group()
