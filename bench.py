@@ -345,6 +345,8 @@ def main():
                     "peak_kind": f"{peaks['source']} cuBLAS bf16 sustained (kernel timed inside a long step)",
                     "launches_per_step": gemm_launches, "gemm_ms_per_step": round(gemm_ms, 3),
                     "gemm_share_of_step": round(gemm_ms / ms_per_step, 4), "traffic": traffic,
+                    "traffic_source": "profiles/gemm_tc_traffic.json: dram bytes per launch from an ncu --set full capture of the same step "
+                                      "(committed file, NOT measured in this run)" if traffic is not None else None,
                     "step_tflops": round(value / world * flops_per_image / 1e12, 1),
                     "step_frac_of_peak": round(value / world * flops_per_image / 1e12 / peaks["tf_sustained"], 4),
                     "step_frac_of_nominal_2250": round(value / world * flops_per_image / 1e12 / 2250.0, 4)}
