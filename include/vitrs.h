@@ -233,9 +233,12 @@ int vitrs_model_train_step_u8(vitrs_model*, const uint8_t* images, int layout, c
 int vitrs_model_prefetch_host_u8(vitrs_model*, const uint8_t* h_images, const int* h_labels, int b);
 int vitrs_model_train_step_host_u8(vitrs_model*, const uint8_t* h_images, int layout, const int* h_labels, int b,
                                    float lr, float beta1, float beta2, float eps, float weight_decay, float* loss_out);
-/* same step with the batch already resident on the device */
+/* same step with the batch already resident on the device.  On one GPU in production mode the launch sequence of the step is
+ * captured the second time the same (batch, images, labels) comes by and replayed as a CUDA graph from then on (the AdamW
+ * hyper-parameters live in device memory); vitrs_model_step_graph_replays counts the replays.  VITRS_NO_STEP_GRAPH=1 disables. */
 int vitrs_model_train_step(vitrs_model* m, const float* images, const int* labels, int b,
                            float lr, float beta1, float beta2, float eps, float weight_decay);
+int vitrs_model_step_graph_replays(vitrs_model* m, uint64_t* replays);
 
 /* ---- inference engine: ViT::forward without targets (rusty_vit.rs:339-350, logits only) ---------------------
  * Borrows the parameters of a production-mode model (which must outlive it; create that model with max_batch 1 when it only

@@ -427,3 +427,34 @@ def test_inference_engine_equals_training_forward_and_replays_graphs(vitrs):
     for e in (eng, eager, eng6):
         e.close()
     m.close(); m6.close()
+
+
+def test_step_graph_replays_the_training_step(vitrs):
+    """vitrs_model_train_step captures the launch sequence the second time a (batch, images, labels) key comes by and replays it
+    as a CUDA graph (AdamW hyper-parameters live in device memory, so lr / step changes need no re-capture).  The replayed
+    steps follow the kernel-by-kernel steps of a VITRS_NO_STEP_GRAPH context (split-K weight gradients use fp32 atomics, so the
+    two runs agree to rounding, not bit for bit)."""
+    b, steps = 16, 10
+    images, labels = po.synthetic_batch(MID_HS64, b)
+    images2, labels2 = po.synthetic_batch(MID_HS64, b, step=1)
+    curves, replays = [], []
+    for no_graph in (False, True):
+        if no_graph:
+            os.environ["VITRS_NO_STEP_GRAPH"] = "1"
+        try:
+            ctx = vitrs.Context(0)  # the switch is read when the context is created
+        finally:
+            os.environ.pop("VITRS_NO_STEP_GRAPH", None)
+        m = vitrs.ViT(MID_HS64, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1, ctx=ctx)
+        batches = [to_dev(images, labels), to_dev(images2, labels2)]
+        curve = []
+        for s in range(steps):
+            x, y = batches[s % 2]
+            m.train_step(x, y, 1e-3 * (1 + s % 3))  # a changing learning rate: not baked into the graph
+            curve.append(m.mean_loss)
+        curves.append(np.array(curve))
+        replays.append(m.step_graph_replays)
+        m.close()
+    assert replays[0] == steps - 4 and replays[1] == 0, replays  # per key: eager, eager + capture, then replays
+    assert curves[0][-1] < curves[0][0]
+    assert np.abs(curves[0] - curves[1]).max() <= 2e-3 * np.abs(curves[1]).max(), (curves[0], curves[1])

@@ -126,6 +126,7 @@ _SIGNATURES = {
     "vitrs_model_prefetch_host": (_int, [_vp, _vp, _vp, _int]),
     "vitrs_model_train_step_host": (_int, [_vp, _vp, _vp, _int, _f, _f, _f, _f, _f, C.POINTER(_f)]),
     "vitrs_model_train_step": (_int, [_vp, _vp, _vp, _int, _f, _f, _f, _f, _f]),
+    "vitrs_model_step_graph_replays": (_int, [_vp, C.POINTER(_u64)]),
     "vitrs_model_set_input_norm": (_int, [_vp, C.POINTER(_f), C.POINTER(_f)]),
     "vitrs_model_forward_u8": (_int, [_vp, _vp, _int, _vp, _int]),
     "vitrs_model_train_step_u8": (_int, [_vp, _vp, _int, _vp, _int, _f, _f, _f, _f, _f]),
@@ -550,6 +551,12 @@ class ViT:
     def optimizer_state_bytes(self):
         n = C.c_size_t()
         self.ctx.check(lib().vitrs_model_optimizer_state_bytes(self._h, C.byref(n)))
+        return n.value
+
+    @property
+    def step_graph_replays(self):
+        n = C.c_uint64()
+        self.ctx.check(lib().vitrs_model_step_graph_replays(self._h, C.byref(n)))
         return n.value
 
     def set_dloss_scale(self, s):

@@ -23,6 +23,16 @@ struct Arena {
     int elem[A_COUNT];          // bytes per element, 0 = not materialised
 };
 
+// one captured training step (zero_grad + forward + backward + AdamW apply) for a given (batch, input pointers, input kind)
+struct StepGraph {
+    const void* images;
+    const int* labels;
+    int b, kind;            // kind 0 = fp32 NCHW, 1 = uint8 NCHW, 2 = uint8 NHWC
+    int sightings;          // the step is captured the second time the same key comes by
+    cudaGraphExec_t exec;
+    uint64_t launches, age;
+};
+
 struct vitrs_model {
     vitrs_ctx* ctx;
     vitrs_config cfg;
@@ -72,6 +82,10 @@ struct vitrs_model {
     float *zp, *zm, *zv;   // [s_total]
     float *m_small, *v_small;  // replicated moments of the small tensors, compact (small_runs)
     size_t small_total;
+    // CUDA-graph replay of the single-GPU production step
+    StepGraph step_graphs[4];
+    cudaStream_t cap_stream;
+    uint64_t graph_tick, graph_replays;
 };
 
 static inline int tokens(const vitrs_config& c) { return (c.image_size / c.patch_size) * (c.image_size / c.patch_size) + 1; }
