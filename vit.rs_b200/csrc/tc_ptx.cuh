@@ -16,8 +16,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Spins on try_wait.  In the diagnostic build (make trace: -DVITRS_ATTN_TRACE) the spin is bounded: a protocol bug then traps
+// (the launch fails with "unspecified launch failure") instead of hanging the GPU until the watchdog of the caller fires.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#ifdef VITRS_ATTN_TRACE
+    unsigned long long spins = 0;
+#endif
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -26,6 +31,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(ok)
             : "r"(bar), "r"(parity)
             : "memory");
+#ifdef VITRS_ATTN_TRACE
+        if (!ok && ++spins > (1ull << 26)) __trap();  // ~10 s of polling: no hand-over of these kernels takes a millisecond
+#endif
     } while (!ok);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
