@@ -26,6 +26,18 @@ TI16_2L = dict(image_size=224, patch_size=16, channels=192, num_layers=2, num_he
 MID_HS64 = dict(image_size=64, patch_size=16, channels=256, num_layers=2, num_heads=4, num_classes=16)
 
 
+def headline_ctx(vitrs):
+    """A context that keeps the GEMM tile choice of the headline run (CTA pairs on 256 x 256 tiles) whatever the problem size:
+    at batch 2-4 the library would otherwise pick its small-problem tiles, and these tests exist to put the production kernels
+    in front of the oracle.  (The default choice is what the inference-engine and toy-shape tests run.)"""
+    import os
+    os.environ["VITRS_GEMM_NO_SMALL"] = "1"
+    try:
+        return vitrs.Context(0)  # switches are read when the context is created
+    finally:
+        os.environ.pop("VITRS_GEMM_NO_SMALL", None)
+
+
 def relerr(got, want):
     got, want = np.asarray(got, np.float64).ravel(), np.asarray(want, np.float64).ravel()
     return np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
@@ -64,7 +76,7 @@ def test_bf16_step_matches_oracle_on_model_configs(vitrs, cfg_name, b, init_mode
     GPU / floor ratios on the two cases: 0.8 .. 2.7, the largest on the LayerNorm bias gradients.)"""
     cfg = po.CONFIGS[cfg_name] if isinstance(cfg_name, str) else cfg_name
     ref = po.ViT(cfg_name, seed=1337, init_mode=init_mode)
-    m = vitrs.ViT(cfg_name, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=init_mode)
+    m = vitrs.ViT(cfg_name, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=init_mode, ctx=headline_ctx(vitrs))
     assert np.array_equal(m.params_flat().cpu().numpy(), ref.params_flat())
     images, labels = po.synthetic_batch(cfg, b)
     ref_loss = ref.forward(images, labels); ref.zero_grad(); ref.backward()
@@ -103,7 +115,7 @@ def test_bf16_loss_curve_100_steps_hs64(vitrs, cfg, b):
     """100 AdamW steps through the tensor-core attention kernels and the CTA-pair GEMM vs the oracle's curve."""
     steps, lr = 100, 3e-4
     ref = po.ViT(cfg, seed=1337, init_mode=1)
-    m = vitrs.ViT(cfg, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1)
+    m = vitrs.ViT(cfg, max_batch=b, mode=vitrs.MODE_BF16, seed=1337, init_mode=1, ctx=headline_ctx(vitrs))
     ref_curve, got_curve = [], []
     for step in range(steps):
         images, labels = po.synthetic_batch(cfg, b, step=step % 8)  # 8 repeating batches: the loss must fall

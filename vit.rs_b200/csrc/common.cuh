@@ -38,16 +38,12 @@ struct vitrs_ctx {
     void* nccl_lib;
     void* nccl_comm;
     int rank, world, nccl_max_ctas;
-    // per-context (= per-device) record of the dynamic shared memory opt-in of each kernel: the attribute belongs to the
-    // device, so a process-wide flag would skip it on a second GPU
-    struct { const void* fn; size_t bytes; } func_smem[96];
-    int func_smem_count;
     // tensor maps are pure functions of (base, extents, strides, box): encoded once, then served from this table
     struct vitrs_map_entry* map_cache;
     int map_cache_used;
     // diagnostic switches, read once at context creation
     int env_gemm_cg1, env_gemm_splits, env_dp_defer, env_attn_fwd_stream, env_attn_bwd_stream, env_attn_bwd_overwrite,
-        env_no_map_cache, env_attn_fwd_legacy, env_attn_fwd_nostagger, env_gemm_static, env_no_step_graph;
+        env_no_map_cache, env_attn_fwd_legacy, env_attn_fwd_nostagger, env_gemm_static, env_no_step_graph, env_gemm_no_small;
     // device-side error flags raised by kernels (bit 0: class label out of range), reported by vitrs_model_mean_loss
     int* dev_flags;
     AdamHyper* d_hyper;  // AdamW hyper-parameters of the current step (same allocation as dev_flags)

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 int vitrs_set_error(vitrs_ctx* ctx, int code, const char* fmt, ...) {
@@ -78,21 +80,41 @@ int vitrs_tensor_map(vitrs_ctx* ctx, CUtensorMap* out, int rank, const void* bas
     return VITRS_OK;
 }
 
+// The dynamic shared memory opt-in is an attribute of (function, device), shared by every context of the process on that device:
+// it is recorded per device here (not per context — a second context on the same GPU that asked for less would lower it under
+// the first one's feet) and only ever raised.
+namespace {
+struct FuncSmem { const void* fn; size_t bytes; };
+constexpr int kMaxDevices = 16, kMaxFuncs = 128;
+FuncSmem g_func_smem[kMaxDevices][kMaxFuncs];
+int g_func_smem_count[kMaxDevices];
+std::mutex g_func_smem_mu;
+}  // namespace
+
 int vitrs_func_smem(vitrs_ctx* ctx, const void* fn, size_t bytes) {
-    for (int i = 0; i < ctx->func_smem_count; ++i) {
-        if (ctx->func_smem[i].fn == fn) {
-            if (ctx->func_smem[i].bytes >= bytes) return VITRS_OK;
+    const int dev = ctx->device >= 0 && ctx->device < kMaxDevices ? ctx->device : 0;
+    std::lock_guard<std::mutex> lk(g_func_smem_mu);
+    FuncSmem* tab = g_func_smem[dev];
+    int& n = g_func_smem_count[dev];
+    for (int i = 0; i < n; ++i) {
+        if (tab[i].fn == fn) {
+            if (tab[i].bytes >= bytes) return VITRS_OK;
             VITRS_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            ctx->func_smem[i].bytes = bytes;
+            tab[i].bytes = bytes;
             return VITRS_OK;
         }
     }
-    VITRS_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    if (ctx->func_smem_count < (int)(sizeof(ctx->func_smem) / sizeof(ctx->func_smem[0]))) {
-        ctx->func_smem[ctx->func_smem_count].fn = fn;
-        ctx->func_smem[ctx->func_smem_count].bytes = bytes;
-        ctx->func_smem_count++;
+    if (n >= kMaxFuncs) {  // (table full: ask the runtime what the function has and never lower it)
+        cudaFuncAttributes at;
+        VITRS_CUDA(ctx, cudaFuncGetAttributes(&at, fn));
+        if ((size_t)at.maxDynamicSharedSizeBytes >= bytes) return VITRS_OK;
+        VITRS_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        return VITRS_OK;
     }
+    VITRS_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    tab[n].fn = fn;
+    tab[n].bytes = bytes;
+    ++n;
     return VITRS_OK;
 }
 
@@ -162,6 +184,7 @@ extern "C" int vitrs_ctx_create(vitrs_ctx** out, int device) {
     ctx->env_attn_fwd_nostagger = flag("VITRS_ATTN_FWD_NOSTAGGER");
     ctx->env_gemm_static = flag("VITRS_GEMM_STATIC");
     ctx->env_no_step_graph = flag("VITRS_NO_STEP_GRAPH");
+    ctx->env_gemm_no_small = flag("VITRS_GEMM_NO_SMALL");
     if (cudaMalloc(&ctx->dev_flags, 128) != cudaSuccess || cudaMemset(ctx->dev_flags, 0, 128) != cudaSuccess) {
         snprintf(g_create_err, sizeof(g_create_err), "cudaMalloc(flags) failed: %s", cudaGetErrorString(cudaGetLastError()));
         free(ctx->map_cache);

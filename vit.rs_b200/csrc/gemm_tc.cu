@@ -728,9 +728,19 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
         return gemm_simt_bf16(ctx, g);
     }
     const bool a_mn = g.a_ks != 1, b_mn = g.b_ks != 1;
-    const int BN = g.N > 128 ? 256 : 128;
+    int BN = g.N > 128 ? 256 : 128;
     // a CTA pair per [256 x 256] tile whenever the problem has that many rows
     int CG = (BN == 256 && g.M > BM) ? 2 : 1;
+    // Small problems (the inference engine at batch 1-64: M = 197 .. 12 608 rows) leave most SMs without a tile at that size and
+    // the launch is a stream of weights through a handful of CTAs: when the large tiles fill less than half of the chip, take the
+    // smaller ones — [256 x 256] pairs -> [128 x 256] -> [128 x 128] single CTAs — as far as that adds CTAs.  (Not for the
+    // split-K weight gradients, which fill the chip by splitting K.)
+    if (g.epi.kind != EPI_ACCUM_F32 && !ctx->env_gemm_no_small) {
+        const long slots = ctx->sm_count;
+        auto ctas = [&](int bn, int cg) { return (long)ceil_div(g.M, BM * cg) * ceil_div(g.N, bn) * cg; };
+        if (CG == 2 && ctas(256, 2) < slots / 2) CG = 1;
+        if (BN == 256 && CG == 1 && ctas(256, 1) < slots / 2) BN = 128;
+    }
     if (ctx->env_gemm_cg1) CG = 1;  // VITRS_GEMM_CG=1: tuning aid (scripts/bench_gemm.py)
     CUtensorMap maps[5];  // A, B, out, out2, aux
     CUtensorMap &tmA = maps[0], &tmB = maps[1];
