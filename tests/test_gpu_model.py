@@ -411,6 +411,13 @@ def test_inference_engine_equals_training_forward_and_replays_graphs(vitrs):
         logits, _ = eng.forward_u8(u8, layout=vitrs.ViT.NHWC)
         assert torch.equal(logits, want_u8)
     assert np.array_equal(eng.forward_host_u8(u8.cpu().numpy(), layout=vitrs.ViT.NHWC), want_u8.cpu().numpy())
+    # the normalisation constants are launch arguments: changing them must not replay a graph recorded with the old ones
+    m.set_input_norm([0.4, 0.5, 0.6], [0.2, 0.25, 0.3])
+    m.forward_u8(u8, None, layout=vitrs.ViT.NHWC)
+    renormed = m.act("logits").clone().view(b, -1)
+    logits, _ = eng.forward_u8(u8, layout=vitrs.ViT.NHWC)
+    assert torch.equal(logits, renormed) and not torch.equal(renormed, want_u8)
+    m.set_input_norm([0.5] * 3, [0.5] * 3)
     # the weights are borrowed: an optimiser step on the model changes what the engine computes
     m.train_step(x, y, 1e-2)
     m.forward(x, None)

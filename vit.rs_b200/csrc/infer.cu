@@ -18,6 +18,7 @@
 struct InferGraph {
     int b, kind;          // kind 0 = fp32 NCHW, 1 = uint8 NCHW, 2 = uint8 NHWC
     const void* src;      // device pointer the graph reads its images from
+    uint64_t epoch;       // the model's graph_epoch at capture (input normalisation constants are launch arguments)
     cudaGraphExec_t exec;
     uint64_t launches;    // kernels inside the graph
     uint64_t age;
@@ -89,7 +90,7 @@ int forward_once(vitrs_infer* e, const void* images, int kind, int b) {
 
 InferGraph* find_graph(vitrs_infer* e, const void* src, int kind, int b) {
     for (InferGraph& g : e->graphs)
-        if (g.exec && g.b == b && g.kind == kind && g.src == src) return &g;
+        if (g.exec && g.b == b && g.kind == kind && g.src == src && g.epoch == e->m->graph_epoch) return &g;
     return nullptr;
 }
 
@@ -116,7 +117,7 @@ int capture_graph(vitrs_infer* e, const void* src, int kind, int b) {
     const cudaError_t ie = cudaGraphInstantiate(&slot->exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) { slot->exec = nullptr; return vitrs_set_error(ctx, VITRS_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
-    slot->b = b; slot->kind = kind; slot->src = src; slot->age = ++e->tick;
+    slot->b = b; slot->kind = kind; slot->src = src; slot->epoch = e->m->graph_epoch; slot->age = ++e->tick;
     return VITRS_OK;
 }
 

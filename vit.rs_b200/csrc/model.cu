@@ -864,6 +864,7 @@ int vitrs_model_act_view(vitrs_model* m, int which, int tensor, void** ptr, size
 
 int vitrs_model_set_dloss_scale(vitrs_model* m, float scale) {
     if (!m) return VITRS_ERR_ARG;
+    if (m->dloss_scale != scale) m->graph_epoch++;  // the scale is a launch argument of the loss kernel: recorded graphs are stale
     m->dloss_scale = scale;
     return VITRS_OK;
 }
@@ -890,6 +891,7 @@ int vitrs_model_set_input_norm(vitrs_model* m, const float* mean, const float* s
     if (!m) return VITRS_ERR_ARG;
     VITRS_ARG(m->ctx, mean && stdev && stdev[0] > 0.f && stdev[1] > 0.f && stdev[2] > 0.f);
     for (int i = 0; i < 3; ++i) { m->norm_mean[i] = mean[i]; m->norm_std[i] = stdev[i]; }
+    m->graph_epoch++;  // the constants are launch arguments of the im2col pass: recorded graphs are stale
     return VITRS_OK;
 }
 
@@ -1068,7 +1070,7 @@ static int train_step_any(vitrs_model* m, const void* images, int kind, const in
     VITRS_TRY(op_adam_set_hyper(ctx, lr, beta1, beta2, eps, weight_decay, m->adam_step, ctx->stream));  // outside the graph
     StepGraph* slot = nullptr;
     for (StepGraph& g : m->step_graphs)
-        if (g.sightings > 0 && g.images == images && g.labels == labels && g.b == b && g.kind == kind) slot = &g;
+        if (g.sightings > 0 && g.images == images && g.labels == labels && g.b == b && g.kind == kind && g.epoch == m->graph_epoch) slot = &g;
     if (slot && slot->exec) {
         VITRS_CUDA(ctx, cudaGraphLaunch(slot->exec, ctx->stream));
         slot->age = ++m->graph_tick;
@@ -1082,7 +1084,7 @@ static int train_step_any(vitrs_model* m, const void* images, int kind, const in
         for (StepGraph& g : m->step_graphs)
             if (g.age < slot->age) slot = &g;
         if (slot->exec) cudaGraphExecDestroy(slot->exec);
-        *slot = StepGraph{images, labels, b, kind, 1, nullptr, 0, ++m->graph_tick};
+        *slot = StepGraph{images, labels, b, kind, 1, m->graph_epoch, nullptr, 0, ++m->graph_tick};
         return VITRS_OK;
     }
     // second sighting: record the sequence that has just run (capture executes nothing)

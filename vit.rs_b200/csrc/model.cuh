@@ -29,6 +29,7 @@ struct StepGraph {
     const int* labels;
     int b, kind;            // kind 0 = fp32 NCHW, 1 = uint8 NCHW, 2 = uint8 NHWC
     int sightings;          // the step is captured the second time the same key comes by
+    uint64_t epoch;         // vitrs_model::graph_epoch at capture: launch arguments baked into the graph are still current
     cudaGraphExec_t exec;
     uint64_t launches, age;
 };
@@ -86,6 +87,8 @@ struct vitrs_model {
     StepGraph step_graphs[4];
     cudaStream_t cap_stream;
     uint64_t graph_tick, graph_replays;
+    uint64_t graph_epoch;   // bumped whenever a value that kernels receive BY VALUE changes (input normalisation, loss scale):
+                            // graphs recorded before that (here and in the inference engines) are stale
 };
 
 static inline int tokens(const vitrs_config& c) { return (c.image_size / c.patch_size) * (c.image_size / c.patch_size) + 1; }
