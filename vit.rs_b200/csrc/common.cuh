@@ -31,6 +31,7 @@ struct vitrs_ctx {
     float* scratch;
     size_t scratch_floats;
     // per-launch GEMM timing (vitrs_profile_begin / _end)
+    uint64_t scratch_gen;  // bumped when the scratch buffer is reallocated: a recorded graph holding the old pointer is stale
     int prof_on, prof_count, prof_cap;
     cudaEvent_t* prof_ev;  // 2 per launch
     double* prof_flops;

@@ -290,6 +290,7 @@ int vitrs_ensure_scratch(vitrs_ctx* ctx, size_t floats) {
     }
     VITRS_CUDA(ctx, cudaMalloc(&ctx->scratch, floats * sizeof(float)));
     ctx->scratch_floats = floats;
+    ctx->scratch_gen++;
     return VITRS_OK;
 }
 

@@ -1071,6 +1071,11 @@ static int train_step_any(vitrs_model* m, const void* images, int kind, const in
     StepGraph* slot = nullptr;
     for (StepGraph& g : m->step_graphs)
         if (g.sightings > 0 && g.images == images && g.labels == labels && g.b == b && g.kind == kind && g.epoch == m->graph_epoch) slot = &g;
+    if (slot && slot->exec && slot->scratch_gen != ctx->scratch_gen) {  // recorded against a scratch buffer that has since moved
+        cudaGraphExecDestroy(slot->exec);
+        slot->exec = nullptr;
+        slot->sightings = 1;
+    }
     if (slot && slot->exec) {
         VITRS_CUDA(ctx, cudaGraphLaunch(slot->exec, ctx->stream));
         slot->age = ++m->graph_tick;
@@ -1084,12 +1089,13 @@ static int train_step_any(vitrs_model* m, const void* images, int kind, const in
         for (StepGraph& g : m->step_graphs)
             if (g.age < slot->age) slot = &g;
         if (slot->exec) cudaGraphExecDestroy(slot->exec);
-        *slot = StepGraph{images, labels, b, kind, 1, m->graph_epoch, nullptr, 0, ++m->graph_tick};
+        *slot = StepGraph{images, labels, b, kind, 1, m->graph_epoch, ctx->scratch_gen, nullptr, 0, ++m->graph_tick};
         return VITRS_OK;
     }
     // second sighting: record the sequence that has just run (capture executes nothing)
     slot->sightings++;
     slot->age = ++m->graph_tick;
+    slot->scratch_gen = ctx->scratch_gen;  // (the eager run above has sized the scratch buffer for this step)
     if (!m->cap_stream) VITRS_CUDA(ctx, cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
     const uint64_t before = ctx->launches;
     cudaGraph_t graph = nullptr;

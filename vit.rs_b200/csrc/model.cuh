@@ -30,6 +30,7 @@ struct StepGraph {
     int b, kind;            // kind 0 = fp32 NCHW, 1 = uint8 NCHW, 2 = uint8 NHWC
     int sightings;          // the step is captured the second time the same key comes by
     uint64_t epoch;         // vitrs_model::graph_epoch at capture: launch arguments baked into the graph are still current
+    uint64_t scratch_gen;   // vitrs_ctx::scratch_gen at capture: the context's scratch buffer (D of the attention backward) has not moved
     cudaGraphExec_t exec;
     uint64_t launches, age;
 };
