@@ -370,3 +370,29 @@ def test_attention_bf16_late_peak_moves_the_exponent_reference(vitrs, t, peak_ke
     want_lse = np.log(np.exp(pre - pre.max(-1, keepdims=True)).sum(-1)) + pre.max(-1)
     assert np.abs(host(lse).reshape(b * nh, t) - want_lse).max() <= 2e-2
     assert (wa.reshape(b * nh, t, t)[:, :, peak_key] > 0.9).all()  # the case is what it claims to be
+
+
+def test_two_contexts_on_one_device_do_not_lower_each_others_shared_memory_opt_in(vitrs):
+    """The dynamic shared memory opt-in belongs to (kernel, device), not to a context: a second context that launches the
+    persistent attention backward with ONE key tile (less shared memory) must not leave the first context's two-key-tile
+    launch without its opt-in (regression: 'launch -> invalid argument' in the full suite)."""
+    c, nh = 128, 2
+    other = vitrs.Context(0)
+
+    def bwd(t, ctx):
+        b = 2
+        qkv = (torch.randn(b, t, 3 * c, device="cuda") * 0.5).to(torch.bfloat16)
+        dout = (torch.randn(b, t, c, device="cuda") * 0.1).to(torch.bfloat16)
+        out = torch.zeros(b, t, c, device="cuda", dtype=torch.bfloat16)
+        dqkv = torch.zeros(b, t, 3 * c, device="cuda", dtype=torch.bfloat16)
+        lse = torch.zeros(b * nh * t, device="cuda")
+        vitrs.attention_forward(out, lse, None, qkv, b, t, c, nh, causal=0, ctx=ctx)
+        vitrs.attention_backward_bf16(dqkv, dout, out, lse, qkv, b, t, c, nh, causal=0, ctx=ctx)
+        torch.cuda.synchronize()
+        assert torch.isfinite(dqkv.float()).all()
+
+    bwd(197, None)    # default context: two key tiles
+    bwd(64, other)    # second context: one key tile
+    bwd(197, None)    # default context again
+    bwd(197, other)
+    other.close()
