@@ -270,6 +270,10 @@ int vitrs_infer_stats(vitrs_infer* e, size_t* workspace_bytes, uint64_t* graph_r
 typedef struct vitrs_loader vitrs_loader;
 int vitrs_loader_open(vitrs_ctx* ctx, const char* const* paths, int num_paths, int image_size, int label_bytes, int batch,
                       int shuffle, uint64_t seed, int drop_last, vitrs_loader** out);
+/* data parallel: every rank opens the same files with the same seed; the (seed, epoch) order is cut into batches and rank r takes
+ * batches r, r + world, ... of each whole round of `world` batches (all ranks see the same number of batches per epoch) */
+int vitrs_loader_open_sharded(vitrs_ctx* ctx, const char* const* paths, int num_paths, int image_size, int label_bytes, int batch,
+                              int shuffle, uint64_t seed, int drop_last, int rank, int world, vitrs_loader** out);
 int vitrs_loader_close(vitrs_loader* loader);
 int vitrs_loader_info(vitrs_loader* loader, size_t* num_records, int* batches_per_epoch, int* num_classes_seen);
 /* blocks until the next batch is assembled: uint8 NCHW images [b,3,H,W] and int labels [b] in host memory that stays valid

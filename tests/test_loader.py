@@ -103,3 +103,38 @@ def test_tiny_model_trains_from_the_loader_and_first_step_matches_oracle(vitrs):
     first, last = np.mean(curve[:8]), np.mean(curve[-8:])
     assert np.isfinite(curve).all() and last < 0.6 * first, (first, last)
     ld.close(); m.close()
+
+
+def test_sharded_loaders_partition_every_epoch(vitrs):
+    """Data parallel: two ranks open the same file with the same seed; per epoch they see disjoint batches of the same (seed,
+    epoch) order, the same number of batches, and together every record of the whole rounds exactly once."""
+    labels, images = records()
+    key = {images[i].tobytes(): i for i in range(N)}
+    world, batch = 2, 24  # 256 // 24 = 10 batches -> 5 rounds of 2; the 16 left-over records are dropped this epoch
+    seen = []
+    for rank in range(world):
+        ld = vitrs.RecordLoader(FIXTURE, image_size=32, batch=batch, shuffle=True, seed=11, pinned=False, rank=rank, world=world)
+        assert ld.batches_per_epoch == 5
+        per_epoch = {0: [], 1: []}
+        for _ in range(10):
+            img, lab, epoch = ld.next()
+            per_epoch[epoch].append([key[img[k].tobytes()] for k in range(len(lab))])
+        ld.close()
+        assert [len(v) for v in per_epoch.values()] == [5, 5]
+        seen.append(per_epoch)
+    # the unsharded order of the same seed: rank r holds its batches r, r + 2, ...
+    ld = vitrs.RecordLoader(FIXTURE, image_size=32, batch=batch, shuffle=True, seed=11, pinned=False)
+    whole = []
+    for _ in range(10):
+        img, lab, epoch = ld.next()
+        assert epoch == 0
+        whole.append([key[img[k].tobytes()] for k in range(len(lab))])
+    ld.close()
+    for rank in range(world):
+        assert seen[rank][0] == whole[rank::world]
+    for ep in (0, 1):
+        ids = sum(seen[0][ep] + seen[1][ep], [])
+        assert len(ids) == len(set(ids)) == 240
+    assert seen[0][0] != seen[0][1]
+    with pytest.raises(vitrs.VitrsError):
+        vitrs.RecordLoader(FIXTURE, image_size=32, batch=200, pinned=False, rank=0, world=2)  # one batch, two ranks

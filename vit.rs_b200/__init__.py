@@ -148,6 +148,7 @@ _SIGNATURES = {
     "vitrs_grad_bucket": (_int, [C.POINTER(Config), _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_int), C.POINTER(_int)]),
     "vitrs_allreduce_f32": (_int, [_vp, _vp, _sz]),
     "vitrs_loader_open": (_int, [_vp, C.POINTER(C.c_char_p), _int, _int, _int, _int, _int, _u64, _int, C.POINTER(C.c_void_p)]),
+    "vitrs_loader_open_sharded": (_int, [_vp, C.POINTER(C.c_char_p), _int, _int, _int, _int, _int, _u64, _int, _int, _int, C.POINTER(C.c_void_p)]),
     "vitrs_loader_close": (_int, [_vp]),
     "vitrs_loader_info": (_int, [_vp, C.POINTER(_sz), C.POINTER(_int), C.POINTER(_int)]),
     "vitrs_loader_next": (_int, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(_int), C.POINTER(_u64)]),
@@ -710,14 +711,14 @@ class RecordLoader:
     """CIFAR-layout record files -> shuffled uint8 batches assembled by a native loader thread into pinned host slots
     (include/vitrs.h: vitrs_loader_*).  ctx=None uses pageable memory (no GPU needed)."""
 
-    def __init__(self, paths, image_size, batch, label_bytes=1, shuffle=True, seed=0, drop_last=True, ctx=None, pinned=True):
+    def __init__(self, paths, image_size, batch, label_bytes=1, shuffle=True, seed=0, drop_last=True, ctx=None, pinned=True, rank=0, world=1):
         paths = [paths] if isinstance(paths, str) else list(paths)
         self.ctx = ctx if ctx is not None else (default_context() if pinned else None)
         self.image_size, self.batch = image_size, batch
         arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
         self._h = C.c_void_p()
-        rc = lib().vitrs_loader_open(self.ctx._h if self.ctx else None, arr, len(paths), image_size, label_bytes, batch, int(shuffle), seed,
-                                     int(drop_last), C.byref(self._h))
+        rc = lib().vitrs_loader_open_sharded(self.ctx._h if self.ctx else None, arr, len(paths), image_size, label_bytes, batch, int(shuffle),
+                                             seed, int(drop_last), rank, world, C.byref(self._h))
         if rc != 0:
             raise VitrsError(f"vitrs_loader_open failed ({rc})" + (f": {lib().vitrs_last_error(self.ctx._h).decode()}" if self.ctx else ""))
         n, bpe, ncls = C.c_size_t(), C.c_int(), C.c_int()

@@ -31,6 +31,7 @@ struct vitrs_loader {
     std::vector<uint8_t> data;  // every record of every file, back to back
     size_t record_bytes, image_bytes, num_records;
     int label_bytes, batch, shuffle, drop_last, num_classes_seen;
+    int rank, world;  // data parallel: every rank walks the same (seed, epoch) order and takes batches rank, rank + world, ...
     uint64_t seed;
     // ring of host slots: the loader thread fills `filled`, the consumer hands slots back through `released`
     uint8_t* images[kSlots];
@@ -59,9 +60,14 @@ void fill_loop(vitrs_loader* L) {
                 const uint32_t t = order[i]; order[i] = order[j]; order[j] = t;
             }
         }
-        for (size_t at = 0; at < L->num_records; at += (size_t)L->batch) {
+        // sharded: only whole rounds of `world` batches, so every rank sees the same number of batches per epoch
+        const size_t full_batches = L->num_records / (size_t)L->batch;
+        const size_t round_limit = L->world > 1 ? full_batches / L->world * L->world * (size_t)L->batch : L->num_records;
+        size_t bi = 0;
+        for (size_t at = 0; at < round_limit; at += (size_t)L->batch, ++bi) {
             const size_t n = L->num_records - at < (size_t)L->batch ? L->num_records - at : (size_t)L->batch;
             if (n < (size_t)L->batch && L->drop_last) break;
+            if ((int)(bi % (size_t)L->world) != L->rank) continue;
             int slot;
             {
                 std::unique_lock<std::mutex> lk(L->mu);
@@ -92,7 +98,13 @@ extern "C" {
 
 int vitrs_loader_open(vitrs_ctx* ctx, const char* const* paths, int num_paths, int image_size, int label_bytes, int batch, int shuffle,
                       uint64_t seed, int drop_last, vitrs_loader** out) {
-    if (!out || !paths || num_paths < 1 || image_size < 1 || label_bytes < 1 || label_bytes > 4 || batch < 1) {
+    return vitrs_loader_open_sharded(ctx, paths, num_paths, image_size, label_bytes, batch, shuffle, seed, drop_last, 0, 1, out);
+}
+
+int vitrs_loader_open_sharded(vitrs_ctx* ctx, const char* const* paths, int num_paths, int image_size, int label_bytes, int batch,
+                              int shuffle, uint64_t seed, int drop_last, int rank, int world, vitrs_loader** out) {
+    if (!out || !paths || num_paths < 1 || image_size < 1 || label_bytes < 1 || label_bytes > 4 || batch < 1 || world < 1 || rank < 0 ||
+        rank >= world) {
         if (ctx) vitrs_set_error(ctx, VITRS_ERR_ARG, "vitrs_loader_open: bad argument");
         return VITRS_ERR_ARG;
     }
@@ -102,6 +114,7 @@ int vitrs_loader_open(vitrs_ctx* ctx, const char* const* paths, int num_paths, i
     L->image_bytes = (size_t)3 * image_size * image_size;
     L->record_bytes = L->image_bytes + label_bytes;
     L->label_bytes = label_bytes; L->batch = batch; L->shuffle = shuffle; L->drop_last = drop_last; L->seed = seed;
+    L->rank = rank; L->world = world;
     auto fail = [&](int code, const char* what, const char* path) {
         if (ctx) vitrs_set_error(ctx, code, "vitrs_loader_open: %s (%s)", what, path);
         delete L;
@@ -125,6 +138,7 @@ int vitrs_loader_open(vitrs_ctx* ctx, const char* const* paths, int num_paths, i
     }
     L->num_records = L->data.size() / L->record_bytes;
     if (drop_last && L->num_records < (size_t)batch) return fail(VITRS_ERR_ARG, "fewer records than one batch", paths[0]);
+    if (world > 1 && L->num_records / (size_t)batch < (size_t)world) return fail(VITRS_ERR_ARG, "fewer batches than ranks", paths[0]);
     int max_label = 0;
     for (size_t r = 0; r < L->num_records; ++r) {
         const int lb = L->data[r * L->record_bytes + label_bytes - 1];
@@ -167,7 +181,8 @@ int vitrs_loader_info(vitrs_loader* L, size_t* num_records, int* batches_per_epo
     if (!L) return VITRS_ERR_ARG;
     if (num_records) *num_records = L->num_records;
     if (batches_per_epoch)
-        *batches_per_epoch = (int)(L->drop_last ? L->num_records / L->batch : (L->num_records + L->batch - 1) / L->batch);
+        *batches_per_epoch = L->world > 1 ? (int)(L->num_records / L->batch / L->world)
+                                          : (int)(L->drop_last ? L->num_records / L->batch : (L->num_records + L->batch - 1) / L->batch);
     if (num_classes_seen) *num_classes_seen = L->num_classes_seen;
     return VITRS_OK;
 }
