@@ -16,14 +16,15 @@
 // {0,C,2C} + h*64, rows >= T zero-filled), so the reference layout needs no permute kernels.
 //
 // forward   S_i = Q_i K^T  (M=128 queries, N=T keys, fp32 in TMEM)  ->  one thread per query row:
-//           max / exp2 / sum from TMEM, P_i (bf16) into a 128B-swizzled shared tile  ->
+//           exp2 / sum from TMEM in one pass, P_i packed to bf16 in place in TMEM (the A operand of the next MMA)  ->
 //           O_i = P_i V  ->  O_i / sum to out[B,T,C] at column h*64, lse.
 //           The two 128-row query tiles run on two 4-warp groups concurrently.
-// backward  transposed orientation, keys on TMEM lanes: for every (key tile j, query tile i)
-//           S^T = K_j Q_i^T and dP^T = V_j dO_i^T  ->  P^T = exp2(S^T*c - lse), dS^T = P^T o (dP^T - D) * scale
-//           written once to shared memory, where the same bytes serve as the K-major A operand of
-//           dV_j += P^T dO_i and dK_j += dS^T Q_i and as the MN-major A operand of dQ_i += dS K_j.
+// backward  transposed orientation, keys on TMEM lanes: for every (key tile j, query sub-tile s)
+//           S^T = K_j Q_s^T and dP^T = V_j dO_s^T  ->  P^T = exp2(S^T*c - lse), dS^T = P^T o (dP^T - D) * scale, both packed
+//           in place in TMEM as the A operands of dV_j += P^T dO_s and dK_j += dS^T Q_s; dS^T is also written to shared
+//           memory, where it is the MN-major A operand of dQ_i += dS K_j.
 //           dV_j, dK_j and both dQ_i accumulate in TMEM; nothing is reduced through global memory.
+// Every tcgen05 instruction is issued by a CONVERGED warp from one elected region per batch (see tc_ptx.cuh: elect_one).
 #include <stdlib.h>
 
 #include "tc_ptx.cuh"
@@ -813,12 +814,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
 // ---- backward, software-pipelined and persistent (non-causal, T <= 256) -----------------------------------
 // Same five matmuls as attn_bwd_tc_kernel, but the work is cut into (128-key tile j) x (64-query sub-tile s)
-// iterations and three agents run concurrently:
-//   issuer (one thread)  : S^T / dP^T MMAs of iteration n+1 are in flight while iteration n is in its SIMT phase,
-//                          then the dV / dK (and, per query tile, dQ) MMAs of iteration n
-//   SIMT group A / B     : 128 threads each (one per key = TMEM lane), alternate iterations; P^T is packed to bf16
-//                          in place in tensor memory (A operand of dV), dS^T goes to one of four shared tiles that
-//                          serve as the K-major A operand of dK and, pairwise, as the MN-major A operand of dQ
+// iterations and four agents run concurrently:
+//   issuer (warp 0)      : the whole warp runs the control flow converged and every step's tcgen05 instructions leave from ONE
+//                          elected region, back to back (an `if (lane == 0)` region costs 94 cycles per MMA in R2UR / vote
+//                          wrappers, an elect per MMA 76; the pipe itself takes 42 cycles for a 128x64x16 MMA whose A operand
+//                          is in tensor memory and 74 from shared memory: scripts/exp_mma_rate.cu).  S^T / dP^T of
+//                          iteration n+2 are queued right behind dV / dK of iteration n, dQ when a query tile is complete.
+//   SIMT group A / B     : 128 threads each (one per key = TMEM lane), alternate iterations; P^T and dS^T are packed to bf16
+//                          in place in tensor memory (the A operands of dV and dK); dS^T also goes to one of four shared
+//                          tiles, which pairwise are the MN-major A operand of dQ.  The groups do nothing else.
+//   read-out group       : 128 threads, takes dV_j / dK_j (per key tile) and dQ_0 / dQ_1 (per head) out of tensor memory,
+//                          hands the accumulators back as soon as the values are in registers, then converts, stages
+//                          (dV / dK through the dead V_j / K_j tiles, dQ through a tile of its own) and TMA-stores.
+//   loader / statistics  : one thread refills operand tiles for the next head as they die, one warp fetches lse / D a head ahead.
 // TMEM: 2 x {S^T 64, dP^T 64} + dV 64 + dK 64 + dQ_0 64 + dQ_1 64 = 512 columns.
 constexpr int kPipeThreads = 512;  // warps 0-3: control (issuer = warp 0, TMEM owner = warp 1), 4-7: group A, 8-11: group B, 12-15: read-out
 
@@ -834,10 +842,10 @@ __device__ __forceinline__ int sub_at(int j, int t, int nsub) {
 // A one-CTA-per-head version of this pipeline spent 2.9 of its 14.5 us (ViT-B/16) on being launched, allocating tensor memory
 // and waiting for its 128 KB of operands with nothing else resident on the SM (the shared memory it needs excludes a second
 // CTA).  Here the CTA stays, and a loader thread refills each operand tile for the next head as soon as the current head is done with it:
-// K_0 / V_0 once the first key tile's dV / dK have left through them, Q and dO when the head's last MMA has retired, K_1 / V_1
-// after the final stores; dQ leaves through the groups' own dS tiles, so the Q tiles carry no staging.  Row statistics are
-// double-buffered and fetched a head ahead by an otherwise idle warp.  Barrier parities are derived from the running head
-// index G (every barrier completes a fixed number of phases per head).
+// K_0 / V_0 once the first key tile's dV / dK have left through them, rows 0-127 of Q and dO when the last key tile is through
+// its first two sub-tiles, the other rows when the head's last MMA has retired, K_1 / V_1 (on a barrier of their own: they are
+// not needed before key tile 1) after the read-out group's stores of that tile.  Row statistics are double-buffered.  Barrier
+// parities are derived from the running head index G (every barrier completes a fixed number of phases per head).
 __global__ void __launch_bounds__(kPipeThreads, 1)
 attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                         const __grid_constant__ CUtensorMap tm_dqkv, bf16* __restrict__ dqkv, const float* __restrict__ lse,
