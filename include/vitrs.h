@@ -290,7 +290,7 @@ int vitrs_model_train_step_loader(vitrs_model* m, vitrs_loader* loader, float lr
 int vitrs_comm_unique_id(vitrs_ctx* ctx, void* id128);
 int vitrs_comm_init(vitrs_ctx* ctx, const void* id128, int rank, int world);
 /* same with an explicit cap on the thread blocks NCCL may use per collective (ncclConfig_t.maxCTAs; 0 = NCCL's default).
- * vitrs_comm_init uses 2 (env VITRS_NCCL_MAX_CTAS overrides): the persistent GEMM / attention kernels occupy every SM with
+ * vitrs_comm_init uses 4 (env VITRS_NCCL_MAX_CTAS overrides): the persistent GEMM / attention kernels occupy every SM with
  * one large-shared-memory CTA, so each SM NCCL takes delays a CTA pair of the next GEMM. */
 int vitrs_comm_init_config(vitrs_ctx* ctx, const void* id128, int rank, int world, int max_ctas);
 /* ncclCommGetAsyncError: *nccl_result != 0 (and a VITRS_ERR_NCCL return) when a peer or the fabric failed */

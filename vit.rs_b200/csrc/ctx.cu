@@ -442,7 +442,9 @@ extern "C" int vitrs_comm_init_config(vitrs_ctx* ctx, const void* id128, int ran
 
 extern "C" int vitrs_comm_init(vitrs_ctx* ctx, const void* id128, int rank, int world) {
     // VITRS_NCCL_MAX_CTAS overrides the default cap (0 = leave NCCL alone)
-    int max_ctas = 2;  // measured on 8 GPUs: 66.9 k images/s at 2 against 65.9 k at 8 (the messages are 14 MB per block)
+    // 8 GPUs: 66.9 k images/s at 2 CTAs against 65.9 k at 8 (one sample each); at 2 a 14 MB bucket takes 0.65 ms (N = 2 timeline), which
+    // is what the last bucket exposes behind backward, so the default sits between
+    int max_ctas = 4;
     if (const char* ov = getenv("VITRS_NCCL_MAX_CTAS")) max_ctas = atoi(ov);
     return vitrs_comm_init_config(ctx, id128, rank, world, max_ctas < 0 ? 0 : max_ctas);
 }
