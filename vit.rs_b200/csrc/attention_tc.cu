@@ -306,7 +306,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 // the arithmetic and only keep the barriers moving.  TMEM: two 256-column regions {S [0,NK) -> P [0,NK/2); O [192,256)}.
 constexpr int kMainCols = 192;  // score columns that do not overlap the O accumulator at [192, 256)
 constexpr float kTau = 12.f;  // probabilities may exceed 1 by up to 2^kTau before the exponent reference is moved
-constexpr int kFwdThreads = 320;  // warp 0 loader, warp 1 issuer / TMEM owner, warps 2-5 group 0, warps 6-9 group 1
+constexpr int kFwdThreads = 320;       // warp 0 loader, warp 1 issuer / TMEM owner, warps 2-5 group 0, warps 6-9 group 1
+constexpr int kFwdSplitThreads = 576;  // SPLIT: two threads per query row — warps 2-9 group 0, warps 10-17 group 1; within a group the
+                                       // first four warps take keys [0, 128), the other four keys [128, T)
 
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -323,8 +325,8 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 // the same for a converged warp: one answer for all lanes (a completed phase stays completed, so "any lane saw it" is exact)
 __device__ __forceinline__ bool mbar_test_warp(uint32_t bar, uint32_t parity) { return __any_sync(0xffffffffu, mbar_test(bar, parity)); }
 
-template <bool STAGGER>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+template <bool STAGGER, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kFwdSplitThreads : kFwdThreads, 1)
 attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
                         int T, int C, int NH, int NK, int total_heads) {
     extern __shared__ uint8_t smem_raw[];
@@ -335,6 +337,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const uint32_t full_qk = bar0, full_v = bar0 + 16, s_main = bar0 + 32, p_ready = bar0 + 48, o_ready = bar0 + 64,
                    tmem_free = bar0 + 80, stage_free = bar0 + 96, s_tail = bar0 + 112;  // two barriers each
     volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 128);
+    float* xch = reinterpret_cast<float*>(gen + (bar0 - base) + 256);  // SPLIT: [group][half][row][3] floats exchanged between a row's two threads
     constexpr uint32_t TMEM_COLS = 512, REGION = 256, cO = REGION - HS;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -349,9 +352,9 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             mbar_init(full_v + 8 * i, 1);
             mbar_init(s_main + 8 * i, 1);
             mbar_init(s_tail + 8 * i, 1);
-            mbar_init(p_ready + 8 * i, 128);
+            mbar_init(p_ready + 8 * i, SPLIT ? 256 : 128);
             mbar_init(o_ready + 8 * i, 1);
-            mbar_init(tmem_free + 8 * i, 128);
+            mbar_init(tmem_free + 8 * i, SPLIT ? 256 : 128);
             mbar_init(stage_free + 8 * i, 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -414,7 +417,9 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                             const uint32_t region = tmem_base + (uint32_t)g * REGION;
                             const uint64_t dv = make_desc(base + st * STAGE + 4 * TILE_BYTES, TILE_BYTES, 1024);
                             if (elect_one()) {
-                                for (int k16 = 0; k16 < NK / 16; ++k16) umma_bf16_ts(region + cO, region + k16 * 8, dv + 128 * k16, idesc_o, k16 > 0);
+                                // (SPLIT: the probabilities of keys >= 128 were packed in place over THEIR OWN scores, from column 128 on)
+                                for (int k16 = 0; k16 < NK / 16; ++k16)
+                                    umma_bf16_ts(region + cO, region + (SPLIT && k16 >= 8 ? 128 + (k16 - 8) * 8 : k16 * 8), dv + 128 * k16, idesc_o, k16 > 0);
                                 umma_commit(o_ready + 8 * g);
                             }
                             __syncwarp();
@@ -458,6 +463,188 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                     }
                 }
             }
+        }
+    } else if (SPLIT) {
+        // ================================ softmax groups, two threads per query row ================================
+        // With one thread per row a group is one warp per scheduler, and its pass over the scores is a chain of dependent MUFU /
+        // FMA / convert instructions (810 cycles per 32-column chunk, measured).  Here a row's columns are split between two
+        // threads of the same TMEM lane quarter: half 0 takes keys [0, 128), half 1 keys [128, NK); each packs its probabilities
+        // in place over its own (already read) scores — half 1 from column 128 on, which the P.V MMAs are told about.  The two
+        // halves agree on the exponent reference before they exponentiate (maximum of their first chunks, through shared
+        // memory) and add their row sums afterwards; a half that had to move its reference later rescales to the common one.
+        const int gi = warp - 2;
+        const int g = gi >> 3, half = (gi >> 2) & 1;
+        const int r = (warp & 3) * 32 + lane;  // TMEM lane = query row within the tile
+        const int q = g * TILE + r;
+        const bool warp_live = g * TILE + (warp & 3) * 32 < T;
+        const bool store_leader = (gi & 7) == 0 && lane == 0;
+        const uint32_t lane_addr = tmem_base + (uint32_t)g * REGION + ((uint32_t)((warp & 3) * 32) << 16);
+        const int nchunks = (NK + 31) >> 5;
+        const int ch_lo = half ? 4 : 0, ch_hi = half ? nchunks : 4;  // (NK > 128 here: half 1 has at least one chunk)
+        const float scale = 1.0f / sqrtf((float)HS);
+        const float sl2 = kLog2e * scale;
+        float* mine = xch + ((g * 2 + half) * TILE + r) * 3;
+        const float* partner = xch + ((g * 2 + (half ^ 1)) * TILE + r) * 3;
+        int pending_stage = -1;  // leader: stage whose O store still has to be confirmed read
+        for (int G = 0; G < nheads; ++G) {
+            const int bh = (int)blockIdx.x + G * (int)gridDim.x, b = bh / NH, h = bh - b * NH;
+            const int st = G & 1;
+            const uint32_t par = (uint32_t)(G & 1);
+            const uint32_t sO = base + st * STAGE + g * TILE_BYTES;  // the dead Q_g tile of this stage
+            TR(41, G);
+            mbar_wait(s_main + 8 * g, par);
+            tc_fence_after();
+            TR(42, G);
+            if (store_leader && pending_stage >= 0) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive_cnt(stage_free + 8 * pending_stage);
+                pending_stage = -1;
+            }
+            float m_ref = 0.f, sum = 0.f;
+            bool tail_ready = false;
+            uint32_t v[32];
+            auto load_chunk = [&](int ch) {
+                if (!tail_ready && ch * 32 + 32 > kMainCols) {  // the columns from kMainCols on arrive with the second piece of the score MMA
+                    mbar_wait(s_tail + 8 * g, par);
+                    tc_fence_after();
+                    tail_ready = true;
+                }
+                tmem_ld32(lane_addr + ch * 32, v);
+            };
+            auto chunk_max = [&](int ch) {
+                const int k0 = ch * 32;
+                if (k0 + 32 <= T) {
+                    float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+                    for (int c = 4; c < 32; c += 4) {
+                        m0 = fmaxf(m0, fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 1])));
+                        m1 = fmaxf(m1, fmaxf(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
+                    }
+                    return fmaxf(m0, m1);
+                }
+                float cm = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (k0 + c < T) cm = fmaxf(cm, __uint_as_float(v[c]));
+                return cm;
+            };
+            auto pcol = [&](int ch) { return half ? 128 + (ch - 4) * 16 : ch * 16; };  // where chunk ch's packed probabilities go
+            // ---- the common exponent reference: the larger of the two halves' first-chunk maxima, rounded up ----
+            float cm2 = -INFINITY;
+            if (warp_live) {
+                load_chunk(ch_lo);
+                cm2 = chunk_max(ch_lo) * sl2;
+            }
+            mine[0] = cm2;
+            named_bar_sync(1 + g, 256);
+            if (warp_live) {
+                m_ref = ceilf(fmaxf(cm2, partner[0]));
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    if (ch != ch_lo) load_chunk(ch);
+                    const int k0 = ch * 32;
+                    const bool full = k0 + 32 <= T;
+                    if (ch != ch_lo) {
+                        const float c2 = chunk_max(ch) * sl2;
+                        if (__any_sync(0xffffffffu, c2 > m_ref + kTau)) {
+                            // rare: move this half's reference up and rescale what it has written (the other half follows after the pass)
+                            const float new_ref = c2 > m_ref + kTau ? ceilf(c2) : m_ref;
+                            const float f = ex2(m_ref - new_ref);  // 2^(integer <= 0): exact
+                            tmem_st_wait();
+                            for (int blk = ch_lo; blk < ch; ++blk) {
+                                uint32_t pk[16];
+                                tmem_ld16(lane_addr + pcol(blk), pk);
+#pragma unroll
+                                for (int c = 0; c < 16; ++c)
+                                    pk[c] = pack_bf16(__uint_as_float(pk[c] << 16) * f, __uint_as_float(pk[c] & 0xFFFF0000u) * f);
+                                tmem_st16(lane_addr + pcol(blk), pk);
+                            }
+                            sum *= f;
+                            m_ref = new_ref;
+                        }
+                    }
+                    uint32_t pk[16];
+                    if (full) {
+                        const float2 sl22 = splat2(sl2), nref2 = splat2(-m_ref);
+                        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {  // one packed FMA per pair of scores
+                            const float2 a = fma2(make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1])), sl22, nref2);
+                            const float p0 = ex2(a.x), p1 = ex2(a.y);
+                            s0 += p0;
+                            s1 += p1;
+                            pk[c] = pack_bf16(p0, p1);
+                        }
+                        sum += s0 + s1;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const int k = k0 + 2 * c;
+                            const float p0 = k < T ? ex2(__uint_as_float(v[2 * c]) * sl2 - m_ref) : 0.f;
+                            const float p1 = k + 1 < T ? ex2(__uint_as_float(v[2 * c + 1]) * sl2 - m_ref) : 0.f;
+                            sum += p0 + p1;
+                            pk[c] = pack_bf16(p0, p1);
+                        }
+                    }
+                    tmem_st16(lane_addr + pcol(ch), pk);  // in place: these columns held scores this thread has already read
+                }
+                tmem_st_wait();
+            }
+            if (!tail_ready) mbar_wait(s_tail + 8 * g, par);  // (keeps the barrier's phase in step when no column needed it)
+            // ---- the two halves of a row meet: common reference, total sum ----
+            mine[1] = m_ref;
+            mine[2] = sum;
+            named_bar_sync(1 + g, 256);
+            float total = 1.f, m_all = m_ref;
+            if (warp_live) {
+                const float pm = partner[1], ps = partner[2];
+                m_all = fmaxf(m_ref, pm);
+                if (__any_sync(0xffffffffu, m_ref < m_all)) {  // rare: the other half moved its reference
+                    const float f = ex2(m_ref - m_all);
+                    for (int blk = ch_lo; blk < ch_hi; ++blk) {
+                        uint32_t pk[16];
+                        tmem_ld16(lane_addr + pcol(blk), pk);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            pk[c] = pack_bf16(__uint_as_float(pk[c] << 16) * f, __uint_as_float(pk[c] & 0xFFFF0000u) * f);
+                        tmem_st16(lane_addr + pcol(blk), pk);
+                    }
+                    tmem_st_wait();
+                    sum *= f;
+                }
+                total = sum + ps * ex2(pm - m_all);
+            }
+            tc_fence_before();
+            mbar_arrive_cnt(p_ready + 8 * g);
+            TR(43, G);
+            mbar_wait(o_ready + 8 * g, par);
+            tc_fence_after();
+            TR(44, G);
+            if (warp_live) {
+                const float inv = 1.0f / total;
+                uint32_t o[32];
+                tmem_ld32(lane_addr + cO + half * 32, o);  // each half takes 32 of the 64 output columns
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8)
+                    st_shared_v4(sw128(sO, r, half * 4 + g8), pack_bf16(__uint_as_float(o[g8 * 8]) * inv, __uint_as_float(o[g8 * 8 + 1]) * inv),
+                                 pack_bf16(__uint_as_float(o[g8 * 8 + 2]) * inv, __uint_as_float(o[g8 * 8 + 3]) * inv),
+                                 pack_bf16(__uint_as_float(o[g8 * 8 + 4]) * inv, __uint_as_float(o[g8 * 8 + 5]) * inv),
+                                 pack_bf16(__uint_as_float(o[g8 * 8 + 6]) * inv, __uint_as_float(o[g8 * 8 + 7]) * inv));
+                if (half == 0 && q < T) lse[(long)bh * T + q] = (m_all + __log2f(total)) * (1.0f / kLog2e);
+            }
+            tc_fence_before();
+            mbar_arrive_cnt(tmem_free + 8 * g);  // S_g of the next head may overwrite this region
+            TR(45, G);
+            fence_proxy_async();
+            named_bar_sync(1 + g, 256);
+            TR(46, G);
+            if (store_leader) {
+                tma_store_3d(&tm_out, sO, h * HS, g * TILE, b);  // rows >= T are clipped by the tensor map
+                pending_stage = st;
+            }
+        }
+        if (store_leader) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the last stores are complete before shared memory is retired
+            if (pending_stage >= 0) mbar_arrive_cnt(stage_free + 8 * pending_stage);
         }
     } else {
         // ================================ softmax groups ================================
@@ -1714,14 +1901,17 @@ int op_attention_forward_tc(vitrs_ctx* ctx, bf16* out, float* lse, const bf16* q
         return VITRS_OK;
     }
     if (NT == 2 && !causal && !ctx->env_attn_fwd_legacy) {  // VITRS_ATTN_FWD_LEGACY (A/B aid): one CTA per query tile
-        const size_t smem = (size_t)12 * TILE_BYTES + 128 + 1024;
+        const size_t smem = (size_t)12 * TILE_BYTES + 256 + 2 * 2 * TILE * 3 * sizeof(float) + 1024;
         const int heads = b * nh, grid = heads < ctx->sm_count ? heads : ctx->sm_count;
         if (ctx->env_attn_fwd_nostagger) {
-            VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_fwd_persist_kernel<false>, smem));
-            attn_fwd_persist_kernel<false><<<grid, kFwdThreads, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, NK, heads);
+            VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_fwd_persist_kernel<false, false>, smem));
+            attn_fwd_persist_kernel<false, false><<<grid, kFwdThreads, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, NK, heads);
+        } else if (ctx->env_attn_fwd_nosplit) {  // VITRS_ATTN_FWD_NOSPLIT (A/B aid): one thread per query row
+            VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_fwd_persist_kernel<true, false>, smem));
+            attn_fwd_persist_kernel<true, false><<<grid, kFwdThreads, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, NK, heads);
         } else {
-            VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_fwd_persist_kernel<true>, smem));
-            attn_fwd_persist_kernel<true><<<grid, kFwdThreads, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, NK, heads);
+            VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_fwd_persist_kernel<true, true>, smem));
+            attn_fwd_persist_kernel<true, true><<<grid, kFwdSplitThreads, smem, ctx->stream>>>(tm, tm_out, lse, t, c, nh, NK, heads);
         }
         VITRS_LAUNCHED(ctx);
         return VITRS_OK;
