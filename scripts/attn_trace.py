@@ -35,7 +35,8 @@ names = {1: "head", 2: "wait s_full", 3: "got s_full+ds_free", 4: "P/dS done", 5
          8: "wait dq_full", 9: "got dq_full", 10: "head end", 20: "I wait p_full", 21: "I got p_full", 22: "I wait load0", 23: "I got load0",
          24: "I issued", 30: "L wait kv0", 31: "L got kv0", 32: "L got q0", 33: "L wait kv1", 34: "L got kv1",
          41: "wait s_main", 42: "got s_main", 43: "P done", 44: "got O", 45: "O staged", 46: "O stored", 50: "I PV g0", 51: "I PV g1",
-         52: "I main g0", 53: "I main g1", 54: "I tail g0", 55: "I tail g1"}
+         52: "I main g0", 53: "I main g1", 54: "I tail g0", 55: "I tail g1",
+         60: "first chunk loaded", 61: "reference agreed", 62: "chunk done", 63: "P stores done", 64: "halves met"}
 print(f"{n.value} stamps, span {ev[-1][0] - t0} cycles, heads per CTA = {b * nh / 148:.1f}")
 # print the full timeline of a steady-state window: from the 3rd 'head'(1)/(41) event of the first SIMT warp
 lo = int(os.environ.get("FROM", 0)); hi = int(os.environ.get("TO", 60000))

@@ -33,7 +33,7 @@
 // hand-over points so the critical path of the persistent kernels can be read off a timeline.  Compiled out otherwise.
 #ifdef VITRS_ATTN_TRACE
 // per-warp rows of 2048 stamps, written with plain stores (an atomic cursor would cost the stamping warp a round trip to L2)
-__device__ unsigned long long g_attn_trace[16 * 2048];
+__device__ unsigned long long g_attn_trace[20 * 2048];  // one row of stamps per warp (the widest kernel has 18)
 #define TR_DECL unsigned int tr_i__ = 0;
 #define TR(ev, a)                                                                                                              \
     do {                                                                                                                       \
@@ -43,11 +43,11 @@ __device__ unsigned long long g_attn_trace[16 * 2048];
                                                                   ((unsigned long long)(ev) << 8) | (unsigned long long)((a) & 255); \
     } while (0)
 extern "C" int vitrs_debug_trace_read(unsigned long long* out, unsigned int* n) {
-    static unsigned long long host[16 * 2048];
+    static unsigned long long host[20 * 2048];
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
     cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(host));
     unsigned int cnt = 0;
-    for (int i = 0; i < 16 * 2048; ++i)
+    for (int i = 0; i < 20 * 2048; ++i)
         if (host[i]) { if (out) out[cnt] = host[i]; ++cnt; }
     memset(host, 0, sizeof(host));
     cudaMemcpyToSymbol(g_attn_trace, host, sizeof(host));
@@ -306,6 +306,10 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 // the arithmetic and only keep the barriers moving.  TMEM: two 256-column regions {S [0,NK) -> P [0,NK/2); O [192,256)}.
 constexpr int kMainCols = 192;  // score columns that do not overlap the O accumulator at [192, 256)
 constexpr float kTau = 12.f;  // probabilities may exceed 1 by up to 2^kTau before the exponent reference is moved
+constexpr float kPBig = 1.8446744e19f;  // 2^64: SPLIT moves a row's exponent reference only when a chunk of probabilities sums past this
+// SPLIT: first score column of a row's second thread — half of NK rounded up to a multiple of 16 (the P.V MMAs consume 16 keys each).
+// For 128 < T <= 256 both parts are at least 32 columns wide and each part's first 32 columns lie below T.
+__host__ __device__ __forceinline__ int fwd_split_point(int NK) { return ((NK >> 1) + 15) & ~15; }
 constexpr int kFwdThreads = 320;       // warp 0 loader, warp 1 issuer / TMEM owner, warps 2-5 group 0, warps 6-9 group 1
 constexpr int kFwdSplitThreads = 576;  // SPLIT: two threads per query row — warps 2-9 group 0, warps 10-17 group 1; within a group the
                                        // first four warps take keys [0, 128), the other four keys [128, T)
@@ -417,9 +421,10 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                             const uint32_t region = tmem_base + (uint32_t)g * REGION;
                             const uint64_t dv = make_desc(base + st * STAGE + 4 * TILE_BYTES, TILE_BYTES, 1024);
                             if (elect_one()) {
-                                // (SPLIT: the probabilities of keys >= 128 were packed in place over THEIR OWN scores, from column 128 on)
+                                // (SPLIT: the probabilities of keys >= SP were packed in place over THEIR OWN scores, from column SP on)
+                                const int sp16 = fwd_split_point(NK) / 16;
                                 for (int k16 = 0; k16 < NK / 16; ++k16)
-                                    umma_bf16_ts(region + cO, region + (SPLIT && k16 >= 8 ? 128 + (k16 - 8) * 8 : k16 * 8), dv + 128 * k16, idesc_o, k16 > 0);
+                                    umma_bf16_ts(region + cO, region + (SPLIT && k16 >= sp16 ? sp16 * 16 + (k16 - sp16) * 8 : k16 * 8), dv + 128 * k16, idesc_o, k16 > 0);
                                 umma_commit(o_ready + 8 * g);
                             }
                             __syncwarp();
@@ -468,10 +473,13 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         // ================================ softmax groups, two threads per query row ================================
         // With one thread per row a group is one warp per scheduler, and its pass over the scores is a chain of dependent MUFU /
         // FMA / convert instructions (810 cycles per 32-column chunk, measured).  Here a row's columns are split between two
-        // threads of the same TMEM lane quarter: half 0 takes keys [0, 128), half 1 keys [128, NK); each packs its probabilities
-        // in place over its own (already read) scores — half 1 from column 128 on, which the P.V MMAs are told about.  The two
-        // halves agree on the exponent reference before they exponentiate (maximum of their first chunks, through shared
-        // memory) and add their row sums afterwards; a half that had to move its reference later rescales to the common one.
+        // threads of the same TMEM lane quarter at SP = NK/2 rounded up to 16 (T = 197: keys [0, 112) | [112, 208)); each packs its
+        // probabilities in place over its own (already read) scores — half 1 from column SP on, which the P.V MMAs are told about.
+        // The two halves agree on the exponent reference before they exponentiate (maximum of their first chunks, through shared
+        // memory).  After that NO maximum is taken: a chunk goes fma -> ex2 -> sum -> pack with the next chunk's tensor-memory
+        // load in flight, and only a chunk whose probabilities sum past 2^64 (a key 44 nats above the first 64: never, in
+        // practice) takes the slow path that moves the reference and rescales what was written by an exact power of two.
+        // bf16 and fp32 share their exponent range, so P <= 2^64 is as exact as P <= 1; the result is the softmax itself.
         const int gi = warp - 2;
         const int g = gi >> 3, half = (gi >> 2) & 1;
         const int r = (warp & 3) * 32 + lane;  // TMEM lane = query row within the tile
@@ -479,8 +487,8 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         const bool warp_live = g * TILE + (warp & 3) * 32 < T;
         const bool store_leader = (gi & 7) == 0 && lane == 0;
         const uint32_t lane_addr = tmem_base + (uint32_t)g * REGION + ((uint32_t)((warp & 3) * 32) << 16);
-        const int nchunks = (NK + 31) >> 5;
-        const int ch_lo = half ? 4 : 0, ch_hi = half ? nchunks : 4;  // (NK > 128 here: half 1 has at least one chunk)
+        const int SP = fwd_split_point(NK);
+        const int c_lo = half ? SP : 0, c_hi = half ? NK : SP;  // this thread's score columns (both extents are multiples of 16, >= 32)
         const float scale = 1.0f / sqrtf((float)HS);
         const float sl2 = kLog2e * scale;
         float* mine = xch + ((g * 2 + half) * TILE + r) * 3;
@@ -503,110 +511,136 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             float m_ref = 0.f, sum = 0.f;
             bool tail_ready = false;
             uint32_t v[32];
-            auto load_chunk = [&](int ch) {
-                if (!tail_ready && ch * 32 + 32 > kMainCols) {  // the columns from kMainCols on arrive with the second piece of the score MMA
+            auto pcol = [&](int col) { return c_lo + ((col - c_lo) >> 1); };  // where the packed probabilities of score column `col` go
+            auto issue_load = [&](int col) {  // (no wait) the chunk at `col`: 32 columns, or the 16 that are left
+                const int w = c_hi - col < 32 ? 16 : 32;
+                if (!tail_ready && col + w > kMainCols) {  // the columns from kMainCols on arrive with the second piece of the score MMA
                     mbar_wait(s_tail + 8 * g, par);
                     tc_fence_after();
                     tail_ready = true;
                 }
-                tmem_ld32(lane_addr + ch * 32, v);
+                if (w == 32) tmem_ld32_issue(lane_addr + col, v);
+                else tmem_ld16_issue(lane_addr + col, v);
             };
-            auto chunk_max = [&](int ch) {
-                const int k0 = ch * 32;
-                if (k0 + 32 <= T) {
-                    float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+            // one chunk of W score columns, already in v: exponentiate against m_ref, pack, store in place; the next chunk's load is
+            // issued as soon as the scores have gone through the FMA (v is dead from there on)
+            auto step = [&](auto Wc, int col) {
+                constexpr int W = decltype(Wc)::value;
+                const bool has_next = col + W < c_hi;
+                const bool full = col + W <= T;
+                float2 a[W / 2];
+                uint32_t pk[16];
+                float csum;
+                auto scale_scores = [&]() {
+                    const float2 sl22 = splat2(sl2), nref2 = splat2(-m_ref);
 #pragma unroll
-                    for (int c = 4; c < 32; c += 4) {
-                        m0 = fmaxf(m0, fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 1])));
-                        m1 = fmaxf(m1, fmaxf(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
-                    }
-                    return fmaxf(m0, m1);
-                }
-                float cm = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    if (k0 + c < T) cm = fmaxf(cm, __uint_as_float(v[c]));
-                return cm;
-            };
-            auto pcol = [&](int ch) { return half ? 128 + (ch - 4) * 16 : ch * 16; };  // where chunk ch's packed probabilities go
-            // ---- the common exponent reference: the larger of the two halves' first-chunk maxima, rounded up ----
-            float cm2 = -INFINITY;
-            if (warp_live) {
-                load_chunk(ch_lo);
-                cm2 = chunk_max(ch_lo) * sl2;
-            }
-            mine[0] = cm2;
-            named_bar_sync(1 + g, 256);
-            if (warp_live) {
-                m_ref = ceilf(fmaxf(cm2, partner[0]));
-                for (int ch = ch_lo; ch < ch_hi; ++ch) {
-                    if (ch != ch_lo) load_chunk(ch);
-                    const int k0 = ch * 32;
-                    const bool full = k0 + 32 <= T;
-                    if (ch != ch_lo) {
-                        const float c2 = chunk_max(ch) * sl2;
-                        if (__any_sync(0xffffffffu, c2 > m_ref + kTau)) {
-                            // rare: move this half's reference up and rescale what it has written (the other half follows after the pass)
-                            const float new_ref = c2 > m_ref + kTau ? ceilf(c2) : m_ref;
-                            const float f = ex2(m_ref - new_ref);  // 2^(integer <= 0): exact
-                            tmem_st_wait();
-                            for (int blk = ch_lo; blk < ch; ++blk) {
-                                uint32_t pk[16];
-                                tmem_ld16(lane_addr + pcol(blk), pk);
-#pragma unroll
-                                for (int c = 0; c < 16; ++c)
-                                    pk[c] = pack_bf16(__uint_as_float(pk[c] << 16) * f, __uint_as_float(pk[c] & 0xFFFF0000u) * f);
-                                tmem_st16(lane_addr + pcol(blk), pk);
-                            }
-                            sum *= f;
-                            m_ref = new_ref;
-                        }
-                    }
-                    uint32_t pk[16];
+                    for (int c = 0; c < W / 2; ++c) a[c] = fma2(make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1])), sl22, nref2);
+                };
+                auto exponentiate = [&]() {
+                    float s0 = 0.f, s1 = 0.f;
                     if (full) {
-                        const float2 sl22 = splat2(sl2), nref2 = splat2(-m_ref);
-                        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {  // one packed FMA per pair of scores
-                            const float2 a = fma2(make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1])), sl22, nref2);
-                            const float p0 = ex2(a.x), p1 = ex2(a.y);
+                        for (int c = 0; c < W / 2; ++c) {
+                            const float p0 = ex2(a[c].x), p1 = ex2(a[c].y);
                             s0 += p0;
                             s1 += p1;
                             pk[c] = pack_bf16(p0, p1);
                         }
-                        sum += s0 + s1;
-                    } else {
+                    } else {  // (a branch of its own, warp-uniform: only the chunk that contains key T pays for the masks)
+                        const int live = T - col;
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const int k = k0 + 2 * c;
-                            const float p0 = k < T ? ex2(__uint_as_float(v[2 * c]) * sl2 - m_ref) : 0.f;
-                            const float p1 = k + 1 < T ? ex2(__uint_as_float(v[2 * c + 1]) * sl2 - m_ref) : 0.f;
-                            sum += p0 + p1;
+                        for (int c = 0; c < W / 2; ++c) {
+                            const float p0 = 2 * c < live ? ex2(a[c].x) : 0.f, p1 = 2 * c + 1 < live ? ex2(a[c].y) : 0.f;
+                            s0 += p0;
+                            s1 += p1;
                             pk[c] = pack_bf16(p0, p1);
                         }
                     }
-                    tmem_st16(lane_addr + pcol(ch), pk);  // in place: these columns held scores this thread has already read
+                    csum = s0 + s1;
+                };
+                scale_scores();
+                if (has_next) issue_load(col + W);
+                exponentiate();
+                if (__any_sync(0xffffffffu, !(csum < kPBig))) {
+                    // never in practice: a probability of this chunk left the comfortable range.  Its scores are still intact in
+                    // tensor memory (the chunk's probabilities have not been stored yet): read them again, move this row's
+                    // reference to their maximum and rescale what the thread has written so far.
+                    if (has_next) tmem_ld_wait32(v);  // retire the load in flight: its registers are needed
+                    if (W == 32) tmem_ld32_issue(lane_addr + col, v);
+                    else tmem_ld16_issue(lane_addr + col, v);
+                    tmem_ld_wait32(v);
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int c = 0; c < W; ++c)
+                        if (full || col + c < T) cm = fmaxf(cm, __uint_as_float(v[c]));
+                    const float new_ref = !(csum < kPBig) ? ceilf(cm * sl2) : m_ref;
+                    const float f = ex2(m_ref - new_ref);  // 2^(integer <= 0): exact
+                    tmem_st_wait();
+                    for (int pc = pcol(c_lo); pc < pcol(col); pc += 16) {  // (every chunk before this one was 32 columns wide)
+                        uint32_t old[16];
+                        tmem_ld16(lane_addr + pc, old);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            old[c] = pack_bf16(__uint_as_float(old[c] << 16) * f, __uint_as_float(old[c] & 0xFFFF0000u) * f);
+                        tmem_st16(lane_addr + pc, old);
+                    }
+                    sum *= f;
+                    m_ref = new_ref;
+                    scale_scores();
+                    if (has_next) issue_load(col + W);
+                    exponentiate();
+                }
+                if (W == 32) tmem_st16(lane_addr + pcol(col), pk);  // in place: these columns held scores this thread has already read
+                else tmem_st8(lane_addr + pcol(col), pk);
+                sum += csum;
+                if (has_next) tmem_ld_wait32(v);
+            };
+            // ---- the common exponent reference: the larger of the two halves' first-chunk maxima, rounded up ----
+            float cm2 = -INFINITY;
+            if (warp_live) {
+                issue_load(c_lo);
+                tmem_ld_wait32(v);
+                TR(60, G);
+                float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+                for (int c = 4; c < 32; c += 4) {  // (the first chunk of either half lies below key 128 + 32 <= T... see fwd_split_point)
+                    m0 = fmaxf(m0, fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 1])));
+                    m1 = fmaxf(m1, fmaxf(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
+                }
+                cm2 = fmaxf(m0, m1) * sl2;
+            }
+            mine[0] = cm2;
+            named_bar_sync(1 + g, 256);
+            TR(61, G);
+            if (warp_live) {
+                m_ref = ceilf(fmaxf(cm2, partner[0]));
+                for (int col = c_lo; col < c_hi; col += 32) {
+                    if (c_hi - col >= 32) step(std::integral_constant<int, 32>{}, col);
+                    else step(std::integral_constant<int, 16>{}, col);
+                    TR(62, col >> 4);
                 }
                 tmem_st_wait();
+                TR(63, G);
             }
             if (!tail_ready) mbar_wait(s_tail + 8 * g, par);  // (keeps the barrier's phase in step when no column needed it)
             // ---- the two halves of a row meet: common reference, total sum ----
             mine[1] = m_ref;
             mine[2] = sum;
             named_bar_sync(1 + g, 256);
+            TR(64, G);
             float total = 1.f, m_all = m_ref;
             if (warp_live) {
                 const float pm = partner[1], ps = partner[2];
                 m_all = fmaxf(m_ref, pm);
-                if (__any_sync(0xffffffffu, m_ref < m_all)) {  // rare: the other half moved its reference
+                if (__any_sync(0xffffffffu, m_ref < m_all)) {  // never in practice: the other half moved its reference
                     const float f = ex2(m_ref - m_all);
-                    for (int blk = ch_lo; blk < ch_hi; ++blk) {
-                        uint32_t pk[16];
-                        tmem_ld16(lane_addr + pcol(blk), pk);
+                    for (int pc = pcol(c_lo); pc < pcol(c_hi); pc += 8) {
+                        uint32_t old[16];
+                        tmem_ld16(lane_addr + pc, old);  // (reads 8 columns more than it rewrites)
 #pragma unroll
-                        for (int c = 0; c < 16; ++c)
-                            pk[c] = pack_bf16(__uint_as_float(pk[c] << 16) * f, __uint_as_float(pk[c] & 0xFFFF0000u) * f);
-                        tmem_st16(lane_addr + pcol(blk), pk);
+                        for (int c = 0; c < 8; ++c)
+                            old[c] = pack_bf16(__uint_as_float(old[c] << 16) * f, __uint_as_float(old[c] & 0xFFFF0000u) * f);
+                        tmem_st8(lane_addr + pc, old);
                     }
                     tmem_st_wait();
                     sum *= f;
@@ -1418,7 +1452,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 
 // =====================================================================================================
 // Streaming kernels: any sequence length (ViT-B/8: T = 785), two CTAs per SM, every probability operand in
-// tensor memory.  Forward streams 128-key K/V tiles with an online softmax.  Backward is split in two
+// tensor memory.  Forward streams 128-key K/V tiles with a single-pass softmax.  Backward is split in two
 // kernels so that nothing is reduced through global memory and each CTA needs only 256 TMEM columns:
 //   dKV: one CTA per (batch, head, 128-key tile), keys on TMEM lanes, streams 64-query tiles of Q and dO;
 //   dQ : one CTA per (batch, head, 128-query tile), queries on TMEM lanes, streams 64-key tiles of K and V.
@@ -1473,7 +1507,14 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     const int kend = causal ? min(T, q + 1) : T;
     const float scale = 1.0f / sqrtf((float)HS);
     const float sl2 = kLog2e * scale;
-    float m_run = -INFINITY, l_run = 0.f;
+    // ONE pass over each score tile: tensor-memory reads (64 B / clock / SM) are what this kernel is made of, so neither a maximum
+    // pass nor a per-tile rescale of O is taken.  The exponent reference m_ref (an integer, log2 domain) is the maximum of the
+    // row's first 32 keys rounded up; every probability is 2^(s - m_ref), P and O simply grow with it (bf16 and fp32 share
+    // their exponent range), and only a chunk whose probabilities sum past 2^64 moves the reference: what the row has
+    // written so far — this tile's P, the running sum and the O accumulator — is then rescaled by an exact power of two.
+    float m_ref = 0.f, l_run = 0.f;
+    // keys below this bound are unmasked for every row of the warp: chunks entirely below it run without per-element masks
+    const int kfull = causal ? min(T, qt * TILE + warp * 32 + 1) : T;
 
     for (int j = 0; j < NJ; ++j) {
         const int buf = j & 1;
@@ -1499,54 +1540,105 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
             mbar_expect_tx(bar_k + 8 * buf, TILE_BYTES);
             tma_load_3d(sK + buf * TILE_BYTES, &tm_qkv, bar_k + 8 * buf, C + h * HS, (j + 2) * TILE, b);
         }
-        const int nchunks = (nk16 + 31) >> 5;
-        float tmax = -INFINITY;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            uint32_t v[32];
-            tmem_ld32(lane_addr + ch * 32, v);
+        const int nchunks = (nk16 + 31) >> 5;  // (a last chunk of 16 columns is read as 32: the stale columns are masked, they lie beyond T)
+        bool o_settled = j == 0;  // P_{j-1} V_{j-1} has landed in O (known only once bar_o has been waited for)
+        uint32_t v[32];
+        tmem_ld32_issue(lane_addr, v);
+        tmem_ld_wait32(v);
+        if (j == 0) {
+            float cm = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 32; ++c)
-                if (k0 + ch * 32 + c < kend) tmax = fmaxf(tmax, __uint_as_float(v[c]));
+                if (c < kend) cm = fmaxf(cm, __uint_as_float(v[c]));  // (key 0 is never masked)
+            m_ref = ceilf(cm * sl2);
         }
-        const float m_new = fmaxf(m_run, tmax);
-        const float mns = m_new * sl2;
-        float rsum = 0.f;
         for (int ch = 0; ch < nchunks; ++ch) {
-            uint32_t v[32], pk[16];
-            tmem_ld32(lane_addr + ch * 32, v);
+            const int kc = k0 + ch * 32;
+            const bool full = kc + 32 <= kfull;  // warp-uniform
+            const bool has_next = ch + 1 < nchunks;
+            float2 a[16];
+            uint32_t pk[16];
+            float csum;
+            auto scale_scores = [&]() {
+                const float2 sl22 = splat2(sl2), nref2 = splat2(-m_ref);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const int k = k0 + ch * 32 + 2 * c;
-                const float p0 = k < kend ? ex2(__uint_as_float(v[2 * c]) * sl2 - mns) : 0.f;
-                const float p1 = k + 1 < kend ? ex2(__uint_as_float(v[2 * c + 1]) * sl2 - mns) : 0.f;
-                rsum += p0 + p1;
-                pk[c] = pack_bf16(p0, p1);
+                for (int c = 0; c < 16; ++c) a[c] = fma2(make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1])), sl22, nref2);
+            };
+            auto exponentiate = [&]() {
+                float s0 = 0.f, s1 = 0.f;
+                if (full) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float p0 = ex2(a[c].x), p1 = ex2(a[c].y);
+                        s0 += p0;
+                        s1 += p1;
+                        pk[c] = pack_bf16(p0, p1);
+                    }
+                } else {
+                    const int live = kend - kc;  // per thread (causal: the diagonal)
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float p0 = 2 * c < live ? ex2(a[c].x) : 0.f, p1 = 2 * c + 1 < live ? ex2(a[c].y) : 0.f;
+                        s0 += p0;
+                        s1 += p1;
+                        pk[c] = pack_bf16(p0, p1);
+                    }
+                }
+                csum = s0 + s1;
+            };
+            scale_scores();
+            if (has_next) tmem_ld32_issue(lane_addr + (ch + 1) * 32, v);  // v is dead: the next chunk's load overlaps the exponentials
+            exponentiate();
+            if (__any_sync(0xffffffffu, !(csum < kPBig))) {
+                // never in practice: move this row's reference to the chunk's maximum (its scores are still intact in tensor memory)
+                if (has_next) tmem_ld_wait32(v);
+                tmem_ld32_issue(lane_addr + ch * 32, v);
+                tmem_ld_wait32(v);
+                float cm = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (kc + c < kend) cm = fmaxf(cm, __uint_as_float(v[c]));
+                const float new_ref = !(csum < kPBig) ? ceilf(cm * sl2) : m_ref;
+                const float f = ex2(m_ref - new_ref);  // 2^(integer <= 0): exact
+                tmem_st_wait();
+                for (int blk = 0; blk < ch; ++blk) {  // this tile's probabilities written so far
+                    uint32_t old[16];
+                    tmem_ld16(lane_addr + blk * 16, old);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        old[c] = pack_bf16(__uint_as_float(old[c] << 16) * f, __uint_as_float(old[c] & 0xFFFF0000u) * f);
+                    tmem_st16(lane_addr + blk * 16, old);
+                }
+                if (j > 0) {  // the accumulator of the earlier tiles
+                    if (!o_settled) {
+                        mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
+                        tc_fence_after();
+                        o_settled = true;
+                    }
+                    for (int blk = 0; blk < HS / 16; ++blk) {
+                        uint32_t o16[16];
+                        tmem_ld16(lane_addr + cO + blk * 16, o16);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) o16[c] = __float_as_uint(__uint_as_float(o16[c]) * f);
+                        tmem_st16(lane_addr + cO + blk * 16, o16);
+                    }
+                }
+                l_run *= f;
+                m_ref = new_ref;
+                scale_scores();
+                if (has_next) tmem_ld32_issue(lane_addr + (ch + 1) * 32, v);
+                exponentiate();
             }
-            tmem_st16(lane_addr + ch * 16, pk);
+            tmem_st16(lane_addr + ch * 16, pk);  // in place: these columns held scores this thread has already read
+            l_run += csum;
+            if (has_next) tmem_ld_wait32(v);
         }
-        const float alpha = m_run == -INFINITY ? 0.f : ex2((m_run - m_new) * sl2);
-        l_run = l_run * alpha + rsum;
-        m_run = m_new;
         if (j > 0) {
-            mbar_wait(bar_o, (uint32_t)((j - 1) & 1));  // P_{j-1} V_{j-1} has landed in O
+            if (!o_settled) mbar_wait(bar_o, (uint32_t)((j - 1) & 1));  // P_{j-1} V_{j-1} has landed in O
             tc_fence_after();
             if (tid == 0 && j + 1 < NJ) {  // its V buffer is free again
                 mbar_expect_tx(bar_v + 8 * ((j + 1) & 1), TILE_BYTES);
                 tma_load_3d(sV + ((j + 1) & 1) * TILE_BYTES, &tm_qkv, bar_v + 8 * ((j + 1) & 1), 2 * C + h * HS, (j + 1) * TILE, b);
-            }
-            if (!__all_sync(0xffffffffu, alpha == 1.0f)) {  // rescale the accumulator to the new running max
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_addr + cO + half * 32, v);
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        uint32_t o16[16];
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) o16[c] = __float_as_uint(__uint_as_float(v[g * 16 + c]) * alpha);
-                        tmem_st16(lane_addr + cO + half * 32 + g * 16, o16);
-                    }
-                }
             }
         }
         tmem_st_wait();
@@ -1579,7 +1671,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
                          pack_bf16(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv),
                          pack_bf16(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv));
     }
-    if (q < T) lse[(long)bh * T + q] = m_run * scale + logf(l_run);
+    if (q < T) lse[(long)bh * T + q] = (m_ref + __log2f(l_run)) * (1.0f / kLog2e);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
