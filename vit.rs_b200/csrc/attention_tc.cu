@@ -1710,9 +1710,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(smem_u32((const void*)slot), TMEM_COLS);
-    for (int i = tid; i < T; i += 256) {
-        stat[i] = lse[(long)bh * T + i] * kLog2e;
-        stat[T + i] = dsum[(long)bh * T + i];
+    // row statistics of the whole head, negated and pre-scaled so that each is the addend of one FMA:
+    // P = exp2(S * sl2 + stat[q]), dS = P * (dP * scale + stat[TP + q])
+    const int TP = (T + SUB - 1) & ~(SUB - 1);
+    for (int i = tid; i < TP; i += 256) {
+        stat[i] = i < T ? -lse[(long)bh * T + i] * kLog2e : 0.f;
+        stat[TP + i] = i < T ? -dsum[(long)bh * T + i] * (1.0f / sqrtf((float)HS)) : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -1736,6 +1739,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const float scale = 1.0f / sqrtf((float)HS);
     const float sl2 = kLog2e * scale;
+    const int warp_key_max = jt * TILE + (warp & 3) * 32 + 31;  // last key of this warp's 32 TMEM lanes
+    const bool warp_keys_live = warp_key_max < T;
 
     for (int s = s0; s < NS; ++s) {
         const int it = s - s0, buf = it & 1;
@@ -1766,27 +1771,51 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
             tmem_ld32(tmem_base + lane_off + cST + half * 32, sv);
             tmem_ld32(tmem_base + lane_off + cDPT + half * 32, dpv);
         }
-        tc_fence_before();
-        __syncthreads();  // every S / dP column has been read: packing in place is safe
+        // packing in place needs no barrier: each thread overwrites only columns it has read itself (the second half of a row
+        // packs from column 32 on, which the dV / dK MMAs are told about)
         if (mine) {
             uint32_t pp[16], dd[16];
+            const int qbase = s * SUB + half * 32;  // first query of this thread's 32 columns
+            // warp-uniform: every key of the warp and every query of the chunk is live and (causal) on or below the diagonal
+            const bool fast = warp_keys_live && half * 32 + 32 <= nq && (!causal || warp_key_max <= qbase);
+            if (fast) {
+                // packed f32x2 arithmetic, statistics by 16-byte shared loads: ~5 instructions per element instead of ~25
+                const float2 sl22 = splat2(sl2), sc2 = splat2(scale);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                float pv[2], dv[2];
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    const float4 l0 = *reinterpret_cast<const float4*>(stat + qbase + g8 * 8), l1 = *reinterpret_cast<const float4*>(stat + qbase + g8 * 8 + 4);
+                    const float4 d0 = *reinterpret_cast<const float4*>(stat + TP + qbase + g8 * 8), d1 = *reinterpret_cast<const float4*>(stat + TP + qbase + g8 * 8 + 4);
+                    const float lq[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                    const float dq[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int qc = half * 32 + 2 * c + e;
-                    const int q = s * SUB + qc;
-                    const bool live = key < T && qc < nq && (!causal || key <= q);
-                    const float p = live ? ex2(__uint_as_float(sv[2 * c + e]) * sl2 - stat[min(q, T - 1)]) : 0.f;
-                    pv[e] = p;
-                    dv[e] = p * (__uint_as_float(dpv[2 * c + e]) - stat[T + min(q, T - 1)]) * scale;
+                    for (int c = 0; c < 8; c += 2) {
+                        const float2 a = fma2(make_float2(__uint_as_float(sv[g8 * 8 + c]), __uint_as_float(sv[g8 * 8 + c + 1])), sl22, make_float2(lq[c], lq[c + 1]));
+                        const float2 pr = make_float2(ex2(a.x), ex2(a.y));
+                        const float2 t = fma2(make_float2(__uint_as_float(dpv[g8 * 8 + c]), __uint_as_float(dpv[g8 * 8 + c + 1])), sc2, make_float2(dq[c], dq[c + 1]));
+                        const float2 d2 = mul2(pr, t);
+                        pp[g8 * 4 + (c >> 1)] = pack_bf16(pr.x, pr.y);
+                        dd[g8 * 4 + (c >> 1)] = pack_bf16(d2.x, d2.y);
+                    }
                 }
-                pp[c] = pack_bf16(pv[0], pv[1]);
-                dd[c] = pack_bf16(dv[0], dv[1]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float pv[2], dv[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int qc = half * 32 + 2 * c + e;
+                        const int q = s * SUB + qc;
+                        const bool live = key < T && qc < nq && (!causal || key <= q);
+                        const float p = live ? ex2(__uint_as_float(sv[2 * c + e]) * sl2 + stat[min(q, T - 1)]) : 0.f;
+                        pv[e] = p;
+                        dv[e] = p * (__uint_as_float(dpv[2 * c + e]) * scale + stat[TP + min(q, T - 1)]);
+                    }
+                    pp[c] = pack_bf16(pv[0], pv[1]);
+                    dd[c] = pack_bf16(dv[0], dv[1]);
+                }
             }
-            tmem_st16(tmem_base + lane_off + cST + half * 16, pp);
-            tmem_st16(tmem_base + lane_off + cDPT + half * 16, dd);
+            tmem_st16(tmem_base + lane_off + cST + half * 32, pp);
+            tmem_st16(tmem_base + lane_off + cDPT + half * 32, dd);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -1797,8 +1826,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
             if (elect_one()) {
                 for (int k16 = 0; k16 < nq16 / 16; ++k16) {
                     const uint32_t acc = (it > 0 || k16 > 0) ? 1u : 0u;
-                    umma_bf16_ts(tmem_base + cDV, tmem_base + cST + k16 * 8, make_desc(sdO + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc, acc);
-                    umma_bf16_ts(tmem_base + cDK, tmem_base + cDPT + k16 * 8, make_desc(sQ + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc, acc);
+                    const uint32_t acol = (uint32_t)((k16 >> 1) * 32 + (k16 & 1) * 8);  // queries [32, 64) were packed from column 32 on
+                    umma_bf16_ts(tmem_base + cDV, tmem_base + cST + acol, make_desc(sdO + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc, acc);
+                    umma_bf16_ts(tmem_base + cDK, tmem_base + cDPT + acol, make_desc(sQ + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc, acc);
                 }
                 if (s + 1 == NS) umma_commit(bar_acc);
             }
@@ -1879,6 +1909,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const float sl2 = kLog2e * scale;
     const float lse2 = q < T ? lse[(long)bh * T + q] * kLog2e : 0.f;
     const float dq_ = q < T ? dsum[(long)bh * T + q] : 0.f;
+    const int warp_q_min = qt * TILE + (warp & 3) * 32;  // first query of this warp's 32 TMEM lanes
+    const bool warp_q_live = warp_q_min + 31 < T;
 
     for (int s = 0; s < NS; ++s) {
         const int buf = s & 1;
@@ -1909,24 +1941,37 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             tmem_ld32(tmem_base + lane_off + cS + half * 32, sv);
             tmem_ld32(tmem_base + lane_off + cDP + half * 32, dpv);
         }
-        tc_fence_before();
-        __syncthreads();
+        // (no barrier: each thread packs dS over score columns it has read itself, the second half of a row from column 32 on)
         if (mine) {
             uint32_t dd[16];
+            // warp-uniform: every query of the warp and every key of the chunk is live and (causal) on or below the diagonal
+            const bool fast = warp_q_live && half * 32 + 32 <= nk && (!causal || s * SUB + half * 32 + 31 <= warp_q_min);
+            if (fast) {
+                const float2 sl22 = splat2(sl2), nl2 = splat2(-lse2), sc2 = splat2(scale), nd2 = splat2(-dq_ * scale);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                float dv[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int kc = half * 32 + 2 * c + e;
-                    const int key = s * SUB + kc;
-                    const bool live = q < T && kc < nk && (!causal || key <= q);
-                    const float p = live ? ex2(__uint_as_float(sv[2 * c + e]) * sl2 - lse2) : 0.f;
-                    dv[e] = p * (__uint_as_float(dpv[2 * c + e]) - dq_) * scale;
+                for (int c = 0; c < 16; ++c) {  // packed f32x2 arithmetic: P = exp2(S sl2 - lse2), dS = P (dP scale - D scale)
+                    const float2 a = fma2(make_float2(__uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1])), sl22, nl2);
+                    const float2 pr = make_float2(ex2(a.x), ex2(a.y));
+                    const float2 t = fma2(make_float2(__uint_as_float(dpv[2 * c]), __uint_as_float(dpv[2 * c + 1])), sc2, nd2);
+                    const float2 d2 = mul2(pr, t);
+                    dd[c] = pack_bf16(d2.x, d2.y);
                 }
-                dd[c] = pack_bf16(dv[0], dv[1]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float dv[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int kc = half * 32 + 2 * c + e;
+                        const int key = s * SUB + kc;
+                        const bool live = q < T && kc < nk && (!causal || key <= q);
+                        const float p = live ? ex2(__uint_as_float(sv[2 * c + e]) * sl2 - lse2) : 0.f;
+                        dv[e] = p * (__uint_as_float(dpv[2 * c + e]) - dq_) * scale;
+                    }
+                    dd[c] = pack_bf16(dv[0], dv[1]);
+                }
             }
-            tmem_st16(tmem_base + lane_off + cS + half * 16, dd);
+            tmem_st16(tmem_base + lane_off + cS + half * 32, dd);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -1935,9 +1980,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             tc_fence_after();
             const uint32_t idesc = make_idesc(TILE, HS, 0, 1);
             if (elect_one()) {
-                for (int k16 = 0; k16 < nk16 / 16; ++k16)  // dQ_i += dS K_s
-                    umma_bf16_ts(tmem_base + cDQ, tmem_base + cS + k16 * 8, make_desc(sK + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc,
-                                 (s > 0 || k16 > 0) ? 1u : 0u);
+                for (int k16 = 0; k16 < nk16 / 16; ++k16)  // dQ_i += dS K_s (keys [32, 64) were packed from column 32 on)
+                    umma_bf16_ts(tmem_base + cDQ, tmem_base + cS + (uint32_t)((k16 >> 1) * 32 + (k16 & 1) * 8),
+                                 make_desc(sK + buf * SUB_BYTES + k16 * 2048, SUB_BYTES, 1024), idesc, (s > 0 || k16 > 0) ? 1u : 0u);
                 if (s + 1 == NS) umma_commit(bar_acc);
             }
             __syncwarp();
@@ -2045,7 +2090,7 @@ int op_attention_backward_tc(vitrs_ctx* ctx, bf16* dqkv, const bf16* dout, const
         VITRS_TRY(encode_map3d(ctx, &tm_do128, dout, (uint64_t)c, t, b, TILE));
         VITRS_TRY(encode_map3d(ctx, &tm_do64, dout, (uint64_t)c, t, b, SUB));
         VITRS_TRY(encode_map3d(ctx, &tm_dqkv, dqkv, 3 * (uint64_t)c, t, b, TILE));
-        const size_t smem_kv = (size_t)2 * TILE_BYTES + 4 * SUB_BYTES + 64 + 2 * (size_t)t * 4 + 1024;
+        const size_t smem_kv = (size_t)2 * TILE_BYTES + 4 * SUB_BYTES + 64 + 2 * (size_t)((t + SUB - 1) & ~(SUB - 1)) * 4 + 1024;  // + lse, D of the head
         const size_t smem_q = (size_t)2 * TILE_BYTES + 4 * SUB_BYTES + 64 + 1024;
         VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_bwd_dkv_kernel, smem_kv));
         VITRS_TRY(vitrs_func_smem(ctx, (const void*)attn_bwd_dq_kernel, smem_q));
