@@ -299,14 +299,22 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 //   issuer (warp 1, one thread)  a polling state machine over the two query tiles: O_g = P_g V as soon as P_g is packed, with the
 //                                next head's S_g = Q_g K^T queued right behind it (in-order tensor pipe), except for the few
 //                                score columns that alias the O accumulator, which follow when the group has read O out;
-//   softmax group g (4 warps)    one thread per query row of tile g: max / exp2 / sum from TMEM, P packed to bf16 in place
-//                                (A operand of P.V), O scaled and staged through the dead Q_g tile, one TMA store.
-// Group 1 starts half a period late, so one group's exponentials (the MUFU pipe is the floor of this kernel: T^2 per head)
-// run under the other group's MMA / read-out phases.  Warps whose 32 rows are all beyond T (rows 224..255 at T = 197) skip
-// the arithmetic and only keep the barriers moving.  TMEM: two 256-column regions {S [0,NK) -> P [0,NK/2); O [192,256)}.
+//   softmax group g (8 warps)    two threads per query row of tile g (4 warps, one thread per row, in the NOSPLIT variant): one
+//                                pass over the scores in TMEM — exp2 / sum against a lazily moved exponent reference, P packed to
+//                                bf16 in place (A operand of P.V) — then O scaled and staged through the dead Q_g tile, one TMA store.
+// Group 1 starts half a period late, so one group's pass runs under the other group's MMA / read-out phases.  Warps whose 32
+// rows are all beyond T (rows 224..255 at T = 197) skip the arithmetic and only keep the barriers moving.
+// TMEM: two 256-column regions {S [0,NK) -> P [0,NK/2); O [192,256)}.
+// What bounds it (profiles/r2_attn_fwd_trace.txt, r2_softmax_chunk_rate.txt): tcgen05.ld moves 64 B / clock / SM, so reading the
+// scores (224 live rows x 208 columns x 4 B) and O takes 3.8 k cycles per head whatever the arithmetic costs — 14 softmax warps
+// each asking for a 4 KB chunk keep that port ~85 % busy while both groups are in their passes, which is why a 32-column chunk
+// takes ~1 050 cycles in the kernel against 610 for the same instruction mix without the loads.  The MUFU pipe (16 ex2 / clock /
+// SM: 3.3 k cycles per head) is the second floor; evaluating a share of the exponentials on the FMA pipe does not pay here
+// (7 issue slots per element against 3: scripts/exp_mufu_rate.cu).  The remaining time is each group's serial chain
+// S -> pass -> P.V -> O out, during which only the other group reads.
 constexpr int kMainCols = 192;  // score columns that do not overlap the O accumulator at [192, 256)
-constexpr float kTau = 12.f;  // probabilities may exceed 1 by up to 2^kTau before the exponent reference is moved
-constexpr float kPBig = 1.8446744e19f;  // 2^64: SPLIT moves a row's exponent reference only when a chunk of probabilities sums past this
+constexpr float kTau = 12.f;  // NOSPLIT: probabilities may exceed 1 by up to 2^kTau before the exponent reference is moved
+constexpr float kPBig = 1.8446744e19f;  // 2^64: SPLIT / streaming forward move a row's exponent reference only when a chunk of probabilities sums past this
 // SPLIT: first score column of a row's second thread — half of NK rounded up to a multiple of 16 (the P.V MMAs consume 16 keys each).
 // For 128 < T <= 256 both parts are at least 32 columns wide and each part's first 32 columns lie below T.
 __host__ __device__ __forceinline__ int fwd_split_point(int NK) { return ((NK >> 1) + 15) & ~15; }

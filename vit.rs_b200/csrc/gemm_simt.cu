@@ -14,10 +14,14 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BK = 16;
 
-template <typename T, bool FAST, bool EXACT>
+// TM x TM outputs per thread, 16 x 16 threads: [64 x 64] tiles (TM = 4), or [32 x 32] (TM = 2) when the larger tile would leave
+// most of the chip idle (the class head of the small models: 12 CTAs for ViT-Ti/16's dX).  The order of additions per output
+// (k ascending) does not depend on the tile: results are bit-identical.
+template <typename T, bool FAST, bool EXACT, int TM>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
+    constexpr int BM = 16 * TM, BN = 16 * TM;
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const T* __restrict__ A = reinterpret_cast<const T*>(g.A);
@@ -28,13 +32,13 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
     const int n0 = blockIdx.x * BN;
     const bool a_kfast = g.a_ks == 1, b_kfast = g.b_ks == 1;
     const Epilogue& e = g.epi;
-    float acc[4][4];
+    float acc[TM][TM];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const long m = m0 + ty * 4 + i;
-            const int n = n0 + tx * 4 + j;
+        for (int j = 0; j < TM; ++j) {
+            const long m = m0 + ty * TM + i;
+            const int n = n0 + tx * TM + j;
             float init = 0.f;
             if (m < g.M && n < g.N) {
                 if (e.kind == EPI_ACCUM_F32) init = reinterpret_cast<const float*>(e.out)[m * e.ldo + n];
@@ -47,7 +51,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
 
     for (int k0 = 0; k0 < g.K; k0 += BK) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TM; ++i) {
             const int e = tid + i * 256;
             // consecutive threads follow the operand's unit-stride index
             const int am = a_kfast ? e / BK : e % BM, ak = a_kfast ? e % BK : e / BM;
@@ -62,26 +66,26 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            float a[4], b[4];
+            float a[TM], b[TM];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+            for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+            for (int j = 0; j < TM; ++j) b[j] = Bs[k][tx * TM + j];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < TM; ++j)
                     acc[i][j] = EXACT ? __fadd_rn(acc[i][j], __fmul_rn(a[i], b[j])) : fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const long m = m0 + ty * 4 + i;
+    for (int i = 0; i < TM; ++i) {
+        const long m = m0 + ty * TM + i;
         if (m >= g.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
+        for (int j = 0; j < TM; ++j) {
+            const int n = n0 + tx * TM + j;
             if (n >= g.N) continue;
             if (e.kind == EPI_ACCUM_F32) {
                 reinterpret_cast<float*>(e.out)[m * e.ldo + n] = acc[i][j];  // the old value is already in acc
@@ -97,8 +101,13 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
 
 template <typename T, bool FAST, bool EXACT> int launch(vitrs_ctx* ctx, const GemmDesc& g) {
     if (g.M <= 0 || g.N <= 0) return VITRS_OK;
-    dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
-    gemm_simt_kernel<T, FAST, EXACT><<<grid, 256, 0, ctx->stream>>>(g);
+    if ((long)ceil_div(g.N, 64) * ceil_div(g.M, 64) >= ctx->sm_count) {
+        dim3 grid(ceil_div(g.N, 64), ceil_div(g.M, 64));
+        gemm_simt_kernel<T, FAST, EXACT, 4><<<grid, 256, 0, ctx->stream>>>(g);
+    } else {
+        dim3 grid(ceil_div(g.N, 32), ceil_div(g.M, 32));
+        gemm_simt_kernel<T, FAST, EXACT, 2><<<grid, 256, 0, ctx->stream>>>(g);
+    }
     VITRS_LAUNCHED(ctx);
     return VITRS_OK;
 }

@@ -229,12 +229,32 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
     if (KIND == EPI_PATCH) {
         const long m = (long)m_base + lane;
         const int tok = (int)(m % e.np);
+        if (n_base + 64 <= N && ((e.ldo | n_base) & 3) == 0 &&
+            ((reinterpret_cast<uintptr_t>(e.pos) | reinterpret_cast<uintptr_t>(e.cls) | reinterpret_cast<uintptr_t>(e.bias)) & 15) == 0) {
+            // this thread's 64 columns of its position row and of the bias (the class token for token 0, whose im2col row is
+            // zero) by 16-byte loads; same order of additions as the scalar form below: (acc + bias) + pos, cls + pos.
+            // (One scalar load per operand and element made this GEMM 9x slower than the same shape with a plain bias.)
+            const float4* prow = reinterpret_cast<const float4*>(e.pos + (long)tok * e.ldo + n_base);
+            const float4* brow = tok == 0 ? reinterpret_cast<const float4*>(e.cls + n_base)
+                                          : (e.bias ? reinterpret_cast<const float4*>(e.bias + n_base) : nullptr);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            const int n = n_base + j;
-            if (m < M && n < N) {
-                float v = tok == 0 ? __ldg(e.cls + n) : acc[j] + (e.bias ? __ldg(e.bias + n) : 0.f);
-                acc[j] = v + __ldg(e.pos + (long)tok * e.ldo + n);
+            for (int j4 = 0; j4 < 16; ++j4) {
+                if ((j4 & 3) == 0) asm volatile("" ::: "memory");  // at most 8 loads in flight: hoisting all 32 would spill
+                const float4 pz = __ldg(prow + j4);
+                const float4 bz = brow ? __ldg(brow + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc[j4 * 4 + 0] = ((tok == 0 ? 0.f : acc[j4 * 4 + 0]) + bz.x) + pz.x;
+                acc[j4 * 4 + 1] = ((tok == 0 ? 0.f : acc[j4 * 4 + 1]) + bz.y) + pz.y;
+                acc[j4 * 4 + 2] = ((tok == 0 ? 0.f : acc[j4 * 4 + 2]) + bz.z) + pz.z;
+                acc[j4 * 4 + 3] = ((tok == 0 ? 0.f : acc[j4 * 4 + 3]) + bz.w) + pz.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const int n = n_base + j;
+                if (m < M && n < N) {
+                    float v = tok == 0 ? __ldg(e.cls + n) : acc[j] + (e.bias ? __ldg(e.bias + n) : 0.f);
+                    acc[j] = v + __ldg(e.pos + (long)tok * e.ldo + n);
+                }
             }
         }
     }
@@ -277,7 +297,9 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const EpiMaps&
     }
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int CG>
+// PATCH: the instantiation that carries the patch-embedding epilogue (and only that one), so that its 16-byte table loads do not
+// weigh on the register allocation of the kernels the training step spends its time in
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool PATCH = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmAux, const TcParams p) {
@@ -610,14 +632,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int c = 1; c < kChunksPerWarp; ++c)
                         if (ch - chalf * kChunksPerWarp == c) b2 = bias2[c];
-                    switch (p.epi.kind) {  // warp-uniform branch to straight-line per-kind code
+                    if (PATCH) {
+                        epilogue_chunk<EPI_PATCH>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre);
+                    } else switch (p.epi.kind) {  // warp-uniform branch to straight-line per-kind code
                         case EPI_BIAS: epilogue_chunk<EPI_BIAS>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_BIAS_RESIDUAL: epilogue_chunk<EPI_BIAS_RESIDUAL>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_GELU_BWD: epilogue_chunk<EPI_GELU_BWD>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_BIAS_GELU_ONLY: epilogue_chunk<EPI_BIAS_GELU_ONLY>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         case EPI_ROWDOT: epilogue_chunk<EPI_ROWDOT>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
-                        case EPI_PATCH: epilogue_chunk<EPI_PATCH>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                         default: epilogue_chunk<EPI_NONE>(p.epi, maps, stage_smem, my_bar, bar_phase, taddr, m_base, nb, p.M, p.N, lane, b2, pre); break;
                     }
                 }
@@ -652,10 +675,10 @@ int encode_map(vitrs_ctx* ctx, CUtensorMap* map, const void* base, uint64_t inne
     return vitrs_tensor_map(ctx, map, 2, base, dims, strides, box);
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int CG>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool PATCH = false>
 int launch_tc(vitrs_ctx* ctx, const CUtensorMap* maps, const TcParams& p) {
     using L = SmemLayout<BN, STAGES, CG>;
-    auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, CG>;
+    auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, CG, PATCH>;
     VITRS_TRY(vitrs_func_smem(ctx, (const void*)kern, L::TOTAL));
     const int units = p.m_tiles * p.n_tiles * p.splits;
     const int slots = ctx->sm_count / CG;
@@ -681,6 +704,10 @@ int launch_tc(vitrs_ctx* ctx, const CUtensorMap* maps, const TcParams& p) {
 
 template <int BN, int STAGES, int CG>
 int launch_tc_major(vitrs_ctx* ctx, bool a_mn, bool b_mn, const CUtensorMap* maps, const TcParams& p) {
+    if (p.epi.kind == EPI_PATCH) {  // (patches and weights are both K-major: tc_eligible)
+        if (a_mn || b_mn) return VITRS_ERR_UNSUPPORTED;
+        return launch_tc<BN, STAGES, false, false, CG, true>(ctx, maps, p);
+    }
     if (!a_mn && !b_mn) return launch_tc<BN, STAGES, false, false, CG>(ctx, maps, p);
     if (!a_mn && b_mn) return launch_tc<BN, STAGES, false, true, CG>(ctx, maps, p);
     if (a_mn && b_mn) return launch_tc<BN, STAGES, true, true, CG>(ctx, maps, p);
@@ -728,6 +755,7 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
         return gemm_simt_bf16(ctx, g);
     }
     const bool a_mn = g.a_ks != 1, b_mn = g.b_ks != 1;
+    if (g.epi.kind == EPI_PATCH && (a_mn || b_mn)) return gemm_simt_bf16(ctx, g);  // (only the K-major instantiation carries this epilogue)
     int BN = g.N > 128 ? 256 : 128;
     // a CTA pair per [256 x 256] tile whenever the problem has that many rows
     int CG = (BN == 256 && g.M > BM) ? 2 : 1;
