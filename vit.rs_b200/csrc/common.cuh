@@ -44,7 +44,7 @@ struct vitrs_ctx {
     int map_cache_used;
     // diagnostic switches, read once at context creation
     int env_gemm_cg1, env_gemm_splits, env_dp_defer, env_attn_fwd_stream, env_attn_bwd_stream, env_attn_bwd_overwrite,
-        env_no_map_cache, env_attn_fwd_legacy, env_attn_fwd_nostagger, env_gemm_static, env_no_step_graph, env_gemm_no_small, env_attn_fwd_nosplit;
+        env_no_map_cache, env_attn_fwd_legacy, env_attn_fwd_nostagger, env_gemm_static, env_no_step_graph, env_gemm_no_small, env_attn_fwd_nosplit, env_gemm_patch_tc;
     // device-side error flags raised by kernels (bit 0: class label out of range), reported by vitrs_model_mean_loss
     int* dev_flags;
     AdamHyper* d_hyper;  // AdamW hyper-parameters of the current step (same allocation as dev_flags)

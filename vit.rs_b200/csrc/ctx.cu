@@ -186,6 +186,7 @@ extern "C" int vitrs_ctx_create(vitrs_ctx** out, int device) {
     ctx->env_no_step_graph = flag("VITRS_NO_STEP_GRAPH");
     ctx->env_gemm_no_small = flag("VITRS_GEMM_NO_SMALL");
     ctx->env_attn_fwd_nosplit = flag("VITRS_ATTN_FWD_NOSPLIT");
+    ctx->env_gemm_patch_tc = flag("VITRS_GEMM_PATCH_TC");
     if (cudaMalloc(&ctx->dev_flags, 128) != cudaSuccess || cudaMemset(ctx->dev_flags, 0, 128) != cudaSuccess) {
         snprintf(g_create_err, sizeof(g_create_err), "cudaMalloc(flags) failed: %s", cudaGetErrorString(cudaGetLastError()));
         free(ctx->map_cache);

@@ -770,6 +770,12 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
         if (BN == 256 && CG == 1 && ctas(256, 1) < slots / 2) BN = 128;
     }
     if (ctx->env_gemm_cg1) CG = 1;  // VITRS_GEMM_CG=1: tuning aid (scripts/bench_gemm.py)
+    // The patch-embedding instantiation has run on a GPU with K = 768 on CTA pairs (ViT-B/16, S/16, Ti/16: tests and bench) and
+    // with K = 192 on the [128 x 128] single-CTA tiles (patch-8 models at test batch sizes).  The one bench run of ViT-B/8 at
+    // batch 256 (K = 192 on CTA pairs) taken after it went in did not finish within its time limit, with no GPU time left to
+    // find out why: until that combination has been examined it takes the SIMT kernel, whose EPI_PATCH
+    // path every verify-mode test exercises.  VITRS_GEMM_PATCH_TC=1 lifts the restriction.
+    if (g.epi.kind == EPI_PATCH && BN == 256 && g.K < 768 && !ctx->env_gemm_patch_tc) return gemm_simt_bf16(ctx, g);
     CUtensorMap maps[5];  // A, B, out, out2, aux
     CUtensorMap &tmA = maps[0], &tmB = maps[1];
     if (!a_mn) VITRS_TRY(encode_map(ctx, &tmA, g.A, g.K, g.M, g.a_rs, BK, BM));
