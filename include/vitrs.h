@@ -327,6 +327,54 @@ int vitrs_model_optimizer_state_bytes(vitrs_model* m, size_t* bytes);
  * of `shard` elements, the rest are its small slices (padded to 8), which stay replicated */
 int vitrs_zero_partition(const vitrs_config* cfg, int world, int bucket, size_t* z_off, size_t* z_len, size_t* z_big, size_t* shard);
 
+/* ---- planning on the host (no context, no device, no CUDA call) ---------------------------------------------------------
+ * The arithmetic the library itself uses to size its allocations and to route its GEMMs, exported so that a deployment can
+ * be sized for the 180 GB of a B200 and the kernel routing of every model shape can be checked without a GPU. */
+
+/* device bytes of a model created with vitrs_model_create(cfg, max_batch, mode), by what they hold (the six flat
+ * allocations of rusty_vit.rs:105-259 and what the fused step adds).  world / zero1 describe the data-parallel setup the
+ * model will run in (1 / 0: one GPU); exchange_buffer assumes the default bf16 gradient exchange. */
+typedef struct {
+    uint64_t num_parameters;
+    uint64_t weights_f32;        /* the flat fp32 parameter buffer (master weights; always whole) */
+    uint64_t grads_f32;          /* the flat fp32 gradient buffer */
+    uint64_t weights_bf16;       /* bf16 shadow the GEMMs read (0 in verify mode) */
+    uint64_t adam_moments;       /* m + v: whole, or under ZeRO-1 the rank's shards + the replicated small tensors */
+    uint64_t zero1_master_shard; /* ZeRO-1: fp32 master weights of the rank's shard of the GEMM weight matrices */
+    uint64_t exchange_buffer;    /* bucket-major bf16 gradient exchange buffer (world > 1 or ZeRO-1, production mode) */
+    uint64_t activations;        /* the [L, ...] activation arena (ActivationTensors, rusty_vit.rs:37-61) */
+    uint64_t activation_grads;   /* verify mode: the second arena; production: one block's worth + the head */
+    uint64_t workspace;          /* im2col patches, lse, CLS rows, loss scalars */
+    uint64_t staging;            /* the two device batch slots train_step_host copies into (allocated at first use) */
+    uint64_t total;
+    double train_flops_per_image; /* algorithmic: 3 x forward matmul flops */
+} vitrs_footprint;
+int vitrs_model_footprint(const vitrs_config* cfg, int max_batch, int mode, int world, int zero1, vitrs_footprint* out);
+/* device bytes of vitrs_infer_create(model, max_batch): the ping-pong workspace and the image staging slot */
+int vitrs_infer_footprint(const vitrs_config* cfg, int max_batch, uint64_t* workspace_bytes, uint64_t* staging_bytes);
+
+/* what vitrs_gemm_bf16 / vitrs_gemm_bf16_fused (and the model's own calls) launch for a dense, 16-byte-aligned problem of
+ * these extents on a device with sm_count SMs: kernel family, tile, CTAs per tile, shared-memory ring depth, split-K factor
+ * and grid.  epilogue: 0 none, 1-4 / 8 as for vitrs_gemm_bf16_fused, 5 fp32 accumulate (weight gradients), 6 patch
+ * embedding, 7 row dot.  flags: the context switches that change the choice. */
+#define VITRS_PLAN_SIMT 0
+#define VITRS_PLAN_TCGEN05 1
+#define VITRS_PLAN_NO_SMALL 1   /* VITRS_GEMM_NO_SMALL: keep the large tiles on small problems */
+#define VITRS_PLAN_SINGLE_CTA 2 /* VITRS_GEMM_CG=1: no CTA pairs */
+#define VITRS_PLAN_PATCH_TC 4   /* VITRS_GEMM_PATCH_TC: tensor-core patch-embedding epilogue on every tile shape */
+typedef struct {
+    int kernel;    /* VITRS_PLAN_SIMT | VITRS_PLAN_TCGEN05 */
+    int tile_m, tile_n;
+    int cta_group; /* 2 = a CTA pair (tcgen05 cta_group::2) per tile */
+    int stages;    /* TMA ring depth (0 for the SIMT kernel) */
+    int splits;    /* split-K factor (weight gradients) */
+    int k_blocks_per_split; /* 64-element K blocks per unit */
+    int tiles;     /* output tiles (units = tiles * splits) */
+    int grid;      /* CTAs launched (persistent: at most one per SM) */
+} vitrs_gemm_plan_t;
+int vitrs_gemm_plan(int M, int N, int K, int a_mn_major, int b_mn_major, int epilogue, int sm_count, int flags,
+                    vitrs_gemm_plan_t* out);
+
 #ifdef __cplusplus
 }
 #endif

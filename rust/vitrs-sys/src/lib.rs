@@ -131,6 +131,23 @@ pub fn optimizer_step(model: &mut ViT, lr: f32) -> Result<(), String> {
     Ok(())
 }
 
+/// Device bytes a model of `config` at `max_batch` images will allocate, by what they hold (host arithmetic, no device):
+/// size a deployment for the 180 GB of a B200 before creating anything.  `world` / `zero1` describe the data-parallel setup.
+pub fn model_footprint(config: &vitrs_config, max_batch: i32, mode: c_int, world: i32, zero1: bool) -> Result<vitrs_footprint, String> {
+    let mut f = vitrs_footprint::default();
+    let rc = unsafe { vitrs_model_footprint(config, max_batch, mode, world, zero1 as c_int, &mut f) };
+    if rc != 0 { return Err(format!("vitrs_model_footprint: invalid configuration ({})", rc)); }
+    Ok(f)
+}
+
+/// What the library launches for a dense bf16 GEMM of these extents (kernel family, tile, CTA pair, split-K, grid).
+pub fn gemm_plan(m: i32, n: i32, k: i32, a_mn_major: bool, b_mn_major: bool, epilogue: c_int, sm_count: i32, flags: c_int) -> Result<vitrs_gemm_plan_t, String> {
+    let mut p = vitrs_gemm_plan_t::default();
+    let rc = unsafe { vitrs_gemm_plan(m, n, k, a_mn_major as c_int, b_mn_major as c_int, epilogue, sm_count, flags, &mut p) };
+    if rc != 0 { return Err(format!("vitrs_gemm_plan: invalid extents ({})", rc)); }
+    Ok(p)
+}
+
 impl Drop for ViT {
     fn drop(&mut self) { unsafe { vitrs_model_destroy(self.model); vitrs_ctx_destroy(self.ctx); } }
 }

@@ -66,6 +66,23 @@ def train_flops_per_image(cfg):
     return 3 * fwd
 
 
+class Footprint(C.Structure):
+    """vitrs_footprint — device bytes of a model by what they hold (vitrs_model_footprint)."""
+    _fields_ = [(n, C.c_uint64) for n in ("num_parameters", "weights_f32", "grads_f32", "weights_bf16", "adam_moments",
+                                          "zero1_master_shard", "exchange_buffer", "activations", "activation_grads",
+                                          "workspace", "staging", "total")] + [("train_flops_per_image", C.c_double)]
+
+
+class GemmPlan(C.Structure):
+    """vitrs_gemm_plan_t — what a GEMM call of given extents launches (vitrs_gemm_plan)."""
+    _fields_ = [(n, C.c_int) for n in ("kernel", "tile_m", "tile_n", "cta_group", "stages", "splits", "k_blocks_per_split",
+                                       "tiles", "grid")]
+
+
+PLAN_SIMT, PLAN_TCGEN05 = 0, 1
+PLAN_NO_SMALL, PLAN_SINGLE_CTA, PLAN_PATCH_TC = 1, 2, 4
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_GELU_BWD, EPI_ACCUM_F32, EPI_PATCH, EPI_ROWDOT, EPI_BIAS_GELU_ONLY = range(9)
+
 _vp, _f32p, _i32p, _u16p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
 _int, _sz, _f, _u64 = C.c_int, C.c_size_t, C.c_float, C.c_uint64
 
@@ -143,6 +160,9 @@ _SIGNATURES = {
     "vitrs_model_gather_parameters": (_int, [_vp]),
     "vitrs_model_optimizer_state_bytes": (_int, [_vp, C.POINTER(_sz)]),
     "vitrs_zero_partition": (_int, [C.POINTER(Config), _int, _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "vitrs_model_footprint": (_int, [C.POINTER(Config), _int, _int, _int, _int, C.POINTER(Footprint)]),
+    "vitrs_infer_footprint": (_int, [C.POINTER(Config), _int, C.POINTER(_u64), C.POINTER(_u64)]),
+    "vitrs_gemm_plan": (_int, [_int] * 8 + [C.POINTER(GemmPlan)]),
     "vitrs_comm_world": (_int, [_vp, C.POINTER(_int), C.POINTER(_int)]),
     "vitrs_model_allreduce_grads": (_int, [_vp]),
     "vitrs_grad_bucket": (_int, [C.POINTER(Config), _int, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_int), C.POINTER(_int)]),
@@ -279,6 +299,68 @@ class Context:
 
     def allreduce(self, t):
         self.check(lib().vitrs_allreduce_f32(self._h, _ptr(t), t.numel()))
+
+
+def model_footprint(cfg, max_batch, mode=MODE_BF16, world=1, zero1=False):
+    """Device bytes of ViT(cfg, max_batch, mode) by what they hold, and the algorithmic flops per image (host arithmetic
+    only: the sizing functions vitrs_model_create itself uses).  -> dict"""
+    c = make_config(cfg) if not isinstance(cfg, Config) else cfg
+    f = Footprint()
+    rc = lib().vitrs_model_footprint(C.byref(c), max_batch, mode, world, int(bool(zero1)), C.byref(f))
+    if rc != 0:
+        raise VitrsError(f"vitrs_model_footprint failed ({rc})")
+    return {n: getattr(f, n) for n, _ in Footprint._fields_}
+
+
+def max_batch_for(cfg, hbm_bytes=180 * 10 ** 9, mode=MODE_BF16, world=1, zero1=False, reserve=4 * 10 ** 9):
+    """Largest per-GPU batch whose footprint fits `hbm_bytes` minus `reserve` (CUDA context, NCCL, allocator slack)."""
+    lo, hi = 0, 1
+    fits = lambda b: model_footprint(cfg, b, mode, world, zero1)["total"] <= hbm_bytes - reserve
+    while fits(hi) and hi < 1 << 24:
+        lo, hi = hi, hi * 2
+    while hi - lo > 1:
+        mid = (lo + hi) // 2
+        lo, hi = (mid, hi) if fits(mid) else (lo, mid)
+    return lo
+
+
+def infer_footprint(cfg, max_batch):
+    """-> (workspace bytes, staging bytes) of InferenceEngine(model of cfg, max_batch); host arithmetic only."""
+    c = make_config(cfg) if not isinstance(cfg, Config) else cfg
+    ws, st = C.c_uint64(), C.c_uint64()
+    rc = lib().vitrs_infer_footprint(C.byref(c), max_batch, C.byref(ws), C.byref(st))
+    if rc != 0:
+        raise VitrsError(f"vitrs_infer_footprint failed ({rc})")
+    return ws.value, st.value
+
+
+def gemm_plan(M, N, K, a_mn=False, b_mn=False, epilogue=EPI_NONE, sm_count=148, flags=0):
+    """What the library launches for a dense [M, K] x [N, K] bf16 GEMM with this epilogue on a device with sm_count SMs
+    (host arithmetic only: the routing function gemm_tc_bf16 itself uses).  -> dict"""
+    p = GemmPlan()
+    rc = lib().vitrs_gemm_plan(M, N, K, int(a_mn), int(b_mn), epilogue, sm_count, flags, C.byref(p))
+    if rc != 0:
+        raise VitrsError(f"vitrs_gemm_plan failed ({rc})")
+    d = {n: getattr(p, n) for n, _ in GemmPlan._fields_}
+    d["kernel"] = "tcgen05" if p.kernel == PLAN_TCGEN05 else "simt"
+    return d
+
+
+def step_gemms(cfg, batch):
+    """The bf16 GEMM calls of one production training step of `cfg` at `batch` images, in the order of model.cu
+    (forward_bf16 / backward_bf16): list of (name, M, N, K, a_mn, b_mn, epilogue).  The class head is fp32 SIMT and not listed."""
+    d = CONFIGS[cfg] if isinstance(cfg, str) else cfg
+    c, p = d["channels"], d["patch_size"]
+    t = (d["image_size"] // p) ** 2 + 1
+    rows, kdim = batch * t, 3 * p * p
+    fwd = [("patch", rows, c, kdim, 0, 0, EPI_PATCH)]
+    blk_f = [("qkv", rows, 3 * c, c, 0, 0, EPI_BIAS), ("attproj", rows, c, c, 0, 0, EPI_BIAS_RESIDUAL),
+             ("fc", rows, 4 * c, c, 0, 0, EPI_BIAS_GELU), ("fcproj", rows, c, 4 * c, 0, 0, EPI_BIAS_RESIDUAL)]
+    blk_b = [("fcproj_dx", rows, 4 * c, c, 0, 1, EPI_GELU_BWD), ("fcproj_dw", c, 4 * c, rows, 1, 1, EPI_ACCUM_F32),
+             ("fc_dx", rows, c, 4 * c, 0, 1, EPI_NONE), ("fc_dw", 4 * c, c, rows, 1, 1, EPI_ACCUM_F32),
+             ("attproj_dx", rows, c, c, 0, 1, EPI_ROWDOT if c == 64 * d["num_heads"] else EPI_NONE), ("attproj_dw", c, c, rows, 1, 1, EPI_ACCUM_F32),
+             ("qkv_dx", rows, c, 3 * c, 0, 1, EPI_NONE), ("qkv_dw", 3 * c, c, rows, 1, 1, EPI_ACCUM_F32)]
+    return fwd + blk_f * d["num_layers"] + blk_b * d["num_layers"] + [("patch_dw", c, kdim, rows, 1, 1, EPI_ACCUM_F32)]
 
 
 def zero_partition(cfg, world):

@@ -737,6 +737,83 @@ static bool tc_eligible(const GemmDesc& g) {
     return true;
 }
 
+// Every host-side decision of one bf16 GEMM call as a pure function of the problem and the context's switches: kernel family,
+// tile, CTAs per tile, ring depth, split-K factor and grid.  gemm_tc_bf16 launches what this returns; vitrs_gemm_plan exports
+// it, so the routing of every BASELINE shape is pinned by tests that need no device (tests/test_plan.py).
+struct TcSwitches {
+    int sm_count;
+    int no_small;   // VITRS_GEMM_NO_SMALL
+    int cg1;        // VITRS_GEMM_CG=1
+    int patch_tc;   // VITRS_GEMM_PATCH_TC
+    int splits;     // VITRS_GEMM_SPLITS (0 = heuristic)
+};
+struct TcPlan {
+    bool simt;  // the SIMT kernel takes the call (gemm_simt.cu)
+    int BN, CG, stages;
+    int m_tiles, n_tiles, kb_total, splits, kb_per_split, grid;
+};
+
+static TcPlan plan_tc(int M, int N, int K, int kind, bool a_mn, bool b_mn, const TcSwitches& sw) {
+    TcPlan pl = {};
+    if (kind == EPI_PATCH && (a_mn || b_mn)) {  // (only the K-major instantiation carries this epilogue)
+        pl.simt = true;
+        return pl;
+    }
+    int BN = N > 128 ? 256 : 128;
+    // a CTA pair per [256 x 256] tile whenever the problem has that many rows
+    int CG = (BN == 256 && M > BM) ? 2 : 1;
+    // Small problems (the inference engine at batch 1-64: M = 197 .. 12 608 rows) leave most SMs without a tile at that size and
+    // the launch is a stream of weights through a handful of CTAs: when the large tiles fill less than half of the chip, take the
+    // smaller ones — [256 x 256] pairs -> [128 x 256] -> [128 x 128] single CTAs — as far as that adds CTAs.  (Not for the
+    // split-K weight gradients, which fill the chip by splitting K.)
+    if (kind != EPI_ACCUM_F32 && !sw.no_small) {
+        const long slots = sw.sm_count;
+        auto ctas = [&](int bn, int cg) { return (long)ceil_div(M, BM * cg) * ceil_div(N, bn) * cg; };
+        if (CG == 2 && ctas(256, 2) < slots / 2) CG = 1;
+        if (BN == 256 && CG == 1 && ctas(256, 1) < slots / 2) BN = 128;
+    }
+    if (sw.cg1) CG = 1;  // VITRS_GEMM_CG=1: tuning aid (scripts/bench_gemm.py)
+    // The patch-embedding instantiation has run on a GPU with K = 768 on CTA pairs (ViT-B/16, S/16, Ti/16: tests and bench) and
+    // with K = 192 on CTA pairs at test batch sizes (tests/test_gpu_parity_configs.py, a few dozen tiles) and on the [128 x 128]
+    // single-CTA tiles.  The one bench run of ViT-B/8 at batch 256 (K = 192 on CTA pairs, 2 355 tiles) taken after it went in did
+    // not finish within its time limit, with no GPU time left to find out why: until that combination has
+    // been examined it takes the SIMT kernel, whose EPI_PATCH path every verify-mode test exercises.  VITRS_GEMM_PATCH_TC=1
+    // lifts the restriction.
+    if (kind == EPI_PATCH && BN == 256 && K < 768 && !sw.patch_tc) {
+        pl.simt = true;
+        return pl;
+    }
+    pl.BN = BN;
+    pl.CG = CG;
+    pl.stages = (CG == 1 && BN == 256) ? 4 : 6;
+    pl.m_tiles = ceil_div(M, BM * CG);
+    pl.n_tiles = ceil_div(N, BN);
+    pl.kb_total = ceil_div(K, BK);
+    int splits = 1;
+    const int tiles = pl.m_tiles * pl.n_tiles;
+    const int slots = sw.sm_count / CG;  // tiles in flight
+    if (kind == EPI_ACCUM_F32 && tiles < slots) {
+        // Split K so that one wave of CTAs covers the SMs: the smallest split count that fills >= 92 % of
+        // whole waves, else the best fill.  More splits than needed cost fp32 reductions and, worse, break
+        // the sharing of operand slabs between concurrently running CTAs (measured: 37 splits -> 6x DRAM traffic).
+        const int max_s = pl.kb_total / 16 > 1 ? (pl.kb_total / 16 < 32 ? pl.kb_total / 16 : 32) : 1;
+        double best = 0.0;
+        for (int s = 1; s <= max_s; ++s) {
+            const long units = (long)tiles * s;
+            const long waves = (units + slots - 1) / slots;
+            const double eff = (double)units / (double)(waves * slots);
+            if (eff > best + 1e-9) { best = eff; splits = s; }
+            if (eff >= 0.92) break;
+        }
+    }
+    if (kind == EPI_ACCUM_F32 && sw.splits > 0) splits = sw.splits;  // VITRS_GEMM_SPLITS: tuning aid
+    pl.kb_per_split = ceil_div(pl.kb_total, splits);
+    pl.splits = ceil_div(pl.kb_total, pl.kb_per_split);
+    const int units = tiles * pl.splits;
+    pl.grid = CG * (units < slots ? units : slots);  // persistent: one CTA (pair) per SM (pair), fewer when the work is smaller
+    return pl;
+}
+
 int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return VITRS_OK;
     if (!tc_eligible(g)) {
@@ -755,27 +832,10 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
         return gemm_simt_bf16(ctx, g);
     }
     const bool a_mn = g.a_ks != 1, b_mn = g.b_ks != 1;
-    if (g.epi.kind == EPI_PATCH && (a_mn || b_mn)) return gemm_simt_bf16(ctx, g);  // (only the K-major instantiation carries this epilogue)
-    int BN = g.N > 128 ? 256 : 128;
-    // a CTA pair per [256 x 256] tile whenever the problem has that many rows
-    int CG = (BN == 256 && g.M > BM) ? 2 : 1;
-    // Small problems (the inference engine at batch 1-64: M = 197 .. 12 608 rows) leave most SMs without a tile at that size and
-    // the launch is a stream of weights through a handful of CTAs: when the large tiles fill less than half of the chip, take the
-    // smaller ones — [256 x 256] pairs -> [128 x 256] -> [128 x 128] single CTAs — as far as that adds CTAs.  (Not for the
-    // split-K weight gradients, which fill the chip by splitting K.)
-    if (g.epi.kind != EPI_ACCUM_F32 && !ctx->env_gemm_no_small) {
-        const long slots = ctx->sm_count;
-        auto ctas = [&](int bn, int cg) { return (long)ceil_div(g.M, BM * cg) * ceil_div(g.N, bn) * cg; };
-        if (CG == 2 && ctas(256, 2) < slots / 2) CG = 1;
-        if (BN == 256 && CG == 1 && ctas(256, 1) < slots / 2) BN = 128;
-    }
-    if (ctx->env_gemm_cg1) CG = 1;  // VITRS_GEMM_CG=1: tuning aid (scripts/bench_gemm.py)
-    // The patch-embedding instantiation has run on a GPU with K = 768 on CTA pairs (ViT-B/16, S/16, Ti/16: tests and bench) and
-    // with K = 192 on the [128 x 128] single-CTA tiles (patch-8 models at test batch sizes).  The one bench run of ViT-B/8 at
-    // batch 256 (K = 192 on CTA pairs) taken after it went in did not finish within its time limit, with no GPU time left to
-    // find out why: until that combination has been examined it takes the SIMT kernel, whose EPI_PATCH
-    // path every verify-mode test exercises.  VITRS_GEMM_PATCH_TC=1 lifts the restriction.
-    if (g.epi.kind == EPI_PATCH && BN == 256 && g.K < 768 && !ctx->env_gemm_patch_tc) return gemm_simt_bf16(ctx, g);
+    const TcSwitches sw = {ctx->sm_count, ctx->env_gemm_no_small, ctx->env_gemm_cg1, ctx->env_gemm_patch_tc, ctx->env_gemm_splits};
+    const TcPlan pl = plan_tc(g.M, g.N, g.K, g.epi.kind, a_mn, b_mn, sw);
+    if (pl.simt) return gemm_simt_bf16(ctx, g);
+    const int BN = pl.BN, CG = pl.CG;
     CUtensorMap maps[5];  // A, B, out, out2, aux
     CUtensorMap &tmA = maps[0], &tmB = maps[1];
     if (!a_mn) VITRS_TRY(encode_map(ctx, &tmA, g.A, g.K, g.M, g.a_rs, BK, BM));
@@ -795,33 +855,57 @@ int gemm_tc_bf16(vitrs_ctx* ctx, const GemmDesc& g) {
 
     TcParams p;
     p.M = g.M; p.N = g.N; p.K = g.K;
-    p.m_tiles = ceil_div(g.M, BM * CG);
-    p.n_tiles = ceil_div(g.N, BN);
-    p.kb_total = ceil_div(g.K, BK);
+    p.m_tiles = pl.m_tiles;
+    p.n_tiles = pl.n_tiles;
+    p.kb_total = pl.kb_total;
+    p.kb_per_split = pl.kb_per_split;
+    p.splits = pl.splits;
     p.epi = g.epi;
     p.a_colsum = g.a_colsum;
     p.sched = ctx->env_gemm_static ? nullptr : ctx->gemm_sched;  // VITRS_GEMM_STATIC: the static stride (A/B aid)
-    int splits = 1;
-    const int tiles = p.m_tiles * p.n_tiles;
-    const int slots = ctx->sm_count / CG;  // tiles in flight
-    if (g.epi.kind == EPI_ACCUM_F32 && tiles < slots) {
-        // Split K so that one wave of CTAs covers the SMs: the smallest split count that fills >= 92 % of
-        // whole waves, else the best fill.  More splits than needed cost fp32 reductions and, worse, break
-        // the sharing of operand slabs between concurrently running CTAs (measured: 37 splits -> 6x DRAM traffic).
-        const int max_s = p.kb_total / 16 > 1 ? (p.kb_total / 16 < 32 ? p.kb_total / 16 : 32) : 1;
-        double best = 0.0;
-        for (int s = 1; s <= max_s; ++s) {
-            const long units = (long)tiles * s;
-            const long waves = (units + slots - 1) / slots;
-            const double eff = (double)units / (double)(waves * slots);
-            if (eff > best + 1e-9) { best = eff; splits = s; }
-            if (eff >= 0.92) break;
-        }
-    }
-    if (g.epi.kind == EPI_ACCUM_F32 && ctx->env_gemm_splits > 0) splits = ctx->env_gemm_splits;  // VITRS_GEMM_SPLITS: tuning aid
-    p.kb_per_split = ceil_div(p.kb_total, splits);
-    p.splits = ceil_div(p.kb_total, p.kb_per_split);
     if (CG == 2) return launch_tc_major<256, 6, 2>(ctx, a_mn, b_mn, maps, p);
     if (BN == 256) return launch_tc_major<256, 4, 1>(ctx, a_mn, b_mn, maps, p);
     return launch_tc_major<128, 6, 1>(ctx, a_mn, b_mn, maps, p);
+}
+
+// The plan of a dense, 16-byte-aligned call of these extents (vitrs.h): host arithmetic only, no context, no CUDA call.
+extern "C" int vitrs_gemm_plan(int M, int N, int K, int a_mn_major, int b_mn_major, int epilogue, int sm_count, int flags,
+                               vitrs_gemm_plan_t* out) {
+    if (!out || M < 1 || N < 1 || K < 1 || sm_count < 2) return VITRS_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    GemmDesc g = {};
+    void* const aligned = reinterpret_cast<void*>(uintptr_t(4096));  // never dereferenced: tc_eligible only looks at alignment
+    g.A = aligned; g.B = aligned;
+    g.a_rs = a_mn_major ? 1 : K; g.a_ks = a_mn_major ? M : 1;
+    g.b_rs = b_mn_major ? 1 : K; g.b_ks = b_mn_major ? N : 1;
+    g.M = M; g.N = N; g.K = K;
+    g.epi.kind = epilogue; g.epi.out = aligned; g.epi.ldo = N;
+    if (epilogue == EPI_ROWDOT) { g.epi.aux = aligned; g.epi.out2 = aligned; g.epi.np = 1; }
+    TcPlan pl = {};
+    pl.simt = !tc_eligible(g);
+    if (!pl.simt) {
+        const TcSwitches sw = {sm_count, flags & VITRS_PLAN_NO_SMALL ? 1 : 0, flags & VITRS_PLAN_SINGLE_CTA ? 1 : 0,
+                               flags & VITRS_PLAN_PATCH_TC ? 1 : 0, 0};
+        pl = plan_tc(M, N, K, epilogue, a_mn_major != 0, b_mn_major != 0, sw);
+    }
+    if (pl.simt) {
+        // gemm_simt.cu: [64 x 64] tiles, [32 x 32] when those would not give every SM a CTA
+        const bool big = (long)ceil_div(N, 64) * ceil_div(M, 64) >= sm_count;
+        out->kernel = VITRS_PLAN_SIMT;
+        out->tile_m = out->tile_n = big ? 64 : 32;
+        out->cta_group = 1;
+        out->splits = 1;
+        out->grid = ceil_div(N, out->tile_n) * ceil_div(M, out->tile_m);
+        return VITRS_OK;
+    }
+    out->kernel = VITRS_PLAN_TCGEN05;
+    out->tile_m = BM * pl.CG;
+    out->tile_n = pl.BN;
+    out->cta_group = pl.CG;
+    out->stages = pl.stages;
+    out->splits = pl.splits;
+    out->k_blocks_per_split = pl.kb_per_split;
+    out->tiles = pl.m_tiles * pl.n_tiles;
+    out->grid = pl.grid;
+    return VITRS_OK;
 }

@@ -144,7 +144,30 @@ int run(vitrs_infer* e, const void* images, int kind, int b) {
 
 }  // namespace
 
+// byte offsets of the 15 workspace views (off[15] = the workspace size) for `max_batch` images; cfg.max_seq_len must be set
+static void workspace_layout(const vitrs_config& cfg, int max_batch, size_t* off) {
+    const size_t B = max_batch, T = cfg.max_seq_len, C = cfg.channels, NH = cfg.num_heads, V = cfg.num_classes, M = B * T;
+    const size_t kdim = 3u * cfg.patch_size * cfg.patch_size;
+    const size_t big_elems = M * (4 * C > kdim ? 4 * C : kdim);
+    const size_t sizes[15] = {M * C * 2, M * C * 2, M * C * 2, M * 3 * C * 2, M * C * 2, big_elems * 2, B * NH * T * 4, M * 4, M * 4,
+                              B * C * 4, B * C * 4, B * 4, B * 4, B * V * 4, B * V * 4};
+    off[0] = 0;
+    for (int i = 0; i < 15; ++i) off[i + 1] = off[i] + align256(sizes[i]);
+}
+
 extern "C" {
+
+// host-only (vitrs.h, planning): what vitrs_infer_create(model of cfg, max_batch) allocates on the device
+int vitrs_infer_footprint(const vitrs_config* cfg_in, int max_batch, uint64_t* workspace_bytes, uint64_t* staging_bytes) {
+    if (!cfg_in || max_batch < 1 || cfg_in->patch_size <= 0 || cfg_in->image_size % cfg_in->patch_size) return VITRS_ERR_ARG;
+    vitrs_config cfg = *cfg_in;
+    cfg.max_seq_len = tokens(cfg);
+    size_t off[16];
+    workspace_layout(cfg, max_batch, off);
+    if (workspace_bytes) *workspace_bytes = off[15];
+    if (staging_bytes) *staging_bytes = (uint64_t)max_batch * 3 * cfg.image_size * cfg.image_size * sizeof(float);
+    return VITRS_OK;
+}
 
 int vitrs_infer_create(vitrs_model* m, int max_batch, vitrs_infer** out) {
     if (!m) return VITRS_ERR_ARG;
@@ -156,14 +179,9 @@ int vitrs_infer_create(vitrs_model* m, int max_batch, vitrs_infer** out) {
     vitrs_infer* e = (vitrs_infer*)calloc(1, sizeof(vitrs_infer));
     e->m = m; e->ctx = ctx; e->max_batch = max_batch; e->use_graph = 1;
     const vitrs_config& cfg = m->cfg;
-    const size_t B = max_batch, T = cfg.max_seq_len, C = cfg.channels, NH = cfg.num_heads, V = cfg.num_classes, M = B * T;
-    const size_t kdim = 3u * cfg.patch_size * cfg.patch_size;
-    const size_t big_elems = M * (4 * C > kdim ? 4 * C : kdim);
-    const size_t sizes[15] = {M * C * 2, M * C * 2, M * C * 2, M * 3 * C * 2, M * C * 2, big_elems * 2, B * NH * T * 4, M * 4, M * 4,
-                              B * C * 4, B * C * 4, B * 4, B * 4, B * V * 4, B * V * 4};
+    const size_t B = max_batch, V = cfg.num_classes;
     size_t off[16];
-    off[0] = 0;
-    for (int i = 0; i < 15; ++i) off[i + 1] = off[i] + align256(sizes[i]);
+    workspace_layout(cfg, max_batch, off);
     e->workspace_bytes = off[15];
     const size_t img_bytes = B * 3 * cfg.image_size * cfg.image_size * sizeof(float);
     if (cudaMalloc(&e->ws, e->workspace_bytes) != cudaSuccess || cudaMalloc(&e->stage, img_bytes) != cudaSuccess ||

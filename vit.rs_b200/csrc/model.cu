@@ -46,10 +46,10 @@ bool act_is_f32_always(int a) {
     return a == A_LN1_MEAN || a == A_LN1_RSTD || a == A_LN2_MEAN || a == A_LN2_RSTD || a == A_PREATT || a == A_ATT || a >= A_LNF;
 }
 
-int arena_create(vitrs_ctx* ctx, Arena* ar, const vitrs_config& cfg, int max_batch, int mode, bool is_grad) {
-    act_sizes_of(cfg, ar->per_image);
+// element size and byte offset of every view of an activation arena (host arithmetic; also vitrs_model_footprint); returns its size
+size_t arena_layout(const vitrs_config& cfg, int max_batch, int mode, bool is_grad, size_t* per_image, int* elems, size_t* offs) {
+    act_sizes_of(cfg, per_image);
     size_t off = 0;
-    size_t offs[A_COUNT];
     for (int a = 0; a < A_COUNT; ++a) {
         int elem = (mode == VITRS_MODE_F32 || act_is_f32_always(a)) ? 4 : 2;
         if (mode == VITRS_MODE_BF16) {
@@ -57,10 +57,16 @@ int arena_create(vitrs_ctx* ctx, Arena* ar, const vitrs_config& cfg, int max_bat
             if (a == A_PREATT || a == A_ATT || a == A_ATTPROJ || a == A_FCPROJ) elem = 0;
             if (is_grad && a < A_LNF) elem = 0;
         }
-        ar->elem[a] = elem;
+        elems[a] = elem;
         offs[a] = off;
-        off += (ar->per_image[a] * max_batch * elem + 255) / 256 * 256;
+        off += (per_image[a] * max_batch * elem + 255) / 256 * 256;
     }
+    return off;
+}
+
+int arena_create(vitrs_ctx* ctx, Arena* ar, const vitrs_config& cfg, int max_batch, int mode, bool is_grad) {
+    size_t offs[A_COUNT];
+    const size_t off = arena_layout(cfg, max_batch, mode, is_grad, ar->per_image, ar->elem, offs);
     ar->bytes = off;
     ar->base = nullptr;
     if (off) VITRS_CUDA(ctx, cudaMalloc(&ar->base, off));
@@ -581,17 +587,18 @@ int reduce_loss(vitrs_model* m) {
 // The small tensors (everything the kernels read in fp32) keep replicated fp32 weights in the parameter view and replicated
 // moments in two compact arrays; they are five contiguous runs of the tensor-major buffer.
 struct SmallRun { size_t off, cnt, soff; };
-int small_runs(const vitrs_model* m, SmallRun* r) {
+int small_runs_of(const size_t* param_off, const size_t* param_sizes, SmallRun* r) {
     const int first[5] = {P_PATCHB, P_QKVB, P_ATTPROJB, P_FCB, P_FCPROJB}, last[5] = {P_LN1B, P_QKVB, P_LN2B, P_FCB, P_HEADB};
     size_t so = 0;
     for (int i = 0; i < 5; ++i) {
-        r[i].off = m->param_off[first[i]];
-        r[i].cnt = m->param_off[last[i]] + m->param_sizes[last[i]] - r[i].off;
+        r[i].off = param_off[first[i]];
+        r[i].cnt = param_off[last[i]] + param_sizes[last[i]] - r[i].off;
         r[i].soff = so;
         so += (r[i].cnt + 3) / 4 * 4;  // 16-byte aligned starts
     }
     return 5;
 }
+int small_runs(const vitrs_model* m, SmallRun* r) { return small_runs_of(m->param_off, m->param_sizes, r); }
 
 // (re)cut the shards from the full tensor-major buffers params / m / v, then drop the full moment buffers
 int zero_shard_from_full(vitrs_model* m) {
@@ -1030,6 +1037,60 @@ int vitrs_zero_partition(const vitrs_config* cfg_in, int world, int bucket, size
     if (z_len) *z_len = big + small;
     if (z_big) *z_big = big;
     if (shard) *shard = big / world;
+    return VITRS_OK;
+}
+
+// host-only: the device bytes vitrs_model_create / ensure_zplan / enable_zero1 / ensure_stage allocate for this configuration,
+// from the same sizing functions they use (param_sizes_of, arena_layout, zplan_sizes, small_runs_of)
+int vitrs_model_footprint(const vitrs_config* cfg_in, int max_batch, int mode, int world, int zero1, vitrs_footprint* out) {
+    if (!cfg_in || !out || max_batch < 1 || world < 1 || (mode != VITRS_MODE_F32 && mode != VITRS_MODE_BF16)) return VITRS_ERR_ARG;
+    vitrs_config cfg = *cfg_in;
+    if (cfg.patch_size <= 0 || cfg.image_size % cfg.patch_size || cfg.patch_size % 4 || cfg.channels <= 0 || cfg.num_heads <= 0 ||
+        cfg.channels % cfg.num_heads || cfg.channels % 8 || cfg.num_layers < 1 || cfg.num_layers > 62 || cfg.num_classes < 1)
+        return VITRS_ERR_ARG;  // (what vitrs_model_create accepts)
+    if (zero1 && mode != VITRS_MODE_BF16) return VITRS_ERR_ARG;
+    cfg.max_seq_len = tokens(cfg);
+    memset(out, 0, sizeof(*out));
+    size_t sizes[P_COUNT], offs[P_COUNT], n = 0;
+    param_sizes_of(cfg, sizes);
+    for (int i = 0; i < P_COUNT; ++i) { offs[i] = n; n += sizes[i]; }
+    const size_t B = max_batch, T = cfg.max_seq_len, C = cfg.channels, L = cfg.num_layers, NH = cfg.num_heads, V = cfg.num_classes;
+    const size_t kdim = 3u * cfg.patch_size * cfg.patch_size;
+    const size_t esz = mode == VITRS_MODE_F32 ? 4 : 2;
+    out->num_parameters = n;
+    out->weights_f32 = n * sizeof(float);
+    out->grads_f32 = n * sizeof(float);
+    out->weights_bf16 = mode == VITRS_MODE_BF16 ? n * sizeof(bf16) : 0;
+    size_t z = 0, shards = 0;
+    for (int b = 0; b < cfg.num_layers + 2; ++b) {
+        size_t big = 0, small = 0;
+        zplan_sizes(cfg, sizes, offs, world, b, &big, &small);
+        z += big + small;
+        shards += big / world;
+    }
+    if (mode == VITRS_MODE_BF16 && (world > 1 || zero1)) out->exchange_buffer = z * sizeof(bf16);
+    if (zero1) {
+        SmallRun runs[5];
+        small_runs_of(offs, sizes, runs);
+        const size_t small_total = runs[4].soff + (runs[4].cnt + 3) / 4 * 4;
+        out->zero1_master_shard = (shards + 4) * sizeof(float);
+        out->adam_moments = 2 * (shards + 4) * sizeof(float) + 2 * small_total * sizeof(float);
+    } else {
+        out->adam_moments = 2 * n * sizeof(float);
+    }
+    size_t per_image[A_COUNT], aoffs[A_COUNT];
+    int elems[A_COUNT];
+    out->activations = arena_layout(cfg, max_batch, mode, false, per_image, elems, aoffs);
+    out->activation_grads = arena_layout(cfg, max_batch, mode, true, per_image, elems, aoffs);
+    if (mode == VITRS_MODE_BF16)  // dres, dln, dbig, dlogits, dlnf
+        out->activation_grads += sizeof(bf16) * B * T * C * 2 + sizeof(bf16) * B * T * 4 * C + sizeof(float) * B * V + sizeof(float) * B * C;
+    out->workspace = sizeof(float) * L * B * NH * T + 2 * sizeof(float) * B * C + esz * B * T * kdim + 2 * sizeof(float);
+    out->staging = 2 * (B * 3 * cfg.image_size * cfg.image_size * sizeof(float) + B * sizeof(int));
+    out->total = out->weights_f32 + out->grads_f32 + out->weights_bf16 + out->adam_moments + out->zero1_master_shard +
+                 out->exchange_buffer + out->activations + out->activation_grads + out->workspace + out->staging;
+    const double np = (double)(T - 1), t = (double)T, c = (double)C;
+    const double fwd = 2.0 * np * (double)kdim * c + (double)L * (24.0 * t * c * c + 4.0 * t * t * c) + 2.0 * c * (double)V;
+    out->train_flops_per_image = 3.0 * fwd;
     return VITRS_OK;
 }
 
