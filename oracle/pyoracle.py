@@ -191,7 +191,7 @@ class ViT:
         self._keep = None
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # (module globals are already gone at interpreter shutdown)
             lib().vit_free(self._h)
             self._h = None
 
