@@ -274,6 +274,28 @@ int vitrs_loader_open(vitrs_ctx* ctx, const char* const* paths, int num_paths, i
  * batches r, r + world, ... of each whole round of `world` batches (all ranks see the same number of batches per epoch) */
 int vitrs_loader_open_sharded(vitrs_ctx* ctx, const char* const* paths, int num_paths, int image_size, int label_bytes, int batch,
                               int shuffle, uint64_t seed, int drop_last, int rank, int world, vitrs_loader** out);
+/* the same with a transform between the stored record and the delivered image, done on the host by `workers` threads (the loader
+ * thread and workers - 1 helpers share the images of a batch): random crop of the record zero-padded by crop_pad pixels on every
+ * side and random horizontal flip (the standard CIFAR augmentations; a function of seed, epoch and record index only, so a batch
+ * is the same bytes whatever the thread count), then a bilinear resize with half-pixel centres from image_size to out_size — 32 x 32
+ * CIFAR records feeding a 224 x 224 model.  Zero / absent fields mean: no resize, no augmentation, one thread. */
+typedef struct {
+    int image_size;  /* side of the stored records */
+    int out_size;    /* side of the delivered images (0: image_size) */
+    int label_bytes;
+    int batch;
+    int shuffle;
+    int drop_last;
+    uint64_t seed;
+    int rank, world; /* data parallel sharding as in vitrs_loader_open_sharded (world 0 is not valid: use 1) */
+    int workers;     /* host threads transforming images (0 or 1: the loader thread alone) */
+    int random_flip; /* horizontal flip with probability 1/2 */
+    int crop_pad;    /* random crop after padding by this many zero pixels per side (0: none) */
+} vitrs_loader_options;
+int vitrs_loader_open_transform(vitrs_ctx* ctx, const char* const* paths, int num_paths, const vitrs_loader_options* options,
+                                vitrs_loader** out);
+/* side of the images the loader delivers */
+int vitrs_loader_image_size(vitrs_loader* loader);
 int vitrs_loader_close(vitrs_loader* loader);
 int vitrs_loader_info(vitrs_loader* loader, size_t* num_records, int* batches_per_epoch, int* num_classes_seen);
 /* blocks until the next batch is assembled: uint8 NCHW images [b,3,H,W] and int labels [b] in host memory that stays valid

@@ -79,6 +79,13 @@ class GemmPlan(C.Structure):
                                        "tiles", "grid")]
 
 
+class LoaderOptions(C.Structure):
+    """vitrs_loader_options — record loader with host-side augmentation and resize (vitrs_loader_open_transform)."""
+    _fields_ = [("image_size", C.c_int), ("out_size", C.c_int), ("label_bytes", C.c_int), ("batch", C.c_int), ("shuffle", C.c_int),
+                ("drop_last", C.c_int), ("seed", C.c_uint64), ("rank", C.c_int), ("world", C.c_int), ("workers", C.c_int),
+                ("random_flip", C.c_int), ("crop_pad", C.c_int)]
+
+
 PLAN_SIMT, PLAN_TCGEN05 = 0, 1
 PLAN_NO_SMALL, PLAN_SINGLE_CTA, PLAN_PATCH_TC = 1, 2, 4
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_GELU_BWD, EPI_ACCUM_F32, EPI_PATCH, EPI_ROWDOT, EPI_BIAS_GELU_ONLY = range(9)
@@ -169,6 +176,8 @@ _SIGNATURES = {
     "vitrs_allreduce_f32": (_int, [_vp, _vp, _sz]),
     "vitrs_loader_open": (_int, [_vp, C.POINTER(C.c_char_p), _int, _int, _int, _int, _int, _u64, _int, C.POINTER(C.c_void_p)]),
     "vitrs_loader_open_sharded": (_int, [_vp, C.POINTER(C.c_char_p), _int, _int, _int, _int, _int, _u64, _int, _int, _int, C.POINTER(C.c_void_p)]),
+    "vitrs_loader_open_transform": (_int, [_vp, C.POINTER(C.c_char_p), _int, C.POINTER(LoaderOptions), C.POINTER(C.c_void_p)]),
+    "vitrs_loader_image_size": (_int, [_vp]),
     "vitrs_loader_close": (_int, [_vp]),
     "vitrs_loader_info": (_int, [_vp, C.POINTER(_sz), C.POINTER(_int), C.POINTER(_int)]),
     "vitrs_loader_next": (_int, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(_int), C.POINTER(_u64)]),
@@ -793,19 +802,29 @@ class RecordLoader:
     """CIFAR-layout record files -> shuffled uint8 batches assembled by a native loader thread into pinned host slots
     (include/vitrs.h: vitrs_loader_*).  ctx=None uses pageable memory (no GPU needed)."""
 
-    def __init__(self, paths, image_size, batch, label_bytes=1, shuffle=True, seed=0, drop_last=True, ctx=None, pinned=True, rank=0, world=1):
+    def __init__(self, paths, image_size, batch, label_bytes=1, shuffle=True, seed=0, drop_last=True, ctx=None, pinned=True, rank=0, world=1,
+                 out_size=0, workers=0, random_flip=False, crop_pad=0):
+        """out_size / random_flip / crop_pad / workers: host-side bilinear resize and the CIFAR augmentations, spread over
+        `workers` threads (vitrs_loader_open_transform); all left at their defaults the records are delivered as stored."""
         paths = [paths] if isinstance(paths, str) else list(paths)
         self.ctx = ctx if ctx is not None else (default_context() if pinned else None)
-        self.image_size, self.batch = image_size, batch
+        self.batch = batch
         arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
         self._h = C.c_void_p()
-        rc = lib().vitrs_loader_open_sharded(self.ctx._h if self.ctx else None, arr, len(paths), image_size, label_bytes, batch, int(shuffle),
-                                             seed, int(drop_last), rank, world, C.byref(self._h))
+        h = self.ctx._h if self.ctx else None
+        if out_size or workers or random_flip or crop_pad:
+            opt = LoaderOptions(image_size, out_size, label_bytes, batch, int(shuffle), int(drop_last), seed, rank, world, workers,
+                                int(random_flip), crop_pad)
+            rc = lib().vitrs_loader_open_transform(h, arr, len(paths), C.byref(opt), C.byref(self._h))
+        else:
+            rc = lib().vitrs_loader_open_sharded(h, arr, len(paths), image_size, label_bytes, batch, int(shuffle), seed, int(drop_last),
+                                                 rank, world, C.byref(self._h))
         if rc != 0:
             raise VitrsError(f"vitrs_loader_open failed ({rc})" + (f": {lib().vitrs_last_error(self.ctx._h).decode()}" if self.ctx else ""))
         n, bpe, ncls = C.c_size_t(), C.c_int(), C.c_int()
         lib().vitrs_loader_info(self._h, C.byref(n), C.byref(bpe), C.byref(ncls))
         self.num_records, self.batches_per_epoch, self.num_classes_seen = n.value, bpe.value, ncls.value
+        self.image_size = lib().vitrs_loader_image_size(self._h)  # side of the delivered images
 
     def next(self):
         """(images uint8 [b,3,H,W], labels int32 [b], epoch) as numpy views of the loader's slot: valid until the call after the next."""
