@@ -217,3 +217,34 @@ def test_plan_invariants_on_random_shapes(vitrs):
         assert 2 * p["tile_n"] <= 512
         stage_bytes = 128 * 64 * 2 + p["tile_n"] // p["cta_group"] * 64 * 2
         assert p["stages"] * stage_bytes + 8 * 32 * 128 + 512 + 1024 <= 227 * 1024
+
+
+# ---- the plan against what a GPU ran ------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("cfg,batch,fname", [("b16", 1024, "r2_launches_vitb16_b1024.csv"), ("ti16", 256, "r2_launches_vitti16_b256.csv")])
+def test_plan_reproduces_the_committed_ncu_launch_lists(vitrs, cfg, batch, fname):
+    """profiles/r2_launches_*.csv are ncu launch lists of one training step on a B200: the kernel instantiation
+    (gemm_tc_kernel<tile_n, stages, A MN-major, B MN-major, CTAs per tile, patch epilogue>) and the grid of every GEMM launch, in
+    order, must be what the host-side plan says for the step's GEMM sequence."""
+    import csv
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", fname)
+    rows = list(csv.reader(line for line in open(path) if line.startswith('"')))
+    ki, gi = rows[0].index("Kernel Name"), rows[0].index("Grid Size")
+    ran = []
+    for r in rows[1:]:
+        m = re.search(r"gemm_tc_kernel<([^>]*)>", r[ki])
+        if m:
+            ran.append((tuple(int(x) for x in m.group(1).split(",")), int(re.match(r"\((\d+)", r[gi]).group(1))))
+    first = next(i for i, (targs, _) in enumerate(ran) if targs[5] == 1)  # the step starts at its patch-embedding GEMM
+    want = []
+    for name, M, N, K, a_mn, b_mn, epi in vitrs.step_gemms(cfg, batch):
+        p = vitrs.gemm_plan(M, N, K, a_mn, b_mn, epi, SM)
+        assert p["kernel"] == "tcgen05", name
+        want.append(((p["tile_n"], p["stages"], a_mn, b_mn, p["cta_group"], int(epi == vitrs.EPI_PATCH)), p["grid"]))
+    got = ran[first:first + len(want)]
+    assert len(got) == len(want) == 2 + 12 * vitrs.CONFIGS[cfg]["num_layers"]
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g == w, (i, vitrs.step_gemms(cfg, batch)[i][0], g, w)
