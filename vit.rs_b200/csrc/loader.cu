@@ -256,6 +256,10 @@ static int open_impl(vitrs_ctx* ctx, const char* const* paths, int num_paths, co
     if (L->transform) bilinear_taps(L);
     auto fail = [&](int code, const char* what, const char* path) {
         if (ctx) vitrs_set_error(ctx, code, "vitrs_loader_open: %s (%s)", what, path);
+        for (int s = 0; s < kSlots; ++s) {  // (slots allocated before the failure; the rest are still null)
+            if (ctx) { cudaFreeHost(L->images[s]); cudaFreeHost(L->labels[s]); }
+            else { free(L->images[s]); free(L->labels[s]); }
+        }
         delete L;
         return code;
     };
