@@ -20,7 +20,7 @@ def forward(p, cfg, images, labels, causal=False, dloss_scale=None):
     C, L, NH = cfg["channels"], cfg["num_layers"], cfg["num_heads"]
     ps, V = cfg["patch_size"], cfg["num_classes"]
     B = images.shape[0]
-    x = torch.as_tensor(images, dtype=torch.float32)
+    x = torch.as_tensor(images, dtype=p["patchw"].dtype)  # (float64 parameters give a float64 evaluation: the conditioning tests)
     w = p["patchw"].view(C, 3, ps, ps)
     tok = F.conv2d(x, w, p["patchb"], stride=ps)                 # [B,C,g,g]
     tok = tok.flatten(2).transpose(1, 2)                          # [B,N,C]
