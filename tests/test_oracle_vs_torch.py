@@ -296,3 +296,30 @@ def test_reference_init_is_ill_conditioned_in_fp32(cfg):
     assert symmetric <= 5e-6, symmetric
     assert reference <= 5e-4, reference
     assert reference >= 10 * symmetric, (reference, symmetric)
+
+
+@pytest.mark.parametrize("cfg,b,floor_logits,floor_worst", [(MID_HS64, 16, 2.1e-2, 7.9e-2), ("ti16", 4, 5.9e-2, 1.2e-1)], ids=["c256", "ti16"])
+def test_bf16_storage_floor_under_the_reference_init(cfg, b, floor_logits, floor_worst):
+    """DEVIATIONS D14, measured: an IDEAL bf16-storage evaluation of the step (exact fp32 arithmetic, values rounded only where
+    the production mode stores bf16: torch_ref.forward_bf16_storage) is already 2e-2 .. 1.2e-1 away from the fp32 oracle under
+    the reference's all-positive init, on logits and the LayerNorm gradients — no bf16 implementation can meet 2e-2 there — while
+    under the symmetric init the same evaluation stays inside 2e-2 on every tensor.  The GPU parity tests
+    (tests/test_gpu_parity_configs.py) therefore hold init_mode 1 to 2e-2 and init_mode 0 to max(2e-2, 3 x this floor)."""
+    c = po.CONFIGS[cfg] if isinstance(cfg, str) else cfg
+
+    def floors(init_mode):
+        ref = po.ViT(cfg, seed=1337, init_mode=init_mode)
+        images, labels = po.synthetic_batch(c, b)
+        ref.forward(images, labels); ref.zero_grad(); ref.backward()
+        p = torch_ref.params_from_flat(ref.params_flat(), c, ref.param_sizes, po.PARAM_NAMES)
+        logits, loss, _ = torch_ref.forward_bf16_storage(p, c, images, labels)
+        loss.backward()
+        rel = lambda a, w: np.abs(np.asarray(a, np.float64).ravel() - np.asarray(w, np.float64).ravel()).max() / np.abs(w).max()
+        out = {"logits": rel(logits.detach().numpy(), ref.act("logits"))}
+        out.update({"d" + n: rel(p[n].grad.numpy(), ref.grad(n)) for n in po.PARAM_NAMES})
+        return out
+    sym, refinit = floors(1), floors(0)
+    assert max(sym.values()) <= 2e-2, sym
+    assert abs(refinit["logits"] - floor_logits) <= 0.1 * floor_logits, refinit["logits"]
+    assert abs(max(refinit.values()) - floor_worst) <= 0.1 * floor_worst, max(refinit.values())
+    assert max(refinit, key=refinit.get) in ("dln1w", "dln2w")
