@@ -81,3 +81,42 @@ def test_config_table_and_flops(vitrs):
         assert abs(vitrs.train_flops_per_image(name) / 1e9 - want) < 2e-3, name
     cfg = vitrs.make_config("b16")
     assert (cfg.max_seq_len, cfg.channels, cfg.num_heads, cfg.num_layers) == (197, 768, 12, 12)
+
+
+def test_header_is_plain_c_and_links_from_c(vitrs, tmp_path):
+    """The boundary is a C ABI: include/vitrs.h compiles as strict C99 (no C++ or torch type in any signature) and a C program
+    links libvitrs.so, calls the host-only planning entry points and is refused a context when there is no GPU."""
+    import shutil
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", HEADER],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = tmp_path / "cabi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "vitrs.h"
+int main(void) {
+    vitrs_config cfg = {0, 0, 12, 12, 768, 224, 16, 1000, 0};
+    vitrs_footprint f;
+    vitrs_gemm_plan_t p;
+    vitrs_ctx* ctx = NULL;
+    if (vitrs_model_footprint(&cfg, 1024, VITRS_MODE_BF16, 1, 0, &f) != VITRS_OK) return 1;
+    if (vitrs_gemm_plan(201728, 2304, 768, 0, 0, 1, 148, 0, &p) != VITRS_OK) return 2;
+    printf("%s|%llu|%d|%d|%d|%d\n", vitrs_version(), (unsigned long long)f.num_parameters, p.kernel, p.tile_n, p.grid,
+           vitrs_ctx_create(&ctx, 0));
+    return 0;
+}
+''')
+    exe = tmp_path / "cabi"
+    libdir = os.path.dirname(vitrs.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe), "-L", libdir, "-lvitrs",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    version, params, kernel, tile_n, grid, ctx_rc = out.stdout.strip().split("|")
+    assert version.startswith("vitrs-b200") and int(params) == 86567656 and (int(kernel), int(tile_n), int(grid)) == (1, 256, 148)
+    import torch
+    if not torch.cuda.is_available():
+        assert int(ctx_rc) < 0  # no device: an error code, never a CPU path
