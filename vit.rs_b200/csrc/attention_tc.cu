@@ -230,7 +230,6 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         tmem_ld32(lane_addr + ch * 32, v);
         if (ch * 32 + 32 <= kend) {
             float s0 = 0.f, s1 = 0.f;
-#pragma unroll
             const float2 sl22 = splat2(sl2), nmx2 = splat2(-mxs);
             for (int c = 0; c < 16; ++c) {  // one packed FMA per pair of scores
                 const float2 a = fma2(make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1])), sl22, nmx2);
