@@ -38,12 +38,12 @@ class MBar:
             self.phase += 1
             self.pending = self.count
 
-    def arrive(self, intended):
+    def arrive(self, intended, n=1):
         if self.phase != intended:
             raise ProtocolError(f"{self.name}: arrival meant for phase {intended} lands in phase {self.phase}")
-        if self.pending <= 0:
+        if self.pending < n:
             raise ProtocolError(f"{self.name}: more arrivals than the barrier expects")
-        self.pending -= 1
+        self.pending -= n
         self._settle()
 
     def arrive_expect_tx(self, nbytes, intended):
@@ -63,20 +63,13 @@ class MBar:
         return (self.phase & 1) != parity
 
 
-class Launch:
-    """One kernel launch: `clusters` clusters of CG CTAs working through `total_units` units of `kb` k-blocks each."""
+class Sim:
+    """Random scheduler over role generators, asynchronous completions and in-order tensor pipes (one FIFO per key of `pipes`)."""
 
-    def __init__(self, rng, sched, total_units, kb, clusters, CG=2, STAGES=6, SLOTS=4, EPI=8, dynamic=True, epi_cost=3, slow=None,
-                 fault=None):
-        self.rng, self.sched, self.total, self.kb, self.clusters = rng, sched, total_units, kb, clusters
-        self.fault = fault  # a deliberately broken protocol (tests: the checker must notice)
-        self.CG, self.STAGES, self.SLOTS, self.EPI, self.dynamic, self.epi_cost = CG, STAGES, SLOTS, EPI, dynamic, epi_cost
+    def __init__(self, rng, slow=None):
+        self.rng = rng
         self.slow = slow or {}  # role kind -> probability of being skipped when picked (makes that role slow)
         self.threads, self.events, self.pipes = [], [], {}
-        self.processed = {}  # unit -> how many epilogue warps finished it
-        self.order = {}      # (cluster, role) -> [units]
-        for cl in range(clusters):
-            self._build_cluster(cl)
 
     # ---- scheduling ------------------------------------------------------------------------------------------------
     def spawn(self, kind, name, gen):
@@ -124,6 +117,21 @@ class Launch:
                     continue
                 heads[i - len(ready) - len(self.events)].pop(0)()  # the tensor pipe retires in order
         raise ProtocolError("step limit reached")
+
+
+class Launch(Sim):
+    """One kernel launch: `clusters` clusters of CG CTAs working through `total_units` units of `kb` k-blocks each."""
+
+    def __init__(self, rng, sched, total_units, kb, clusters, CG=2, STAGES=6, SLOTS=4, EPI=8, dynamic=True, epi_cost=3, slow=None,
+                 fault=None):
+        super().__init__(rng, slow)
+        self.sched, self.total, self.kb, self.clusters = sched, total_units, kb, clusters
+        self.fault = fault  # a deliberately broken protocol (tests: the checker must notice)
+        self.CG, self.STAGES, self.SLOTS, self.EPI, self.dynamic, self.epi_cost = CG, STAGES, SLOTS, EPI, dynamic, epi_cost
+        self.processed = {}  # unit -> how many epilogue warps finished it
+        self.order = {}      # (cluster, role) -> [units]
+        for cl in range(clusters):
+            self._build_cluster(cl)
 
     # ---- one cluster -----------------------------------------------------------------------------------------------
     def _build_cluster(self, cl):
